@@ -1,0 +1,195 @@
+/*
+ * kgcn_b200.h -- C ABI of libkgcn_b200.so: the B200 (sm_100a) batched graph-convolution path.
+ *
+ * This is the drop-in boundary for the three custom-op libraries kGCN loads with
+ * tf.load_op_library but does not ship (citations relative to clinfo/kGCN @ 32328d5):
+ *
+ *     ./bspmm.so    op "Bspmm"              kgcn/bspmm_call.py:8,15,18
+ *     ./bconv.so    op "Bconv"              kgcn/bconv_call.py:8,21,24-25
+ *     ./batched.so  ops "Bspmm", "Bspmdt"   kgcn/batched_call.py:8,14,26,29
+ *
+ * and for the TensorFlow ops the default branch of GraphConv / GraphDense / GraphGather lowers
+ * to (kgcn/layers.py:105-116, 243-262, 163-164).  INTEGRATION.md shows the binding a kGCN
+ * maintainer would add on top of it.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no C++ / torch types.  Unless a parameter says "host", every
+ *    pointer is a DEVICE pointer valid on the current CUDA device.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream).  Nothing synchronises the device; nothing allocates or frees device memory: the
+ *    caller owns every buffer, scratch space is passed in explicitly (kgcn_*_workspace_bytes).
+ *  - Every entry point returns a kgcn_status (0 = OK).  No exceptions cross the ABI, nothing
+ *    calls exit().  kgcn_last_error() returns a thread-local message for the last failure.
+ *  - Re-entrant; no global mutable state except that thread-local string and one-time
+ *    cudaFuncSetAttribute calls.  One host thread per GPU is the intended use.
+ *  - float = IEEE fp32.  Index arrays are int32 unless stated.
+ *
+ * Batched adjacency layout ("BatchedCSR")
+ *  A batch holds n_graphs * channels sparse matrices, each [n_rows, n_cols], ordered
+ *  graph-major / channel-minor exactly like the flattened lists of kgcn/bconv_call.py:11-15.
+ *  Matrix m = g*channels + c owns CSR rows [m*n_rows, (m+1)*n_rows):
+ *      rowptr[n_graphs*channels*n_rows + 1]  offsets into col/val, rowptr[0] = 0
+ *      col[nnz]                              column inside the matrix, 0 <= col < n_cols
+ *      val[nnz]                              fp32 value
+ *  Within a row, entries keep their COO *storage order* (stable sort), so per-output-element
+ *  summation order equals tf.sparse_tensor_dense_matmul's CPU kernel; duplicates are kept and
+ *  therefore accumulate.  The transpose ("adjoint_a") is a second BatchedCSR with n_rows and
+ *  n_cols swapped, built by the same packer.
+ */
+#ifndef KGCN_B200_H_
+#define KGCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGCN_B200_ABI_VERSION 1
+
+typedef enum kgcn_status {
+    KGCN_OK = 0,
+    KGCN_ERR_BAD_SHAPE = 1,     /* negative / zero / inconsistent sizes                        */
+    KGCN_ERR_MISALIGNED = 2,    /* pointer not aligned as the entry point requires             */
+    KGCN_ERR_INDEX_RANGE = 3,   /* sparse index outside dense_shape (TF: InvalidArgumentError) */
+    KGCN_ERR_CUDA = 4,          /* a CUDA runtime call failed; text in kgcn_last_error()       */
+    KGCN_ERR_WORKSPACE = 5,     /* workspace too small / NULL                                  */
+    KGCN_ERR_UNSUPPORTED = 6,   /* valid request this build has no kernel for                  */
+    KGCN_ERR_NULL = 7           /* required pointer is NULL                                    */
+} kgcn_status;
+
+/* Activation fused into epilogues; the set the shipped models apply after GraphConv /
+ * GraphDense (example_model/model.py:43-53 sigmoid, sparse_infer.py:43-58 relu, tanh). */
+typedef enum kgcn_act { KGCN_ACT_NONE = 0, KGCN_ACT_RELU = 1, KGCN_ACT_SIGMOID = 2, KGCN_ACT_TANH = 3 } kgcn_act;
+
+/* `flags` bits of the GraphConv entry points. */
+#define KGCN_FLAG_DEFAULT 0          /* library picks the fastest kernel that meets fp32 parity        */
+#define KGCN_FLAG_REFERENCE_ORDER 1  /* force the decomposed W-first path: (X.W + b) with exact-fp32    */
+                                     /* FFMA, then A.( ), i.e. the operation order of layers.py:112-113 */
+
+int kgcn_abi_version(void);
+/* Thread-local, never NULL, valid until the next failing call on this thread. */
+const char* kgcn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Ingest: COO (as fed through kgcn/feed.py:112-126 SparseTensorValue triples) -> BatchedCSR.
+ * HOST function, HOST pointers.  Replaces the per-placeholder feed of B*C sparse tensors
+ * (kgcn/default_model.py:10, kgcn/core.py:267-269).
+ *
+ *   n_mat          number of matrices (= n_graphs*channels), graph-major / channel-minor
+ *   n_rows,n_cols  dense_shape shared by all matrices (kgcn/data_util.py:30-37 align_size)
+ *   nnz_off[n_mat+1] exclusive prefix sum of per-matrix nnz (int64)
+ *   indices        [nnz,2] (row, col) pairs; idx_is_i64 != 0 -> int64 (TF placeholder dtype),
+ *                  else int32 (what data_util.py:40-45 produces)
+ *   values[nnz]    fp32
+ * Outputs (caller-allocated, host): rowptr[n_mat*n_rows+1], col[nnz], val[nnz], and
+ *   perm[nnz] (optional, may be NULL): CSR position -> original COO position.
+ * Pass transpose != 0 to build the adjoint instead (rowptr then has n_mat*n_cols+1 entries).
+ * Stable counting sort: entries of one CSR row keep COO storage order.
+ * Errors: KGCN_ERR_INDEX_RANGE for an index outside [0,n_rows) x [0,n_cols).
+ */
+int kgcn_pack_coo_host(int64_t n_mat, int32_t n_rows, int32_t n_cols, const int64_t* nnz_off,
+                       const void* indices, int32_t idx_is_i64, const float* values, int32_t transpose,
+                       int32_t* rowptr, int32_t* col, float* val, int32_t* perm);
+
+/* Same, on the device: inputs/outputs are DEVICE pointers, int32 indices only, one CTA per
+ * matrix does a stable counting sort in shared memory.  `status_flag` (device int32, caller
+ * zeroes it) is set to KGCN_ERR_INDEX_RANGE if any index is out of range. */
+int kgcn_pack_coo_device(int64_t n_mat, int32_t n_rows, int32_t n_cols, const int64_t* nnz_off,
+                         const int32_t* indices, const float* values, int32_t transpose,
+                         int32_t* rowptr, int32_t* col, float* val, int32_t* perm,
+                         int32_t* status_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched SpMM -- the "Bspmm" / "Bconv" / "Bspmdt" ops.
+ *
+ * For every graph g and channel c:   OUT(g,c) (+)= A[g,c] . RHS(g,c)
+ *     RHS(g,c) = rhs + g*rhs_stride_g + c*rhs_stride_c   row-major [n_cols, feat]
+ *     OUT(g,c) = out + g*out_stride_g + c*out_stride_c   row-major [n_rows, feat]
+ * (strides in floats).  With out_stride_c == 0 the channel contributions of one graph are
+ * summed in channel order into the same output (Bconv, kgcn/bconv_call.py:10-21; the tf.add_n
+ * of layers.py:115); with rhs_stride_c == 0 all channels share one right-hand side
+ * (GINAggregate, layers.py:468; the aggregate-first GraphConv).  Bspmm
+ * (kgcn/bspmm_call.py:10-15) is channels = 1; Bspmdt (kgcn/batched_call.py:21-26) is
+ * channels = 1 with rhs_stride_g = n_cols*feat over the stacked dense matrix.
+ * `self_scale` (device, [channels], may be NULL): adds self_scale[c] * RHS(g,c) row-wise
+ * (requires n_rows == n_cols) -- the epsilon term of GINAggregate (layers.py:469).
+ * adjoint_a is expressed by passing the transposed BatchedCSR.
+ * Output is fully overwritten (rows without entries become 0).
+ */
+int kgcn_bspmm_f32(const int32_t* rowptr, const int32_t* col, const float* val,
+                   int64_t n_graphs, int32_t channels, int32_t n_rows, int32_t n_cols, int32_t feat,
+                   const float* rhs, int64_t rhs_stride_g, int64_t rhs_stride_c,
+                   float* out, int64_t out_stride_g, int64_t out_stride_c,
+                   const float* self_scale, void* stream);
+
+/* Gradient w.r.t. the sparse values (kgcn/bspmm_call.py:49-54):
+ *   dval[perm ? perm[e] : e] = < DY(g,c)[row_e, :], RHS(g,c)[col_e, :] >   for every CSR entry e.
+ * DY strides follow the OUT convention above (stride_c = 0 replicates dY over channels as
+ * kgcn/bconv_call.py:46 does). */
+int kgcn_bspmm_dvalues_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                           int64_t n_graphs, int32_t channels, int32_t n_rows, int32_t n_cols, int32_t feat,
+                           const float* dy, int64_t dy_stride_g, int64_t dy_stride_c,
+                           const float* rhs, int64_t rhs_stride_g, int64_t rhs_stride_c,
+                           float* dval, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GraphConv forward (kgcn/layers.py:64-116, all four branches compute the same function):
+ *     y[g,i,:] = act( sum_c sum_{(i,j,v) in A[g,c]} v * ( x[g,j,:] . w[c] + bias[c] ) )
+ *   x [n_graphs, n_nodes, f_in]; w [channels, f_in, f_out]; bias [channels, f_out] (may be
+ *   NULL = zeros); y [n_graphs, n_nodes, f_out]; act = kgcn_act (KGCN_ACT_NONE reproduces the
+ *   layer itself; the others fuse the tf.sigmoid / tf.nn.relu the models apply next).
+ * The bias is applied BEFORE aggregation as the reference does (layers.py:112-113), i.e. a
+ * node receives rowsum(A[g,c])[i] * bias[c], and a row without entries outputs act(0).
+ * `workspace` must hold kgcn_graphconv_workspace_bytes(...) bytes.
+ */
+size_t kgcn_graphconv_workspace_bytes(int64_t n_graphs, int32_t channels, int32_t n_nodes,
+                                      int32_t f_in, int32_t f_out);
+int kgcn_graphconv_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val,
+                           int64_t n_graphs, int32_t channels, int32_t n_nodes,
+                           const float* x, int32_t f_in, const float* w, const float* bias, int32_t f_out,
+                           int32_t act, float* y, int32_t flags, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* GraphConv backward (TF autodiff through layers.py:112-116; the sparse half is
+ * kgcn/bspmm_call.py:44: dB = Bspmm(A, dY, adjoint_a=True)).
+ *   rowptr_t/col_t/val_t  transposed BatchedCSR of the forward adjacency
+ *   y, dy                 forward output (post-activation) and its gradient
+ *   dx [n_graphs,n_nodes,f_in] (may be NULL: first layer), dw [channels,f_in,f_out],
+ *   dbias [channels,f_out] -- all overwritten, not accumulated.
+ */
+int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t,
+                           int64_t n_graphs, int32_t channels, int32_t n_nodes,
+                           const float* x, int32_t f_in, const float* w, int32_t f_out,
+                           int32_t act, const float* y, const float* dy,
+                           float* dx, float* dw, float* dbias, int32_t flags,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GraphDense (kgcn/layers.py:223-265): y = act(x . kernel + bias) on all n_graphs*n_nodes rows
+ * (padding included, layers.py:255-262).  If enabled_node_nums (device int32 [n_graphs]) is
+ * non-NULL, rows i >= enabled_node_nums[g] are written as exact zeros (layers.py:243-254).
+ * kernel [f_in,f_out], bias [f_out] or NULL.
+ */
+int kgcn_graphdense_fwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t f_in,
+                            const float* kernel, const float* bias, int32_t f_out, int32_t act,
+                            const int32_t* enabled_node_nums, float* y, void* stream);
+size_t kgcn_graphdense_workspace_bytes(int64_t n_graphs, int32_t n_nodes, int32_t f_in, int32_t f_out);
+int kgcn_graphdense_bwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t f_in,
+                            const float* kernel, int32_t f_out, int32_t act,
+                            const int32_t* enabled_node_nums, const float* y, const float* dy,
+                            float* dx, float* dkernel, float* dbias,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GraphGather (kgcn/layers.py:156-167): out[g,:] = sum_i x[g,i,:] over ALL n_nodes rows
+ * (padding included).  Backward broadcasts: dx[g,i,:] = dout[g,:].
+ */
+int kgcn_gather_fwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* out, void* stream);
+int kgcn_gather_bwd_f32(const float* dout, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGCN_B200_H_ */

@@ -1,0 +1,22 @@
+// ABI bookkeeping: version and the thread-local last-error string (include/kgcn_b200.h).
+#include "common.cuh"
+
+namespace kgcn {
+
+char* error_buffer() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+}  // namespace kgcn
+
+extern "C" int kgcn_abi_version(void) { return KGCN_B200_ABI_VERSION; }
+extern "C" const char* kgcn_last_error(void) { return kgcn::error_buffer(); }

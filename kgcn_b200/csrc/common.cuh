@@ -1,0 +1,95 @@
+// Shared helpers for libkgcn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/kgcn_b200.h"
+
+namespace kgcn {
+
+// thread-local last-error text (include/kgcn_b200.h: kgcn_last_error)
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+
+#define KGCN_CUDA_OK(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t err__ = (expr);                                                             \
+        if (err__ != cudaSuccess)                                                               \
+            return ::kgcn::fail(KGCN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                                cudaGetErrorString(err__), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define KGCN_LAUNCH_OK(what)                                                                    \
+    do {                                                                                        \
+        cudaError_t err__ = cudaGetLastError();                                                 \
+        if (err__ != cudaSuccess)                                                               \
+            return ::kgcn::fail(KGCN_ERR_CUDA, "launch of %s failed: %s", what,                 \
+                                cudaGetErrorString(err__));                                     \
+    } while (0)
+
+#define KGCN_REQUIRE(cond, code, ...)                                                           \
+    do {                                                                                        \
+        if (!(cond)) return ::kgcn::fail(code, __VA_ARGS__);                                    \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+    return (a + b - 1) / b;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Activations.  Accurate expf/tanhf on purpose: parity tolerance is 1e-5 relative and these are
+// never the bottleneck (the kernels are HBM-bound).
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case KGCN_ACT_RELU: return fmaxf(x, 0.0f);
+        case KGCN_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+        case KGCN_ACT_TANH: return tanhf(x);
+        default: return x;
+    }
+}
+
+// d act / d pre-activation, expressed through the activation OUTPUT y (what forward stored).
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+    switch (act) {
+        case KGCN_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+        case KGCN_ACT_SIGMOID: return y * (1.0f - y);
+        case KGCN_ACT_TANH: return 1.0f - y * y;
+        default: return 1.0f;
+    }
+}
+
+// ---- internal launchers shared between translation units (all enqueue on `st`) ----
+
+// C[M,N] (ldc) = epilogue( op(A)[M,K] . op(B)[K,N] ), optional accumulate into C.
+struct GemmEpilogue {
+    const float* bias = nullptr;          // [N], added per column
+    int act = KGCN_ACT_NONE;              // applied after bias
+    const int32_t* enabled = nullptr;     // [M / n_nodes] rows >= enabled[g] -> 0
+    int n_nodes = 0;
+    bool accumulate = false;              // C += result (no bias/act allowed then)
+};
+int launch_sgemm(bool trans_a, bool trans_b, int64_t M, int N, int K, const float* A, int64_t lda,
+                 const float* B, int64_t ldb, float* C, int64_t ldc, const GemmEpilogue& ep, cudaStream_t st);
+
+// out[Ka, N] = A[M, Ka]^T . B[M, N], reduced over the (long) M dimension with a deterministic
+// two-pass split-K; also emits colsum_b[N] = column sums of B (may be null).
+size_t reduce_gemm_workspace_bytes(int64_t M, int Ka, int N);
+int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda, const float* B, int64_t ldb,
+                          float* out, float* colsum_b, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// du = dy * act'(y) (elementwise), optional row mask by enabled_node_nums.
+int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act,
+                    const int32_t* enabled, int n_nodes, cudaStream_t st);
+
+int launch_bspmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
+                 int n_rows, int n_cols, int feat, const float* rhs, int64_t rs_g, int64_t rs_c, float* out,
+                 int64_t os_g, int64_t os_c, const float* self_scale, int act, cudaStream_t st);
+
+}  // namespace kgcn

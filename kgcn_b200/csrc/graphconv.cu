@@ -1,0 +1,123 @@
+// GraphConv forward / backward entry points (include/kgcn_b200.h).
+//
+// Two implementations sit behind kgcn_graphconv_fwd_f32:
+//   * the fused single-kernel layer (graphconv_fused.cu) -- aggregate-first, tensor-core X.W,
+//     used whenever the shape is eligible and KGCN_FLAG_REFERENCE_ORDER is not set;
+//   * the decomposed path in this file, which keeps the reference's operation order
+//     (kgcn/layers.py:112-113: fw = x.W_c + b_c, then A.fw, then the channel sum of :115) with
+//     exact-fp32 FFMA GEMMs.  It handles every shape (odd feature widths, B=1 / huge N) and is
+//     the in-library cross-check for the fused kernel.
+#include "common.cuh"
+
+namespace kgcn {
+
+// implemented in graphconv_fused.cu
+bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x,
+                        const float* y);
+int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                               int channels, int n_nodes, const float* x, int f_in, const float* w, const float* bias,
+                               int f_out, int act, float* y, cudaStream_t st);
+
+namespace {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+}  // namespace kgcn
+
+using namespace kgcn;
+
+extern "C" size_t kgcn_graphconv_workspace_bytes(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in,
+                                                 int32_t f_out) {
+    if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || f_in <= 0 || f_out <= 0) return 0;
+    const size_t act_elems = static_cast<size_t>(n_graphs) * n_nodes * f_out;
+    // forward: H[C][B*N][f_out]; backward: du[B*N][f_out] + G[C][B*N][f_out] + split-K partials
+    return align_up((1 + static_cast<size_t>(channels)) * act_elems * sizeof(float), 256) +
+           align_up(reduce_gemm_workspace_bytes(n_graphs * n_nodes, f_in, f_out), 256);
+}
+
+extern "C" int kgcn_graphconv_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                                      int32_t channels, int32_t n_nodes, const float* x, int32_t f_in, const float* w,
+                                      const float* bias, int32_t f_out, int32_t act, float* y, int32_t flags,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    KGCN_REQUIRE(rowptr && col && val && x && w && y, KGCN_ERR_NULL, "graphconv_fwd: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs >= 0 && channels > 0 && n_nodes > 0 && f_in > 0 && f_out > 0, KGCN_ERR_BAD_SHAPE,
+                 "graphconv_fwd: bad shape n_graphs=%lld channels=%d n_nodes=%d f_in=%d f_out=%d", (long long)n_graphs,
+                 channels, n_nodes, f_in, f_out);
+    KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "graphconv_fwd: unknown act %d", act);
+    if (n_graphs == 0) return KGCN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && fused_fwd_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y))
+        return launch_graphconv_fused_fwd(rowptr, col, val, n_graphs, channels, n_nodes, x, f_in, w, bias, f_out, act,
+                                          y, st);
+
+    const int64_t rows = n_graphs * n_nodes;
+    const size_t need = static_cast<size_t>(channels) * rows * f_out * sizeof(float);
+    KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= need, KGCN_ERR_WORKSPACE,
+                 "graphconv_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+    float* h = static_cast<float*>(workspace);  // [C][B*N][f_out]
+    for (int c = 0; c < channels; ++c) {
+        GemmEpilogue ep;
+        ep.bias = bias ? bias + static_cast<size_t>(c) * f_out : nullptr;
+        int rc = launch_sgemm(false, false, rows, f_out, f_in, x, f_in, w + static_cast<size_t>(c) * f_in * f_out,
+                              f_out, h + static_cast<size_t>(c) * rows * f_out, f_out, ep, st);
+        if (rc) return rc;
+    }
+    return launch_bspmm(rowptr, col, val, n_graphs, channels, n_nodes, n_nodes, f_out, h,
+                        static_cast<int64_t>(n_nodes) * f_out, rows * f_out, y, static_cast<int64_t>(n_nodes) * f_out,
+                        0, nullptr, act, st);
+}
+
+extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t,
+                                      int64_t n_graphs, int32_t channels, int32_t n_nodes, const float* x,
+                                      int32_t f_in, const float* w, int32_t f_out, int32_t act, const float* y,
+                                      const float* dy, float* dx, float* dw, float* dbias, int32_t flags,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    (void)flags;
+    KGCN_REQUIRE(rowptr_t && col_t && val_t && x && w && dy && dw, KGCN_ERR_NULL, "graphconv_bwd: NULL pointer argument");
+    KGCN_REQUIRE(act == KGCN_ACT_NONE || y != nullptr, KGCN_ERR_NULL, "graphconv_bwd: y required when act != none");
+    KGCN_REQUIRE(n_graphs >= 0 && channels > 0 && n_nodes > 0 && f_in > 0 && f_out > 0, KGCN_ERR_BAD_SHAPE,
+                 "graphconv_bwd: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_graphs == 0) {
+        KGCN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * channels * f_in * f_out, st));
+        if (dbias) KGCN_CUDA_OK(cudaMemsetAsync(dbias, 0, sizeof(float) * channels * f_out, st));
+        return KGCN_OK;
+    }
+    const int64_t rows = n_graphs * n_nodes;
+    const size_t act_elems = static_cast<size_t>(rows) * f_out;
+    KGCN_REQUIRE(workspace != nullptr &&
+                     workspace_bytes >= kgcn_graphconv_workspace_bytes(n_graphs, channels, n_nodes, f_in, f_out),
+                 KGCN_ERR_WORKSPACE, "graphconv_bwd: workspace too small");
+    float* du = static_cast<float*>(workspace);                     // [B*N][f_out]
+    float* gbuf = du + act_elems;                                   // [C][B*N][f_out]
+    const size_t used = align_up((1 + static_cast<size_t>(channels)) * act_elems * sizeof(float), 256);
+    void* ws2 = static_cast<char*>(workspace) + used;
+    const size_t ws2_bytes = workspace_bytes - used;
+
+    const float* du_ptr = dy;
+    if (act != KGCN_ACT_NONE) {
+        int rc = launch_act_grad(y, dy, du, static_cast<int64_t>(act_elems), f_out, act, nullptr, n_nodes, st);
+        if (rc) return rc;
+        du_ptr = du;
+    }
+    // G[c] = A_c^T . dU   (bspmm_call.py:44), channel-major so each G[c] is a contiguous [B*N, f_out]
+    int rc = launch_bspmm(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, n_nodes, f_out, du_ptr,
+                          static_cast<int64_t>(n_nodes) * f_out, 0, gbuf, static_cast<int64_t>(n_nodes) * f_out,
+                          static_cast<int64_t>(act_elems), nullptr, KGCN_ACT_NONE, st);
+    if (rc) return rc;
+    for (int c = 0; c < channels; ++c) {
+        const float* g_c = gbuf + static_cast<size_t>(c) * act_elems;
+        rc = launch_reduce_gemm_tn(rows, f_in, f_out, x, f_in, g_c, f_out, dw + static_cast<size_t>(c) * f_in * f_out,
+                                   dbias ? dbias + static_cast<size_t>(c) * f_out : nullptr, ws2, ws2_bytes, st);
+        if (rc) return rc;
+        if (dx != nullptr) {
+            GemmEpilogue ep;
+            ep.accumulate = c > 0;
+            rc = launch_sgemm(false, true, rows, f_in, f_out, g_c, f_out, w + static_cast<size_t>(c) * f_in * f_out,
+                              f_out, dx, f_in, ep, st);
+            if (rc) return rc;
+        }
+    }
+    return KGCN_OK;
+}

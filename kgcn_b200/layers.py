@@ -1,0 +1,256 @@
+"""kGCN graph layers on the B200 library -- the host-side mirror of ``kgcn/layers.py``.
+
+Same class names, constructor arguments, call signatures and weight names as the reference
+(clinfo/kGCN @ 32328d5) so that model definitions written against ``kgcn.layers`` read the same:
+
+    GraphConv(output_dim, adj_channel_num, initializer='glorot_uniform')(x, adj=adjs)   layers.py:32-119
+    GraphDense(output_dim, **dense_kw)(x, enabled_node_nums=None, shape=None, max_node_num=None)  :223-265
+    GraphGather()(x)                                                                   :156-167
+    GINAggregate(adj_channel_num, initializer='zeros')(x, adj=adjs)                    :400-475
+    BatchGraphConv(output_dim, ...)([x, adj])                                          :363-398
+    load_bspmm(args)                                                                   :19-29
+
+Tensors are CUDA ``torch.Tensor``s; ``adj`` is either the reference's ``list[B][C]`` of
+``(indices, values, dense_shape)`` triples (what kgcn/feed.py:112-126 feeds) or a pre-packed
+:class:`kgcn_b200.csr.BatchedCSR`.  All arithmetic happens in ``libkgcn_b200.so``; there is no
+CPU fallback (a missing library is an ImportError, a CPU tensor is a KgcnError).
+"""
+import math
+import os
+
+import torch
+
+from . import _lib, ops
+from .csr import BatchedCSR, as_batched_csr
+
+enabled_batched = False
+enabled_bspmm = False
+enabled_bconv = False
+
+
+def load_bspmm(args):
+    """Mode switch of kgcn/layers.py:19-29.  The reference enables a plugin branch only when its
+    flag is set AND ``./<name>.so`` exists; here all three ops live in ``libkgcn_b200.so``, which
+    is always present (importing this package fails otherwise), so the flag alone decides --
+    first of batched / bspmm / bconv, as in the reference."""
+    global enabled_batched, enabled_bspmm, enabled_bconv
+    enabled_batched = enabled_bspmm = enabled_bconv = False
+    if getattr(args, "batched", False):
+        enabled_batched = True
+    elif getattr(args, "bspmm", False):
+        enabled_bspmm = True
+    elif getattr(args, "bconv", False):
+        enabled_bconv = True
+
+
+def _init_tensor(initializer, shape, fan_in, fan_out, device):
+    if callable(initializer):
+        t = torch.as_tensor(initializer(shape), dtype=torch.float32)
+        return t.reshape(shape).to(device)
+    if initializer in ("glorot_uniform", None):
+        lim = math.sqrt(6.0 / (fan_in + fan_out))  # Keras glorot_uniform (layers.py:54-57)
+        return torch.empty(shape, dtype=torch.float32, device=device).uniform_(-lim, lim)
+    if initializer == "zeros":
+        return torch.zeros(shape, dtype=torch.float32, device=device)
+    if initializer == "ones":
+        return torch.ones(shape, dtype=torch.float32, device=device)
+    raise ValueError("unsupported initializer %r" % (initializer,))
+
+
+class Layer(torch.nn.Module):
+    """Keras-style lazily built layer: weights are created on the first call from the input shape."""
+
+    def __init__(self, name=None, trainable=True, dtype=None, **kwargs):
+        super().__init__()
+        self._layer_name = name
+        self.trainable = trainable
+        self.built = False
+
+    def add_weight(self, name, shape, initializer, trainable=True, fan_in=1, fan_out=1, device="cuda"):
+        value = _init_tensor(initializer, tuple(shape), fan_in, fan_out, device)
+        param = torch.nn.Parameter(value, requires_grad=bool(trainable and self.trainable))
+        self.register_parameter(name, param)
+        return param
+
+    def build(self, input_shape):
+        self.built = True
+
+    def forward(self, inputs, *args, **kwargs):
+        if not self.built:
+            first = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+            self._build_device = first.device
+            self.build([tuple(t.shape) for t in inputs] if isinstance(inputs, (list, tuple)) else tuple(inputs.shape))
+            self.built = True
+        return self.call(inputs, *args, **kwargs)
+
+
+class GraphConv(Layer):
+    """``out[b] = sum_c A[b][c] . (x[b] . kernel_c + bias_c)`` (kgcn/layers.py:105-116).
+
+    ``activation`` (extension, default None = reference behaviour) fuses the ``tf.sigmoid`` /
+    ``tf.nn.relu`` that the shipped models apply right after the layer into the same kernel."""
+
+    def __init__(self, output_dim, adj_channel_num, initializer="glorot_uniform", activation=None,
+                 reference_order=False, **kwargs):
+        super().__init__(**kwargs)
+        self.output_dim = int(output_dim)
+        self.adj_channel_num = int(adj_channel_num)
+        self.initializer = initializer
+        self.activation = activation
+        self.reference_order = reference_order
+        if enabled_bspmm:
+            from . import bspmm_call as bspmm
+            self.bspmm_obj = bspmm.BatchedSpMM()
+        if enabled_bconv:
+            from . import bconv_call as bconv
+            self.bconv_obj = bconv.BatchedConv()
+        if enabled_batched:
+            from . import batched_call as batched
+            self.bspmdt_obj = batched.BatchedSpMDT()
+
+    def build(self, input_shape):  # input: batch_size x node_num x #inputs
+        f_in = int(input_shape[2])
+        self.w, self.bias = [], []
+        for i in range(self.adj_channel_num):
+            self.w.append(self.add_weight("kernel" + str(i), (f_in, self.output_dim), self.initializer,
+                                          fan_in=f_in, fan_out=self.output_dim, device=self._build_device))
+            self.bias.append(self.add_weight("bias" + str(i), (1, self.output_dim), "zeros", device=self._build_device))
+
+    def _stacked(self):
+        if self.adj_channel_num == 1:
+            return self.w[0].unsqueeze(0), self.bias[0]
+        return torch.stack(list(self.w)), torch.cat(list(self.bias), 0)
+
+    def call(self, inputs, adj=None):
+        if adj is None:
+            raise ValueError("GraphConv needs adj=")
+        csr = as_batched_csr(adj, inputs.device)
+        act = ops.act_id(self.activation)
+        B, N, _ = inputs.shape
+        if enabled_bconv or enabled_bspmm or enabled_batched:
+            # plugin branches (layers.py:68-104): dense X.W_c + b_c for the whole batch, then ONE
+            # batched sparse op.  fw[b][c] of the reference is fw[b, c] here.
+            fw = torch.stack([ops.GraphDenseFunction.apply(inputs, self.w[c], self.bias[c].reshape(-1), 0, None)
+                              for c in range(self.adj_channel_num)], dim=1)          # [B, C, N, F_out]
+            if enabled_bconv:
+                out = self.bconv_obj.call_packed(csr, fw)
+            elif enabled_bspmm:
+                out = self.bspmm_obj.call_packed(csr, fw).sum(dim=1) if self.adj_channel_num > 1 else \
+                    self.bspmm_obj.call_packed(csr, fw)[:, 0]
+            else:
+                out = self.bspmdt_obj.call_packed(csr, fw)
+            return _apply_act_torch(out, self.activation)
+        w, bias = self._stacked()
+        flags = _lib.FLAG_REFERENCE_ORDER if self.reference_order else _lib.FLAG_DEFAULT
+        return ops.GraphConvFunction.apply(inputs, w, bias, csr, act, flags)
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0], input_shape[1], self.output_dim
+
+
+def _apply_act_torch(x, activation):
+    if activation in (None, "none", "linear"):
+        return x
+    return {"relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[activation](x)
+
+
+class GraphGather(Layer):
+    """``reduce_sum(inputs, axis=1)`` over ALL node rows, padding included (layers.py:163-164)."""
+
+    def call(self, inputs, **kwargs):
+        return ops.GraphGatherFunction.apply(inputs)
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0], input_shape[2]
+
+
+class GraphDense(Layer):
+    """Keras ``Dense`` applied to every node row (layers.py:223-265).  Accepted Dense kwargs:
+    ``activation`` (None / 'relu' / 'sigmoid' / 'tanh' fused; any other callable is applied after),
+    ``use_bias``, ``kernel_initializer``, ``bias_initializer``."""
+
+    def __init__(self, output_dim, activation=None, use_bias=True, kernel_initializer="glorot_uniform",
+                 bias_initializer="zeros", **kwargs):
+        super().__init__(**kwargs)
+        self.output_dim = self.units = int(output_dim)
+        self.activation = activation
+        self.use_bias = use_bias
+        self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
+
+    def build(self, input_shape):  # input: batch_size x node_num x #inputs
+        self.data_shape = input_shape
+        f_in = int(input_shape[-1])
+        self.kernel = self.add_weight("kernel", (f_in, self.units), self.kernel_initializer, fan_in=f_in,
+                                      fan_out=self.units, device=self._build_device)
+        self.bias = self.add_weight("bias", (self.units,), self.bias_initializer, device=self._build_device) \
+            if self.use_bias else None
+
+    def call(self, inputs, enabled_node_nums=None, shape=None, max_node_num=None, **kwargs):
+        fused = self.activation if (self.activation is None or isinstance(self.activation, str)) else None
+        x = inputs
+        if shape is not None:
+            x = x.reshape(int(shape[0]), int(shape[1]), int(shape[2]))
+        elif x.dim() == 2:  # already flattened [B*N, F]
+            x = x.unsqueeze(0)
+        if enabled_node_nums is not None and not torch.is_tensor(enabled_node_nums):
+            enabled_node_nums = torch.as_tensor(enabled_node_nums, dtype=torch.int32, device=x.device)
+        out = ops.GraphDenseFunction.apply(x, self.kernel, self.bias, ops.act_id(fused), enabled_node_nums)
+        if callable(self.activation):
+            out = self.activation(out)
+            if enabled_node_nums is not None:  # padded rows stay exactly zero (layers.py:249-253)
+                keep = torch.arange(x.shape[1], device=x.device)[None, :] < enabled_node_nums[:, None]
+                out = out * keep[:, :, None]
+        return out
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0], input_shape[1], self.output_dim
+
+
+class GINAggregate(Layer):
+    """``sum_c (epsilon_c * x[b] + A[b][c] . x[b])`` (layers.py:459-471); no weights besides epsilon."""
+
+    def __init__(self, adj_channel_num, initializer="zeros", **kwargs):
+        super().__init__(**kwargs)
+        self.adj_channel_num = int(adj_channel_num)
+        self.initializer = initializer
+
+    def build(self, input_shape):
+        self.epsilon = [self.add_weight("epsilon" + str(i), (), self.initializer, device=self._build_device)
+                        for i in range(self.adj_channel_num)]
+
+    def call(self, inputs, adj=None):
+        csr = as_batched_csr(adj, inputs.device)
+        agg = ops.BspmmFunction.apply(inputs, None, csr, "shared_sum")
+        eps = torch.stack(list(self.epsilon)).sum()
+        return agg + eps * inputs
+
+    def compute_output_shape(self, input_shape):
+        return input_shape
+
+
+class BatchGraphConv(Layer):
+    """Block-diagonal form ``relu(A . (x . W + b))`` with inputs ``[x [sumN, F_in], A]``
+    (layers.py:363-398; used by example_model/sparse.py with batch dimension 1)."""
+
+    def __init__(self, output_dim, adj_channel_num=1, initializer="glorot_uniform", input_dim=None, **kwargs):
+        super().__init__(**kwargs)
+        self.output_dim, self.adj_channel_num = int(output_dim), int(adj_channel_num)
+        self.initializer, self.input_dim = initializer, input_dim
+
+    def build(self, input_shape):
+        f_in = int(input_shape[0][1]) if self.input_dim is None else int(self.input_dim)
+        # the reference loop overwrites self.w / self.bias per channel (layers.py:376-386): one pair survives
+        last = self.adj_channel_num - 1
+        self.w = self.add_weight("kernel" + str(last), (f_in, self.output_dim), self.initializer, fan_in=f_in,
+                                 fan_out=self.output_dim, device=self._build_device)
+        self.bias = self.add_weight("bias" + str(last), (self.output_dim,), "zeros", device=self._build_device)
+
+    def call(self, inputs, **kwargs):
+        net, adj = inputs[0], inputs[1]
+        csr = adj if isinstance(adj, BatchedCSR) else as_batched_csr([[adj]], net.device)
+        out = ops.GraphConvFunction.apply(net.unsqueeze(0), self.w.unsqueeze(0), self.bias.reshape(1, -1), csr,
+                                          ops.act_id("relu"), _lib.FLAG_DEFAULT)
+        return out[0]
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0][0], self.output_dim
