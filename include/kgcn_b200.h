@@ -71,6 +71,9 @@ typedef enum kgcn_act { KGCN_ACT_NONE = 0, KGCN_ACT_RELU = 1, KGCN_ACT_SIGMOID =
 int kgcn_abi_version(void);
 /* Thread-local, never NULL, valid until the next failing call on this thread. */
 const char* kgcn_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (monotonic, relaxed
+ * atomic; launches recorded during CUDA-graph capture count once).  Diagnostics only. */
+uint64_t kgcn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Ingest: COO (as fed through kgcn/feed.py:112-126 SparseTensorValue triples) -> BatchedCSR.
@@ -188,6 +191,35 @@ int kgcn_graphdense_bwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, i
  */
 int kgcn_gather_fwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* out, void* stream);
 int kgcn_gather_bwd_f32(const float* dout, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Step-loop helpers (the minimal trainer around the layers; kgcn/core.py:121-127, 267-269).
+ *
+ * Readout head of the shipped classifiers (example_model/model.py:56-69):
+ *   logits = g . w + bias;  prediction = softmax(logits);
+ *   cost[b] = mask[b] * softmax_cross_entropy(labels[b], logits[b]);
+ *   stats[0] = cost_sum = sum_b cost[b];  stats[1] = correct_count (argmax match, masked);
+ *   gradients of cost_opt = inv_batch * sum_b cost[b] (reduce_mean, inv_batch = 1/batch_size):
+ *   dlogits [B,L], dg [B,F] = dlogits . w^T, dw [F,L] = g^T . dlogits, dbias [L].
+ * g [n_graphs, feat]; w [feat, n_labels]; labels [n_graphs, n_labels] (one-hot or soft);
+ * mask [n_graphs] or NULL.  Any output pointer may be NULL (dw needs dlogits).  n_labels <= 32.
+ */
+size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels);
+int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const float* w, const float* bias,
+                          int32_t n_labels, const float* labels, const float* mask, float inv_batch,
+                          float* logits, float* prediction, float* stats, float* dlogits, float* dg,
+                          float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adam with TensorFlow's formulation (tf.train.AdamOptimizer, kgcn/core.py:121-127):
+ *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   param -= lr * sqrt(1-b2^step)/(1-b1^step) * m / (sqrt(v) + eps);     step counts from 1.
+ * One launch over a flat buffer of n floats (all layers' kernels and biases back to back).
+ * step_state (device int32[2], zero-initialised by the caller, may be NULL): when given, the step
+ * number is read from and advanced on the DEVICE (step = step_state[0] + 1) and the host `step`
+ * argument is ignored -- launch parameters then never change, so a training step can be captured
+ * once in a CUDA graph and replayed. */
+int kgcn_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, float grad_scale, int32_t* step_state, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,7 @@ _i32, _i64, _sz, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c
 SIGNATURES = {
     "kgcn_abi_version": (ctypes.c_int, []),
     "kgcn_last_error": (ctypes.c_char_p, []),
+    "kgcn_launch_count": (ctypes.c_uint64, []),
     "kgcn_pack_coo_host": (ctypes.c_int, [_i64, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "kgcn_pack_coo_device": (ctypes.c_int, [_i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kgcn_bspmm_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
@@ -74,6 +75,9 @@ SIGNATURES = {
     "kgcn_graphdense_bwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_gather_fwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "kgcn_gather_bwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "kgcn_readout_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "kgcn_readout_xent_f32": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "kgcn_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i64, ctypes.c_float, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

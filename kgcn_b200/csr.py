@@ -40,7 +40,9 @@ def flatten_coo(adjs):
         for c, sp in enumerate(row):
             i, v, s = _triple(sp)
             if torch.is_tensor(i):
-                i, v = i.detach().cpu().numpy(), v.detach().cpu().numpy()
+                i = i.detach().cpu().numpy()
+            if torch.is_tensor(v):
+                v = v.detach().cpu().numpy()
             i = np.asarray(i).reshape(-1, 2)
             v = np.asarray(v, np.float32).reshape(-1)
             if i.shape[0] != v.shape[0]:

@@ -1,4 +1,6 @@
 // ABI bookkeeping: version and the thread-local last-error string (include/kgcn_b200.h).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace kgcn {
@@ -16,7 +18,11 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 }  // namespace kgcn
 
+extern "C" uint64_t kgcn_launch_count(void) { return kgcn::g_launches.load(std::memory_order_relaxed); }
 extern "C" int kgcn_abi_version(void) { return KGCN_B200_ABI_VERSION; }
 extern "C" const char* kgcn_last_error(void) { return kgcn::error_buffer(); }

@@ -13,6 +13,7 @@ namespace kgcn {
 // thread-local last-error text (include/kgcn_b200.h: kgcn_last_error)
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
+void count_launch();  // process-wide counter of kernel launches issued by this library (kgcn_launch_count)
 
 #define KGCN_CUDA_OK(expr)                                                                      \
     do {                                                                                        \
@@ -24,6 +25,7 @@ int fail(int code, const char* fmt, ...);
 
 #define KGCN_LAUNCH_OK(what)                                                                    \
     do {                                                                                        \
+        ::kgcn::count_launch();                                                                 \
         cudaError_t err__ = cudaGetLastError();                                                 \
         if (err__ != cudaSuccess)                                                               \
             return ::kgcn::fail(KGCN_ERR_CUDA, "launch of %s failed: %s", what,                 \

@@ -1,0 +1,146 @@
+// Step-loop kernels around the graph layers: the readout head of the shipped classifiers
+// (example_model/model.py:56-69: Dense(label_dim) -> softmax -> mask * softmax_cross_entropy ->
+// reduce_mean / reduce_sum / correct_count) with its backward, and Adam (kgcn/core.py:121-127,
+// TF defaults beta1 .9, beta2 .999, eps 1e-8) over one flat parameter buffer.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace kgcn {
+namespace {
+
+constexpr int kMaxLabels = 32;
+
+// One warp per graph.
+__global__ void __launch_bounds__(128) readout_xent_kernel(const float* __restrict__ g, int64_t n_graphs, int feat,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           int n_labels, const float* __restrict__ labels,
+                                                           const float* __restrict__ mask, float inv_batch,
+                                                           float* __restrict__ logits, float* __restrict__ prediction,
+                                                           float* __restrict__ dlogits, float* __restrict__ dg,
+                                                           float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_graphs) return;
+    const float* gb = g + b * feat;
+    float z[kMaxLabels];
+#pragma unroll 1
+    for (int l = 0; l < n_labels; ++l) {
+        float acc = 0.0f;
+        for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w[static_cast<int64_t>(f) * n_labels + l], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        z[l] = acc + (bias ? bias[l] : 0.0f);
+    }
+    // softmax cross-entropy with (possibly soft) labels: cost = -sum_l y_l * log_softmax(z)_l
+    float zmax = z[0];
+    for (int l = 1; l < n_labels; ++l) zmax = fmaxf(zmax, z[l]);
+    float sum = 0.0f;
+    for (int l = 0; l < n_labels; ++l) sum += expf(z[l] - zmax);
+    const float lse = logf(sum) + zmax;
+    const float m = mask ? mask[b] : 1.0f;
+    float cost = 0.0f, ysum = 0.0f;
+    int arg_p = 0, arg_y = 0;
+    for (int l = 0; l < n_labels; ++l) {
+        const float y = labels[b * n_labels + l];
+        cost -= y * (z[l] - lse);
+        ysum += y;
+        if (z[l] > z[arg_p]) arg_p = l;
+        if (y > labels[b * n_labels + arg_y]) arg_y = l;
+    }
+    float dz[kMaxLabels];
+    for (int l = 0; l < n_labels; ++l) {
+        const float pr = expf(z[l] - lse);
+        dz[l] = m * inv_batch * (pr * ysum - labels[b * n_labels + l]);
+        if (lane == 0) {
+            if (logits) logits[b * n_labels + l] = z[l];
+            if (prediction) prediction[b * n_labels + l] = pr;
+            if (dlogits) dlogits[b * n_labels + l] = dz[l];
+        }
+    }
+    if (dg != nullptr) {
+        for (int f = lane; f < feat; f += 32) {
+            float acc = 0.0f;
+            for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w[static_cast<int64_t>(f) * n_labels + l], acc);
+            dg[b * feat + f] = acc;
+        }
+    }
+    if (lane == 0 && stats != nullptr) {
+        atomicAdd(stats + 0, m * cost);                                 // cost_sum   (model.py:64)
+        atomicAdd(stats + 1, m * (arg_p == arg_y ? 1.0f : 0.0f));       // correct_count (model.py:66-69)
+    }
+}
+
+// step_state (device, may be null): [0] = number of steps already applied, [1] = block ticket.
+// Reading the step on the device keeps the launch parameters constant, so the whole training step
+// can be replayed from a CUDA graph; the last block to finish advances the counter.
+__global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                            float grad_scale, int host_step, int* __restrict__ step_state) {
+    const int t = step_state != nullptr ? step_state[0] + 1 : host_step;
+    // TF AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+    const float lr_t = lr * sqrtf(1.0f - powf(beta2, static_cast<float>(t))) / (1.0f - powf(beta1, static_cast<float>(t)));
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float gr = grad[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        param[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+    if (step_state != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(step_state + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+                step_state[0] = t;
+                step_state[1] = 0;
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace kgcn
+
+using namespace kgcn;
+
+extern "C" size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels) {
+    if (n_graphs <= 0) return 0;
+    return reduce_gemm_workspace_bytes(n_graphs, feat, n_labels);
+}
+
+extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const float* w, const float* bias,
+                                     int32_t n_labels, const float* labels, const float* mask, float inv_batch,
+                                     float* logits, float* prediction, float* stats, float* dlogits, float* dg,
+                                     float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+    KGCN_REQUIRE(g && w && labels, KGCN_ERR_NULL, "readout_xent: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && feat > 0 && n_labels > 0 && n_labels <= kMaxLabels, KGCN_ERR_BAD_SHAPE,
+                 "readout_xent: bad shape (n_labels <= %d)", kMaxLabels);
+    KGCN_REQUIRE(dw == nullptr || dlogits != nullptr, KGCN_ERR_NULL, "readout_xent: dw needs a dlogits buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (stats) KGCN_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * sizeof(float), st));
+    const int64_t blocks = ceil_div<int64_t>(n_graphs * 32, 128);
+    readout_xent_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(g, n_graphs, feat, w, bias, n_labels, labels,
+                                                                       mask, inv_batch, logits, prediction, dlogits, dg,
+                                                                       stats);
+    KGCN_LAUNCH_OK("readout_xent_kernel");
+    if (dw != nullptr)
+        return launch_reduce_gemm_tn(n_graphs, feat, n_labels, g, feat, dlogits, n_labels, dw, dbias, workspace,
+                                     workspace_bytes, st);
+    return KGCN_OK;
+}
+
+extern "C" int kgcn_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int64_t step, float grad_scale, int32_t* step_state, void* stream) {
+    KGCN_REQUIRE(param && grad && m && v, KGCN_ERR_NULL, "adam: NULL pointer argument");
+    KGCN_REQUIRE(n >= 0 && (step_state != nullptr || step >= 1), KGCN_ERR_BAD_SHAPE, "adam: bad n/step");
+    if (n == 0) return KGCN_OK;
+    const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(n, 256), kNumSMs * 8);
+    adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, static_cast<int>(step), step_state);
+    KGCN_LAUNCH_OK("adam_kernel");
+    return KGCN_OK;
+}

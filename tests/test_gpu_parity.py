@@ -318,6 +318,7 @@ def test_device_pack_equals_host_pack(K):
     val = rng.standard_normal(nnz).astype(np.float32)
     off = np.zeros(counts.size + 1, np.int64)
     np.cumsum(counts.reshape(-1), out=off[1:])
+    d_off, d_idx, d_val = dev(off, torch.int64), dev(idx, torch.int32), dev(val)     # keep alive across the launches
     for transpose in (0, 1):
         want = K["csr"].pack_host(counts, idx, val, 17, 17, transpose=bool(transpose), want_perm=True)
         rowptr = torch.empty(counts.size * 17 + 1, dtype=torch.int32, device="cuda")
@@ -325,16 +326,17 @@ def test_device_pack_equals_host_pack(K):
         v = torch.empty(nnz, dtype=torch.float32, device="cuda")
         perm = torch.empty(nnz, dtype=torch.int32, device="cuda")
         flag = torch.zeros(1, dtype=torch.int32, device="cuda")
-        _lib.check(_lib.lib.kgcn_pack_coo_device(counts.size, 17, 17, dev(off, torch.int64).data_ptr(), dev(idx, torch.int32).data_ptr(),
-                                                 dev(val).data_ptr(), transpose, rowptr.data_ptr(), col.data_ptr(), v.data_ptr(),
+        _lib.check(_lib.lib.kgcn_pack_coo_device(counts.size, 17, 17, d_off.data_ptr(), d_idx.data_ptr(),
+                                                 d_val.data_ptr(), transpose, rowptr.data_ptr(), col.data_ptr(), v.data_ptr(),
                                                  perm.data_ptr(), flag.data_ptr(), torch.cuda.current_stream().cuda_stream))
         assert int(flag.item()) == 0
         for g, w in zip((rowptr, col, v, perm), want):
             np.testing.assert_array_equal(g.cpu().numpy(), w)
     bad = idx.copy(); bad[3, 1] = 17
+    d_bad = dev(bad, torch.int32)
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _lib.check(_lib.lib.kgcn_pack_coo_device(counts.size, 17, 17, dev(off, torch.int64).data_ptr(), dev(bad, torch.int32).data_ptr(),
-                                             dev(val).data_ptr(), 0, rowptr.data_ptr(), col.data_ptr(), v.data_ptr(), perm.data_ptr(),
+    _lib.check(_lib.lib.kgcn_pack_coo_device(counts.size, 17, 17, d_off.data_ptr(), d_bad.data_ptr(),
+                                             d_val.data_ptr(), 0, rowptr.data_ptr(), col.data_ptr(), v.data_ptr(), perm.data_ptr(),
                                              flag.data_ptr(), torch.cuda.current_stream().cuda_stream))
     assert int(flag.item()) == 3   # KGCN_ERR_INDEX_RANGE
 
