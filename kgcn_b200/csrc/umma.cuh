@@ -1,0 +1,83 @@
+// tcgen05 (5th-generation tensor core) / TMEM PTX wrappers for sm_100a, kind::tf32, cta_group::1.
+//
+// Shared-memory operand layout used throughout: K-major, SWIZZLE_128B.  One swizzle atom is
+// 8 rows x 128 bytes (32 tf32); 8-row groups are 1024 B apart (SBO), atoms along K are placed
+// `atom_stride` bytes apart and are addressed by moving the descriptor start address; inside an
+// atom a K-step of 8 tf32 is +32 B.  The 16-byte chunk `c` of row `r` lives at chunk position
+// c ^ (r & 7) (the XOR is on absolute address bits [4,7) ^ [7,10), so atoms are 1024-B aligned).
+#pragma once
+#include <cstdint>
+
+namespace kgcn {
+
+// byte offset of element (row r, k-index kk) inside an operand whose atoms are atom_stride apart
+__device__ __forceinline__ uint32_t sw128_offset(int r, int kk, uint32_t atom_stride) {
+    const uint32_t atom = static_cast<uint32_t>(kk) >> 5;
+    const uint32_t chunk = (static_cast<uint32_t>(kk) >> 2) & 7u;
+    return atom * atom_stride + (static_cast<uint32_t>(r) >> 3) * 1024u + (static_cast<uint32_t>(r) & 7u) * 128u +
+           ((chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4) + (static_cast<uint32_t>(kk) & 3u) * 4u;
+}
+
+// 64-bit shared-memory matrix descriptor (K-major, SWIZZLE_128B, SBO = 1024 B, version 1)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) /* LBO (unused) */ |
+           (static_cast<uint64_t>(1024 >> 4) << 32) /* SBO */ | (1ull << 46) /* version */ |
+           (2ull << 61) /* SWIZZLE_128B */;
+}
+
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n (multiple of 16)
+__device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {  // round-to-nearest tf32, low 13 mantissa bits zero
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// warp-collective: allocate `cols` (power of two >= 32) TMEM columns, base address -> *smem_slot
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(smem_slot))),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns starting at taddr
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace kgcn
