@@ -16,8 +16,10 @@
 //   3. Tensor cores: Y = Z . [W_1; ...; W_C] with tcgen05.mma kind::tf32, M = 128, accumulator in
 //      TMEM.  3xTF32 split (Zhi.Whi + Zlo.Whi + Zhi.Wlo) keeps fp32-level accuracy (~1e-6) while
 //      the contraction stays far below the HBM time of the tile.
-//   4. Epilogue: tcgen05.ld TMEM -> registers, + rowsum (x) bias, activation, staged through padded
-//      shared memory and written with coalesced 16-byte stores.
+//   4. Epilogue: tcgen05.ld TMEM -> registers, + rowsum (x) bias, activation, 16-byte global stores
+//      (a thread owns 64 contiguous bytes of one output row; L2 merges the sectors).
+// Tiles are 64 rows (UMMA M = 64) when that lets two CTAs share an SM -- their phases (TMA wait,
+// CUDA-core aggregation, tensor-core contraction, epilogue) then overlap -- else 128 rows.
 // HBM traffic per layer = x once + y once + CSR once + W once per CTA: the algorithmic minimum.
 #include <algorithm>
 
@@ -29,7 +31,6 @@ namespace kgcn {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBM = 128;  // rows per tile = UMMA M
 
 struct FusedParams {
     const int32_t* rowptr;
@@ -45,8 +46,8 @@ struct FusedParams {
     int Kp, Np;       // K = channels * f_in padded to 32, N = f_out padded to 16
     int cv_cap;       // staged {offset, value} capacity (entries)
     int lpr_log2;     // lanes per row in the aggregation
-    uint32_t off_zhi, off_zlo, off_whi, off_wlo, off_x, off_y, off_rp, off_cv, off_deg, off_bias, smem_total;
-    uint32_t y_pitch;     // bytes per staged output row
+    int bm;           // rows per tile = UMMA M (64 or 128)
+    uint32_t off_zhi, off_zlo, off_whi, off_wlo, off_x, off_rp, off_cv, off_deg, off_bias, smem_total;
     uint32_t tmem_cols;
 };
 
@@ -89,34 +90,234 @@ __device__ __forceinline__ void sts_f<1>(uint32_t addr, const float (&r)[1]) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(r[0]) : "memory");
 }
 
-// epilogue for one 16-column accumulator chunk of this thread's row
+// Activations for the epilogue: ex2.approx / rcp.approx based, |error| ~1e-6 (inside the 1e-5 parity
+// tolerance) at 4-6 instructions per element instead of ~30 for expf + IEEE division.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 template <int ACT>
-__device__ __forceinline__ void epilogue_chunk(float (&v)[16], int col0, int f_out, int channels, uint32_t deg_addr,
-                                               uint32_t bias_addr, int row, uint32_t yrow_addr) {
+__device__ __forceinline__ float fast_act(float x) {
+    if (ACT == KGCN_ACT_RELU) return fmaxf(x, 0.0f);
+    if (ACT == KGCN_ACT_SIGMOID) return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));  // FMUL, EX2, FADD, RCP
+    if (ACT == KGCN_ACT_TANH) {
+        const float t = ex2_approx(-2.8853900817779268f * fabsf(x));   // exp(-2|x|) in (0, 1]: no overflow
+        return copysignf((1.0f - t) * rcp_approx(1.0f + t), x);
+    }
+    return x;
+}
+
+// epilogue for one 16-column accumulator chunk of this thread's row: + rowsum (x) bias, act, store
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk(float (&v)[16], int col0, int f_out, int channels, int bm, uint32_t deg_addr,
+                                               uint32_t bias_addr, int row, float* y_row, bool vec_ok) {
     for (int c = 0; c < channels; ++c) {
-        const float d = __uint_as_float(lds_u32(deg_addr + 4u * (c * kBM + row)));
+        const float d = __uint_as_float(lds_u32(deg_addr + 4u * (c * bm + row)));
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int colj = col0 + j;
-            const float b = colj < f_out ? __uint_as_float(lds_u32(bias_addr + 4u * (c * f_out + colj))) : 0.0f;
-            v[j] = fmaf(d, b, v[j]);
+        for (int q = 0; q < 4; ++q) {
+            float b[4];
+            lds_f<4>(b, bias_addr + 4u * (c * 256 + col0 + 4 * q));   // bias rows are padded to 256 floats
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[4 * q + j] = fmaf(d, b[j], v[4 * q + j]);
         }
     }
-    if (ACT != KGCN_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], ACT);
+    for (int j = 0; j < 16; ++j) v[j] = fast_act<ACT>(v[j]);
+    if (vec_ok && col0 + 16 <= f_out) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(y_row + col0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (col0 + j < f_out) y_row[col0 + j] = v[j];
     }
+}
+
+// ---- aggregation of one tile: Z[w, c*f_in + f] = sum_e val_e * x[col_e, f] as tf32 hi / lo, plus row sums ----
+struct AggCtx {
+    uint32_t zhi, zlo, xs, rp_addr, cv_addr, deg_addr;
+    int e0, rows, C, N, f_in;
+    uint32_t row_pitch, tile_bytes_graph;
+    const int32_t* col;
+    const float* val;
+};
+
+// hot path: one channel, the whole feature row covered by one lane group (f_in <= LPR * 4), CSR staged
+template <int BM>
+__device__ __forceinline__ void aggregate_simple(const AggCtx& a, int group, int n_groups, int sub) {
+    // addresses live in registers for the whole tile; the empty asm keeps ptxas from rematerialising
+    // them (it otherwise rebuilds the shared-window base from SR_CgaCtaId for every row)
+    uint32_t xb = a.xs + 16u * sub, rp = a.rp_addr, cvb = a.cv_addr - 8u * static_cast<uint32_t>(a.e0);
+    uint32_t zh = a.zhi + (static_cast<uint32_t>(sub) >> 3) * (BM * 128u), zl = a.zlo + (static_cast<uint32_t>(sub) >> 3) * (BM * 128u);
+    uint32_t dg = a.deg_addr;
+    asm volatile("" : "+r"(xb), "+r"(rp), "+r"(cvb), "+r"(zh), "+r"(zl), "+r"(dg));
+    const uint32_t kchunk = static_cast<uint32_t>(sub) & 7u;  // 16-byte chunk inside the 128-byte atom row
+    const bool active = sub * 4 < a.f_in;
+    for (int w = group; w < a.rows; w += n_groups) {
+        uint32_t p = cvb + 8u * lds_u32(rp + 4u * w);
+        const uint32_t p_end = cvb + 8u * lds_u32(rp + 4u * w + 4u);
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float deg = 0.0f;
+#pragma unroll 1
+        for (; p < p_end; p += 8) {
+            const int2 cv = lds_i2(p);           // broadcast LDS.64 {byte offset of the neighbour row, value}
+            float xv[4];
+            lds_f<4>(xv, xb + static_cast<uint32_t>(cv.x));
+            const float v = __int_as_float(cv.y);
+            deg += v;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (col0 + 4 * q < f_out) {  // the staged row pitch is padded to 16 B, so a partial last float4 is fine
-            const float t[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
-            sts_f<4>(yrow_addr + 4u * (col0 + 4 * q), t);
+            for (int t = 0; t < 4; ++t) acc[t] = fmaf(v, xv[t], acc[t]);
+        }
+        if (active) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                hi[t] = tf32_hi(acc[t]);
+                lo[t] = acc[t] - hi[t];
+            }
+            const uint32_t uw = static_cast<uint32_t>(w);
+            const uint32_t off = (uw << 7) + ((kchunk ^ (uw & 7u)) << 4);   // (w>>3)*1024 + (w&7)*128 == w*128
+            sts_f<4>(zh + off, hi);
+            sts_f<4>(zl + off, lo);
+        }
+        if (sub == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dg + 4u * w), "f"(deg) : "memory");
+    }
+}
+
+// general path: any channel count / feature width / vector width, optional un-staged CSR
+template <int VEC, int BM>
+__device__ __noinline__ void aggregate_general(const AggCtx& a, int group, int n_groups, int sub, int chunk_f, bool staged) {
+    constexpr uint32_t z_atom = BM * 128u;
+    int i = group, gl = 0;  // carry counters: row w = gl * N + i
+    while (i >= a.N) { i -= a.N; ++gl; }
+    for (int w = group; w < a.rows; w += n_groups) {
+        for (int c = 0; c < a.C; ++c) {
+            const int r = (gl * a.C + c) * a.N + i;
+            const int s = static_cast<int>(lds_u32(a.rp_addr + 4u * r)) - a.e0;
+            const int e = static_cast<int>(lds_u32(a.rp_addr + 4u * r + 4u)) - a.e0;
+            float deg = 0.0f;
+            for (int f0 = sub * VEC; f0 < a.f_in; f0 += chunk_f) {
+                float acc[VEC];
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) acc[t] = 0.0f;
+                deg = 0.0f;
+                const uint32_t xb = a.xs + 4u * f0;
+                if (staged) {
+                    for (uint32_t p = a.cv_addr + 8u * s; p < a.cv_addr + 8u * e; p += 8) {
+                        const int2 cv = lds_i2(p);
+                        float xv[VEC];
+                        lds_f<VEC>(xv, xb + static_cast<uint32_t>(cv.x));
+                        const float v = __int_as_float(cv.y);
+                        deg += v;
+#pragma unroll
+                        for (int t = 0; t < VEC; ++t) acc[t] = fmaf(v, xv[t], acc[t]);
+                    }
+                } else {  // unusually dense tile: entries straight from global memory
+                    for (int k = s; k < e; ++k) {
+                        const uint32_t off = static_cast<uint32_t>(__ldg(a.col + a.e0 + k)) * a.row_pitch + gl * a.tile_bytes_graph;
+                        const float v = __ldg(a.val + a.e0 + k);
+                        float xv[VEC];
+                        lds_f<VEC>(xv, xb + off);
+                        deg += v;
+#pragma unroll
+                        for (int t = 0; t < VEC; ++t) acc[t] = fmaf(v, xv[t], acc[t]);
+                    }
+                }
+                const int kk = c * a.f_in + f0;
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) {
+                    const float hi = tf32_hi(acc[t]);
+                    const uint32_t off = sw128_offset(w, kk + t, z_atom);
+                    const float h1[1] = {hi}, l1[1] = {acc[t] - hi};
+                    sts_f<1>(a.zhi + off, h1);
+                    sts_f<1>(a.zlo + off, l1);
+                }
+            }
+            if (sub == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a.deg_addr + 4u * (c * BM + w)), "f"(deg) : "memory");
+        }
+        i += n_groups;
+        while (i >= a.N) { i -= a.N; ++gl; }
+    }
+}
+
+// ---- epilogue math on one accumulator element ----
+template <int ACT>
+__device__ __forceinline__ float finish(float acc, float degbias) { return fast_act<ACT>(acc + degbias); }
+
+// M = 64 epilogue: .16x256b loads keep all 32 lanes busy.  Warp w owns tile rows 16*(w&3) .. +15
+// (TMEM lanes 32*(w&3) .. +15) and the 32-column slabs (w>>2), (w>>2)+2, ...
+template <int ACT>
+__device__ __forceinline__ void epilogue_m64(uint32_t tmem_d, int warp, int lane, int rows, int f_out, int C,
+                                             uint32_t deg_addr, uint32_t bias_addr, float* y_tile, bool vec2_ok) {
+    const int q = warp & 3;
+    const int ra = q * 16 + (lane >> 2), rb = ra + 8;
+    float dega[8], degb[8];  // row sums per channel (C <= 8 on this path; larger C loops in chunks)
+    for (int slab = warp >> 2; slab * 32 < f_out; slab += 2) {
+        float v[16];
+        tmem_ld_16x256b_x4(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slab * 32), v);
+        float ba[8], bb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ba[i] = bb[i] = 0.0f;
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            const int cn = min(8, C - c0);
+            for (int c = 0; c < cn; ++c) {
+                dega[c] = __uint_as_float(lds_u32(deg_addr + 4u * ((c0 + c) * 64 + ra)));
+                degb[c] = __uint_as_float(lds_u32(deg_addr + 4u * ((c0 + c) * 64 + rb)));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = slab * 32 + 8 * i + 2 * (lane & 3);
+                for (int c = 0; c < cn; ++c) {
+                    float b2[2];
+                    lds_f<2>(b2, bias_addr + 4u * ((c0 + c) * 256 + col));
+                    ba[2 * i] = fmaf(dega[c], b2[0], ba[2 * i]);
+                    ba[2 * i + 1] = fmaf(dega[c], b2[1], ba[2 * i + 1]);
+                    bb[2 * i] = fmaf(degb[c], b2[0], bb[2 * i]);
+                    bb[2 * i + 1] = fmaf(degb[c], b2[1], bb[2 * i + 1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int col = slab * 32 + 8 * i + 2 * (lane & 3);
+            const float a0 = finish<ACT>(v[4 * i], ba[2 * i]), a1 = finish<ACT>(v[4 * i + 1], ba[2 * i + 1]);
+            const float b0 = finish<ACT>(v[4 * i + 2], bb[2 * i]), b1 = finish<ACT>(v[4 * i + 3], bb[2 * i + 1]);
+            if (vec2_ok && col + 1 < f_out) {
+                if (ra < rows) *reinterpret_cast<float2*>(y_tile + static_cast<size_t>(ra) * f_out + col) = make_float2(a0, a1);
+                if (rb < rows) *reinterpret_cast<float2*>(y_tile + static_cast<size_t>(rb) * f_out + col) = make_float2(b0, b1);
+            } else {
+                if (ra < rows && col < f_out) y_tile[static_cast<size_t>(ra) * f_out + col] = a0;
+                if (ra < rows && col + 1 < f_out) y_tile[static_cast<size_t>(ra) * f_out + col + 1] = a1;
+                if (rb < rows && col < f_out) y_tile[static_cast<size_t>(rb) * f_out + col] = b0;
+                if (rb < rows && col + 1 < f_out) y_tile[static_cast<size_t>(rb) * f_out + col + 1] = b1;
+            }
         }
     }
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(kThreads, 1) graphconv_fused_fwd_kernel(const FusedParams p) {
+// M = 128 epilogue: accumulator row m lives in TMEM lane m; a thread owns one row, 16 columns at a time
+template <int ACT>
+__device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, int warp, int lane, int rows, int f_out, int C,
+                                              uint32_t deg_addr, uint32_t bias_addr, float* y_tile, bool vec4_ok) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* y_row = y_tile + static_cast<size_t>(row) * f_out;
+    for (int j = warp >> 2; j * 16 < f_out; j += 2) {
+        float v[16];
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16), v);
+        if (row < rows) epilogue_chunk<ACT>(v, j * 16, f_out, C, 128, deg_addr, bias_addr, row, y_row, vec4_ok);
+    }
+}
+
+template <int VEC, int BM>
+__global__ void __launch_bounds__(kThreads, BM == 64 ? 2 : 1) graphconv_fused_fwd_kernel(const FusedParams p) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_x, bar_mma;
     __shared__ uint32_t tmem_slot;
@@ -124,14 +325,15 @@ __global__ void __launch_bounds__(kThreads, 1) graphconv_fused_fwd_kernel(const 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));  // generic pointer to the same place
     const uint32_t zhi = base + p.off_zhi, zlo = base + p.off_zlo, whi = base + p.off_whi, wlo = base + p.off_wlo;
-    const uint32_t xs = base + p.off_x, ys = base + p.off_y, rp_addr = base + p.off_rp, cv_addr = base + p.off_cv;
+    const uint32_t xs = base + p.off_x, rp_addr = base + p.off_rp, cv_addr = base + p.off_cv;
     const uint32_t deg_addr = base + p.off_deg, bias_addr = base + p.off_bias;
     int32_t* rp_s = reinterpret_cast<int32_t*>(gen + p.off_rp);
     int2* cv_s = reinterpret_cast<int2*>(gen + p.off_cv);
 
     const int C = p.channels, N = p.n_nodes, f_in = p.f_in, f_out = p.f_out;
     const int K = C * f_in, Kp = p.Kp, Np = p.Np;
-    const uint32_t z_atom = kBM * 128u, w_atom = static_cast<uint32_t>(Np) * 128u;
+    constexpr uint32_t z_atom = BM * 128u;
+    const uint32_t w_atom = static_cast<uint32_t>(Np) * 128u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---------------- one-time setup ----------------
@@ -146,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) graphconv_fused_fwd_kernel(const 
         const uint32_t n16 = (p.off_x - p.off_zhi) >> 4;  // Zhi, Zlo, Whi, Wlo are contiguous
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t i = tid; i < n16; i += kThreads) sts_f<4>(zhi + (i << 4), z4);
+        for (uint32_t i = tid; i < static_cast<uint32_t>(C) * 64u; i += kThreads) sts_f<4>(bias_addr + (i << 4), z4);
     }
     __syncthreads();
     // W -> (Whi, Wlo) in the K-major SWIZZLE_128B B-operand layout: B row n = output column n,
@@ -167,52 +370,56 @@ __global__ void __launch_bounds__(kThreads, 1) graphconv_fused_fwd_kernel(const 
             sts_f<4>(whi + off, hi);
             sts_f<4>(wlo + off, lo);
         }
-        for (int idx = tid; idx < C * f_out; idx += kThreads) {
-            const float b = p.bias ? __ldg(p.bias + idx) : 0.0f;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_addr + 4u * idx), "f"(b) : "memory");
-        }
+        if (p.bias != nullptr)
+            for (int idx = tid; idx < C * f_out; idx += kThreads) {
+                const int c = idx / f_out, n = idx - c * f_out;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_addr + 4u * (c * 256 + n)), "f"(__ldg(p.bias + idx)) : "memory");
+            }
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_d = tmem_slot;
-    const uint32_t idesc = umma_idesc_tf32_m128(Np);
+    const uint32_t idesc = umma_idesc_tf32(BM, Np);
+    // operand descriptors are tile-invariant: build them once, step them by adding to the address field
+    const uint64_t desc_zhi = umma_desc_sw128(zhi), desc_zlo = umma_desc_sw128(zlo);
+    const uint64_t desc_whi = umma_desc_sw128(whi), desc_wlo = umma_desc_sw128(wlo);
+    const int n_atoms = Kp >> 5;
 
     const int lpr = 1 << p.lpr_log2;
     const int sub = tid & (lpr - 1);
     const int group = tid >> p.lpr_log2;
     const int n_groups = kThreads >> p.lpr_log2;
-    const int chunk_f = lpr * VEC;
     const uint32_t row_pitch = static_cast<uint32_t>(f_in) * 4u;
     const uint32_t tile_bytes_graph = static_cast<uint32_t>(N) * row_pitch;
+    const bool simple = (VEC == 4) && C == 1 && f_in <= lpr * 4;
+    const bool y_vec4 = (f_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0;
+    const bool y_vec2 = (f_out & 1) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 7u) == 0;
 
-    uint32_t parity = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, parity ^= 1u) {
-        const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
-        const int ng = static_cast<int>(min(static_cast<int64_t>(p.graphs_per_tile), p.n_graphs - g0));
-        const int rows = ng * N;
-        const uint32_t x_bytes = static_cast<uint32_t>(ng) * tile_bytes_graph;
-        const float* x_tile = p.x + g0 * N * f_in;
-        const bool bulk_ok = (x_bytes & 15u) == 0;
-
-        // ---- 1. features: one TMA bulk copy (or a cooperative copy for an unaligned tail tile) ----
-        if (bulk_ok) {
-            if (tid == 0) {
-                mbar_expect_tx(&bar_x, x_bytes);
-                bulk_g2s(gen + p.off_x, x_tile, x_bytes, &bar_x);
-            }
-        } else {
-            for (uint32_t i = tid; i < (x_bytes >> 2); i += kThreads)
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(xs + 4u * i), "f"(__ldg(x_tile + i)) : "memory");
+    auto tile_graphs = [&](int t) {
+        return static_cast<int>(min(static_cast<int64_t>(p.graphs_per_tile), p.n_graphs - static_cast<int64_t>(t) * p.graphs_per_tile));
+    };
+    auto issue_x = [&](int t) {  // thread 0: bulk copy of tile t's feature rows (if 16-byte sized)
+        const int64_t g0 = static_cast<int64_t>(t) * p.graphs_per_tile;
+        const uint32_t bytes = static_cast<uint32_t>(tile_graphs(t)) * tile_bytes_graph;
+        if ((bytes & 15u) == 0) {
+            mbar_expect_tx(&bar_x, bytes);
+            bulk_g2s(gen + p.off_x, p.x + g0 * N * f_in, bytes, &bar_x);
         }
-        // ---- CSR slice of the tile ----
+    };
+    // CSR slice of tile t -> shared: row extents, then {byte offset, value} pairs.  Two block barriers inside.
+    int32_t e0 = 0;
+    bool staged = true;
+    auto stage_csr = [&](int t) {
+        const int64_t g0 = static_cast<int64_t>(t) * p.graphs_per_tile;
+        const int ng = tile_graphs(t);
         const int rows_csr = ng * C * N;
         const int32_t* rp_g = p.rowptr + g0 * C * N;
         for (int r = tid; r <= rows_csr; r += kThreads) rp_s[r] = __ldg(rp_g + r);
         __syncthreads();
-        const int32_t e0 = rp_s[0];
+        e0 = rp_s[0];
         const int n_entries = rp_s[rows_csr] - e0;
-        const bool staged = n_entries <= p.cv_cap;
+        staged = n_entries <= p.cv_cap;
         if (staged) {
             const int mat_rows = C * N;  // CSR rows per graph: all channels gather from the same feature tile
             for (int k = tid; k < n_entries; k += kThreads) {
@@ -223,145 +430,92 @@ __global__ void __launch_bounds__(kThreads, 1) graphconv_fused_fwd_kernel(const 
             }
         }
         __syncthreads();
-        if (bulk_ok) mbar_wait(&bar_x, parity);
+    };
 
-        // ---- 2. aggregation Z[w, c*f_in + f] = sum_e val_e * x[col_e, f], written as tf32 hi / lo ----
-        {
-            int i = group, gl = 0;  // carry counters: row w = gl * N + i
-            while (i >= N) { i -= N; ++gl; }
-            for (int w = group; w < rows; w += n_groups) {
-                for (int c = 0; c < C; ++c) {
-                    const int r = (gl * C + c) * N + i;
-                    const int s = static_cast<int>(lds_u32(rp_addr + 4u * r)) - e0;
-                    const int e = static_cast<int>(lds_u32(rp_addr + 4u * r + 4u)) - e0;
-                    float deg = 0.0f;
-                    for (int f0 = sub * VEC; f0 < f_in; f0 += chunk_f) {
-                        float acc[VEC];
-#pragma unroll
-                        for (int t = 0; t < VEC; ++t) acc[t] = 0.0f;
-                        deg = 0.0f;
-                        const uint32_t xb = xs + 4u * f0;
-                        if (staged) {
-                            uint32_t a = cv_addr + 8u * s;
-                            const uint32_t a_end = cv_addr + 8u * e;
-#pragma unroll 2
-                            for (; a < a_end; a += 8) {
-                                const int2 cv = lds_i2(a);
-                                float xv[VEC];
-                                lds_f<VEC>(xv, xb + static_cast<uint32_t>(cv.x));
-                                const float v = __int_as_float(cv.y);
-                                deg += v;
-#pragma unroll
-                                for (int t = 0; t < VEC; ++t) acc[t] = fmaf(v, xv[t], acc[t]);
-                            }
-                        } else {  // unusually dense tile: entries straight from global memory
-                            for (int k = s; k < e; ++k) {
-                                const uint32_t off = static_cast<uint32_t>(__ldg(p.col + e0 + k)) * row_pitch + gl * tile_bytes_graph;
-                                const float v = __ldg(p.val + e0 + k);
-                                float xv[VEC];
-                                lds_f<VEC>(xv, xb + off);
-                                deg += v;
-#pragma unroll
-                                for (int t = 0; t < VEC; ++t) acc[t] = fmaf(v, xv[t], acc[t]);
-                            }
-                        }
-                        float hi[VEC], lo[VEC];
-#pragma unroll
-                        for (int t = 0; t < VEC; ++t) {
-                            hi[t] = tf32_hi(acc[t]);
-                            lo[t] = acc[t] - hi[t];
-                        }
-                        const int kk = c * f_in + f0;
-                        if (VEC == 4 && (kk & 3) == 0) {
-                            const uint32_t off = sw128_offset(w, kk, z_atom);
-                            sts_f<VEC>(zhi + off, hi);
-                            sts_f<VEC>(zlo + off, lo);
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < VEC; ++t) {
-                                const uint32_t off = sw128_offset(w, kk + t, z_atom);
-                                const float h1[1] = {hi[t]}, l1[1] = {lo[t]};
-                                sts_f<1>(zhi + off, h1);
-                                sts_f<1>(zlo + off, l1);
-                            }
-                        }
-                    }
-                    if (sub == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(deg_addr + 4u * (c * kBM + w)), "f"(deg) : "memory");
-                }
-                i += n_groups;
-                while (i >= N) { i -= N; ++gl; }
-            }
+    const int first = blockIdx.x;
+    if (first < p.n_tiles) {
+        if (tid == 0) issue_x(first);
+        stage_csr(first);
+    }
+
+    uint32_t parity = 0;
+    for (int tile = first; tile < p.n_tiles; tile += gridDim.x, parity ^= 1u) {
+        const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
+        const int ng = tile_graphs(tile);
+        const int rows = ng * N;
+        const uint32_t x_bytes = static_cast<uint32_t>(ng) * tile_bytes_graph;
+        const int next = tile + gridDim.x;
+
+        // ---- 1. features: the TMA bulk copy was issued one tile ahead; an unaligned tail tile is
+        //         copied cooperatively instead ----
+        if ((x_bytes & 15u) == 0) {
+            mbar_wait(&bar_x, parity);
+        } else {
+            const float* x_tile = p.x + g0 * N * f_in;
+            for (uint32_t i = tid; i < (x_bytes >> 2); i += kThreads)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(xs + 4u * i), "f"(__ldg(x_tile + i)) : "memory");
+            __syncthreads();
         }
-        // generic-proxy writes of Z must be visible to the tensor core (async proxy)
-        fence_proxy_async_smem();
+
+        // ---- 2. aggregation on the CUDA cores ----
+        {
+            AggCtx a{zhi, zlo, xs, rp_addr, cv_addr, deg_addr, e0, rows, C, N, f_in, row_pitch, tile_bytes_graph, p.col, p.val};
+            if (simple && staged) aggregate_simple<BM>(a, group, n_groups, sub);
+            else aggregate_general<VEC, BM>(a, group, n_groups, sub, lpr * VEC, staged);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes of Z -> visible to the tensor core (async proxy)
         tc_fence_before_sync();
         __syncthreads();
 
         // ---- 3. Y = Z . W on the tensor cores (3xTF32), accumulator in TMEM ----
         if (tid == 0) {
             tc_fence_after_sync();
-            bool acc_flag = false;
-            const int n_atoms = Kp >> 5;
+            uint32_t acc_flag = 0;
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t a_base = (pass == 1) ? zlo : zhi;
-                const uint32_t b_base = (pass == 2) ? wlo : whi;
-                for (int at = 0; at < n_atoms; ++at) {
+                uint64_t da = (pass == 1) ? desc_zlo : desc_zhi;
+                uint64_t db = (pass == 2) ? desc_wlo : desc_whi;
+                int k_left = K;
+#pragma unroll 1
+                for (int at = 0; at < n_atoms; ++at, da += (z_atom >> 4), db += (w_atom >> 4), k_left -= 32) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        if (at * 32 + ks * 8 < K) {  // skip k-steps that only see padding
-                            umma_tf32(tmem_d, umma_desc_sw128(a_base + at * z_atom + ks * 32u),
-                                      umma_desc_sw128(b_base + at * w_atom + ks * 32u), idesc, acc_flag);
-                            acc_flag = true;
+                        if (ks * 8 < k_left) {  // skip k-steps that only see padding
+                            umma_tf32(tmem_d, da + 2u * ks, db + 2u * ks, idesc, acc_flag);   // +32 B per k-step
+                            acc_flag = 1;
                         }
                     }
                 }
             }
             umma_commit(&bar_mma);
+            if (next < p.n_tiles) issue_x(next);  // the feature buffer is free: prefetch under MMA + epilogue
         }
+        // CSR of the next tile is fetched while the tensor core works (rp_s / cv_s are free again)
+        if (next < p.n_tiles) stage_csr(next);
         mbar_wait(&bar_mma, parity);
         tc_fence_after_sync();
 
-        // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> padded smem ----
+        // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> global ----
         {
-            const int q = warp & 3, h = warp >> 2;  // TMEM lane quarter / which 16-column chunks
-            const int row = q * 32 + lane;
-            const uint32_t yrow = ys + static_cast<uint32_t>(row) * p.y_pitch;
-            for (int j = h; j * 16 < f_out; j += 2) {
-                float v[16];
-                tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16), v);
-                if (row < rows) {
-                    switch (p.act) {
-                        case KGCN_ACT_RELU: epilogue_chunk<KGCN_ACT_RELU>(v, j * 16, f_out, C, deg_addr, bias_addr, row, yrow); break;
-                        case KGCN_ACT_SIGMOID: epilogue_chunk<KGCN_ACT_SIGMOID>(v, j * 16, f_out, C, deg_addr, bias_addr, row, yrow); break;
-                        case KGCN_ACT_TANH: epilogue_chunk<KGCN_ACT_TANH>(v, j * 16, f_out, C, deg_addr, bias_addr, row, yrow); break;
-                        default: epilogue_chunk<KGCN_ACT_NONE>(v, j * 16, f_out, C, deg_addr, bias_addr, row, yrow);
-                    }
+            float* y_tile = p.y + g0 * N * f_out;
+            if (BM == 64) {
+                switch (p.act) {
+                    case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                    case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                    case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                    default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2);
+                }
+            } else {
+                switch (p.act) {
+                    case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                    case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                    case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                    default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4);
                 }
             }
         }
         tc_fence_before_sync();
-        __syncthreads();
-
-        // ---- coalesced copy-out of the tile's [rows, f_out] block ----
-        {
-            float* y_tile = p.y + g0 * N * f_out;
-            if ((f_out & 3) == 0 && (reinterpret_cast<uintptr_t>(y_tile) & 15u) == 0) {
-                const int q4 = f_out >> 2;
-                for (int idx = tid; idx < rows * q4; idx += kThreads) {
-                    const int r = idx / q4, cq = idx - r * q4;
-                    float t[4];
-                    lds_f<4>(t, ys + static_cast<uint32_t>(r) * p.y_pitch + 16u * cq);
-                    *reinterpret_cast<float4*>(y_tile + static_cast<size_t>(r) * f_out + 4 * cq) = make_float4(t[0], t[1], t[2], t[3]);
-                }
-            } else {
-                for (int idx = tid; idx < rows * f_out; idx += kThreads) {
-                    const int r = idx / f_out, cc = idx - r * f_out;
-                    y_tile[idx] = __uint_as_float(lds_u32(ys + static_cast<uint32_t>(r) * p.y_pitch + 4u * cc));
-                }
-            }
-        }
-        // the next iteration's first __syncthreads orders this copy-out before Ystage / Z are rewritten
+        __syncthreads();  // TMEM / row sums consumed before the next tile overwrites them
     }
 
     tc_fence_before_sync();
@@ -371,35 +525,45 @@ __global__ void __launch_bounds__(kThreads, 1) graphconv_fused_fwd_kernel(const 
 
 inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-bool plan(FusedParams& p, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
-    if (n_nodes > kBM || f_out > 256 || f_out < 1) return false;
+bool plan_bm(FusedParams& p, int bm, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    if (n_nodes > bm || f_out > 256 || f_out < 1) return false;
     const int K = channels * f_in;
+    p.bm = bm;
     p.Kp = static_cast<int>(up(K, 32));
     p.Np = static_cast<int>(up(f_out, 16));
-    p.graphs_per_tile = std::max(1, kBM / n_nodes);
-    // keep every SM busy when the batch is small: shrink tiles until there are >= 148 of them
-    while (p.graphs_per_tile > 1 && ceil_div<int64_t>(n_graphs, p.graphs_per_tile) < kNumSMs) --p.graphs_per_tile;
+    p.graphs_per_tile = std::max(1, bm / n_nodes);
+    // keep every SM busy when the batch is small: shrink tiles until there are >= 2 per SM
+    while (p.graphs_per_tile > 1 && ceil_div<int64_t>(n_graphs, p.graphs_per_tile) < 2 * kNumSMs) --p.graphs_per_tile;
     p.n_tiles = static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_tile));
     const uint32_t rows_max = static_cast<uint32_t>(p.graphs_per_tile) * n_nodes;
     const uint32_t n_atoms = p.Kp / 32;
     uint32_t off = 0;
-    p.off_zhi = off; off += n_atoms * kBM * 128u;
-    p.off_zlo = off; off += n_atoms * kBM * 128u;
+    p.off_zhi = off; off += n_atoms * bm * 128u;
+    p.off_zlo = off; off += n_atoms * bm * 128u;
     p.off_whi = off; off += n_atoms * p.Np * 128u;
     p.off_wlo = off; off += n_atoms * p.Np * 128u;
     p.off_x = off; off += up(rows_max * f_in * 4u, 128);
-    p.y_pitch = up(f_out * 4u, 16) + 16u;
-    p.off_y = off; off += up(rows_max * p.y_pitch, 128);
     p.off_rp = off; off += up((rows_max * channels + 2) * 4u, 16);
     p.cv_cap = static_cast<int>(std::max<uint32_t>(256, 6 * rows_max * channels));
     p.off_cv = off; off += static_cast<uint32_t>(p.cv_cap) * 8u;
-    p.off_deg = off; off += static_cast<uint32_t>(channels) * kBM * 4u;
-    p.off_bias = off; off += up(static_cast<uint32_t>(channels) * f_out * 4u, 16);
+    p.off_deg = off; off += static_cast<uint32_t>(channels) * bm * 4u;
+    p.off_bias = off; off += static_cast<uint32_t>(channels) * 256u * 4u;
     p.smem_total = off + 1024;  // slack for the manual 1024-B alignment
     uint32_t cols = 32;
     while (cols < static_cast<uint32_t>(p.Np)) cols <<= 1;
     p.tmem_cols = cols;
     return p.smem_total <= 227 * 1024 - 256;  // static __shared__ (barriers, TMEM slot) shares the 227 KB
+}
+
+// 64-row tiles when two CTAs then fit one SM (their phases overlap), else 128-row tiles.
+bool plan(FusedParams& p, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    FusedParams q = p;
+    if (plan_bm(q, 64, n_graphs, channels, n_nodes, f_in, f_out) && q.smem_total <= 113 * 1024) {
+        p = q;
+        return true;
+    }
+    if (plan_bm(p, 128, n_graphs, channels, n_nodes, f_in, f_out)) return true;
+    return plan_bm(p, 64, n_graphs, channels, n_nodes, f_in, f_out);
 }
 
 }  // namespace
@@ -408,9 +572,10 @@ bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, i
                         const float* y) {
     FusedParams p{};
     if (n_graphs <= 0 || !plan(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
-    // tiles must start 16-byte aligned for the bulk copy / float4 stores
+    // tiles must start 16-byte aligned for the bulk copy
     const uint64_t tile_x = static_cast<uint64_t>(p.graphs_per_tile) * n_nodes * f_in * 4;
-    return aligned16(x) && aligned16(y) && tile_x % 16 == 0 && n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
+    return aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 3u) == 0 && tile_x % 16 == 0 &&
+           n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
 }
 
 int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
@@ -425,17 +590,25 @@ int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const 
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < 32 && (1 << lpr_log2) * vec < f_in) ++lpr_log2;
     p.lpr_log2 = lpr_log2;
-    const unsigned grid = static_cast<unsigned>(std::min<int>(p.n_tiles, kNumSMs));
+    const int ctas_per_sm = (p.bm == 64 && p.smem_total <= 113 * 1024) ? 2 : 1;
+    const unsigned grid = static_cast<unsigned>(std::min<int>(p.n_tiles, kNumSMs * ctas_per_sm));
     auto go = [&](auto kernel) -> int {
         KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
         kernel<<<grid, kThreads, p.smem_total, st>>>(p);
         KGCN_LAUNCH_OK("graphconv_fused_fwd_kernel");
         return KGCN_OK;
     };
+    if (p.bm == 64) {
+        switch (vec) {
+            case 4: return go(graphconv_fused_fwd_kernel<4, 64>);
+            case 2: return go(graphconv_fused_fwd_kernel<2, 64>);
+            default: return go(graphconv_fused_fwd_kernel<1, 64>);
+        }
+    }
     switch (vec) {
-        case 4: return go(graphconv_fused_fwd_kernel<4>);
-        case 2: return go(graphconv_fused_fwd_kernel<2>);
-        default: return go(graphconv_fused_fwd_kernel<1>);
+        case 4: return go(graphconv_fused_fwd_kernel<4, 128>);
+        case 2: return go(graphconv_fused_fwd_kernel<2, 128>);
+        default: return go(graphconv_fused_fwd_kernel<1, 128>);
     }
 }
 

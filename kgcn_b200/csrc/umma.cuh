@@ -25,15 +25,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
            (2ull << 61) /* SWIZZLE_128B */;
 }
 
-// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n (multiple of 16)
-__device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = m (64 or 128), N = n
+// (multiple of 8 for M = 64, of 16 for M = 128)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) {  // round-to-nearest tf32, low 13 mantissa bits zero
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// Round-to-nearest (ties away) tf32 with the low 13 mantissa bits zero, in 2 integer instructions.
+// (cvt.rna.tf32.f32 lowers to 4+ instructions per element because it special-cases Inf/NaN; here
+// Inf stays Inf, NaN stays NaN, and the largest finite values round to Inf like any rounding would.)
+__device__ __forceinline__ float tf32_hi(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // warp-collective: allocate `cols` (power of two >= 32) TMEM columns, base address -> *smem_slot
@@ -51,12 +53,12 @@ __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.f
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
@@ -71,6 +73,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// TMEM -> registers, 16 lanes x (8 * REPS) fp32 columns starting at taddr (shape .16x256b).
+// For repetition i (columns 8i .. 8i+7) thread t holds:
+//   v[4i+0], v[4i+1] : row  t/4      , columns 8i + 2*(t%4) + {0, 1}
+//   v[4i+2], v[4i+3] : row  t/4 + 8  , same columns
+// (the m16n8 accumulator fragment layout), so all 32 threads carry data of a 16-row M=64 slab.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)

@@ -96,7 +96,8 @@ def test_graph_replay_equals_eager():
     torch.cuda.synchronize()
     assert torch.equal(a.params, b.params)     # same kernels, same order, deterministic reductions
     assert int(b.step_state[0].item()) == 5
-    assert a.read_stats() == b.read_stats()
+    sa, sb = a.read_stats(), b.read_stats()      # cost_sum is accumulated with float atomics: order-dependent last bits
+    assert abs(sa[0] - sb[0]) <= 1e-5 * abs(sa[0]) and sa[1] == sb[1]
 
 
 def test_training_reduces_loss_on_ring_task():
