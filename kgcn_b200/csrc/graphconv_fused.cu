@@ -30,7 +30,6 @@
 namespace kgcn {
 namespace {
 
-constexpr int kThreads = 256;
 
 struct FusedParams {
     const int32_t* rowptr;
@@ -47,7 +46,9 @@ struct FusedParams {
     int cv_cap;       // staged {offset, value} capacity (entries)
     int lpr_log2;     // lanes per row in the aggregation
     int bm;           // rows per tile = UMMA M (64 or 128)
-    uint32_t off_zhi, off_zlo, off_whi, off_wlo, off_x, off_rp, off_cv, off_deg, off_bias, smem_total;
+    int n_stages;     // TMA pipeline depth
+    uint32_t off_zhi, off_zlo, off_whi, off_wlo, off_stage, off_cv, off_deg, off_bias, smem_total;
+    uint32_t stage_bytes, st_rp, st_col, st_val;   // per-stage layout: features at 0, then the CSR slices
     uint32_t tmem_cols;
 };
 
@@ -316,216 +317,242 @@ __device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, int warp, int lan
     }
 }
 
+constexpr int kConsumers = 256;           // aggregation / epilogue threads (8 warps)
+constexpr int kBlock = kConsumers + 32;   // + one TMA producer warp
+constexpr int kMaxStages = 3;
+
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct StageInfo {   // written by the producer before it arms full[s]
+    int32_t e_first;  // first CSR entry of the tile
+    int32_t n_entries;
+    int32_t rp_skip;  // ints to skip in the staged rowptr slice (16-byte alignment of the copy)
+    int32_t e_skip;   // entries to skip in the staged col / val slices
+    int32_t staged;   // 0: the tile has more entries than the stage holds -> read col/val from global
+    int32_t pad[3];
+};
+
 template <int VEC, int BM>
-__global__ void __launch_bounds__(kThreads, BM == 64 ? 2 : 1) graphconv_fused_fwd_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kBlock, BM == 64 ? 2 : 1) graphconv_fused_fwd_kernel(const FusedParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_x, bar_mma;
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_mma;
+    __shared__ __align__(16) StageInfo sinfo[kMaxStages];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));  // generic pointer to the same place
     const uint32_t zhi = base + p.off_zhi, zlo = base + p.off_zlo, whi = base + p.off_whi, wlo = base + p.off_wlo;
-    const uint32_t xs = base + p.off_x, rp_addr = base + p.off_rp, cv_addr = base + p.off_cv;
-    const uint32_t deg_addr = base + p.off_deg, bias_addr = base + p.off_bias;
-    int32_t* rp_s = reinterpret_cast<int32_t*>(gen + p.off_rp);
-    int2* cv_s = reinterpret_cast<int2*>(gen + p.off_cv);
+    const uint32_t cv_addr = base + p.off_cv, deg_addr = base + p.off_deg, bias_addr = base + p.off_bias;
 
     const int C = p.channels, N = p.n_nodes, f_in = p.f_in, f_out = p.f_out;
     const int K = C * f_in, Kp = p.Kp, Np = p.Np;
     constexpr uint32_t z_atom = BM * 128u;
     const uint32_t w_atom = static_cast<uint32_t>(Np) * 128u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.n_stages;
+    const uint32_t row_pitch = static_cast<uint32_t>(f_in) * 4u;
+    const uint32_t tile_bytes_graph = static_cast<uint32_t>(N) * row_pitch;
 
-    // ---------------- one-time setup ----------------
+    auto tile_graphs = [&](int t) {
+        return static_cast<int>(min(static_cast<int64_t>(p.graphs_per_tile), p.n_graphs - static_cast<int64_t>(t) * p.graphs_per_tile));
+    };
+
+    // ---------------- one-time setup (all 9 warps) ----------------
     if (tid == 0) {
-        mbar_init(&bar_x, 1);
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], 1);
+        }
         mbar_init(&bar_mma, 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
     // zero the operand regions once: K / N padding must contribute exact zeros (never NaN garbage)
     {
-        const uint32_t n16 = (p.off_x - p.off_zhi) >> 4;  // Zhi, Zlo, Whi, Wlo are contiguous
+        const uint32_t n16 = (p.off_stage - p.off_zhi) >> 4;  // Zhi, Zlo, Whi, Wlo are contiguous
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (uint32_t i = tid; i < n16; i += kThreads) sts_f<4>(zhi + (i << 4), z4);
-        for (uint32_t i = tid; i < static_cast<uint32_t>(C) * 64u; i += kThreads) sts_f<4>(bias_addr + (i << 4), z4);
+        for (uint32_t i = tid; i < n16; i += kBlock) sts_f<4>(zhi + (i << 4), z4);
+        for (uint32_t i = tid; i < static_cast<uint32_t>(C) * 64u; i += kBlock) sts_f<4>(bias_addr + (i << 4), z4);
     }
     __syncthreads();
-    // W -> (Whi, Wlo) in the K-major SWIZZLE_128B B-operand layout: B row n = output column n,
-    // k index = c * f_in + k.  One thread per (n, 4 consecutive k): coalesced over n in global,
-    // conflict-free 16-byte stores in shared (that is what the swizzle is for).
-    {
-        const int kq = (K + 3) >> 2;
-        for (int idx = tid; idx < kq * f_out; idx += kThreads) {
-            const int n = idx % f_out, k4 = (idx / f_out) << 2;
-            float hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int kk = k4 + j;
-                const float wv = kk < K ? __ldg(p.w + static_cast<size_t>(kk) * f_out + n) : 0.0f;  // w is [C][f_in][f_out]
-                hi[j] = tf32_hi(wv);
-                lo[j] = wv - hi[j];
-            }
-            const uint32_t off = sw128_offset(n, k4, w_atom);
-            sts_f<4>(whi + off, hi);
-            sts_f<4>(wlo + off, lo);
-        }
-        if (p.bias != nullptr)
-            for (int idx = tid; idx < C * f_out; idx += kThreads) {
-                const int c = idx / f_out, n = idx - c * f_out;
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_addr + 4u * (c * 256 + n)), "f"(__ldg(p.bias + idx)) : "memory");
-            }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_d = tmem_slot;
-    const uint32_t idesc = umma_idesc_tf32(BM, Np);
-    // operand descriptors are tile-invariant: build them once, step them by adding to the address field
-    const uint64_t desc_zhi = umma_desc_sw128(zhi), desc_zlo = umma_desc_sw128(zlo);
-    const uint64_t desc_whi = umma_desc_sw128(whi), desc_wlo = umma_desc_sw128(wlo);
-    const int n_atoms = Kp >> 5;
 
-    const int lpr = 1 << p.lpr_log2;
-    const int sub = tid & (lpr - 1);
-    const int group = tid >> p.lpr_log2;
-    const int n_groups = kThreads >> p.lpr_log2;
-    const uint32_t row_pitch = static_cast<uint32_t>(f_in) * 4u;
-    const uint32_t tile_bytes_graph = static_cast<uint32_t>(N) * row_pitch;
-    const bool simple = (VEC == 4) && C == 1 && f_in <= lpr * 4;
-    const bool y_vec4 = (f_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0;
-    const bool y_vec2 = (f_out & 1) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 7u) == 0;
-
-    auto tile_graphs = [&](int t) {
-        return static_cast<int>(min(static_cast<int64_t>(p.graphs_per_tile), p.n_graphs - static_cast<int64_t>(t) * p.graphs_per_tile));
-    };
-    auto issue_x = [&](int t) {  // thread 0: bulk copy of tile t's feature rows (if 16-byte sized)
-        const int64_t g0 = static_cast<int64_t>(t) * p.graphs_per_tile;
-        const uint32_t bytes = static_cast<uint32_t>(tile_graphs(t)) * tile_bytes_graph;
-        if ((bytes & 15u) == 0) {
-            mbar_expect_tx(&bar_x, bytes);
-            bulk_g2s(gen + p.off_x, p.x + g0 * N * f_in, bytes, &bar_x);
-        }
-    };
-    // CSR slice of tile t -> shared: row extents, then {byte offset, value} pairs.  Two block barriers inside.
-    int32_t e0 = 0;
-    bool staged = true;
-    auto stage_csr = [&](int t) {
-        const int64_t g0 = static_cast<int64_t>(t) * p.graphs_per_tile;
-        const int ng = tile_graphs(t);
-        const int rows_csr = ng * C * N;
-        const int32_t* rp_g = p.rowptr + g0 * C * N;
-        for (int r = tid; r <= rows_csr; r += kThreads) rp_s[r] = __ldg(rp_g + r);
-        __syncthreads();
-        e0 = rp_s[0];
-        const int n_entries = rp_s[rows_csr] - e0;
-        staged = n_entries <= p.cv_cap;
-        if (staged) {
-            const int mat_rows = C * N;  // CSR rows per graph: all channels gather from the same feature tile
-            for (int k = tid; k < n_entries; k += kThreads) {
-                int m = 0;
-                while (m + 1 < ng && e0 + k >= rp_s[(m + 1) * mat_rows]) ++m;
-                cv_s[k] = make_int2(__ldg(p.col + e0 + k) * static_cast<int>(row_pitch) + m * static_cast<int>(tile_bytes_graph),
-                                    __float_as_int(__ldg(p.val + e0 + k)));
+    if (warp == kConsumers / 32) {
+        // =============================== TMA producer warp ===============================
+        // Runs up to S tiles ahead: per tile one bulk copy each for the feature rows, the row-extent
+        // slice, the column slice and the value slice, all completing on full[s].
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(&bar_empty[s], ((it / S) - 1) & 1);
+                const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
+                const int ng = tile_graphs(tile);
+                const int64_t r0 = g0 * C * N;
+                const int rows_csr = ng * C * N;
+                const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
+                // bulk copies need 16-byte aligned sources and sizes: copy the enclosing aligned slices
+                const int64_t rp_lo = r0 & ~3ll;
+                const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
+                const int32_t e_lo = e_first & ~3;
+                const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
+                const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap);
+                unsigned char* st = gen + p.off_stage + static_cast<size_t>(s) * p.stage_bytes;
+                StageInfo& si = sinfo[s];
+                si.e_first = e_first;
+                si.n_entries = e_last - e_first;
+                si.rp_skip = static_cast<int32_t>(r0 - rp_lo);
+                si.e_skip = e_first - e_lo;
+                si.staged = staged ? 1 : 0;
+                const uint32_t x_bytes = static_cast<uint32_t>(ng) * tile_bytes_graph;
+                mbar_expect_tx(&bar_full[s], x_bytes + 4u * rp_cnt + (staged ? 8u * e_cnt : 0u));
+                bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, &bar_full[s]);
+                bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, &bar_full[s]);
+                if (staged && e_cnt) {
+                    bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, &bar_full[s]);
+                    bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, &bar_full[s]);
+                }
             }
         }
-        __syncthreads();
-    };
-
-    const int first = blockIdx.x;
-    if (first < p.n_tiles) {
-        if (tid == 0) issue_x(first);
-        stage_csr(first);
-    }
-
-    uint32_t parity = 0;
-    for (int tile = first; tile < p.n_tiles; tile += gridDim.x, parity ^= 1u) {
-        const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
-        const int ng = tile_graphs(tile);
-        const int rows = ng * N;
-        const uint32_t x_bytes = static_cast<uint32_t>(ng) * tile_bytes_graph;
-        const int next = tile + gridDim.x;
-
-        // ---- 1. features: the TMA bulk copy was issued one tile ahead; an unaligned tail tile is
-        //         copied cooperatively instead ----
-        if ((x_bytes & 15u) == 0) {
-            mbar_wait(&bar_x, parity);
-        } else {
-            const float* x_tile = p.x + g0 * N * f_in;
-            for (uint32_t i = tid; i < (x_bytes >> 2); i += kThreads)
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(xs + 4u * i), "f"(__ldg(x_tile + i)) : "memory");
-            __syncthreads();
-        }
-
-        // ---- 2. aggregation on the CUDA cores ----
+    } else {
+        // =============================== consumer warps ===============================
+        // W -> (Whi, Wlo) in the K-major SWIZZLE_128B B-operand layout: B row n = output column n,
+        // k index = c * f_in + k.  One thread per (n, 4 consecutive k): coalesced over n in global,
+        // conflict-free 16-byte stores in shared (that is what the swizzle is for).
         {
-            AggCtx a{zhi, zlo, xs, rp_addr, cv_addr, deg_addr, e0, rows, C, N, f_in, row_pitch, tile_bytes_graph, p.col, p.val};
-            if (simple && staged) aggregate_simple<BM>(a, group, n_groups, sub);
-            else aggregate_general<VEC, BM>(a, group, n_groups, sub, lpr * VEC, staged);
-        }
-        fence_proxy_async_smem();  // generic-proxy writes of Z -> visible to the tensor core (async proxy)
-        tc_fence_before_sync();
-        __syncthreads();
-
-        // ---- 3. Y = Z . W on the tensor cores (3xTF32), accumulator in TMEM ----
-        if (tid == 0) {
-            tc_fence_after_sync();
-            uint32_t acc_flag = 0;
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-                uint64_t da = (pass == 1) ? desc_zlo : desc_zhi;
-                uint64_t db = (pass == 2) ? desc_wlo : desc_whi;
-                int k_left = K;
-#pragma unroll 1
-                for (int at = 0; at < n_atoms; ++at, da += (z_atom >> 4), db += (w_atom >> 4), k_left -= 32) {
+            const int kq = (K + 3) >> 2;
+            for (int idx = tid; idx < kq * f_out; idx += kConsumers) {
+                const int n = idx % f_out, k4 = (idx / f_out) << 2;
+                float hi[4], lo[4];
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        if (ks * 8 < k_left) {  // skip k-steps that only see padding
-                            umma_tf32(tmem_d, da + 2u * ks, db + 2u * ks, idesc, acc_flag);   // +32 B per k-step
-                            acc_flag = 1;
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = k4 + j;
+                    const float wv = kk < K ? __ldg(p.w + static_cast<size_t>(kk) * f_out + n) : 0.0f;  // w is [C][f_in][f_out]
+                    hi[j] = tf32_hi(wv);
+                    lo[j] = wv - hi[j];
+                }
+                const uint32_t off = sw128_offset(n, k4, w_atom);
+                sts_f<4>(whi + off, hi);
+                sts_f<4>(wlo + off, lo);
+            }
+            if (p.bias != nullptr)
+                for (int idx = tid; idx < C * f_out; idx += kConsumers) {
+                    const int c = idx / f_out, n = idx - c * f_out;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_addr + 4u * (c * 256 + n)), "f"(__ldg(p.bias + idx)) : "memory");
+                }
+        }
+        fence_proxy_async_smem();  // W is read by the tensor core through the async proxy
+        tc_fence_before_sync();
+        consumer_sync();
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_slot;
+        const uint32_t idesc = umma_idesc_tf32(BM, Np);
+        // operand descriptors are tile-invariant: build them once, step them by adding to the address field
+        const uint64_t desc_zhi = umma_desc_sw128(zhi), desc_zlo = umma_desc_sw128(zlo);
+        const uint64_t desc_whi = umma_desc_sw128(whi), desc_wlo = umma_desc_sw128(wlo);
+        const int n_atoms = Kp >> 5;
+
+        const int lpr = 1 << p.lpr_log2;
+        const int sub = tid & (lpr - 1);
+        const int group = tid >> p.lpr_log2;
+        const int n_groups = kConsumers >> p.lpr_log2;
+        const bool simple = (VEC == 4) && C == 1 && f_in <= lpr * 4;
+        const bool y_vec4 = (f_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0;
+        const bool y_vec2 = (f_out & 1) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 7u) == 0;
+
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % S;
+            const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
+            const int ng = tile_graphs(tile);
+            const int rows = ng * N;
+            const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
+
+            // ---- 1. wait for the stage: features + CSR slices landed by TMA ----
+            mbar_wait(&bar_full[s], (it / S) & 1);
+            const StageInfo si = sinfo[s];
+            const uint32_t rp_addr = st + p.st_rp + 4u * static_cast<uint32_t>(si.rp_skip);
+            // {column, value} -> {byte offset of the neighbour's feature row in the stage, value}
+            if (si.staged) {
+                const uint32_t col_a = st + p.st_col + 4u * static_cast<uint32_t>(si.e_skip);
+                const uint32_t val_a = st + p.st_val + 4u * static_cast<uint32_t>(si.e_skip);
+                const int mat_rows = C * N;
+                for (int k = tid; k < si.n_entries; k += kConsumers) {
+                    int m = 0;
+                    while (m + 1 < ng && si.e_first + k >= static_cast<int>(lds_u32(rp_addr + 4u * (m + 1) * mat_rows))) ++m;
+                    const uint32_t off = lds_u32(col_a + 4u * k) * row_pitch + static_cast<uint32_t>(m) * tile_bytes_graph;
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cv_addr + 8u * k), "r"(off), "r"(lds_u32(val_a + 4u * k)) : "memory");
+                }
+            }
+            consumer_sync();
+
+            // ---- 2. aggregation on the CUDA cores ----
+            {
+                AggCtx a{zhi, zlo, st, rp_addr, cv_addr, deg_addr, si.e_first, rows, C, N, f_in, row_pitch, tile_bytes_graph, p.col, p.val};
+                if (simple && si.staged) aggregate_simple<BM>(a, group, n_groups, sub);
+                else aggregate_general<VEC, BM>(a, group, n_groups, sub, lpr * VEC, si.staged != 0);
+            }
+            fence_proxy_async_smem();  // generic-proxy writes of Z -> visible to the tensor core (async proxy)
+            tc_fence_before_sync();
+            consumer_sync();
+
+            // ---- 3. Y = Z . W on the tensor cores (3xTF32), accumulator in TMEM ----
+            if (tid == 0) {
+                mbar_arrive(&bar_empty[s]);  // every consumer is past the barrier: the stage can be refilled
+                tc_fence_after_sync();
+                uint32_t acc_flag = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    uint64_t da = (pass == 1) ? desc_zlo : desc_zhi;
+                    uint64_t db = (pass == 2) ? desc_wlo : desc_whi;
+                    int k_left = K;
+#pragma unroll 1
+                    for (int at = 0; at < n_atoms; ++at, da += (z_atom >> 4), db += (w_atom >> 4), k_left -= 32) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (ks * 8 < k_left) {  // skip k-steps that only see padding
+                                umma_tf32(tmem_d, da + 2u * ks, db + 2u * ks, idesc, acc_flag);  // +32 B per k-step
+                                acc_flag = 1;
+                            }
                         }
                     }
                 }
+                umma_commit(&bar_mma);
             }
-            umma_commit(&bar_mma);
-            if (next < p.n_tiles) issue_x(next);  // the feature buffer is free: prefetch under MMA + epilogue
-        }
-        // CSR of the next tile is fetched while the tensor core works (rp_s / cv_s are free again)
-        if (next < p.n_tiles) stage_csr(next);
-        mbar_wait(&bar_mma, parity);
-        tc_fence_after_sync();
+            mbar_wait(&bar_mma, it & 1);
+            tc_fence_after_sync();
 
-        // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> global ----
-        {
-            float* y_tile = p.y + g0 * N * f_out;
-            if (BM == 64) {
-                switch (p.act) {
-                    case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                    case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                    case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                    default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2);
-                }
-            } else {
-                switch (p.act) {
-                    case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                    case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                    case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                    default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4);
+            // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> global ----
+            {
+                float* y_tile = p.y + g0 * N * f_out;
+                if (BM == 64) {
+                    switch (p.act) {
+                        case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                        case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                        case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                        default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2);
+                    }
+                } else {
+                    switch (p.act) {
+                        case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                        case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                        case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                        default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4);
+                    }
                 }
             }
+            tc_fence_before_sync();
+            consumer_sync();  // TMEM / row sums / cv pairs consumed before the next tile overwrites them
         }
-        tc_fence_before_sync();
-        __syncthreads();  // TMEM / row sums consumed before the next tile overwrites them
     }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, p.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_slot, p.tmem_cols);
 }
 
 inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-bool plan_bm(FusedParams& p, int bm, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+bool plan_bm(FusedParams& p, int bm, int max_smem, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
     if (n_nodes > bm || f_out > 256 || f_out < 1) return false;
     const int K = channels * f_in;
     p.bm = bm;
@@ -534,6 +561,11 @@ bool plan_bm(FusedParams& p, int bm, int64_t n_graphs, int channels, int n_nodes
     p.graphs_per_tile = std::max(1, bm / n_nodes);
     // keep every SM busy when the batch is small: shrink tiles until there are >= 2 per SM
     while (p.graphs_per_tile > 1 && ceil_div<int64_t>(n_graphs, p.graphs_per_tile) < 2 * kNumSMs) --p.graphs_per_tile;
+    // every tile (the last, shorter one included) is fetched with a bulk copy: 16-byte sizes only
+    const uint64_t graph_bytes = static_cast<uint64_t>(n_nodes) * f_in * 4;
+    while (p.graphs_per_tile > 1 && (p.graphs_per_tile * graph_bytes) % 16 != 0) --p.graphs_per_tile;
+    if ((p.graphs_per_tile * graph_bytes) % 16 != 0) return false;
+    if (graph_bytes % 16 != 0 && n_graphs % p.graphs_per_tile != 0) return false;
     p.n_tiles = static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_tile));
     const uint32_t rows_max = static_cast<uint32_t>(p.graphs_per_tile) * n_nodes;
     const uint32_t n_atoms = p.Kp / 32;
@@ -542,9 +574,19 @@ bool plan_bm(FusedParams& p, int bm, int64_t n_graphs, int channels, int n_nodes
     p.off_zlo = off; off += n_atoms * bm * 128u;
     p.off_whi = off; off += n_atoms * p.Np * 128u;
     p.off_wlo = off; off += n_atoms * p.Np * 128u;
-    p.off_x = off; off += up(rows_max * f_in * 4u, 128);
-    p.off_rp = off; off += up((rows_max * channels + 2) * 4u, 16);
-    p.cv_cap = static_cast<int>(std::max<uint32_t>(256, 6 * rows_max * channels));
+    p.off_stage = off;
+    p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * channels), 4));
+    p.st_rp = up(rows_max * f_in * 4u, 128);
+    p.st_col = p.st_rp + up((rows_max * channels + 8) * 4u, 16);
+    p.st_val = p.st_col + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u;
+    p.stage_bytes = up(p.st_val + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u, 128);
+    const uint32_t fixed = static_cast<uint32_t>(p.cv_cap) * 8u + static_cast<uint32_t>(channels) * bm * 4u +
+                           static_cast<uint32_t>(channels) * 256u * 4u + 1024u;
+    p.n_stages = 0;
+    for (int st = kMaxStages; st >= 1; --st)
+        if (off + st * p.stage_bytes + fixed <= static_cast<uint32_t>(max_smem)) { p.n_stages = st; break; }
+    if (p.n_stages == 0) return false;
+    off += p.n_stages * p.stage_bytes;
     p.off_cv = off; off += static_cast<uint32_t>(p.cv_cap) * 8u;
     p.off_deg = off; off += static_cast<uint32_t>(channels) * bm * 4u;
     p.off_bias = off; off += static_cast<uint32_t>(channels) * 256u * 4u;
@@ -552,18 +594,21 @@ bool plan_bm(FusedParams& p, int bm, int64_t n_graphs, int channels, int n_nodes
     uint32_t cols = 32;
     while (cols < static_cast<uint32_t>(p.Np)) cols <<= 1;
     p.tmem_cols = cols;
-    return p.smem_total <= 227 * 1024 - 256;  // static __shared__ (barriers, TMEM slot) shares the 227 KB
+    return true;
 }
+
+constexpr int kSmemOneCta = 227 * 1024 - 512;   // static __shared__ (barriers, stage info) shares the 227 KB
+constexpr int kSmemTwoCtas = 113 * 1024 - 512;
 
 // 64-row tiles when two CTAs then fit one SM (their phases overlap), else 128-row tiles.
 bool plan(FusedParams& p, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
     FusedParams q = p;
-    if (plan_bm(q, 64, n_graphs, channels, n_nodes, f_in, f_out) && q.smem_total <= 113 * 1024) {
+    if (plan_bm(q, 64, kSmemTwoCtas, n_graphs, channels, n_nodes, f_in, f_out) && q.n_stages >= 2) {
         p = q;
         return true;
     }
-    if (plan_bm(p, 128, n_graphs, channels, n_nodes, f_in, f_out)) return true;
-    return plan_bm(p, 64, n_graphs, channels, n_nodes, f_in, f_out);
+    if (plan_bm(p, 128, kSmemOneCta, n_graphs, channels, n_nodes, f_in, f_out)) return true;
+    return plan_bm(p, 64, kSmemOneCta, n_graphs, channels, n_nodes, f_in, f_out);
 }
 
 }  // namespace
@@ -572,10 +617,7 @@ bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, i
                         const float* y) {
     FusedParams p{};
     if (n_graphs <= 0 || !plan(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
-    // tiles must start 16-byte aligned for the bulk copy
-    const uint64_t tile_x = static_cast<uint64_t>(p.graphs_per_tile) * n_nodes * f_in * 4;
-    return aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 3u) == 0 && tile_x % 16 == 0 &&
-           n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
+    return aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 3u) == 0 && n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
 }
 
 int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
@@ -584,17 +626,20 @@ int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const 
     FusedParams p{};
     KGCN_REQUIRE(plan(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED,
                  "fused GraphConv: shape does not fit one SM's shared memory");
+    // the CSR slices are fetched with 16-byte bulk copies of the enclosing aligned ranges
+    KGCN_REQUIRE(aligned16(rowptr) && aligned16(col) && aligned16(val), KGCN_ERR_MISALIGNED,
+                 "fused GraphConv: rowptr/col/val must be 16-byte aligned");
     p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = bias; p.y = y;
     p.n_graphs = n_graphs; p.channels = channels; p.n_nodes = n_nodes; p.f_in = f_in; p.f_out = f_out; p.act = act;
     const int vec = (f_in % 4 == 0) ? 4 : ((f_in % 2 == 0) ? 2 : 1);
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < 32 && (1 << lpr_log2) * vec < f_in) ++lpr_log2;
     p.lpr_log2 = lpr_log2;
-    const int ctas_per_sm = (p.bm == 64 && p.smem_total <= 113 * 1024) ? 2 : 1;
+    const int ctas_per_sm = (p.bm == 64 && p.smem_total <= static_cast<uint32_t>(kSmemTwoCtas) + 1024) ? 2 : 1;
     const unsigned grid = static_cast<unsigned>(std::min<int>(p.n_tiles, kNumSMs * ctas_per_sm));
     auto go = [&](auto kernel) -> int {
         KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-        kernel<<<grid, kThreads, p.smem_total, st>>>(p);
+        kernel<<<grid, kBlock, p.smem_total, st>>>(p);
         KGCN_LAUNCH_OK("graphconv_fused_fwd_kernel");
         return KGCN_OK;
     };
