@@ -176,18 +176,25 @@ def run_own(args):
                for d in host]
     nnz_mean = float(np.mean([b.csr.nnz for b in batches]))
 
+    def note(msg):
+        if args.verbose:
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    # ---- launches of this library's kernels per step (counted on one eager step) ----
+    c0 = _lib.lib.kgcn_launch_count()
+    tr.step_eager(batches[0])
+    launches_per_step = _lib.lib.kgcn_launch_count() - c0
+    c0 = _lib.lib.kgcn_launch_count()
+    tr.forward_eager(batches[0])
+    launches_per_infer = _lib.lib.kgcn_launch_count() - c0
+    torch.cuda.synchronize()
+    note("eager step ok, %d launches" % launches_per_step)
     # ---- capture one CUDA graph per resident batch (train) + one inference graph per batch ----
-    c0 = _lib.lib.kgcn_launch_count()
-    tr.capture(("train", 0), batches[0])
-    # capture() runs 2 eager warm-up steps + 1 captured step
-    launches_per_step = (_lib.lib.kgcn_launch_count() - c0) // 3
-    for i in range(1, N_ROT):
+    for i in range(N_ROT):
         tr.capture(("train", i), batches[i])
-    c0 = _lib.lib.kgcn_launch_count()
-    tr.capture(("infer", 0), batches[0], train=False)
-    launches_per_infer = (_lib.lib.kgcn_launch_count() - c0) // 3
-    for i in range(1, N_ROT):
+    for i in range(N_ROT):
         tr.capture(("infer", i), batches[i], train=False)
+    note("graphs captured")
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,7 +221,9 @@ def run_own(args):
     sampler.start()
     ms_train = timed("train", args.steps, args.warmup)
     clocks = sampler.result()
+    note("train timed %.3f ms" % ms_train)
     ms_infer = timed("infer", args.steps, args.warmup)
+    note("infer timed")
     cost_sum, correct = tr.read_stats()
 
     # ---- dominant-kernel roofline: the batched SpMM  Y = A.X  on the step's own shape, timed alone ----
@@ -257,6 +266,7 @@ def run_own(args):
     pipe = HostFedPipeline(tr, max_nnz, train=True)
     pinned = [HostFedPipeline.pin_host_batch(d["counts"], d["indices"], d["values"], d["features"], d["labels"]) for d in host]
     pipe.capture()
+    note("e2e pipeline captured")
     e2e_steps = max(10, min(args.steps, 300))
     for i in range(5):
         pipe.run(pinned[i % N_ROT])
@@ -310,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

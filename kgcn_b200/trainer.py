@@ -206,34 +206,55 @@ class Trainer:
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=False)
 
-    def step_eager(self, batch, apply_update=True):
+    def _fwd_bwd(self, batch):
         st = torch.cuda.current_stream().cuda_stream
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=True)
         self._backward(batch, f, st)
+
+    def step_eager(self, batch, apply_update=True):
+        self._fwd_bwd(batch)
         self._allreduce()
         if apply_update:
-            self._optimizer(st)
+            self._optimizer(torch.cuda.current_stream().cuda_stream)
 
     # -- CUDA-graph replay ------------------------------------------------------------------------
-    def capture(self, key, batch, train=True):
-        """Capture the step for ``batch``'s static buffers; replay with :meth:`replay`."""
-        fn = (lambda: self.step_eager(batch)) if train else (lambda: self.forward_eager(batch))
+    def _capture_fn(self, fn):
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(2):      # warm-up outside capture (lazy cudaFuncSetAttribute calls, NCCL setup)
+            for _ in range(2):      # warm-up outside capture (lazy cudaFuncSetAttribute calls)
                 fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             fn()
-        self.graphs[key] = g
         return g
 
+    def capture(self, key, batch, train=True):
+        """Capture the step for ``batch``'s static buffers; replay with :meth:`replay`.
+
+        Single GPU: the whole step (forward, head, backward, Adam) is ONE graph.  Data parallel:
+        forward+backward is one graph and Adam another, with the NCCL all-reduce of the flat
+        gradient buffer issued eagerly between the two replays (collectives are kept out of graph
+        capture on purpose: the eager call is the plain, always-supported ``torch.distributed`` path)."""
+        if not train:
+            self.graphs[key] = (self._capture_fn(lambda: self.forward_eager(batch)),)
+        elif self.world_size == 1:
+            self.graphs[key] = (self._capture_fn(lambda: self.step_eager(batch)),)
+        else:
+            if getattr(self, "_opt_graph", None) is None:
+                self._opt_graph = self._capture_fn(lambda: self._optimizer(torch.cuda.current_stream().cuda_stream))
+            self.graphs[key] = (self._capture_fn(lambda: self._fwd_bwd(batch)), "allreduce", self._opt_graph)
+        return self.graphs[key]
+
     def replay(self, key):
-        self.graphs[key].replay()
+        for g in self.graphs[key]:
+            if g == "allreduce":
+                self._allreduce()
+            else:
+                g.replay()
 
     def read_stats(self):
         """(cost_sum, correct_count) of the last step -- a device->host read."""
@@ -277,28 +298,32 @@ class HostFedPipeline:
         self.train = train
         self.graph = None
 
-    def _device_part(self):
+    def _pack(self):
         t, b = self.trainer, self.batch
         st = torch.cuda.current_stream().cuda_stream
-        s, B, N, C = t.spec, t.B, t.spec.n_nodes, t.spec.channels
+        B, N, C = t.B, t.spec.n_nodes, t.spec.channels
         for tr, (rp, col, val) in ((0, (b.csr.rowptr, b.csr.col, b.csr.val)), (1, (b.csr.rowptr_t, b.csr.col_t, b.csr.val_t))):
             check(lib.kgcn_pack_coo_device(B * C, N, N, ptr(self.d_off), ptr(self.d_idx), ptr(self.d_val), tr, ptr(rp),
                                            ptr(col), ptr(val), None, ptr(self.d_flag), st))
+
+    def _device_part(self):
+        self._pack()
         if self.train:
-            t.step_eager(b)
+            self.trainer.step_eager(self.batch)
         else:
-            t.forward_eager(b)
+            self.trainer.forward_eager(self.batch)
 
     def capture(self):
-        side = torch.cuda.Stream(device=self.trainer.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            self._device_part()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._device_part()
+        t = self.trainer
+        if self.train and t.world_size > 1:   # collectives stay outside graph capture (see Trainer.capture)
+            def fb():
+                self._pack()
+                t._fwd_bwd(self.batch)
+            if getattr(t, "_opt_graph", None) is None:
+                t._opt_graph = t._capture_fn(lambda: t._optimizer(torch.cuda.current_stream().cuda_stream))
+            self.graph = (t._capture_fn(fb), "allreduce", t._opt_graph)
+        else:
+            self.graph = (t._capture_fn(self._device_part),)
 
     @staticmethod
     def pin_host_batch(counts, indices, values, features, labels, mask=None):
@@ -329,7 +354,11 @@ class HostFedPipeline:
         b.labels.copy_(host["labels"], non_blocking=True)
         b.mask.copy_(host["mask"], non_blocking=True)
         if self.graph is not None:
-            self.graph.replay()
+            for g in self.graph:
+                if g == "allreduce":
+                    self.trainer._allreduce()
+                else:
+                    g.replay()
         else:
             self._device_part()
         self.h_stats.copy_(self.trainer.stats, non_blocking=True)
