@@ -67,6 +67,9 @@ typedef enum kgcn_act { KGCN_ACT_NONE = 0, KGCN_ACT_RELU = 1, KGCN_ACT_SIGMOID =
 #define KGCN_FLAG_DEFAULT 0          /* library picks the fastest kernel that meets fp32 parity        */
 #define KGCN_FLAG_REFERENCE_ORDER 1  /* force the decomposed W-first path: (X.W + b) with exact-fp32    */
                                      /* FFMA, then A.( ), i.e. the operation order of layers.py:112-113 */
+#define KGCN_FLAG_DY_BROADCAST 2     /* backward only: dy is [n_graphs, f_out] and stands for the same   */
+                                     /* row repeated over all n_nodes (gradient of GraphGather,         */
+                                     /* layers.py:164): fuses the broadcast into the backward           */
 
 int kgcn_abi_version(void);
 /* Thread-local, never NULL, valid until the next failing call on this thread. */

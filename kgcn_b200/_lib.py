@@ -18,6 +18,7 @@ STATUS_NAMES = {
 ACT_IDS = {None: 0, "none": 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 FLAG_DEFAULT = 0
 FLAG_REFERENCE_ORDER = 1
+FLAG_DY_BROADCAST = 2
 
 
 class KgcnError(RuntimeError):

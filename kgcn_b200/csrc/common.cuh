@@ -88,7 +88,7 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
 
 // du = dy * act'(y) (elementwise), optional row mask by enabled_node_nums.
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act,
-                    const int32_t* enabled, int n_nodes, cudaStream_t st);
+                    const int32_t* enabled, int n_nodes, bool dy_bcast, cudaStream_t st);
 
 int launch_bspmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                  int n_rows, int n_cols, int feat, const float* rhs, int64_t rs_g, int64_t rs_c, float* out,

@@ -155,15 +155,23 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p
     }
 }
 
-// out[r, n] = sum_z partial[z][r][n] in fixed z order (deterministic); row M -> colsum output.
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N, int has_colsum,
-                                     float* __restrict__ out, float* __restrict__ colsum_out) {
+// out[r, n] = sum_z partial[z][r][n] (deterministic order); row M -> colsum output.
+// Block = 64 consecutive outputs x 4 interleaved split lanes, combined through shared memory.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
+                                                            int has_colsum, float* __restrict__ out,
+                                                            float* __restrict__ colsum_out) {
+    __shared__ float red[4][64];
     const int64_t rows = M + (has_colsum ? 1 : 0);
     const int64_t total = rows * N;
-    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += partial[static_cast<int64_t>(z) * total + idx];
+    const int o = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * 64 + o;
+    float s = 0.0f;
+    if (idx < total)
+        for (int z = lane4; z < splits; z += 4) s += partial[static_cast<int64_t>(z) * total + idx];
+    red[lane4][o] = s;
+    __syncthreads();
+    if (lane4 == 0 && idx < total) {
+        s = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
         if (idx < M * N)
             out[idx] = s;
         else if (colsum_out != nullptr)
@@ -171,11 +179,16 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
     }
 }
 
+// dy_bcast != 0: dy is [n_graphs, feat] and is broadcast over the n_nodes rows of each graph (the
+// gradient of GraphGather, layers.py:164) -- fuses gather_bwd into this pass.
 __global__ void act_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ du,
-                                int64_t n, int feat, int act, const int32_t* __restrict__ enabled, int n_nodes) {
+                                int64_t n, int feat, int act, const int32_t* __restrict__ enabled, int n_nodes,
+                                int dy_bcast) {
+    const int64_t per_graph = static_cast<int64_t>(n_nodes) * feat;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float v = dy[idx] * act_grad_from_output(y[idx], act);
+        const float g = dy_bcast ? dy[(idx / per_graph) * feat + (idx % feat)] : dy[idx];
+        float v = g * (y != nullptr ? act_grad_from_output(y[idx], act) : 1.0f);
         if (enabled != nullptr) {
             const int64_t row = idx / feat;
             if ((row % n_nodes) >= enabled[row / n_nodes]) v = 0.0f;
@@ -216,7 +229,7 @@ inline unsigned ew_blocks(int64_t n) {
 
 int choose_splits(int64_t M_out, int N, int64_t K) {
     const int64_t tiles = ceil_div<int64_t>(M_out, BM) * ceil_div(N, BN);
-    int64_t splits = ceil_div<int64_t>(2 * kNumSMs, tiles);
+    int64_t splits = ceil_div<int64_t>(kNumSMs, tiles);
     const int64_t max_by_k = ceil_div<int64_t>(K, 4 * BK);  // at least 4 k-steps per split
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
@@ -282,16 +295,16 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
     dim3 grid(ceil_div(N, BN), ceil_div(Ka, BM), splits);
     sgemm_kernel<true, false><<<grid, GEMM_THREADS, 0, st>>>(p);
     KGCN_LAUNCH_OK("sgemm_kernel(split-K)");
-    splitk_reduce_kernel<<<ew_blocks((static_cast<int64_t>(Ka) + 1) * N), 256, 0, st>>>(
+    splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<int64_t>((static_cast<int64_t>(Ka) + 1) * N, 64)), 256, 0, st>>>(
         static_cast<const float*>(workspace), splits, Ka, N, 1, out, colsum_b);
     KGCN_LAUNCH_OK("splitk_reduce_kernel");
     return KGCN_OK;
 }
 
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act, const int32_t* enabled,
-                    int n_nodes, cudaStream_t st) {
+                    int n_nodes, bool dy_bcast, cudaStream_t st) {
     if (n == 0) return KGCN_OK;
-    act_grad_kernel<<<ew_blocks(n), 256, 0, st>>>(y, dy, du, n, feat, act, enabled, n_nodes);
+    act_grad_kernel<<<ew_blocks(n), 256, 0, st>>>(y, dy, du, n, feat, act, enabled, n_nodes, dy_bcast ? 1 : 0);
     KGCN_LAUNCH_OK("act_grad_kernel");
     return KGCN_OK;
 }
@@ -358,7 +371,7 @@ extern "C" int kgcn_graphdense_bwd_f32(const float* x, int64_t n_graphs, int32_t
     float* du = static_cast<float*>(workspace);
     void* ws2 = du + rows * f_out;
     const size_t ws2_bytes = workspace_bytes - static_cast<size_t>(rows) * f_out * sizeof(float);
-    int rc = launch_act_grad(y, dy, du, rows * f_out, f_out, act, enabled_node_nums, n_nodes, st);
+    int rc = launch_act_grad(y, dy, du, rows * f_out, f_out, act, enabled_node_nums, n_nodes, false, st);
     if (rc) return rc;
     rc = launch_reduce_gemm_tn(rows, f_in, f_out, x, f_in, du, f_out, dkernel, dbias, ws2, ws2_bytes, st);
     if (rc) return rc;

@@ -73,7 +73,7 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
                                       int32_t f_in, const float* w, int32_t f_out, int32_t act, const float* y,
                                       const float* dy, float* dx, float* dw, float* dbias, int32_t flags,
                                       void* workspace, size_t workspace_bytes, void* stream) {
-    (void)flags;
+    const bool dy_bcast = (flags & KGCN_FLAG_DY_BROADCAST) != 0;
     KGCN_REQUIRE(rowptr_t && col_t && val_t && x && w && dy && dw, KGCN_ERR_NULL, "graphconv_bwd: NULL pointer argument");
     KGCN_REQUIRE(act == KGCN_ACT_NONE || y != nullptr, KGCN_ERR_NULL, "graphconv_bwd: y required when act != none");
     KGCN_REQUIRE(n_graphs >= 0 && channels > 0 && n_nodes > 0 && f_in > 0 && f_out > 0, KGCN_ERR_BAD_SHAPE,
@@ -96,8 +96,9 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
     const size_t ws2_bytes = workspace_bytes - used;
 
     const float* du_ptr = dy;
-    if (act != KGCN_ACT_NONE) {
-        int rc = launch_act_grad(y, dy, du, static_cast<int64_t>(act_elems), f_out, act, nullptr, n_nodes, st);
+    if (act != KGCN_ACT_NONE || dy_bcast) {
+        int rc = launch_act_grad(act != KGCN_ACT_NONE ? y : nullptr, dy, du, static_cast<int64_t>(act_elems), f_out, act,
+                                 nullptr, n_nodes, dy_bcast, st);
         if (rc) return rc;
         du_ptr = du;
     }

@@ -22,6 +22,7 @@
 // CUDA-core aggregation, tensor-core contraction, epilogue) then overlap -- else 128 rows.
 // HBM traffic per layer = x once + y once + CSR once + W once per CTA: the algorithmic minimum.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -161,34 +162,81 @@ __device__ __forceinline__ void aggregate_simple(const AggCtx& a, int group, int
     asm volatile("" : "+r"(xb), "+r"(rp), "+r"(cvb), "+r"(zh), "+r"(zl), "+r"(dg));
     const uint32_t kchunk = static_cast<uint32_t>(sub) & 7u;  // 16-byte chunk inside the 128-byte atom row
     const bool active = sub * 4 < a.f_in;
-    for (int w = group; w < a.rows; w += n_groups) {
-        uint32_t p = cvb + 8u * lds_u32(rp + 4u * w);
-        const uint32_t p_end = cvb + 8u * lds_u32(rp + 4u * w + 4u);
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        float deg = 0.0f;
+    // Two rows (w and w + n_groups) are walked together: their LDS -> LDS -> FFMA chains are
+    // independent, which doubles the memory-level parallelism of this latency-bound loop.
+    for (int w0 = group; w0 < a.rows; w0 += 2 * n_groups) {
+        const int w1 = w0 + n_groups;
+        const bool has1 = w1 < a.rows;
+        uint32_t p0 = cvb + 8u * lds_u32(rp + 4u * w0);
+        const uint32_t e0 = cvb + 8u * lds_u32(rp + 4u * w0 + 4u);
+        uint32_t p1 = has1 ? cvb + 8u * lds_u32(rp + 4u * w1) : 0u;
+        const uint32_t e1 = has1 ? cvb + 8u * lds_u32(rp + 4u * w1 + 4u) : 0u;
+        float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float deg0 = 0.0f, deg1 = 0.0f;
 #pragma unroll 1
-        for (; p < p_end; p += 8) {
-            const int2 cv = lds_i2(p);           // broadcast LDS.64 {byte offset of the neighbour row, value}
-            float xv[4];
-            lds_f<4>(xv, xb + static_cast<uint32_t>(cv.x));
-            const float v = __int_as_float(cv.y);
-            deg += v;
+        while (p0 < e0 && p1 < e1) {
+            const int2 c0 = lds_i2(p0), c1 = lds_i2(p1);   // broadcast LDS.64 {byte offset of the neighbour row, value}
+            float x0[4], x1[4];
+            lds_f<4>(x0, xb + static_cast<uint32_t>(c0.x));
+            lds_f<4>(x1, xb + static_cast<uint32_t>(c1.x));
+            const float v0 = __int_as_float(c0.y), v1 = __int_as_float(c1.y);
+            deg0 += v0;
+            deg1 += v1;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) acc[t] = fmaf(v, xv[t], acc[t]);
+            for (int t = 0; t < 4; ++t) {
+                acc0[t] = fmaf(v0, x0[t], acc0[t]);
+                acc1[t] = fmaf(v1, x1[t], acc1[t]);
+            }
+            p0 += 8;
+            p1 += 8;
+        }
+#pragma unroll 1
+        for (; p0 < e0; p0 += 8) {
+            const int2 c0 = lds_i2(p0);
+            float x0[4];
+            lds_f<4>(x0, xb + static_cast<uint32_t>(c0.x));
+            const float v0 = __int_as_float(c0.y);
+            deg0 += v0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc0[t] = fmaf(v0, x0[t], acc0[t]);
+        }
+#pragma unroll 1
+        for (; p1 < e1; p1 += 8) {
+            const int2 c1 = lds_i2(p1);
+            float x1[4];
+            lds_f<4>(x1, xb + static_cast<uint32_t>(c1.x));
+            const float v1 = __int_as_float(c1.y);
+            deg1 += v1;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc1[t] = fmaf(v1, x1[t], acc1[t]);
         }
         if (active) {
             float hi[4], lo[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                hi[t] = tf32_hi(acc[t]);
-                lo[t] = acc[t] - hi[t];
+                hi[t] = tf32_hi(acc0[t]);
+                lo[t] = acc0[t] - hi[t];
             }
-            const uint32_t uw = static_cast<uint32_t>(w);
-            const uint32_t off = (uw << 7) + ((kchunk ^ (uw & 7u)) << 4);   // (w>>3)*1024 + (w&7)*128 == w*128
-            sts_f<4>(zh + off, hi);
-            sts_f<4>(zl + off, lo);
+            const uint32_t u0 = static_cast<uint32_t>(w0);
+            const uint32_t off0 = (u0 << 7) + ((kchunk ^ (u0 & 7u)) << 4);   // (w>>3)*1024 + (w&7)*128 == w*128
+            sts_f<4>(zh + off0, hi);
+            sts_f<4>(zl + off0, lo);
+            if (has1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    hi[t] = tf32_hi(acc1[t]);
+                    lo[t] = acc1[t] - hi[t];
+                }
+                const uint32_t u1 = static_cast<uint32_t>(w1);
+                const uint32_t off1 = (u1 << 7) + ((kchunk ^ (u1 & 7u)) << 4);
+                sts_f<4>(zh + off1, hi);
+                sts_f<4>(zl + off1, lo);
+            }
         }
-        if (sub == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dg + 4u * w), "f"(deg) : "memory");
+        if (sub == 0) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(dg + 4u * w0), "f"(deg0) : "memory");
+            if (has1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dg + 4u * w1), "f"(deg1) : "memory");
+        }
     }
 }
 
@@ -310,18 +358,18 @@ __device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, int warp, int lan
     const int q = warp & 3;
     const int row = q * 32 + lane;
     float* y_row = y_tile + static_cast<size_t>(row) * f_out;
-    for (int j = warp >> 2; j * 16 < f_out; j += 2) {
+    for (int j = warp >> 2; j * 16 < f_out; j += 4) {   // 16 warps: 4 lane quarters x 4 column phases
         float v[16];
         tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16), v);
         if (row < rows) epilogue_chunk<ACT>(v, j * 16, f_out, C, 128, deg_addr, bias_addr, row, y_row, vec4_ok);
     }
 }
 
-constexpr int kConsumers = 256;           // aggregation / epilogue threads (8 warps)
-constexpr int kBlock = kConsumers + 32;   // + one TMA producer warp
 constexpr int kMaxStages = 3;
 
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// 4 consumer threads per tile row (8 warps for 64-row tiles, 16 warps for 128-row tiles) + 1 producer warp
+template <int NC>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 
 struct StageInfo {   // written by the producer before it arms full[s]
     int32_t e_first;  // first CSR entry of the tile
@@ -333,7 +381,9 @@ struct StageInfo {   // written by the producer before it arms full[s]
 };
 
 template <int VEC, int BM>
-__global__ void __launch_bounds__(kBlock, BM == 64 ? 2 : 1) graphconv_fused_fwd_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused_fwd_kernel(const FusedParams p) {
+    constexpr int kConsumers = BM * 4;
+    constexpr int kBlock = kConsumers + 32;
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_mma;
     __shared__ __align__(16) StageInfo sinfo[kMaxStages];
@@ -442,7 +492,7 @@ __global__ void __launch_bounds__(kBlock, BM == 64 ? 2 : 1) graphconv_fused_fwd_
         }
         fence_proxy_async_smem();  // W is read by the tensor core through the async proxy
         tc_fence_before_sync();
-        consumer_sync();
+        consumer_sync<kConsumers>();
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_slot;
         const uint32_t idesc = umma_idesc_tf32(BM, Np);
@@ -483,7 +533,7 @@ __global__ void __launch_bounds__(kBlock, BM == 64 ? 2 : 1) graphconv_fused_fwd_
                     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cv_addr + 8u * k), "r"(off), "r"(lds_u32(val_a + 4u * k)) : "memory");
                 }
             }
-            consumer_sync();
+            consumer_sync<kConsumers>();
 
             // ---- 2. aggregation on the CUDA cores ----
             {
@@ -493,7 +543,7 @@ __global__ void __launch_bounds__(kBlock, BM == 64 ? 2 : 1) graphconv_fused_fwd_
             }
             fence_proxy_async_smem();  // generic-proxy writes of Z -> visible to the tensor core (async proxy)
             tc_fence_before_sync();
-            consumer_sync();
+            consumer_sync<kConsumers>();
 
             // ---- 3. Y = Z . W on the tensor cores (3xTF32), accumulator in TMEM ----
             if (tid == 0) {
@@ -541,7 +591,7 @@ __global__ void __launch_bounds__(kBlock, BM == 64 ? 2 : 1) graphconv_fused_fwd_
                 }
             }
             tc_fence_before_sync();
-            consumer_sync();  // TMEM / row sums / cv pairs consumed before the next tile overwrites them
+            consumer_sync<kConsumers>();  // TMEM / row sums / cv pairs consumed before the next tile overwrites them
         }
     }
 
@@ -602,6 +652,13 @@ constexpr int kSmemTwoCtas = 113 * 1024 - 512;
 
 // 64-row tiles when two CTAs then fit one SM (their phases overlap), else 128-row tiles.
 bool plan(FusedParams& p, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    static const char* force = getenv("KGCN_FUSED_BM");   // tuning knob: 64 / 128 forces the tile height
+    if (force != nullptr) {
+        const int bm = atoi(force);
+        if (bm == 128) return plan_bm(p, 128, kSmemOneCta, n_graphs, channels, n_nodes, f_in, f_out);
+        if (bm == 64) return plan_bm(p, 64, kSmemTwoCtas, n_graphs, channels, n_nodes, f_in, f_out) ||
+                             plan_bm(p, 64, kSmemOneCta, n_graphs, channels, n_nodes, f_in, f_out);
+    }
     FusedParams q = p;
     if (plan_bm(q, 64, kSmemTwoCtas, n_graphs, channels, n_nodes, f_in, f_out) && q.n_stages >= 2) {
         p = q;
@@ -639,7 +696,7 @@ int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const 
     const unsigned grid = static_cast<unsigned>(std::min<int>(p.n_tiles, kNumSMs * ctas_per_sm));
     auto go = [&](auto kernel) -> int {
         KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-        kernel<<<grid, kBlock, p.smem_total, st>>>(p);
+        kernel<<<grid, p.bm * 4 + 32, p.smem_total, st>>>(p);
         KGCN_LAUNCH_OK("graphconv_fused_fwd_kernel");
         return KGCN_OK;
     };

@@ -167,11 +167,11 @@ class Trainer:
         csr = batch.csr
         n_conv = len(s.conv_dims)
         k = n_conv + (1 if s.dense_dim else 0)
-        dy = self.dact[0][:, :, :f]
-        dy = self.dact[0].view(-1)[:B * N * f].view(B, N, f)
-        check(lib.kgcn_gather_bwd_f32(ptr(self.dgathered), B, N, f, ptr(dy), st))
         cur = 0
+        bcast = 0
         if s.dense_dim:
+            dy = self.dact[0].view(-1)[:B * N * f].view(B, N, f)
+            check(lib.kgcn_gather_bwd_f32(ptr(self.dgathered), B, N, f, ptr(dy), st))
             fin = s.conv_dims[-1]
             dx = self.dact[1].view(-1)[:B * N * fin].view(B, N, fin)
             check(lib.kgcn_graphdense_bwd_f32(ptr(self.acts[k - 1]), B, N, fin, ptr(self.views["graph_dense/kernel"]),
@@ -179,6 +179,9 @@ class Trainer:
                                               ptr(self.gviews["graph_dense/kernel"]), ptr(self.gviews["graph_dense/bias"]),
                                               ptr(self.ws), self.ws.numel(), st))
             dy, cur, k, f = dx, 1, k - 1, fin
+        else:
+            # the GraphGather gradient ([B, F] broadcast over nodes) is consumed directly by the last conv layer
+            dy, bcast = self.dgathered, _lib.FLAG_DY_BROADCAST
         for i in range(n_conv - 1, -1, -1):
             fin = s.conv_dims[i - 1] if i > 0 else s.feature_dim
             dx = None
@@ -188,9 +191,9 @@ class Trainer:
             check(lib.kgcn_graphconv_bwd_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N,
                                              ptr(self.acts[i]), fin, ptr(self.views["conv%d/kernel" % i]), f, self.act,
                                              ptr(self.acts[i + 1]), ptr(dy), ptr(dx), ptr(self.gviews["conv%d/kernel" % i]),
-                                             ptr(self.gviews["conv%d/bias" % i]), self.flags, ptr(self.ws),
+                                             ptr(self.gviews["conv%d/bias" % i]), self.flags | bcast, ptr(self.ws),
                                              self.ws.numel(), st))
-            dy, f = dx, fin
+            dy, f, bcast = dx, fin, 0
 
     def _optimizer(self, st):
         check(lib.kgcn_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
