@@ -51,6 +51,7 @@ struct FusedParams {
     uint32_t off_zhi, off_zlo, off_whi, off_wlo, off_stage, off_cv, off_deg, off_bias, smem_total;
     uint32_t stage_bytes, st_rp, st_col, st_val;   // per-stage layout: features at 0, then the CSR slices
     uint32_t tmem_cols;
+    long long* dbg;   // optional [grid][8] per-CTA phase cycle sums (thread 0), tuning aid
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -303,14 +304,22 @@ __device__ __forceinline__ float finish(float acc, float degbias) { return fast_
 // M = 64 epilogue: .16x256b loads keep all 32 lanes busy.  Warp w owns tile rows 16*(w&3) .. +15
 // (TMEM lanes 32*(w&3) .. +15) and the 32-column slabs (w>>2), (w>>2)+2, ...
 template <int ACT>
-__device__ __forceinline__ void epilogue_m64(uint32_t tmem_d, int warp, int lane, int rows, int f_out, int C,
+__device__ __forceinline__ void epilogue_m64(uint32_t tmem_d, uint32_t np, int warp, int lane, int rows, int f_out, int C,
                                              uint32_t deg_addr, uint32_t bias_addr, float* y_tile, bool vec2_ok) {
     const int q = warp & 3;
     const int ra = q * 16 + (lane >> 2), rb = ra + 8;
     float dega[8], degb[8];  // row sums per channel (C <= 8 on this path; larger C loops in chunks)
     for (int slab = warp >> 2; slab * 32 < f_out; slab += 2) {
         float v[16];
-        tmem_ld_16x256b_x4(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slab * 32), v);
+        {
+            float v1[16], v2[16];
+            const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slab * 32);
+            tmem_ld_16x256b_x4(ta, v);
+            tmem_ld_16x256b_x4(ta + np, v1);
+            tmem_ld_16x256b_x4(ta + 2 * np, v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v1[i] + v2[i];   // Zhi.Whi + (Zlo.Whi + Zhi.Wlo)
+        }
         float ba[8], bb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ba[i] = bb[i] = 0.0f;
@@ -353,19 +362,65 @@ __device__ __forceinline__ void epilogue_m64(uint32_t tmem_d, int warp, int lane
 
 // M = 128 epilogue: accumulator row m lives in TMEM lane m; a thread owns one row, 16 columns at a time
 template <int ACT>
-__device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, int warp, int lane, int rows, int f_out, int C,
+__device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, uint32_t np, int warp, int lane, int rows, int f_out, int C,
                                               uint32_t deg_addr, uint32_t bias_addr, float* y_tile, bool vec4_ok) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     float* y_row = y_tile + static_cast<size_t>(row) * f_out;
     for (int j = warp >> 2; j * 16 < f_out; j += 4) {   // 16 warps: 4 lane quarters x 4 column phases
         float v[16];
-        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16), v);
+        {
+            float v1[16], v2[16];
+            const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16);
+            tmem_ld16(ta, v);
+            tmem_ld16(ta + np, v1);
+            tmem_ld16(ta + 2 * np, v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v1[i] + v2[i];   // Zhi.Whi + (Zlo.Whi + Zhi.Wlo)
+        }
         if (row < rows) epilogue_chunk<ACT>(v, j * 16, f_out, C, 128, deg_addr, bias_addr, row, y_row, vec4_ok);
     }
 }
 
 constexpr int kMaxStages = 3;
+
+__device__ __forceinline__ bool elect_one() {   // exactly one lane of the (converged) warp gets true
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// One pass of the 3xTF32 contraction (pass 0: Zhi.Whi, 1: Zlo.Whi, 2: Zhi.Wlo) in K-steps of 8
+// (32 bytes), fully unrolled for NA K-atoms so that every descriptor is a uniform-register add of a
+// constant.  A single thread needs ~100+ cycles of scalar work per tcgen05.mma (tools/ubench), so the
+// three passes are issued by three different warps into three TMEM accumulators that the epilogue adds.
+template <int NA>
+__device__ __forceinline__ void issue_pass(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                           uint32_t z_atom16, uint32_t w_atom16, int K) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int at = 0; at < NA; ++at) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            if (at * 32 + ks * 8 < K) {  // skip k-steps that only see padding
+                umma_tf32(tmem_d, da + static_cast<uint64_t>(at * z_atom16 + 2 * ks),
+                          db + static_cast<uint64_t>(at * w_atom16 + 2 * ks), idesc, acc);
+                acc = 1;
+            }
+        }
+    }
+}
+__device__ __noinline__ void issue_pass_loop(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                             uint32_t z_atom16, uint32_t w_atom16, int K, int n_atoms) {
+    uint32_t acc = 0;
+    int k_left = K;
+    for (int at = 0; at < n_atoms; ++at, da += z_atom16, db += w_atom16, k_left -= 32)
+        for (int ks = 0; ks < 4; ++ks)
+            if (ks * 8 < k_left) {
+                umma_tf32(tmem_d, da + 2u * ks, db + 2u * ks, idesc, acc);
+                acc = 1;
+            }
+}
 
 // 4 consumer threads per tile row (8 warps for 64-row tiles, 16 warps for 128-row tiles) + 1 producer warp
 template <int NC>
@@ -413,7 +468,7 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], 1);
         }
-        mbar_init(&bar_mma, 1);
+        mbar_init(&bar_mma, 3);   // one commit per issuing warp
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
@@ -509,6 +564,15 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
         const bool y_vec4 = (f_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0;
         const bool y_vec2 = (f_out & 1) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 7u) == 0;
 
+        long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tlast = clock64();
+        auto mark = [&](int ph) {
+            if (p.dbg != nullptr && tid == 0) {
+                const long long now = clock64();
+                tph[ph] += now - tlast;
+                tlast = now;
+            }
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int s = it % S;
@@ -519,6 +583,7 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
 
             // ---- 1. wait for the stage: features + CSR slices landed by TMA ----
             mbar_wait(&bar_full[s], (it / S) & 1);
+            mark(0);
             const StageInfo si = sinfo[s];
             const uint32_t rp_addr = st + p.st_rp + 4u * static_cast<uint32_t>(si.rp_skip);
             // {column, value} -> {byte offset of the neighbour's feature row in the stage, value}
@@ -534,6 +599,7 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
                 }
             }
             consumer_sync<kConsumers>();
+            mark(1);
 
             // ---- 2. aggregation on the CUDA cores ----
             {
@@ -544,55 +610,57 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
             fence_proxy_async_smem();  // generic-proxy writes of Z -> visible to the tensor core (async proxy)
             tc_fence_before_sync();
             consumer_sync<kConsumers>();
+            mark(2);
 
             // ---- 3. Y = Z . W on the tensor cores (3xTF32), accumulator in TMEM ----
-            if (tid == 0) {
-                mbar_arrive(&bar_empty[s]);  // every consumer is past the barrier: the stage can be refilled
-                tc_fence_after_sync();
-                uint32_t acc_flag = 0;
-#pragma unroll 1
-                for (int pass = 0; pass < 3; ++pass) {
-                    uint64_t da = (pass == 1) ? desc_zlo : desc_zhi;
-                    uint64_t db = (pass == 2) ? desc_wlo : desc_whi;
-                    int k_left = K;
-#pragma unroll 1
-                    for (int at = 0; at < n_atoms; ++at, da += (z_atom >> 4), db += (w_atom >> 4), k_left -= 32) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            if (ks * 8 < k_left) {  // skip k-steps that only see padding
-                                umma_tf32(tmem_d, da + 2u * ks, db + 2u * ks, idesc, acc_flag);  // +32 B per k-step
-                                acc_flag = 1;
-                            }
-                        }
+            if (warp < 3) {   // whole warp converged, one elected lane issues pass `warp` into accumulator `warp`
+                if (elect_one()) {
+                    if (warp == 0) mbar_arrive(&bar_empty[s]);  // every consumer is past the barrier: the stage can be refilled
+                    tc_fence_after_sync();
+                    const uint64_t da = (warp == 1) ? desc_zlo : desc_zhi;
+                    const uint64_t db = (warp == 2) ? desc_wlo : desc_whi;
+                    const uint32_t d = tmem_d + static_cast<uint32_t>(warp * Np);
+                    switch (n_atoms) {
+                        case 1: issue_pass<1>(d, da, db, idesc, z_atom >> 4, w_atom >> 4, K); break;
+                        case 2: issue_pass<2>(d, da, db, idesc, z_atom >> 4, w_atom >> 4, K); break;
+                        case 3: issue_pass<3>(d, da, db, idesc, z_atom >> 4, w_atom >> 4, K); break;
+                        case 4: issue_pass<4>(d, da, db, idesc, z_atom >> 4, w_atom >> 4, K); break;
+                        default: issue_pass_loop(d, da, db, idesc, z_atom >> 4, w_atom >> 4, K, n_atoms);
                     }
+                    umma_commit(&bar_mma);
                 }
-                umma_commit(&bar_mma);
+                __syncwarp();
             }
+            mark(3);
             mbar_wait(&bar_mma, it & 1);
             tc_fence_after_sync();
+            mark(4);
 
             // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> global ----
             {
                 float* y_tile = p.y + g0 * N * f_out;
                 if (BM == 64) {
                     switch (p.act) {
-                        case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                        case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                        case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                        default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2);
+                        case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                        case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                        case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
+                        default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2);
                     }
                 } else {
                     switch (p.act) {
-                        case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                        case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                        case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                        default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4);
+                        case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                        case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                        case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
+                        default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4);
                     }
                 }
             }
             tc_fence_before_sync();
             consumer_sync<kConsumers>();  // TMEM / row sums / cv pairs consumed before the next tile overwrites them
+            mark(5);
         }
+        if (p.dbg != nullptr && tid == 0)
+            for (int i = 0; i < 8; ++i) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + i] = (i == 7) ? it : tph[i];
     }
 
     tc_fence_before_sync();
@@ -603,7 +671,7 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
 inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 bool plan_bm(FusedParams& p, int bm, int max_smem, int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
-    if (n_nodes > bm || f_out > 256 || f_out < 1) return false;
+    if (n_nodes > bm || f_out > 160 || f_out < 1) return false;   // 3 * Np TMEM columns <= 512
     const int K = channels * f_in;
     p.bm = bm;
     p.Kp = static_cast<int>(up(K, 32));
@@ -642,7 +710,7 @@ bool plan_bm(FusedParams& p, int bm, int max_smem, int64_t n_graphs, int channel
     p.off_bias = off; off += static_cast<uint32_t>(channels) * 256u * 4u;
     p.smem_total = off + 1024;  // slack for the manual 1024-B alignment
     uint32_t cols = 32;
-    while (cols < static_cast<uint32_t>(p.Np)) cols <<= 1;
+    while (cols < 3u * static_cast<uint32_t>(p.Np)) cols <<= 1;   // three accumulators (one per 3xTF32 pass)
     p.tmem_cols = cols;
     return true;
 }
@@ -677,6 +745,8 @@ bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, i
     return aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 3u) == 0 && n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
 }
 
+static long long* g_dbg = nullptr;   // set through kgcn_debug_fused_times (tuning only)
+
 int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
                                int channels, int n_nodes, const float* x, int f_in, const float* w, const float* bias,
                                int f_out, int act, float* y, cudaStream_t st) {
@@ -688,6 +758,7 @@ int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const 
                  "fused GraphConv: rowptr/col/val must be 16-byte aligned");
     p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = bias; p.y = y;
     p.n_graphs = n_graphs; p.channels = channels; p.n_nodes = n_nodes; p.f_in = f_in; p.f_out = f_out; p.act = act;
+    p.dbg = g_dbg;
     const int vec = (f_in % 4 == 0) ? 4 : ((f_in % 2 == 0) ? 2 : 1);
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < 32 && (1 << lpr_log2) * vec < f_in) ++lpr_log2;
@@ -715,3 +786,7 @@ int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const 
 }
 
 }  // namespace kgcn
+
+// Tuning hook (not part of the documented ABI): device buffer of [grid][8] int64 that the fused kernel
+// fills with per-CTA phase cycle sums {wait stage, convert, aggregate, mma issue, mma wait, epilogue, -, tiles}.
+extern "C" void kgcn_debug_fused_times(long long* device_buffer) { kgcn::g_dbg = device_buffer; }
