@@ -50,6 +50,7 @@ struct FusedParams {
     int n_stages;     // TMA pipeline depth
     uint32_t off_zhi, off_zlo, off_whi, off_wlo, off_stage, off_cv, off_deg, off_bias, smem_total;
     uint32_t stage_bytes, st_rp, st_col, st_val;   // per-stage layout: features at 0, then the CSR slices
+    uint32_t y_pitch;   // bytes per row of the staged output tile (multiple of 128)
     uint32_t tmem_cols;
     long long* dbg;   // optional [grid][8] per-CTA phase cycle sums (thread 0), tuning aid
 };
@@ -116,33 +117,6 @@ __device__ __forceinline__ float fast_act(float x) {
     return x;
 }
 
-// epilogue for one 16-column accumulator chunk of this thread's row: + rowsum (x) bias, act, store
-template <int ACT>
-__device__ __forceinline__ void epilogue_chunk(float (&v)[16], int col0, int f_out, int channels, int bm, uint32_t deg_addr,
-                                               uint32_t bias_addr, int row, float* y_row, bool vec_ok) {
-    for (int c = 0; c < channels; ++c) {
-        const float d = __uint_as_float(lds_u32(deg_addr + 4u * (c * bm + row)));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float b[4];
-            lds_f<4>(b, bias_addr + 4u * (c * 256 + col0 + 4 * q));   // bias rows are padded to 256 floats
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[4 * q + j] = fmaf(d, b[j], v[4 * q + j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fast_act<ACT>(v[j]);
-    if (vec_ok && col0 + 16 <= f_out) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(y_row + col0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (col0 + j < f_out) y_row[col0 + j] = v[j];
-    }
-}
-
 // ---- aggregation of one tile: Z[w, c*f_in + f] = sum_e val_e * x[col_e, f] as tf32 hi / lo, plus row sums ----
 struct AggCtx {
     uint32_t zhi, zlo, xs, rp_addr, cv_addr, deg_addr;
@@ -163,8 +137,10 @@ __device__ __forceinline__ void aggregate_simple(const AggCtx& a, int group, int
     asm volatile("" : "+r"(xb), "+r"(rp), "+r"(cvb), "+r"(zh), "+r"(zl), "+r"(dg));
     const uint32_t kchunk = static_cast<uint32_t>(sub) & 7u;  // 16-byte chunk inside the 128-byte atom row
     const bool active = sub * 4 < a.f_in;
-    // Two rows (w and w + n_groups) are walked together: their LDS -> LDS -> FFMA chains are
-    // independent, which doubles the memory-level parallelism of this latency-bound loop.
+    // Two rows (w and w + n_groups) are walked together and the {offset, value} pair of the NEXT
+    // entry is fetched before the FFMAs of the current one: the LDS -> LDS -> FFMA chain of this
+    // latency-bound loop then overlaps across entries and rows.  Reading one pair past the end of a
+    // row is harmless (it is the next row's first pair or staging slack) and is never used.
     for (int w0 = group; w0 < a.rows; w0 += 2 * n_groups) {
         const int w1 = w0 + n_groups;
         const bool has1 = w1 < a.rows;
@@ -174,13 +150,17 @@ __device__ __forceinline__ void aggregate_simple(const AggCtx& a, int group, int
         const uint32_t e1 = has1 ? cvb + 8u * lds_u32(rp + 4u * w1 + 4u) : 0u;
         float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         float deg0 = 0.0f, deg1 = 0.0f;
+        int2 c0 = lds_i2(p0), c1 = lds_i2(has1 ? p1 : p0);
 #pragma unroll 1
         while (p0 < e0 && p1 < e1) {
-            const int2 c0 = lds_i2(p0), c1 = lds_i2(p1);   // broadcast LDS.64 {byte offset of the neighbour row, value}
             float x0[4], x1[4];
             lds_f<4>(x0, xb + static_cast<uint32_t>(c0.x));
             lds_f<4>(x1, xb + static_cast<uint32_t>(c1.x));
             const float v0 = __int_as_float(c0.y), v1 = __int_as_float(c1.y);
+            p0 += 8;
+            p1 += 8;
+            c0 = lds_i2(p0);   // prefetch the next pairs before the FFMAs wait on x0 / x1
+            c1 = lds_i2(p1);
             deg0 += v0;
             deg1 += v1;
 #pragma unroll
@@ -188,25 +168,25 @@ __device__ __forceinline__ void aggregate_simple(const AggCtx& a, int group, int
                 acc0[t] = fmaf(v0, x0[t], acc0[t]);
                 acc1[t] = fmaf(v1, x1[t], acc1[t]);
             }
-            p0 += 8;
-            p1 += 8;
         }
 #pragma unroll 1
-        for (; p0 < e0; p0 += 8) {
-            const int2 c0 = lds_i2(p0);
+        while (p0 < e0) {
             float x0[4];
             lds_f<4>(x0, xb + static_cast<uint32_t>(c0.x));
             const float v0 = __int_as_float(c0.y);
+            p0 += 8;
+            c0 = lds_i2(p0);
             deg0 += v0;
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc0[t] = fmaf(v0, x0[t], acc0[t]);
         }
 #pragma unroll 1
-        for (; p1 < e1; p1 += 8) {
-            const int2 c1 = lds_i2(p1);
+        while (p1 < e1) {
             float x1[4];
             lds_f<4>(x1, xb + static_cast<uint32_t>(c1.x));
             const float v1 = __int_as_float(c1.y);
+            p1 += 8;
+            c1 = lds_i2(p1);
             deg1 += v1;
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc1[t] = fmaf(v1, x1[t], acc1[t]);
@@ -297,88 +277,128 @@ __device__ __noinline__ void aggregate_general(const AggCtx& a, int group, int n
     }
 }
 
-// ---- epilogue math on one accumulator element ----
+// ---------------------------------------------------------------------------------------------
+// Epilogue.  Accumulators (three per tile, one per 3xTF32 pass) are read from TMEM, summed,
+// + rowsum (x) bias, activated, and written into a staging tile in shared memory (the Zhi region,
+// free once the MMAs have completed) with a 16-byte-chunk XOR swizzle, so that both the
+// row-per-thread writes and the row-major read-out are bank-conflict free; the tile then leaves
+// with fully coalesced 16-byte global stores.  (Storing straight from the TMEM register layout
+// costs one 16/32-byte sector write per lane: measured 2-3.6k cycles per tile.)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ystage_off(uint32_t row, uint32_t col, uint32_t ypitch) {   // col % 4 == 0 or 2
+    const uint32_t chunk = col >> 2;
+    return row * ypitch + ((((chunk & 7u) ^ (row & 7u)) | (chunk & ~7u)) << 4) + ((col & 3u) << 2);
+}
+
 template <int ACT>
 __device__ __forceinline__ float finish(float acc, float degbias) { return fast_act<ACT>(acc + degbias); }
 
-// M = 64 epilogue: .16x256b loads keep all 32 lanes busy.  Warp w owns tile rows 16*(w&3) .. +15
-// (TMEM lanes 32*(w&3) .. +15) and the 32-column slabs (w>>2), (w>>2)+2, ...
+// M = 64: .16x256b loads keep all 32 lanes busy.  Warp w owns tile rows 16*(w&3) .. +15 (TMEM lanes
+// 32*(w&3) .. +15) and the 32-column slabs (w>>2), (w>>2)+2, ...
 template <int ACT>
-__device__ __forceinline__ void epilogue_m64(uint32_t tmem_d, uint32_t np, int warp, int lane, int rows, int f_out, int C,
-                                             uint32_t deg_addr, uint32_t bias_addr, float* y_tile, bool vec2_ok) {
+__device__ __forceinline__ void epilogue_m64(uint32_t tmem_d, uint32_t np, int warp, int lane, int f_out, int C,
+                                             uint32_t deg_addr, uint32_t bias_addr, uint32_t ys, uint32_t ypitch) {
     const int q = warp & 3;
-    const int ra = q * 16 + (lane >> 2), rb = ra + 8;
-    float dega[8], degb[8];  // row sums per channel (C <= 8 on this path; larger C loops in chunks)
+    const uint32_t ra = q * 16 + (lane >> 2), rb = ra + 8;
     for (int slab = warp >> 2; slab * 32 < f_out; slab += 2) {
-        float v[16];
-        {
-            float v1[16], v2[16];
-            const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slab * 32);
-            tmem_ld_16x256b_x4(ta, v);
-            tmem_ld_16x256b_x4(ta + np, v1);
-            tmem_ld_16x256b_x4(ta + 2 * np, v2);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += v1[i] + v2[i];   // Zhi.Whi + (Zlo.Whi + Zhi.Wlo)
-        }
+        float v[16], v1[16], v2[16];
+        const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slab * 32);
+        tmem_ld_16x256b_x4(ta, v);
+        tmem_ld_16x256b_x4(ta + np, v1);
+        tmem_ld_16x256b_x4(ta + 2 * np, v2);
         float ba[8], bb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ba[i] = bb[i] = 0.0f;
-        for (int c0 = 0; c0 < C; c0 += 8) {
-            const int cn = min(8, C - c0);
-            for (int c = 0; c < cn; ++c) {
-                dega[c] = __uint_as_float(lds_u32(deg_addr + 4u * ((c0 + c) * 64 + ra)));
-                degb[c] = __uint_as_float(lds_u32(deg_addr + 4u * ((c0 + c) * 64 + rb)));
-            }
+        for (int c = 0; c < C; ++c) {
+            const float da = __uint_as_float(lds_u32(deg_addr + 4u * (c * 64 + ra)));
+            const float db = __uint_as_float(lds_u32(deg_addr + 4u * (c * 64 + rb)));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int col = slab * 32 + 8 * i + 2 * (lane & 3);
-                for (int c = 0; c < cn; ++c) {
-                    float b2[2];
-                    lds_f<2>(b2, bias_addr + 4u * ((c0 + c) * 256 + col));
-                    ba[2 * i] = fmaf(dega[c], b2[0], ba[2 * i]);
-                    ba[2 * i + 1] = fmaf(dega[c], b2[1], ba[2 * i + 1]);
-                    bb[2 * i] = fmaf(degb[c], b2[0], bb[2 * i]);
-                    bb[2 * i + 1] = fmaf(degb[c], b2[1], bb[2 * i + 1]);
-                }
+                float b2[2];
+                lds_f<2>(b2, bias_addr + 4u * (c * 256 + slab * 32 + 8 * i + 2 * (lane & 3)));
+                ba[2 * i] = fmaf(da, b2[0], ba[2 * i]);
+                ba[2 * i + 1] = fmaf(da, b2[1], ba[2 * i + 1]);
+                bb[2 * i] = fmaf(db, b2[0], bb[2 * i]);
+                bb[2 * i + 1] = fmaf(db, b2[1], bb[2 * i + 1]);
             }
         }
+        tmem_ld_wait();
+        tmem_ld_fence(v);
+        tmem_ld_fence(v1);
+        tmem_ld_fence(v2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int col = slab * 32 + 8 * i + 2 * (lane & 3);
-            const float a0 = finish<ACT>(v[4 * i], ba[2 * i]), a1 = finish<ACT>(v[4 * i + 1], ba[2 * i + 1]);
-            const float b0 = finish<ACT>(v[4 * i + 2], bb[2 * i]), b1 = finish<ACT>(v[4 * i + 3], bb[2 * i + 1]);
-            if (vec2_ok && col + 1 < f_out) {
-                if (ra < rows) *reinterpret_cast<float2*>(y_tile + static_cast<size_t>(ra) * f_out + col) = make_float2(a0, a1);
-                if (rb < rows) *reinterpret_cast<float2*>(y_tile + static_cast<size_t>(rb) * f_out + col) = make_float2(b0, b1);
-            } else {
-                if (ra < rows && col < f_out) y_tile[static_cast<size_t>(ra) * f_out + col] = a0;
-                if (ra < rows && col + 1 < f_out) y_tile[static_cast<size_t>(ra) * f_out + col + 1] = a1;
-                if (rb < rows && col < f_out) y_tile[static_cast<size_t>(rb) * f_out + col] = b0;
-                if (rb < rows && col + 1 < f_out) y_tile[static_cast<size_t>(rb) * f_out + col + 1] = b1;
+            const uint32_t col = slab * 32 + 8 * i + 2 * (lane & 3);
+            if (col < static_cast<uint32_t>(f_out)) {
+                const float oa[2] = {finish<ACT>(v[4 * i] + (v1[4 * i] + v2[4 * i]), ba[2 * i]),
+                                     finish<ACT>(v[4 * i + 1] + (v1[4 * i + 1] + v2[4 * i + 1]), ba[2 * i + 1])};
+                const float ob[2] = {finish<ACT>(v[4 * i + 2] + (v1[4 * i + 2] + v2[4 * i + 2]), bb[2 * i]),
+                                     finish<ACT>(v[4 * i + 3] + (v1[4 * i + 3] + v2[4 * i + 3]), bb[2 * i + 1])};
+                sts_f<2>(ys + ystage_off(ra, col, ypitch), oa);
+                sts_f<2>(ys + ystage_off(rb, col, ypitch), ob);
             }
         }
     }
 }
 
-// M = 128 epilogue: accumulator row m lives in TMEM lane m; a thread owns one row, 16 columns at a time
+// M = 128: accumulator row m lives in TMEM lane m; a thread owns one row, 16 columns at a time
 template <int ACT>
-__device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, uint32_t np, int warp, int lane, int rows, int f_out, int C,
-                                              uint32_t deg_addr, uint32_t bias_addr, float* y_tile, bool vec4_ok) {
+__device__ __forceinline__ void epilogue_m128(uint32_t tmem_d, uint32_t np, int warp, int lane, int f_out, int C,
+                                              uint32_t deg_addr, uint32_t bias_addr, uint32_t ys, uint32_t ypitch) {
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    float* y_row = y_tile + static_cast<size_t>(row) * f_out;
+    const uint32_t row = q * 32 + lane;
     for (int j = warp >> 2; j * 16 < f_out; j += 4) {   // 16 warps: 4 lane quarters x 4 column phases
-        float v[16];
-        {
-            float v1[16], v2[16];
-            const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16);
-            tmem_ld16(ta, v);
-            tmem_ld16(ta + np, v1);
-            tmem_ld16(ta + 2 * np, v2);
+        float v[16], v1[16], v2[16];
+        const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 16);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + np, v1);
+        tmem_ld16(ta + 2 * np, v2);
+        float bsum[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += v1[i] + v2[i];   // Zhi.Whi + (Zlo.Whi + Zhi.Wlo)
+        for (int i = 0; i < 16; ++i) bsum[i] = 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const float d = __uint_as_float(lds_u32(deg_addr + 4u * (c * 128 + row)));
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                float b[4];
+                lds_f<4>(b, bias_addr + 4u * (c * 256 + j * 16 + 4 * qd));   // bias rows are padded to 256 floats
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bsum[4 * qd + i] = fmaf(d, b[i], bsum[4 * qd + i]);
+            }
         }
-        if (row < rows) epilogue_chunk<ACT>(v, j * 16, f_out, C, 128, deg_addr, bias_addr, row, y_row, vec4_ok);
+        tmem_ld_wait();
+        tmem_ld_fence(v);
+        tmem_ld_fence(v1);
+        tmem_ld_fence(v2);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const uint32_t col = j * 16 + 4 * qd;
+            if (col < static_cast<uint32_t>(f_out)) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = finish<ACT>(v[4 * qd + i] + (v1[4 * qd + i] + v2[4 * qd + i]), bsum[4 * qd + i]);
+                sts_f<4>(ys + ystage_off(row, col, ypitch), o);
+            }
+        }
+    }
+}
+
+// staged tile -> global, coalesced.  y_tile points at the tile's first output row.
+template <int NC>
+__device__ __forceinline__ void copy_out(uint32_t ys, uint32_t ypitch, float* y_tile, int rows, int f_out, int tid, bool vec4) {
+    if (vec4) {
+        const int cpr = f_out >> 2;   // 16-byte chunks per row
+        for (int idx = tid; idx < rows * cpr; idx += NC) {
+            const uint32_t r = static_cast<uint32_t>(idx / cpr), c = static_cast<uint32_t>(idx - r * cpr);
+            float t[4];
+            lds_f<4>(t, ys + ystage_off(r, c << 2, ypitch));
+            *reinterpret_cast<float4*>(y_tile + static_cast<size_t>(r) * f_out + (c << 2)) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    } else {
+        for (int idx = tid; idx < rows * f_out; idx += NC) {
+            const uint32_t r = static_cast<uint32_t>(idx / f_out), c = static_cast<uint32_t>(idx - r * f_out);
+            y_tile[idx] = __uint_as_float(lds_u32(ys + ystage_off(r, c & ~3u, ypitch) + ((c & 3u) << 2)));
+        }
     }
 }
 
@@ -562,8 +582,7 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
         const int n_groups = kConsumers >> p.lpr_log2;
         const bool simple = (VEC == 4) && C == 1 && f_in <= lpr * 4;
         const bool y_vec4 = (f_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15u) == 0;
-        const bool y_vec2 = (f_out & 1) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 7u) == 0;
-
+    
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tlast = clock64();
         auto mark = [&](int ph) {
@@ -636,24 +655,27 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
             tc_fence_after_sync();
             mark(4);
 
-            // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> global ----
+            // ---- 4. epilogue: TMEM -> registers -> + rowsum (x) bias -> act -> staged tile -> global ----
             {
-                float* y_tile = p.y + g0 * N * f_out;
+                const uint32_t ys = zhi;   // the operand region is free once the MMAs have completed
                 if (BM == 64) {
                     switch (p.act) {
-                        case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                        case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                        case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2); break;
-                        default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec2);
+                        case KGCN_ACT_RELU: epilogue_m64<KGCN_ACT_RELU>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch); break;
+                        case KGCN_ACT_SIGMOID: epilogue_m64<KGCN_ACT_SIGMOID>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch); break;
+                        case KGCN_ACT_TANH: epilogue_m64<KGCN_ACT_TANH>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch); break;
+                        default: epilogue_m64<KGCN_ACT_NONE>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch);
                     }
                 } else {
                     switch (p.act) {
-                        case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                        case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                        case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4); break;
-                        default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, Np, warp, lane, rows, f_out, C, deg_addr, bias_addr, y_tile, y_vec4);
+                        case KGCN_ACT_RELU: epilogue_m128<KGCN_ACT_RELU>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch); break;
+                        case KGCN_ACT_SIGMOID: epilogue_m128<KGCN_ACT_SIGMOID>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch); break;
+                        case KGCN_ACT_TANH: epilogue_m128<KGCN_ACT_TANH>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch); break;
+                        default: epilogue_m128<KGCN_ACT_NONE>(tmem_d, Np, warp, lane, f_out, C, deg_addr, bias_addr, ys, p.y_pitch);
                     }
                 }
+                tc_fence_before_sync();
+                consumer_sync<kConsumers>();
+                copy_out<kConsumers>(ys, p.y_pitch, p.y + g0 * N * f_out, rows, f_out, tid, y_vec4);
             }
             tc_fence_before_sync();
             consumer_sync<kConsumers>();  // TMEM / row sums / cv pairs consumed before the next tile overwrites them
@@ -690,6 +712,9 @@ bool plan_bm(FusedParams& p, int bm, int max_smem, int64_t n_graphs, int channel
     uint32_t off = 0;
     p.off_zhi = off; off += n_atoms * bm * 128u;
     p.off_zlo = off; off += n_atoms * bm * 128u;
+    // the output tile is staged in the Zhi|Zlo region after the MMAs: rows of y_pitch bytes, whole 128-byte groups
+    p.y_pitch = up(f_out * 4u, 128);
+    if (p.y_pitch * static_cast<uint32_t>(bm) > 2u * n_atoms * bm * 128u) return false;
     p.off_whi = off; off += n_atoms * p.Np * 128u;
     p.off_wlo = off; off += n_atoms * p.Np * 128u;
     p.off_stage = off;
