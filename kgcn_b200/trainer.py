@@ -273,97 +273,156 @@ def shard_range(n_items, rank, world_size):
     return lo, lo + per + (1 if rank < rem else 0)
 
 
-class HostFedPipeline:
-    """End-to-end step from HOST buffers, the call a kGCN user makes per step (feed -> sess.run,
-    kgcn/core.py:267-269): pinned host COO + features + labels are copied to static device buffers,
-    packed to CSR (+ transposed CSR) ON THE DEVICE (kgcn_pack_coo_device), the training step runs,
-    and ``cost_sum`` / ``correct_count`` come back to the host.  The device part (2 pack launches +
-    the step) is one CUDA graph; the copies are cudaMemcpyAsync on the same stream."""
+class _Slot:
+    """Device staging + CSR buffers + captured graph for one in-flight host-fed step."""
 
-    def __init__(self, trainer, max_nnz, train=True):
-        t = self.trainer = trainer
+    def __init__(self, trainer, layout, max_nnz):
+        t = trainer
         s, B, N, C = t.spec, t.B, t.spec.n_nodes, t.spec.channels
         dev = t.device
-        self.max_nnz = int(max_nnz)
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        self.d_off = torch.zeros(B * C + 1, dtype=torch.int64, device=dev)
-        self.d_idx = torch.zeros(self.max_nnz, 2, **i32)
-        self.d_val = torch.zeros(self.max_nnz, **f32)
+        self.d_packed = torch.zeros(layout["bytes"], dtype=torch.uint8, device=dev)
+        v = lambda name, dt: self.d_packed[layout[name][0]:layout[name][1]].view(dt)
+        self.d_off, self.d_idx, self.d_val = v("off", torch.int64), v("idx", torch.int32), v("val", torch.float32)
+        labels, mask = v("labels", torch.float32).view(B, s.label_dim), v("mask", torch.float32)
         self.d_flag = torch.zeros(1, **i32)
-        mk = lambda: (torch.zeros(B * C * N + 1, **i32), torch.zeros(self.max_nnz, **i32), torch.zeros(self.max_nnz, **f32))
+        mk = lambda: (torch.zeros(B * C * N + 1, **i32), torch.zeros(max_nnz, **i32), torch.zeros(max_nnz, **f32))
         rp, col, val = mk()
         rpt, colt, valt = mk()
-        csr = BatchedCSR(B, C, N, N, rp, col, val, rpt, colt, valt)
-        self.batch = DeviceBatch(csr, torch.zeros(B, N, s.feature_dim, **f32), torch.zeros(B, s.label_dim, **f32),
-                                 torch.ones(B, **f32))
+        self.batch = DeviceBatch(BatchedCSR(B, C, N, N, rp, col, val, rpt, colt, valt),
+                                 torch.zeros(B, N, s.feature_dim, **f32), labels, mask)
         self.h_stats = torch.zeros(2, dtype=torch.float32).pin_memory()
-        self.train = train
+        self.copied, self.done = torch.cuda.Event(), torch.cuda.Event()
         self.graph = None
+        self.busy = False
 
-    def _pack(self):
-        t, b = self.trainer, self.batch
+
+class HostFedPipeline:
+    """End-to-end step from HOST buffers, the call a kGCN user makes per step (feed -> sess.run,
+    kgcn/core.py:267-269): pinned host COO + features + labels are copied to static device buffers
+    (two cudaMemcpyAsync per step: one packed CSR/label/mask block, one feature block), packed to CSR
+    (+ transposed CSR) ON THE DEVICE (kgcn_pack_coo_device), the training step runs, and ``cost_sum`` /
+    ``correct_count`` come back to the host.  The device part (2 pack launches + the step) is one CUDA
+    graph per slot.  With ``depth`` = 2 slots the copies of step i+1 run on a copy stream while step i
+    computes (``submit`` / ``collect``); ``run`` is the simple synchronous form."""
+
+    def __init__(self, trainer, max_nnz, train=True, depth=2):
+        t = self.trainer = trainer
+        s, B, C = t.spec, t.B, t.spec.channels
+        self.max_nnz = int(max_nnz)
+        # static layout of the packed block (16-byte aligned sections)
+        sizes = [("off", 8 * (B * C + 1)), ("idx", 8 * self.max_nnz), ("val", 4 * self.max_nnz),
+                 ("labels", 4 * B * s.label_dim), ("mask", 4 * B)]
+        self.layout, pos = {}, 0
+        for name, n in sizes:
+            self.layout[name] = (pos, pos + n)
+            pos = (pos + n + 15) // 16 * 16
+        self.layout["bytes"] = pos
+        self.train = train
+        self.slots = [_Slot(t, self.layout, self.max_nnz) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=t.device)
+        self.compute_stream = torch.cuda.Stream(device=t.device)
+        self.n_submitted = self.n_collected = 0
+
+    # -- device work of one slot ----------------------------------------------------------------
+    def _pack(self, slot):
+        t, b = self.trainer, slot.batch
         st = torch.cuda.current_stream().cuda_stream
         B, N, C = t.B, t.spec.n_nodes, t.spec.channels
         for tr, (rp, col, val) in ((0, (b.csr.rowptr, b.csr.col, b.csr.val)), (1, (b.csr.rowptr_t, b.csr.col_t, b.csr.val_t))):
-            check(lib.kgcn_pack_coo_device(B * C, N, N, ptr(self.d_off), ptr(self.d_idx), ptr(self.d_val), tr, ptr(rp),
-                                           ptr(col), ptr(val), None, ptr(self.d_flag), st))
+            check(lib.kgcn_pack_coo_device(B * C, N, N, ptr(slot.d_off), ptr(slot.d_idx), ptr(slot.d_val), tr, ptr(rp),
+                                           ptr(col), ptr(val), None, ptr(slot.d_flag), st))
 
-    def _device_part(self):
-        self._pack()
+    def _device_part(self, slot):
+        self._pack(slot)
         if self.train:
-            self.trainer.step_eager(self.batch)
+            self.trainer.step_eager(slot.batch)
         else:
-            self.trainer.forward_eager(self.batch)
+            self.trainer.forward_eager(slot.batch)
 
     def capture(self):
         t = self.trainer
-        if self.train and t.world_size > 1:   # collectives stay outside graph capture (see Trainer.capture)
-            def fb():
-                self._pack()
-                t._fwd_bwd(self.batch)
-            if getattr(t, "_opt_graph", None) is None:
-                t._opt_graph = t._capture_fn(lambda: t._optimizer(torch.cuda.current_stream().cuda_stream))
-            self.graph = (t._capture_fn(fb), "allreduce", t._opt_graph)
-        else:
-            self.graph = (t._capture_fn(self._device_part),)
+        for slot in self.slots:
+            if self.train and t.world_size > 1:   # collectives stay outside graph capture (see Trainer.capture)
+                def fb(slot=slot):
+                    self._pack(slot)
+                    t._fwd_bwd(slot.batch)
+                if getattr(t, "_opt_graph", None) is None:
+                    t._opt_graph = t._capture_fn(lambda: t._optimizer(torch.cuda.current_stream().cuda_stream))
+                slot.graph = (t._capture_fn(fb), "allreduce", t._opt_graph)
+            else:
+                slot.graph = (t._capture_fn(lambda slot=slot: self._device_part(slot)),)
 
-    @staticmethod
-    def pin_host_batch(counts, indices, values, features, labels, mask=None):
-        """Host-side batch in pinned memory: flat COO exactly as kgcn/feed.py emits it per graph and
-        channel (concatenated), fp32 features [B,N,F], labels [B,L], mask [B]."""
+    # -- host side ------------------------------------------------------------------------------
+    def pin_host_batch(self, counts, indices, values, features, labels, mask=None):
+        """Host-side batch in pinned memory: the flat COO exactly as kgcn/feed.py emits it per graph
+        and channel (concatenated), labels [B,L] and mask [B] in ONE packed block + fp32 features."""
         counts = np.asarray(counts, np.int64)
-        off = np.zeros(counts.size + 1, np.int64)
-        np.cumsum(counts.reshape(-1), out=off[1:])
-        B = features.shape[0]
-        mask = np.ones(B, np.float32) if mask is None else mask
-        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).pin_memory()
-        return {"off": pin(off, np.int64), "idx": pin(indices, np.int32), "val": pin(values, np.float32),
-                "features": pin(features, np.float32), "labels": pin(labels, np.float32), "mask": pin(mask, np.float32)}
-
-    def h2d_bytes(self, host):
-        return sum(v.numel() * v.element_size() for v in host.values())
-
-    def run(self, host):
-        """One end-to-end step; returns (cost_sum, correct_count) after a stream synchronize."""
-        nnz = host["val"].numel()
+        nnz = int(counts.sum())
         if nnz > self.max_nnz:
             raise _lib.KgcnError(1, "batch has %d nnz, pipeline capacity is %d" % (nnz, self.max_nnz))
-        b = self.batch
-        self.d_off.copy_(host["off"], non_blocking=True)
-        self.d_idx[:nnz].copy_(host["idx"], non_blocking=True)
-        self.d_val[:nnz].copy_(host["val"], non_blocking=True)
-        b.features.copy_(host["features"], non_blocking=True)
-        b.labels.copy_(host["labels"], non_blocking=True)
-        b.mask.copy_(host["mask"], non_blocking=True)
-        if self.graph is not None:
-            for g in self.graph:
-                if g == "allreduce":
-                    self.trainer._allreduce()
-                else:
-                    g.replay()
-        else:
-            self._device_part()
-        self.h_stats.copy_(self.trainer.stats, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(self.h_stats[0]), float(self.h_stats[1])
+        B = features.shape[0]
+        packed = np.zeros(self.layout["bytes"], np.uint8)
+        sec = lambda name, dt: packed[self.layout[name][0]:self.layout[name][1]].view(dt)
+        off = sec("off", np.int64)
+        off[0] = 0
+        np.cumsum(counts.reshape(-1), out=off[1:])
+        sec("idx", np.int32)[:2 * nnz] = np.ascontiguousarray(indices, np.int32).reshape(-1)
+        sec("val", np.float32)[:nnz] = np.asarray(values, np.float32)
+        sec("labels", np.float32)[:] = np.asarray(labels, np.float32).reshape(-1)
+        sec("mask", np.float32)[:] = np.ones(B, np.float32) if mask is None else np.asarray(mask, np.float32)
+        used = self.layout["idx"][0] + 8 * nnz   # the idx section is copied only up to the entries in use
+        return {"packed": torch.from_numpy(packed).pin_memory(), "nnz": nnz, "idx_used_end": used,
+                "features": torch.from_numpy(np.ascontiguousarray(features, np.float32)).pin_memory()}
+
+    def h2d_bytes(self, host):
+        return int(host["packed"].numel() + host["features"].numel() * 4)
+
+    def submit(self, host):
+        """Enqueue one step: H2D on the copy stream, graph replay + D2H of the stats on the compute stream."""
+        slot = self.slots[self.n_submitted % len(self.slots)]
+        if slot.busy:
+            raise RuntimeError("pipeline full: collect() a result before submitting more than %d steps" % len(self.slots))
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.done)          # the slot's previous step has finished with these buffers
+            slot.d_packed.copy_(host["packed"], non_blocking=True)
+            slot.batch.features.copy_(host["features"], non_blocking=True)
+            slot.copied.record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(slot.copied)
+            if slot.graph is not None:
+                for g in slot.graph:
+                    if g == "allreduce":
+                        self.trainer._allreduce()
+                    else:
+                        g.replay()
+            else:
+                self._device_part(slot)
+            slot.h_stats.copy_(self.trainer.stats, non_blocking=True)
+            slot.done.record(self.compute_stream)
+        slot.busy = True
+        self.n_submitted += 1
+
+    def collect(self):
+        """Wait for the oldest submitted step; returns its (cost_sum, correct_count)."""
+        slot = self.slots[self.n_collected % len(self.slots)]
+        slot.done.synchronize()
+        slot.busy = False
+        self.n_collected += 1
+        return float(slot.h_stats[0]), float(slot.h_stats[1])
+
+    def run(self, host):
+        """One synchronous end-to-end step."""
+        self.submit(host)
+        return self.collect()
+
+    def run_many(self, hosts):
+        """Pipelined loop over host batches; yields (cost_sum, correct_count) per step, in order."""
+        depth = len(self.slots)
+        for i, h in enumerate(hosts):
+            if i >= depth:
+                yield self.collect()
+            self.submit(h)
+        while self.n_collected < self.n_submitted:
+            yield self.collect()
