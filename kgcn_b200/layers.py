@@ -16,7 +16,7 @@ Tensors are CUDA ``torch.Tensor``s; ``adj`` is either the reference's ``list[B][
 CPU fallback (a missing library is an ImportError, a CPU tensor is a KgcnError).
 """
 import math
-import os
+import sys
 
 import torch
 
@@ -26,6 +26,11 @@ from .csr import BatchedCSR, as_batched_csr
 enabled_batched = False
 enabled_bspmm = False
 enabled_bconv = False
+
+
+def _active_store():
+    mod = sys.modules.get("kgcn_b200.compat.facade")
+    return mod.active_store() if mod is not None else None
 
 
 def load_bspmm(args):
@@ -63,12 +68,24 @@ class Layer(torch.nn.Module):
     def __init__(self, name=None, trainable=True, dtype=None, **kwargs):
         super().__init__()
         self._layer_name = name
+        self._store_name = None
         self.trainable = trainable
         self.built = False
 
     def add_weight(self, name, shape, initializer, trainable=True, fan_in=1, fan_out=1, device="cuda"):
-        value = _init_tensor(initializer, tuple(shape), fan_in, fan_out, device)
-        param = torch.nn.Parameter(value, requires_grad=bool(trainable and self.trainable))
+        def make():
+            value = _init_tensor(initializer, tuple(shape), fan_in, fan_out, device)
+            return torch.nn.Parameter(value, requires_grad=bool(trainable and self.trainable))
+
+        store = _active_store()
+        if store is not None:   # eager re-execution of a TF-style build_model: reuse variables by TF-style name
+            if self._store_name is None:
+                self._store_name = self._layer_name or store.layer_name(type(self).__name__)
+            param = store.get(self._store_name + "/" + name, make)
+            if tuple(param.shape) != tuple(shape):
+                raise ValueError("variable %s/%s has shape %r, layer wants %r" % (self._store_name, name, tuple(param.shape), tuple(shape)))
+        else:
+            param = make()
         self.register_parameter(name, param)
         return param
 
@@ -204,6 +221,43 @@ class GraphDense(Layer):
 
     def compute_output_shape(self, input_shape):
         return input_shape[0], input_shape[1], self.output_dim
+
+
+class GraphBatchNormalization(Layer):
+    """Keras ``BatchNormalization`` over node rows as the reference trainer runs it (layers.py:170-220).
+
+    [TF-semantics, SURVEY.md Appendix A.10] The layer is called without ``training=`` in graph mode, so it
+    follows Keras' learning phase, which kgcn/core.py never feeds: it normalises with the MOVING
+    statistics (initial mean 0 / variance 1, never updated) in training and inference alike, i.e.
+    ``y = gamma * x / sqrt(1 + 1e-3) + beta`` with trainable ``gamma`` (ones) and ``beta`` (zeros).  With
+    ``enabled_node_nums`` only the first ``n_b`` rows of graph ``b`` are normalised and the rest are exact
+    zeros (the extract / split / pad sequence of layers.py:202-214).  Plain torch elementwise ops: this
+    row is "next" in SURVEY.md section 8(f), not yet a fused kernel."""
+
+    EPS = 1e-3
+
+    def __init__(self, bn_name=None, **kwargs):
+        super().__init__(**kwargs)
+        self.bn_name = bn_name
+
+    def build(self, input_shape):
+        f = int(input_shape[-1])
+        self.data_shape = input_shape
+        self.gamma = self.add_weight("gamma", (f,), "ones", device=self._build_device)
+        self.beta = self.add_weight("beta", (f,), "zeros", device=self._build_device)
+        self.register_buffer("moving_mean", torch.zeros(f, device=self._build_device))
+        self.register_buffer("moving_variance", torch.ones(f, device=self._build_device))
+
+    def call(self, inputs, enabled_node_nums=None, shape=None, max_node_num=None, training=True):
+        out = (inputs - self.moving_mean) * (self.gamma / torch.sqrt(self.moving_variance + self.EPS)) + self.beta
+        if enabled_node_nums is not None:
+            n = torch.as_tensor(enabled_node_nums, device=inputs.device).reshape(-1)
+            keep = torch.arange(inputs.shape[1], device=inputs.device)[None, :] < n[:, None]
+            out = out * keep[:, :, None].to(out.dtype)
+        return out
+
+    def compute_output_shape(self, input_shape):
+        return input_shape
 
 
 class GINAggregate(Layer):
