@@ -301,9 +301,37 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
     return KGCN_OK;
 }
 
+// 16-byte vectorised variant (feat % 4 == 0, aligned pointers, no row mask)
+__global__ void act_grad_vec4_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ du,
+                                     int64_t n4, int feat4, int act, int n_nodes, int dy_bcast) {
+    const int64_t per_graph4 = static_cast<int64_t>(n_nodes) * feat4;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n4;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float4 g = dy_bcast ? dy[(idx / per_graph4) * feat4 + (idx % feat4)] : dy[idx];
+        float4 o = g;
+        if (y != nullptr) {
+            const float4 yy = y[idx];
+            o.x *= act_grad_from_output(yy.x, act);
+            o.y *= act_grad_from_output(yy.y, act);
+            o.z *= act_grad_from_output(yy.z, act);
+            o.w *= act_grad_from_output(yy.w, act);
+        }
+        du[idx] = o;
+    }
+}
+
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act, const int32_t* enabled,
                     int n_nodes, bool dy_bcast, cudaStream_t st) {
     if (n == 0) return KGCN_OK;
+    if (enabled == nullptr && feat % 4 == 0 && aligned16(dy) && aligned16(du) && (y == nullptr || aligned16(y))) {
+        const int64_t n4 = n / 4;
+        const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(n4, 256), kNumSMs * 8);
+        act_grad_vec4_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(du), n4,
+            feat / 4, act, n_nodes, dy_bcast ? 1 : 0);
+        KGCN_LAUNCH_OK("act_grad_vec4_kernel");
+        return KGCN_OK;
+    }
     act_grad_kernel<<<ew_blocks(n), 256, 0, st>>>(y, dy, du, n, feat, act, enabled, n_nodes, dy_bcast ? 1 : 0);
     KGCN_LAUNCH_OK("act_grad_kernel");
     return KGCN_OK;

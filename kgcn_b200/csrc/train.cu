@@ -75,6 +75,43 @@ __global__ void __launch_bounds__(128) readout_xent_kernel(const float* __restri
 // step_state (device, may be null): [0] = number of steps already applied, [1] = block ticket.
 // Reading the step on the device keeps the launch parameters constant, so the whole training step
 // can be replayed from a CUDA graph; the last block to finish advances the counter.
+// d out_w[f, l] = sum_b g[b, f] * dz[b, l], d out_b[l] = sum_b dz[b, l] for the tiny readout head.
+// Each block reduces a slice of the batch into `partial[block]`; the last block to finish (ticket)
+// sums the partials in block order, so the result is deterministic.  ticket must be zero on entry
+// and is reset on exit.
+__global__ void __launch_bounds__(256) readout_dw_kernel(const float* __restrict__ g, const float* __restrict__ dz,
+                                                         int64_t n_graphs, int feat, int n_labels,
+                                                         float* __restrict__ partial, int* __restrict__ ticket,
+                                                         float* __restrict__ dw, float* __restrict__ dbias) {
+    const int n_out = (feat + 1) * n_labels;   // row `feat` is the bias gradient
+    const int64_t per = (n_graphs + gridDim.x - 1) / gridDim.x;
+    const int64_t b0 = blockIdx.x * per, b1 = min(n_graphs, b0 + per);
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        const int f = o / n_labels, l = o - f * n_labels;
+        float acc = 0.0f;
+        if (f < feat)
+            for (int64_t b = b0; b < b1; ++b) acc = fmaf(g[b * feat + f], dz[b * n_labels + l], acc);
+        else
+            for (int64_t b = b0; b < b1; ++b) acc += dz[b * n_labels + l];
+        partial[static_cast<size_t>(blockIdx.x) * n_out + o] = acc;
+    }
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        float acc = 0.0f;
+        for (unsigned k = 0; k < gridDim.x; ++k) acc += partial[static_cast<size_t>(k) * n_out + o];
+        const int f = o / n_labels, l = o - f * n_labels;
+        if (f < feat) dw[o] = acc;
+        else if (dbias != nullptr) dbias[l] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
                             float grad_scale, int host_step, int* __restrict__ step_state) {
@@ -107,9 +144,12 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
 
 using namespace kgcn;
 
+constexpr int kReadoutBlocks = 32;
+
 extern "C" size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels) {
     if (n_graphs <= 0) return 0;
-    return reduce_gemm_workspace_bytes(n_graphs, feat, n_labels);
+    // [ticket (16 bytes)] [partial sums: blocks x (feat + 1) x n_labels]
+    return 16 + static_cast<size_t>(kReadoutBlocks) * (static_cast<size_t>(feat) + 1) * n_labels * sizeof(float);
 }
 
 extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const float* w, const float* bias,
@@ -127,9 +167,16 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
                                                                        mask, inv_batch, logits, prediction, dlogits, dg,
                                                                        stats);
     KGCN_LAUNCH_OK("readout_xent_kernel");
-    if (dw != nullptr)
-        return launch_reduce_gemm_tn(n_graphs, feat, n_labels, g, feat, dlogits, n_labels, dw, dbias, workspace,
-                                     workspace_bytes, st);
+    if (dw != nullptr) {
+        KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= kgcn_readout_workspace_bytes(n_graphs, feat, n_labels),
+                     KGCN_ERR_WORKSPACE, "readout_xent: workspace too small");
+        int* ticket = static_cast<int*>(workspace);
+        float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
+        KGCN_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int), st));
+        const int nb = static_cast<int>(std::min<int64_t>(kReadoutBlocks, n_graphs));
+        readout_dw_kernel<<<nb, 256, 0, st>>>(g, dlogits, n_graphs, feat, n_labels, partial, ticket, dw, dbias);
+        KGCN_LAUNCH_OK("readout_dw_kernel");
+    }
     return KGCN_OK;
 }
 
