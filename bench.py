@@ -258,8 +258,40 @@ def run_own(args):
     roofline = {"kernel": "bspmm_tile_kernel (kgcn_bspmm_f32, Y[b]=A[b].X[b], B=%d N=%d F=%d)" % (B, N, F), "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peak_kind + " copy bandwidth (burst)", "frac_of_8TBs_spec": achieved / 8000.0,
-                "algorithmic_bytes_per_launch": bytes_spmm, "us_per_launch": spmm_us, "traffic": None,
+                "algorithmic_bytes_per_launch": bytes_spmm, "us_per_launch": spmm_us,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full launch of this kernel on this
+                # shape (profiles/r01_spmm_tile_c2.txt): the 8.4 MB output was still in the 126 MB L2 at kernel end
+                "traffic": 9386000.0,
                 "timing": "CUDA events around %d back-to-back launches (graph replay) over %d rotating batches" % (reps * N_ROT, N_ROT)}
+
+    # ---- the fused GraphConv layer kernel (x -> act(A.x.W + deg*b)) timed the same way ----
+    w0, b0 = tr.views["conv0/kernel"], tr.views["conv0/bias"]
+
+    def layer(i):
+        b = batches[i % N_ROT]
+        ops.graphconv_fwd(b.csr, b.features, w0, b0, 2, 0, out=ys[i % N_ROT])
+
+    g_layer = torch.cuda.CUDAGraph()
+    for i in range(N_ROT):
+        layer(i)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g_layer):
+        for i in range(N_ROT):
+            layer(i)
+    for _ in range(3):
+        g_layer.replay()
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        g_layer.replay()
+    e.record()
+    torch.cuda.synchronize()
+    layer_us = s.elapsed_time(e) * 1e3 / (reps * N_ROT)
+    bytes_layer = 4 * B * N * (F + F) + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1) + 4 * F * F + 4 * F
+    fused_roofline = {"kernel": "graphconv_fused_fwd_kernel (kgcn_graphconv_fwd_f32: TMA + aggregation + tcgen05 3xTF32 + bias/sigmoid)",
+                      "bound": "hbm", "achieved": bytes_layer / layer_us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                      "frac": bytes_layer / layer_us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_layer,
+                      "us_per_launch": layer_us, "molecules_per_s_per_layer": B / layer_us * 1e6}
 
     # ---- end to end from pinned host buffers through the public step call ----
     max_nnz = int(max(d["values"].shape[0] for d in host) * 1.1) + 64
@@ -305,7 +337,8 @@ def run_own(args):
                        "l2": "rotating %d resident batches (%.0f MB of inputs > 126 MB L2)" % (N_ROT, N_ROT * (B * N * F * 4 + 12 * nnz_mean) / 1e6),
                        "launch": "one CUDA graph replay per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "launches_per_step": int(launches_per_step), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "launches_per_step": int(launches_per_step), "roofline": roofline, "roofline_fused_layer": fused_roofline,
+            "cpu_baseline": cpu_baseline,
             "infer": {"value": mols * args.steps / (ms_infer * 1e-3), "unit": UNIT, "ms_per_step": ms_infer / args.steps,
                       "launches_per_step": int(launches_per_infer), "step": "forward only (layers + readout)"},
             "last_step": {"cost_sum": cost_sum, "correct_count": correct},

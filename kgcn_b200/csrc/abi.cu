@@ -1,5 +1,6 @@
 // ABI bookkeeping: version and the thread-local last-error string (include/kgcn_b200.h).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -16,6 +17,14 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(error_buffer(), 512, fmt, ap);
     va_end(ap);
     return code;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KGCN_PDL");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
 }
 
 static std::atomic<uint64_t> g_launches{0};

@@ -39,6 +39,37 @@ void count_launch();  // process-wide counter of kernel launches issued by this 
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Programmatic dependent launch: every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_prologue(), so inside a stream /
+// CUDA graph the next kernel's grid is already resident and past its launch latency when the
+// previous one drains (the per-step work is ~15 launches of a few microseconds each).
+// KGCN_PDL=0 in the environment disables the attribute (plain stream order).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    // No explicit launch_dependents: the implicit trigger at block exit lets the next grid's CTAs move in
+    // as this grid's tail drains.  (Triggering at kernel entry was measured slower: the waiting grid
+    // then competes for SM resources with the running one.)
+    pdl_wait();   // all global reads / writes of this kernel come after the producer grid has completed
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
     return (a + b - 1) / b;

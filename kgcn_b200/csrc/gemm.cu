@@ -36,6 +36,7 @@ struct SgemmParams {
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p) {
+    pdl_prologue();
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
 
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
                                                             int has_colsum, float* __restrict__ out,
                                                             float* __restrict__ colsum_out) {
+    pdl_prologue();
     __shared__ float red[4][64];
     const int64_t rows = M + (has_colsum ? 1 : 0);
     const int64_t total = rows * N;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 __global__ void act_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ du,
                                 int64_t n, int feat, int act, const int32_t* __restrict__ enabled, int n_nodes,
                                 int dy_bcast) {
+    pdl_prologue();
     const int64_t per_graph = static_cast<int64_t>(n_nodes) * feat;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -200,6 +203,7 @@ __global__ void act_grad_kernel(const float* __restrict__ y, const float* __rest
 // GraphGather forward: out[g, f] = sum_i x[g, i, f], rows added in index order (layers.py:164).
 __global__ void gather_fwd_kernel(const float* __restrict__ x, int64_t n_graphs, int n_nodes, int feat,
                                   float* __restrict__ out) {
+    pdl_prologue();
     const int64_t total = n_graphs * feat;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -214,6 +218,7 @@ __global__ void gather_fwd_kernel(const float* __restrict__ x, int64_t n_graphs,
 
 __global__ void gather_bwd_kernel(const float* __restrict__ dout, int64_t n_graphs, int n_nodes, int feat,
                                   float* __restrict__ dx) {
+    pdl_prologue();
     const int64_t total = n_graphs * n_nodes * feat;
     const int64_t per_graph = static_cast<int64_t>(n_nodes) * feat;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -264,10 +269,10 @@ int launch_sgemm(bool trans_a, bool trans_b, int64_t M, int N, int K, const floa
             q.enabled = ep.enabled + row_off / ep.n_nodes;
         }
         dim3 grid(ceil_div(N, BN), static_cast<unsigned>(rows_here), 1);
-        if (trans_a && trans_b) sgemm_kernel<true, true><<<grid, GEMM_THREADS, 0, st>>>(q);
-        else if (trans_a) sgemm_kernel<true, false><<<grid, GEMM_THREADS, 0, st>>>(q);
-        else if (trans_b) sgemm_kernel<false, true><<<grid, GEMM_THREADS, 0, st>>>(q);
-        else sgemm_kernel<false, false><<<grid, GEMM_THREADS, 0, st>>>(q);
+        if (trans_a && trans_b) launch_pdl(sgemm_kernel<true, true>, grid, GEMM_THREADS, 0, st, q);
+        else if (trans_a) launch_pdl(sgemm_kernel<true, false>, grid, GEMM_THREADS, 0, st, q);
+        else if (trans_b) launch_pdl(sgemm_kernel<false, true>, grid, GEMM_THREADS, 0, st, q);
+        else launch_pdl(sgemm_kernel<false, false>, grid, GEMM_THREADS, 0, st, q);
         KGCN_LAUNCH_OK("sgemm_kernel");
     }
     return KGCN_OK;
@@ -293,9 +298,9 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
     p.partial = static_cast<float*>(workspace);
     p.colsum = 1;
     dim3 grid(ceil_div(N, BN), ceil_div(Ka, BM), splits);
-    sgemm_kernel<true, false><<<grid, GEMM_THREADS, 0, st>>>(p);
+    launch_pdl(sgemm_kernel<true, false>, grid, GEMM_THREADS, 0, st, p);
     KGCN_LAUNCH_OK("sgemm_kernel(split-K)");
-    splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<int64_t>((static_cast<int64_t>(Ka) + 1) * N, 64)), 256, 0, st>>>(
+    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((static_cast<int64_t>(Ka) + 1) * N, 64)), 256, 0, st, 
         static_cast<const float*>(workspace), splits, Ka, N, 1, out, colsum_b);
     KGCN_LAUNCH_OK("splitk_reduce_kernel");
     return KGCN_OK;
@@ -304,6 +309,7 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
 // 16-byte vectorised variant (feat % 4 == 0, aligned pointers, no row mask)
 __global__ void act_grad_vec4_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ du,
                                      int64_t n4, int feat4, int act, int n_nodes, int dy_bcast) {
+    pdl_prologue();
     const int64_t per_graph4 = static_cast<int64_t>(n_nodes) * feat4;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n4;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -326,13 +332,13 @@ int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int f
     if (enabled == nullptr && feat % 4 == 0 && aligned16(dy) && aligned16(du) && (y == nullptr || aligned16(y))) {
         const int64_t n4 = n / 4;
         const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(n4, 256), kNumSMs * 8);
-        act_grad_vec4_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        launch_pdl(act_grad_vec4_kernel, static_cast<unsigned>(blocks), 256, 0, st, 
             reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(du), n4,
             feat / 4, act, n_nodes, dy_bcast ? 1 : 0);
         KGCN_LAUNCH_OK("act_grad_vec4_kernel");
         return KGCN_OK;
     }
-    act_grad_kernel<<<ew_blocks(n), 256, 0, st>>>(y, dy, du, n, feat, act, enabled, n_nodes, dy_bcast ? 1 : 0);
+    launch_pdl(act_grad_kernel, ew_blocks(n), 256, 0, st, y, dy, du, n, feat, act, enabled, n_nodes, dy_bcast ? 1 : 0);
     KGCN_LAUNCH_OK("act_grad_kernel");
     return KGCN_OK;
 }
@@ -346,7 +352,7 @@ extern "C" int kgcn_gather_fwd_f32(const float* x, int64_t n_graphs, int32_t n_n
     KGCN_REQUIRE(x && out, KGCN_ERR_NULL, "gather_fwd: NULL pointer argument");
     KGCN_REQUIRE(n_graphs >= 0 && n_nodes > 0 && feat > 0, KGCN_ERR_BAD_SHAPE, "gather_fwd: bad shape");
     if (n_graphs == 0) return KGCN_OK;
-    gather_fwd_kernel<<<ew_blocks(n_graphs * feat), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n_graphs, n_nodes,
+    launch_pdl(gather_fwd_kernel, ew_blocks(n_graphs * feat), 256, 0, static_cast<cudaStream_t>(stream), x, n_graphs, n_nodes,
                                                                                                   feat, out);
     KGCN_LAUNCH_OK("gather_fwd_kernel");
     return KGCN_OK;
@@ -357,7 +363,7 @@ extern "C" int kgcn_gather_bwd_f32(const float* dout, int64_t n_graphs, int32_t 
     KGCN_REQUIRE(dout && dx, KGCN_ERR_NULL, "gather_bwd: NULL pointer argument");
     KGCN_REQUIRE(n_graphs >= 0 && n_nodes > 0 && feat > 0, KGCN_ERR_BAD_SHAPE, "gather_bwd: bad shape");
     if (n_graphs == 0) return KGCN_OK;
-    gather_bwd_kernel<<<ew_blocks(n_graphs * n_nodes * feat), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(gather_bwd_kernel, ew_blocks(n_graphs * n_nodes * feat), 256, 0, static_cast<cudaStream_t>(stream), 
         dout, n_graphs, n_nodes, feat, dx);
     KGCN_LAUNCH_OK("gather_bwd_kernel");
     return KGCN_OK;

@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(BM * 4 + 32, BM == 64 ? 2 : 1) graphconv_fused
         for (uint32_t i = tid; i < n16; i += kBlock) sts_f<4>(zhi + (i << 4), z4);
         for (uint32_t i = tid; i < static_cast<uint32_t>(C) * 64u; i += kBlock) sts_f<4>(bias_addr + (i << 4), z4);
     }
+    pdl_wait();   // barrier init, TMEM allocation and the zero fill above overlap the previous kernel's tail
     __syncthreads();
 
     if (warp == kConsumers / 32) {
@@ -792,7 +793,7 @@ int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const 
     const unsigned grid = static_cast<unsigned>(std::min<int>(p.n_tiles, kNumSMs * ctas_per_sm));
     auto go = [&](auto kernel) -> int {
         KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-        kernel<<<grid, p.bm * 4 + 32, p.smem_total, st>>>(p);
+        launch_pdl(kernel, grid, p.bm * 4 + 32, p.smem_total, st, p);
         KGCN_LAUNCH_OK("graphconv_fused_fwd_kernel");
         return KGCN_OK;
     };

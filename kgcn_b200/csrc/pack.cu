@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_coo_kernel(int64_t n_mat, i
                                                                 int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
                                                                 float* __restrict__ val, int32_t* __restrict__ perm,
                                                                 int32_t* __restrict__ status) {
+    pdl_prologue();
     extern __shared__ int32_t start[];  // [out_rows + 1]
     const int64_t m = blockIdx.x;
     const int64_t s = nnz_off[m], e = nnz_off[m + 1];
@@ -186,7 +187,7 @@ extern "C" int kgcn_pack_coo_device(int64_t n_mat, int32_t n_rows, int32_t n_col
     KGCN_REQUIRE(smem <= 200 * 1024, KGCN_ERR_UNSUPPORTED, "pack_coo_device: %d rows exceed the shared-memory sort", out_rows);
     if (smem > 48 * 1024)
         KGCN_CUDA_OK(cudaFuncSetAttribute(pack_coo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    pack_coo_kernel<<<static_cast<unsigned>(n_mat), kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(pack_coo_kernel, static_cast<unsigned>(n_mat), kPackThreads, smem, static_cast<cudaStream_t>(stream), 
         n_mat, out_rows, other, nnz_off, indices, values, transpose, rowptr, col, val, perm, status_flag);
     KGCN_LAUNCH_OK("pack_coo_kernel");
     return KGCN_OK;

@@ -158,6 +158,7 @@ __device__ __forceinline__ void flat_rows(uint32_t rp_addr, uint32_t cv_addr, ui
 // track (graph, out-channel, row) and up to C CSR rows are summed per output row.
 template <int VEC, int LPR, bool FLAT>
 __global__ void __launch_bounds__(kTileThreads) bspmm_tile_kernel(const SpmmParams p) {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.channels, n_rows = p.n_rows, feat = p.feat;
     const bool sum_channels = (p.os_c == 0);
@@ -293,6 +294,7 @@ constexpr int kRowThreads = 128;
 
 template <int VEC>
 __global__ void __launch_bounds__(kRowThreads) bspmm_row_kernel(const SpmmParams p, int64_t total_out_rows) {
+    pdl_prologue();
     const int C = p.channels, n_rows = p.n_rows, feat = p.feat;
     const bool sum_channels = (p.os_c == 0);
     const int lpr = 1 << p.lpr_log2;
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(128) bspmm_dvalues_kernel(const int32_t* __res
                                                             const float* __restrict__ dy, int64_t ds_g, int64_t ds_c,
                                                             const float* __restrict__ rhs, int64_t rs_g, int64_t rs_c,
                                                             float* __restrict__ dval) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= total_rows) return;
@@ -375,7 +378,7 @@ int launch_tile(const SpmmParams& p, unsigned grid, size_t smem, cudaStream_t st
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    bspmm_tile_kernel<VEC, LPR, FLAT><<<grid, kTileThreads, smem, st>>>(p);
+    launch_pdl(bspmm_tile_kernel<VEC, LPR, FLAT>, grid, kTileThreads, smem, st, p);
     KGCN_LAUNCH_OK("bspmm_tile_kernel");
     return KGCN_OK;
 }
@@ -459,9 +462,9 @@ int launch_bspmm(const int32_t* rowptr, const int32_t* col, const float* val, in
     const int64_t blocks = ceil_div<int64_t>(total_out_rows << lpr_log2, kRowThreads);
     KGCN_REQUIRE(blocks < (1ll << 31), KGCN_ERR_BAD_SHAPE, "bspmm: too many rows for one launch");
     switch (vec) {
-        case 4: bspmm_row_kernel<4><<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(p, total_out_rows); break;
-        case 2: bspmm_row_kernel<2><<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(p, total_out_rows); break;
-        default: bspmm_row_kernel<1><<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(p, total_out_rows); break;
+        case 4: launch_pdl(bspmm_row_kernel<4>, static_cast<unsigned>(blocks), kRowThreads, 0, st, p, total_out_rows); break;
+        case 2: launch_pdl(bspmm_row_kernel<2>, static_cast<unsigned>(blocks), kRowThreads, 0, st, p, total_out_rows); break;
+        default: launch_pdl(bspmm_row_kernel<1>, static_cast<unsigned>(blocks), kRowThreads, 0, st, p, total_out_rows); break;
     }
     KGCN_LAUNCH_OK("bspmm_row_kernel");
     return KGCN_OK;
@@ -490,7 +493,7 @@ extern "C" int kgcn_bspmm_dvalues_f32(const int32_t* rowptr, const int32_t* col,
     if (total_rows == 0) return KGCN_OK;
     const int64_t blocks = ceil_div<int64_t>(total_rows * 32, 128);
     KGCN_REQUIRE(blocks < (1ll << 31), KGCN_ERR_BAD_SHAPE, "bspmm_dvalues: too many rows for one launch");
-    bspmm_dvalues_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(bspmm_dvalues_kernel, static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream), 
         rowptr, col, perm, total_rows, channels, n_rows, feat, dy, dy_stride_g, dy_stride_c, rhs, rhs_stride_g,
         rhs_stride_c, dval);
     KGCN_LAUNCH_OK("bspmm_dvalues_kernel");

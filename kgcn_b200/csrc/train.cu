@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(128) readout_xent_kernel(const float* __restri
                                                            float* __restrict__ logits, float* __restrict__ prediction,
                                                            float* __restrict__ dlogits, float* __restrict__ dg,
                                                            float* __restrict__ stats) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (b >= n_graphs) return;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) readout_dw_kernel(const float* __restrict
                                                          int64_t n_graphs, int feat, int n_labels,
                                                          float* __restrict__ partial, int* __restrict__ ticket,
                                                          float* __restrict__ dw, float* __restrict__ dbias) {
+    pdl_prologue();
     const int n_out = (feat + 1) * n_labels;   // row `feat` is the bias gradient
     const int64_t per = (n_graphs + gridDim.x - 1) / gridDim.x;
     const int64_t b0 = blockIdx.x * per, b1 = min(n_graphs, b0 + per);
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(256) readout_dw_kernel(const float* __restrict
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
                             float grad_scale, int host_step, int* __restrict__ step_state) {
+    pdl_prologue();
     const int t = step_state != nullptr ? step_state[0] + 1 : host_step;
     // TF AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
     const float lr_t = lr * sqrtf(1.0f - powf(beta2, static_cast<float>(t))) / (1.0f - powf(beta1, static_cast<float>(t)));
@@ -163,7 +166,7 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (stats) KGCN_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * sizeof(float), st));
     const int64_t blocks = ceil_div<int64_t>(n_graphs * 32, 128);
-    readout_xent_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(g, n_graphs, feat, w, bias, n_labels, labels,
+    launch_pdl(readout_xent_kernel, static_cast<unsigned>(blocks), 128, 0, st, g, n_graphs, feat, w, bias, n_labels, labels,
                                                                        mask, inv_batch, logits, prediction, dlogits, dg,
                                                                        stats);
     KGCN_LAUNCH_OK("readout_xent_kernel");
@@ -174,7 +177,7 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
         float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
         KGCN_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int), st));
         const int nb = static_cast<int>(std::min<int64_t>(kReadoutBlocks, n_graphs));
-        readout_dw_kernel<<<nb, 256, 0, st>>>(g, dlogits, n_graphs, feat, n_labels, partial, ticket, dw, dbias);
+        launch_pdl(readout_dw_kernel, nb, 256, 0, st, g, dlogits, n_graphs, feat, n_labels, partial, ticket, dw, dbias);
         KGCN_LAUNCH_OK("readout_dw_kernel");
     }
     return KGCN_OK;
@@ -186,7 +189,7 @@ extern "C" int kgcn_adam_f32(float* param, const float* grad, float* m, float* v
     KGCN_REQUIRE(n >= 0 && (step_state != nullptr || step >= 1), KGCN_ERR_BAD_SHAPE, "adam: bad n/step");
     if (n == 0) return KGCN_OK;
     const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(n, 256), kNumSMs * 8);
-    adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(adam_kernel, static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
         param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, static_cast<int>(step), step_state);
     KGCN_LAUNCH_OK("adam_kernel");
     return KGCN_OK;
