@@ -55,43 +55,41 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 
-    for (int64_t k0 = k_begin; k0 < k_end; k0 += BK) {
-        // ---- stage A tile as As[k][m] ----
+    // Register-staged double buffering: the global loads of tile k0+BK are issued before the FFMAs of
+    // tile k0, so their latency overlaps the math (these GEMMs run at ~1 CTA per SM).
+    constexpr int kLdA = (BM * BK) / GEMM_THREADS, kLdB = (BN * BK) / GEMM_THREADS;
+    float ra[kLdA], rb[kLdB];
+    auto fetch = [&](int64_t k0) {
 #pragma unroll
-        for (int it = 0; it < (BM * BK) / GEMM_THREADS; ++it) {
+        for (int it = 0; it < kLdA; ++it) {
             const int idx = t + it * GEMM_THREADS;
-            int m, k;
-            if (TA) {  // A stored [K, M]: consecutive threads walk m (contiguous)
-                k = idx / BM;
-                m = idx % BM;
-            } else {  // A stored [M, K]: consecutive threads walk k (contiguous)
-                m = idx / BK;
-                k = idx % BK;
-            }
+            const int m = TA ? idx % BM : idx / BK, k = TA ? idx / BM : idx % BK;
             const int64_t gm = m0 + m, gk = k0 + k;
-            float v = 0.0f;
-            if (gm < p.M && gk < k_end) v = TA ? p.A[gk * p.lda + gm] : p.A[gm * p.lda + gk];
-            As[k][m] = v;
+            ra[it] = (gm < p.M && gk < k_end) ? (TA ? p.A[gk * p.lda + gm] : p.A[gm * p.lda + gk]) : 0.0f;
         }
-        // ---- stage B tile as Bs[k][n] ----
 #pragma unroll
-        for (int it = 0; it < (BN * BK) / GEMM_THREADS; ++it) {
+        for (int it = 0; it < kLdB; ++it) {
             const int idx = t + it * GEMM_THREADS;
-            int n, k;
-            if (TB) {  // B stored [N, K]
-                n = idx / BK;
-                k = idx % BK;
-            } else {  // B stored [K, N]
-                k = idx / BN;
-                n = idx % BN;
-            }
+            const int n = TB ? idx / BK : idx % BN, k = TB ? idx % BK : idx / BN;
             const int gn = n0 + n;
             const int64_t gk = k0 + k;
-            float v = 0.0f;
-            if (gn < p.N && gk < k_end) v = TB ? p.B[static_cast<int64_t>(gn) * p.ldb + gk] : p.B[gk * p.ldb + gn];
-            Bs[k][n] = v;
+            rb[it] = (gn < p.N && gk < k_end) ? (TB ? p.B[static_cast<int64_t>(gn) * p.ldb + gk] : p.B[gk * p.ldb + gn]) : 0.0f;
+        }
+    };
+    if (k_begin < k_end) fetch(k_begin);
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int it = 0; it < kLdA; ++it) {
+            const int idx = t + it * GEMM_THREADS;
+            As[TA ? idx / BM : idx % BK][TA ? idx % BM : idx / BK] = ra[it];
+        }
+#pragma unroll
+        for (int it = 0; it < kLdB; ++it) {
+            const int idx = t + it * GEMM_THREADS;
+            Bs[TB ? idx % BK : idx / BN][TB ? idx / BK : idx % BN] = rb[it];
         }
         __syncthreads();
+        if (k0 + BK < k_end) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
