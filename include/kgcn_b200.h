@@ -202,10 +202,14 @@ int kgcn_gather_bwd_f32(const float* dout, int64_t n_graphs, int32_t n_nodes, in
  *   logits = g . w + bias;  prediction = softmax(logits);
  *   cost[b] = mask[b] * softmax_cross_entropy(labels[b], logits[b]);
  *   stats[0] = cost_sum = sum_b cost[b];  stats[1] = correct_count (argmax match, masked);
+ *   `stats` is a float[4] device buffer the caller zero-initialises ONCE: [2] holds an internal block
+ *   ticket that the kernel restores to zero, [3] is reserved (deterministic last-block reductions,
+ *   no memset and no second launch per call);
  *   gradients of cost_opt = inv_batch * sum_b cost[b] (reduce_mean, inv_batch = 1/batch_size):
  *   dlogits [B,L], dg [B,F] = dlogits . w^T, dw [F,L] = g^T . dlogits, dbias [L].
  * g [n_graphs, feat]; w [feat, n_labels]; labels [n_graphs, n_labels] (one-hot or soft);
- * mask [n_graphs] or NULL.  Any output pointer may be NULL (dw needs dlogits).  n_labels <= 32.
+ * mask [n_graphs] or NULL.  Any output pointer except stats may be NULL.  n_labels <= 32;
+ * n_graphs <= 75776 per launch.
  */
 size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels);
 int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const float* w, const float* bias,

@@ -232,7 +232,7 @@ inline unsigned ew_blocks(int64_t n) {
 
 int choose_splits(int64_t M_out, int N, int64_t K) {
     const int64_t tiles = ceil_div<int64_t>(M_out, BM) * ceil_div(N, BN);
-    int64_t splits = ceil_div<int64_t>(kNumSMs, tiles);
+    int64_t splits = ceil_div<int64_t>(kNumSMs, tiles);   // one wave (2 CTAs/SM measured slower: more partials to reduce)
     const int64_t max_by_k = ceil_div<int64_t>(K, 4 * BK);  // at least 4 k-steps per split
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;

@@ -16,6 +16,7 @@
 // large-N block-diagonal use (example_model/sparse.py:65-69), split the flat row space over CTAs
 // and gather straight from global / L2.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -429,9 +430,11 @@ int launch_bspmm(const int32_t* rowptr, const int32_t* col, const float* val, in
     const bool stageable = tile_bytes % 16 == 0 && aligned16(rhs) && (rs_g * 4) % 16 == 0 && (rs_c * 4) % 16 == 0 &&
                            graph_bytes <= 96 * 1024 && rows_per_graph <= 8192;
     if (stageable) {
-        // graphs per CTA: ~32 KB of features, at most 8 graphs, but keep >= 2 CTAs per SM when B allows
-        int64_t G = std::max<int64_t>(1, std::min<int64_t>(8, (32 * 1024) / static_cast<int64_t>(graph_bytes)));
-        G = std::min<int64_t>(G, std::max<int64_t>(1, n_graphs / (2 * kNumSMs)));
+        // graphs per CTA: ~16 KB of features (measured best at C2: 2 graphs of 32x64 -> 6.1 us at B=1024,
+        // 83 % of the measured HBM peak at B=16384; 1, 3, 4 and 8 graphs per CTA are all slower)
+        int64_t G = std::max<int64_t>(1, std::min<int64_t>(8, (16 * 1024) / static_cast<int64_t>(graph_bytes)));
+        static const char* force_g = getenv("KGCN_SPMM_G");   // tuning knob
+        if (force_g != nullptr && atoi(force_g) > 0) G = std::min<int64_t>(atoi(force_g), (96 * 1024) / static_cast<int64_t>(graph_bytes));
         const int64_t cap = std::max<int64_t>(256, 6 * G * rows_per_graph);
         const size_t smem = 128 + G * graph_bytes + ((G * rows_per_graph + 2) & ~1ll) * 4 + cap * 8;
         const int64_t grid = ceil_div<int64_t>(n_graphs, G);

@@ -12,65 +12,121 @@ namespace {
 
 constexpr int kMaxLabels = 32;
 
-// One warp per graph.
-__global__ void __launch_bounds__(128) readout_xent_kernel(const float* __restrict__ g, int64_t n_graphs, int feat,
-                                                           const float* __restrict__ w, const float* __restrict__ bias,
-                                                           int n_labels, const float* __restrict__ labels,
-                                                           const float* __restrict__ mask, float inv_batch,
-                                                           float* __restrict__ logits, float* __restrict__ prediction,
-                                                           float* __restrict__ dlogits, float* __restrict__ dg,
-                                                           float* __restrict__ stats) {
+// One kernel for the whole head.  Each block owns a contiguous slice of the batch:
+//   phase 1 (warp per graph): logits, softmax, masked cross-entropy, d logits, d gathered;
+//   phase 2 (thread per weight): d out_w[f,l] / d out_b[l] over the slice, in graph order;
+// block partials go to `partial`; the last block to finish (ticket in state[2]) adds them in block
+// order, so every sum is deterministic and no memset / second launch is needed.
+constexpr int kReadoutThreads = 256;
+constexpr int kReadoutMaxSlice = 128;
+
+__global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
+    const float* __restrict__ g, int64_t n_graphs, int feat, const float* __restrict__ w, const float* __restrict__ bias,
+    int n_labels, const float* __restrict__ labels, const float* __restrict__ mask, float inv_batch,
+    float* __restrict__ logits, float* __restrict__ prediction, float* __restrict__ dlogits, float* __restrict__ dg,
+    float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state) {
     pdl_prologue();
-    const int lane = threadIdx.x & 31;
-    const int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (b >= n_graphs) return;
-    const float* gb = g + b * feat;
-    float z[kMaxLabels];
+    __shared__ float dz_s[kReadoutMaxSlice * kMaxLabels];
+    __shared__ float cost_s[kReadoutMaxSlice], corr_s[kReadoutMaxSlice];
+    __shared__ int is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (n_graphs + gridDim.x - 1) / gridDim.x;
+    const int64_t b0 = blockIdx.x * per;
+    const int n_here = static_cast<int>(max(static_cast<int64_t>(0), min(n_graphs, b0 + per) - b0));
+
+    // ---- phase 1 ----
+    for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
+        const int64_t b = b0 + i;
+        const float* gb = g + b * feat;
+        float z[kMaxLabels];
 #pragma unroll 1
-    for (int l = 0; l < n_labels; ++l) {
-        float acc = 0.0f;
-        for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w[static_cast<int64_t>(f) * n_labels + l], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        z[l] = acc + (bias ? bias[l] : 0.0f);
-    }
-    // softmax cross-entropy with (possibly soft) labels: cost = -sum_l y_l * log_softmax(z)_l
-    float zmax = z[0];
-    for (int l = 1; l < n_labels; ++l) zmax = fmaxf(zmax, z[l]);
-    float sum = 0.0f;
-    for (int l = 0; l < n_labels; ++l) sum += expf(z[l] - zmax);
-    const float lse = logf(sum) + zmax;
-    const float m = mask ? mask[b] : 1.0f;
-    float cost = 0.0f, ysum = 0.0f;
-    int arg_p = 0, arg_y = 0;
-    for (int l = 0; l < n_labels; ++l) {
-        const float y = labels[b * n_labels + l];
-        cost -= y * (z[l] - lse);
-        ysum += y;
-        if (z[l] > z[arg_p]) arg_p = l;
-        if (y > labels[b * n_labels + arg_y]) arg_y = l;
-    }
-    float dz[kMaxLabels];
-    for (int l = 0; l < n_labels; ++l) {
-        const float pr = expf(z[l] - lse);
-        dz[l] = m * inv_batch * (pr * ysum - labels[b * n_labels + l]);
-        if (lane == 0) {
-            if (logits) logits[b * n_labels + l] = z[l];
-            if (prediction) prediction[b * n_labels + l] = pr;
-            if (dlogits) dlogits[b * n_labels + l] = dz[l];
-        }
-    }
-    if (dg != nullptr) {
-        for (int f = lane; f < feat; f += 32) {
+        for (int l = 0; l < n_labels; ++l) {
             float acc = 0.0f;
-            for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w[static_cast<int64_t>(f) * n_labels + l], acc);
-            dg[b * feat + f] = acc;
+            for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w[static_cast<int64_t>(f) * n_labels + l], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            z[l] = acc + (bias ? bias[l] : 0.0f);
+        }
+        float zmax = z[0];
+        for (int l = 1; l < n_labels; ++l) zmax = fmaxf(zmax, z[l]);
+        float sum = 0.0f;
+        for (int l = 0; l < n_labels; ++l) sum += expf(z[l] - zmax);
+        const float lse = logf(sum) + zmax;
+        const float m = mask ? mask[b] : 1.0f;
+        float cost = 0.0f, ysum = 0.0f;
+        int arg_p = 0, arg_y = 0;
+        for (int l = 0; l < n_labels; ++l) {
+            const float y = labels[b * n_labels + l];
+            cost -= y * (z[l] - lse);            // softmax cross-entropy with (possibly soft) labels
+            ysum += y;
+            if (z[l] > z[arg_p]) arg_p = l;
+            if (y > labels[b * n_labels + arg_y]) arg_y = l;
+        }
+        float dz[kMaxLabels];
+        for (int l = 0; l < n_labels; ++l) {
+            const float pr = expf(z[l] - lse);
+            dz[l] = m * inv_batch * (pr * ysum - labels[b * n_labels + l]);
+            if (lane == 0) {
+                if (logits) logits[b * n_labels + l] = z[l];
+                if (prediction) prediction[b * n_labels + l] = pr;
+                if (dlogits) dlogits[b * n_labels + l] = dz[l];
+                dz_s[i * n_labels + l] = dz[l];
+            }
+        }
+        if (dg != nullptr)
+            for (int f = lane; f < feat; f += 32) {
+                float acc = 0.0f;
+                for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w[static_cast<int64_t>(f) * n_labels + l], acc);
+                dg[b * feat + f] = acc;
+            }
+        if (lane == 0) {
+            cost_s[i] = m * cost;                                   // cost_sum term   (model.py:64)
+            corr_s[i] = m * (arg_p == arg_y ? 1.0f : 0.0f);         // correct_count term (model.py:66-69)
         }
     }
-    if (lane == 0 && stats != nullptr) {
-        atomicAdd(stats + 0, m * cost);                                 // cost_sum   (model.py:64)
-        atomicAdd(stats + 1, m * (arg_p == arg_y ? 1.0f : 0.0f));       // correct_count (model.py:66-69)
+    __syncthreads();
+
+    // ---- phase 2: block partials, graph order inside the slice ----
+    const int n_w = (feat + 1) * n_labels;      // row `feat` is the bias gradient
+    const int n_out = n_w + 2;                  // + cost_sum, correct_count
+    float* my = partial + static_cast<size_t>(blockIdx.x) * n_out;
+    for (int o = threadIdx.x; o < n_out; o += kReadoutThreads) {
+        float acc = 0.0f;
+        if (o < n_w) {
+            if (dw != nullptr) {
+                const int f = o / n_labels, l = o - f * n_labels;
+                if (f < feat)
+                    for (int i = 0; i < n_here; ++i) acc = fmaf(g[(b0 + i) * feat + f], dz_s[i * n_labels + l], acc);
+                else
+                    for (int i = 0; i < n_here; ++i) acc += dz_s[i * n_labels + l];
+            }
+        } else {
+            const float* src = (o == n_w) ? cost_s : corr_s;
+            for (int i = 0; i < n_here; ++i) acc += src[i];
+        }
+        my[o] = acc;
     }
+    __threadfence();
+    __syncthreads();
+    int* ticket = reinterpret_cast<int*>(state + 2);
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int o = threadIdx.x; o < n_out; o += kReadoutThreads) {
+        float acc = 0.0f;
+        for (unsigned k = 0; k < gridDim.x; ++k) acc += partial[static_cast<size_t>(k) * n_out + o];
+        if (o < n_w) {
+            const int f = o / n_labels, l = o - f * n_labels;
+            if (dw != nullptr) {
+                if (f < feat) dw[o] = acc;
+                else if (dbias != nullptr) dbias[l] = acc;
+            }
+        } else {
+            state[o - n_w] = acc;
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // step_state (device, may be null): [0] = number of steps already applied, [1] = block ticket.
@@ -147,39 +203,34 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
 
 using namespace kgcn;
 
-constexpr int kReadoutBlocks = 32;
+static int readout_blocks(int64_t n_graphs) {
+    int64_t nb = ceil_div<int64_t>(n_graphs, 8);   // one graph per warp in phase 1
+    nb = std::min<int64_t>(nb, kNumSMs);
+    nb = std::max<int64_t>(nb, ceil_div<int64_t>(n_graphs, kReadoutMaxSlice));
+    return static_cast<int>(nb);
+}
 
 extern "C" size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels) {
     if (n_graphs <= 0) return 0;
-    // [ticket (16 bytes)] [partial sums: blocks x (feat + 1) x n_labels]
-    return 16 + static_cast<size_t>(kReadoutBlocks) * (static_cast<size_t>(feat) + 1) * n_labels * sizeof(float);
+    return static_cast<size_t>(readout_blocks(n_graphs)) * ((static_cast<size_t>(feat) + 1) * n_labels + 2) * sizeof(float);
 }
 
 extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const float* w, const float* bias,
                                      int32_t n_labels, const float* labels, const float* mask, float inv_batch,
                                      float* logits, float* prediction, float* stats, float* dlogits, float* dg,
                                      float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
-    KGCN_REQUIRE(g && w && labels, KGCN_ERR_NULL, "readout_xent: NULL pointer argument");
+    KGCN_REQUIRE(g && w && labels && stats, KGCN_ERR_NULL, "readout_xent: NULL pointer argument");
     KGCN_REQUIRE(n_graphs > 0 && feat > 0 && n_labels > 0 && n_labels <= kMaxLabels, KGCN_ERR_BAD_SHAPE,
                  "readout_xent: bad shape (n_labels <= %d)", kMaxLabels);
-    KGCN_REQUIRE(dw == nullptr || dlogits != nullptr, KGCN_ERR_NULL, "readout_xent: dw needs a dlogits buffer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (stats) KGCN_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * sizeof(float), st));
-    const int64_t blocks = ceil_div<int64_t>(n_graphs * 32, 128);
-    launch_pdl(readout_xent_kernel, static_cast<unsigned>(blocks), 128, 0, st, g, n_graphs, feat, w, bias, n_labels, labels,
-                                                                       mask, inv_batch, logits, prediction, dlogits, dg,
-                                                                       stats);
-    KGCN_LAUNCH_OK("readout_xent_kernel");
-    if (dw != nullptr) {
-        KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= kgcn_readout_workspace_bytes(n_graphs, feat, n_labels),
-                     KGCN_ERR_WORKSPACE, "readout_xent: workspace too small");
-        int* ticket = static_cast<int*>(workspace);
-        float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
-        KGCN_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int), st));
-        const int nb = static_cast<int>(std::min<int64_t>(kReadoutBlocks, n_graphs));
-        launch_pdl(readout_dw_kernel, nb, 256, 0, st, g, dlogits, n_graphs, feat, n_labels, partial, ticket, dw, dbias);
-        KGCN_LAUNCH_OK("readout_dw_kernel");
-    }
+    KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= kgcn_readout_workspace_bytes(n_graphs, feat, n_labels),
+                 KGCN_ERR_WORKSPACE, "readout_xent: workspace too small");
+    const int nb = readout_blocks(n_graphs);
+    KGCN_REQUIRE(ceil_div<int64_t>(n_graphs, nb) <= kReadoutMaxSlice, KGCN_ERR_UNSUPPORTED,
+                 "readout_xent: batch too large for one launch (%lld graphs)", (long long)n_graphs);
+    launch_pdl(readout_kernel, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), g, n_graphs, feat, w, bias,
+               n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg, dw, dbias, static_cast<float*>(workspace),
+               stats);
+    KGCN_LAUNCH_OK("readout_kernel");
     return KGCN_OK;
 }
 

@@ -93,7 +93,7 @@ class Trainer:
         self.logits = torch.empty(B, s.label_dim, **f32)
         self.prediction = torch.empty(B, s.label_dim, **f32)
         self.dlogits = torch.empty(B, s.label_dim, **f32)
-        self.stats = torch.zeros(2, **f32)
+        self.stats = torch.zeros(4, **f32)   # [cost_sum, correct_count, block ticket, reserved]
         ws = 0
         f = s.feature_dim
         for d in s.conv_dims:
@@ -399,7 +399,7 @@ class HostFedPipeline:
                         g.replay()
             else:
                 self._device_part(slot)
-            slot.h_stats.copy_(self.trainer.stats, non_blocking=True)
+            slot.h_stats.copy_(self.trainer.stats[:2], non_blocking=True)
             slot.done.record(self.compute_stream)
         slot.busy = True
         self.n_submitted += 1
