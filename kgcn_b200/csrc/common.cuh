@@ -117,6 +117,10 @@ size_t reduce_gemm_workspace_bytes(int64_t M, int Ka, int N);
 int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda, const float* B, int64_t ldb,
                           float* out, float* colsum_b, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// out[M, N] (+ colsum_out[N], may be null) = sum over `splits` partial blocks of (M + 1) * N floats, fixed order.
+int launch_splitk_reduce(const float* partial, int splits, int64_t M, int N, float* out, float* colsum_out,
+                         cudaStream_t st);
+
 // du = dy * act'(y) (elementwise), optional row mask by enabled_node_nums.
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act,
                     const int32_t* enabled, int n_nodes, bool dy_bcast, cudaStream_t st);

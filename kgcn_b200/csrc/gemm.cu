@@ -276,6 +276,14 @@ int launch_sgemm(bool trans_a, bool trans_b, int64_t M, int N, int K, const floa
     return KGCN_OK;
 }
 
+int launch_splitk_reduce(const float* partial, int splits, int64_t M, int N, float* out, float* colsum_out,
+                         cudaStream_t st) {
+    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((M + 1) * N, 64)), 256, 0, st, partial, splits,
+               M, N, 1, out, colsum_out);
+    KGCN_LAUNCH_OK("splitk_reduce_kernel");
+    return KGCN_OK;
+}
+
 size_t reduce_gemm_workspace_bytes(int64_t M, int Ka, int N) {
     const int splits = choose_splits(Ka, N, M);
     return static_cast<size_t>(splits) * (static_cast<size_t>(Ka) + 1) * N * sizeof(float);

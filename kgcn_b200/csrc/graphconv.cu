@@ -7,6 +7,8 @@
 //     (kgcn/layers.py:112-113: fw = x.W_c + b_c, then A.fw, then the channel sum of :115) with
 //     exact-fp32 FFMA GEMMs.  It handles every shape (odd feature widths, B=1 / huge N) and is
 //     the in-library cross-check for the fused kernel.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace kgcn {
@@ -17,6 +19,15 @@ bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, i
 int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
                                int channels, int n_nodes, const float* x, int f_in, const float* w, const float* bias,
                                int f_out, int act, float* y, cudaStream_t st);
+
+bool fused_bwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int act, bool dy_bcast,
+                        const float* x, const float* w, const float* y, const float* dy, const float* dx,
+                        const int32_t* rowptr, const int32_t* col, const float* val);
+size_t fused_bwd_partial_bytes(int f_in, int f_out);
+int launch_graphconv_fused_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                               int n_nodes, const float* x, int f_in, const float* w, int f_out, int act, const float* y,
+                               const float* dy, bool dy_bcast, float* dx, float* dw, float* dbias, void* workspace,
+                               size_t workspace_bytes, cudaStream_t st);
 
 namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -32,7 +43,8 @@ extern "C" size_t kgcn_graphconv_workspace_bytes(int64_t n_graphs, int32_t chann
     const size_t act_elems = static_cast<size_t>(n_graphs) * n_nodes * f_out;
     // forward: H[C][B*N][f_out]; backward: du[B*N][f_out] + G[C][B*N][f_out] + split-K partials
     return align_up((1 + static_cast<size_t>(channels)) * act_elems * sizeof(float), 256) +
-           align_up(reduce_gemm_workspace_bytes(n_graphs * n_nodes, f_in, f_out), 256);
+           align_up(std::max(reduce_gemm_workspace_bytes(n_graphs * n_nodes, f_in, f_out),
+                             fused_bwd_partial_bytes(f_in, f_out)), 256);
 }
 
 extern "C" int kgcn_graphconv_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
@@ -94,6 +106,12 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
     const size_t used = align_up((1 + static_cast<size_t>(channels)) * act_elems * sizeof(float), 256);
     void* ws2 = static_cast<char*>(workspace) + used;
     const size_t ws2_bytes = workspace_bytes - used;
+
+    // fused single-kernel backward (graphconv_fused_bwd.cu) when the shape is eligible
+    if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && ws2_bytes >= fused_bwd_partial_bytes(f_in, f_out) &&
+        fused_bwd_eligible(n_graphs, channels, n_nodes, f_in, f_out, act, dy_bcast, x, w, y, dy, dx, rowptr_t, col_t, val_t))
+        return launch_graphconv_fused_bwd(rowptr_t, col_t, val_t, n_graphs, n_nodes, x, f_in, w, f_out, act, y, dy, dy_bcast,
+                                          dx, dw, dbias, ws2, ws2_bytes, st);
 
     const float* du_ptr = dy;
     if (act != KGCN_ACT_NONE || dy_bcast) {

@@ -106,4 +106,32 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// same shape, 16 columns: v[4i + {0,1}] row t/4, v[4i + {2,3}] row t/4 + 8, columns 8i + 2*(t%4) + {0,1}, i = 0..1
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_fence8(float (&v)[8]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+}
+
+// MN-major operands (the contraction index is the ROW index of a row-major tile).  For tf32 the only
+// MN-major shared-memory layout is SWIZZLE_128B with a 32-byte base: rows of 128 bytes (32 values along
+// M/N) for consecutive k, 32-value chunks `lbo` bytes apart, and inside a row the 32-byte granule
+// index is XORed with (k & 3).  One K = 8 instruction spans two 4-row swizzle atoms (`sbo` = 512 B).
+__device__ __forceinline__ uint32_t mn32_offset(uint32_t krow, uint32_t mn, uint32_t lbo) {   // mn % 4 == 0 for 16-byte accesses
+    return (mn >> 5) * lbo + krow * 128u + ((((mn >> 3) & 3u) ^ (krow & 3u)) << 5) + ((mn & 7u) << 2);
+}
+__device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) /* version */ |
+           (1ull << 61) /* SWIZZLE_128B_BASE32B */;
+}
+constexpr uint32_t kUmmaMajorMnA = 1u << 15, kUmmaMajorMnB = 1u << 16;   // instruction-descriptor bits
+
 }  // namespace kgcn

@@ -203,6 +203,46 @@ def test_graphconv_backward(K, B, N, C, fi, fo, act):
     assert torch.equal(gdw, gdw2)   # deterministic reduction order
 
 
+FUSED_BWD_SHAPES = [  # B, N, fi, fo, max_nnz: single-channel shapes the one-kernel tensor-core backward takes
+    (24, 32, 64, 64, None),    # C2
+    (700, 32, 64, 64, None),   # more tiles than CTAs: the dW accumulator lives across tiles
+    (7, 50, 36, 48, None),     # one graph per tile (50 of 64 rows), lane groups wider than the row, odd graph count
+    (5, 64, 64, 32, None),     # full 64-row graphs
+    (33, 16, 8, 128, None),    # 4 graphs per tile, last tile short, widest output
+    (6, 32, 64, 64, 900),      # more entries per tile than the stage holds (entries read from global memory)
+    (3, 1, 4, 4, 1),           # degenerate
+]
+
+
+@pytest.mark.parametrize("B,N,fi,fo,max_nnz", FUSED_BWD_SHAPES)
+@pytest.mark.parametrize("act", ["none", "sigmoid", "relu", "tanh"])
+@pytest.mark.parametrize("bcast", [False, True])
+def test_graphconv_backward_fused(K, B, N, fi, fo, max_nnz, act, bcast):
+    """Fused backward (default) vs the oracle and vs the decomposed exact-fp32 path (REFERENCE_ORDER flag)."""
+    rng = np.random.default_rng(B * 7 + fo)
+    adjs, x = random_batch(rng, B, N, 1, fi, max_nnz=max_nnz, empty_graphs=(0,))
+    w = [R.glorot_uniform(rng, fi, fo)]
+    b = [rng.uniform(-0.5, 0.5, (1, fo)).astype(np.float32)]
+    y = R.activation(R.graph_conv(x, adjs, w, b, fast=True), act)
+    dy = rng.standard_normal((B, fo) if bcast else y.shape).astype(np.float32)
+    dy_full = np.broadcast_to(dy[:, None, :], y.shape) if bcast else dy
+    du = dy_full * R.activation_grad_from_output(y, act)
+    dx, dw, db = R.graph_conv_grad(x, adjs, w, b, du)
+    csr = K["csr"].BatchedCSR.from_coo_lists(adjs)
+    base = 2 if bcast else 0   # KGCN_FLAG_DY_BROADCAST
+    gdx, gdw, gdb = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), flags=base)
+    rdx, rdw, rdb = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), flags=base | 1)
+    scale = max(1.0, float(np.abs(dw[0]).max()))
+    close(gdx, dx, 1e-4)
+    close(gdx, rdx.cpu().numpy(), 1e-4)
+    np.testing.assert_allclose(gdw.cpu().numpy(), np.stack(dw), rtol=1e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(gdw.cpu().numpy(), rdw.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(gdb.cpu().numpy(), np.concatenate(db), rtol=1e-4, atol=2e-5 * scale)
+    _, gdw2, gdb2 = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), need_dx=False,
+                                           flags=base)
+    assert torch.equal(gdw, gdw2) and torch.equal(gdb, gdb2)   # same tiles, same accumulation order
+
+
 # ---------------------------------------------------------------------------------------------
 # GraphDense / GraphGather
 # ---------------------------------------------------------------------------------------------
