@@ -1,0 +1,597 @@
+// Fused GraphConv layer for sm_100a, warp-specialised pipeline ("v4"):
+//
+//     y[g] = act( sum_c (A[g,c] . x[g]) . W_c  +  rowsum(A[g,c]) (x) bias_c )        (kgcn/layers.py:105-116,
+//                                                          re-associated aggregate-first)
+//
+// One persistent CTA per SM owns a contiguous range of graphs and walks it in tiles of G whole graphs
+// (G * N <= 128 rows = the 128 TMEM lanes).  Four roles run concurrently on DIFFERENT tiles:
+//
+//   producer warp    TMA bulk copies of the tile's feature rows and CSR slices into a ring of smem stages
+//   aggregation      one THREAD per (tile row, 32-feature slab): walks the row's CSR entries and gathers the
+//   warps            neighbours' 128-byte slab segments out of the stage with 8 LDS.128 per entry.  The
+//                    16-byte chunk order is rotated per lane (chunk i ^ (lane & 7)) so that the 8 lanes of an
+//                    LDS phase always hit 8 different bank groups although every neighbour row starts at the
+//                    same bank.  The row of Z = A.X is split into tf32 hi / lo and written with tcgen05.st
+//                    straight into TENSOR MEMORY (lane = row), next to the row sum of the adjacency values.
+//   MMA warp         one thread issues tcgen05.mma kind::tf32 with the A operand in TMEM and B = [W ; bias]
+//                    in shared memory (K-major SWIZZLE_128B): 3xTF32 (Zhi.Whi + Zlo.Whi + Zhi.Wlo) into ONE
+//                    fp32 accumulator in TMEM.  The bias rides in the GEMM: Z carries rowsum(A_c) in column
+//                    K + c and B carries bias_c in row K + c, so the epilogue is activation only.
+//   epilogue warps   tcgen05.ld the accumulator (double-buffered), activation, swizzled per-warp staging
+//                    tile, coalesced 16-byte global stores (four full 128-byte lines per store instruction).
+//
+// Z (in TMEM) and the accumulator are double-buffered, so aggregation of tile i+1, the contraction of
+// tile i and the epilogue of tile i-1 overlap; shared memory is left for a deep (3-4 tile) TMA ring.
+// HBM traffic per layer = x once + y once + CSR once + W once per CTA: the algorithmic minimum.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace kgcn {
+namespace {
+
+constexpr int kV4MaxStages = 4;
+constexpr int kAggWarpsPerGroup = 8;    // 4 lane quarters x 2 slab phases
+constexpr int kEpiWarps = 4;
+
+struct V4Params {
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* val;
+    const float* x;
+    const float* w;
+    const float* bias;
+    float* y;
+    int64_t n_graphs;
+    int C, N, f_in, f_out, act;
+    int G;                // graphs per tile
+    int graphs_per_cta;   // contiguous graph range per CTA
+    int K, Kp, Np;        // K = C * f_in; Kp = K + 8 (row-sum columns); Np = f_out padded to 16
+    int n_slabs, slabs_per_ch;
+    int n_stages, cv_cap;
+    int zbufs;            // Z buffers in TMEM (2 when they fit, else 1)
+    uint32_t off_whi, off_wlo, off_ystage, off_stage, stage_bytes, st_rp, st_col, st_val, smem_total;
+    uint32_t w_atom;      // bytes between K atoms of the B operand
+    uint32_t tm_z;        // first TMEM column of Z buffer 0 (accumulators at columns 0 and Np)
+    long long* dbg;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+template <int ACT>
+__device__ __forceinline__ float fast_act(float x) {
+    if (ACT == KGCN_ACT_RELU) return fmaxf(x, 0.0f);
+    if (ACT == KGCN_ACT_SIGMOID) return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+    if (ACT == KGCN_ACT_TANH) {
+        const float t = ex2_approx(-2.8853900817779268f * fabsf(x));
+        return copysignf((1.0f - t) * rcp_approx(1.0f + t), x);
+    }
+    return x;
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T ; A: lane = row, one tf32 per 32-bit column, 8 columns per K-step
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+
+// ---- tile bookkeeping shared by every role ----
+struct TileRange {
+    int64_t g_begin;
+    int n_graphs_cta, n_tiles;
+};
+__device__ __forceinline__ TileRange cta_range(const V4Params& p) {
+    TileRange t;
+    t.g_begin = static_cast<int64_t>(blockIdx.x) * p.graphs_per_cta;
+    const int64_t left = p.n_graphs - t.g_begin;
+    t.n_graphs_cta = static_cast<int>(left < p.graphs_per_cta ? (left > 0 ? left : 0) : p.graphs_per_cta);
+    t.n_tiles = (t.n_graphs_cta + p.G - 1) / p.G;
+    return t;
+}
+
+// One (row, slab) of Z = A.X: gather + FFMA over the row's entries; acc block i holds chunk (i ^ s7).
+template <bool STAGED>
+__device__ __forceinline__ void gather_row(float (&acc)[32], float& deg, int rs, int re, uint32_t col_addr, uint32_t val_addr,
+                                           const int32_t* gcol, const float* gval, uint32_t xbase, uint32_t pitch) {
+    if (STAGED) {
+        uint32_t ce = col_addr + 4u * static_cast<uint32_t>(rs), ve = val_addr + 4u * static_cast<uint32_t>(rs);
+        const uint32_t cend = col_addr + 4u * static_cast<uint32_t>(re);
+        uint32_t cn = lds_u32(ce);     // one entry of look-ahead; reading one past the row is harmless (slack)
+        float vn = lds_f32(ve);
+#pragma unroll 1
+        while (ce < cend) {
+            const uint32_t xa = xbase + cn * pitch;
+            const float v = vn;
+            ce += 4;
+            ve += 4;
+            cn = lds_u32(ce);
+            vn = lds_f32(ve);
+            float xv[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) lds_f<4>(xv[i], xa ^ (static_cast<uint32_t>(i) << 4));
+            deg += v;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[4 * i + j] = fmaf(v, xv[i][j], acc[4 * i + j]);
+        }
+    } else {   // unusually dense tile: the CSR slice did not fit the stage, entries come from global memory
+        for (int e = rs; e < re; ++e) {
+            const uint32_t xa = xbase + static_cast<uint32_t>(__ldg(gcol + e)) * pitch;
+            const float v = __ldg(gval + e);
+            float xv[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) lds_f<4>(xv[i], xa ^ (static_cast<uint32_t>(i) << 4));
+            deg += v;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[4 * i + j] = fmaf(v, xv[i][j], acc[4 * i + j]);
+        }
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ void act16(float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fast_act<ACT>(v[i]);
+}
+__device__ __forceinline__ void act16_rt(float (&v)[16], int act) {
+    switch (act) {
+        case KGCN_ACT_RELU: act16<KGCN_ACT_RELU>(v); break;
+        case KGCN_ACT_SIGMOID: act16<KGCN_ACT_SIGMOID>(v); break;
+        case KGCN_ACT_TANH: act16<KGCN_ACT_TANH>(v); break;
+        default: break;
+    }
+}
+
+// KS K-steps of one 3xTF32 pass, unrolled so every operand address is a constant add
+template <int KS>
+__device__ __forceinline__ void issue_tile(uint32_t d, uint32_t zhi, uint32_t zlo, uint64_t dwhi, uint64_t dwlo, uint32_t idesc,
+                                           uint32_t w_atom16) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t za = (pass == 1) ? zlo : zhi;
+        const uint64_t db = (pass == 2) ? dwlo : dwhi;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            umma_tf32_ts(d, za + 8u * j, db + static_cast<uint64_t>((j >> 2) * w_atom16 + 2 * (j & 3)), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+__device__ __noinline__ void issue_tile_loop(uint32_t d, uint32_t zhi, uint32_t zlo, uint64_t dwhi, uint64_t dwlo, uint32_t idesc,
+                                             uint32_t w_atom16, int ks) {
+    uint32_t acc = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t za = (pass == 1) ? zlo : zhi;
+        const uint64_t db = (pass == 2) ? dwlo : dwhi;
+        for (int j = 0; j < ks; ++j) {
+            umma_tf32_ts(d, za + 8u * j, db + static_cast<uint64_t>((j >> 2) * w_atom16 + 2 * (j & 3)), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+// NG aggregation groups of 8 warps (group g takes the tiles with index % NG == g)
+template <int NG>
+__global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32, 1) graphconv_fused_v4_kernel(const V4Params p) {
+    constexpr int kAggWarps = NG * kAggWarpsPerGroup;
+    constexpr int kWarpEpi0 = kAggWarps;
+    constexpr int kWarpMma = kAggWarps + kEpiWarps;
+    constexpr int kWarpTma = kWarpMma + 1;
+    constexpr int kBlock = (kWarpTma + 1) * 32;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
+    __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = p.C, N = p.N, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp, Np = p.Np, S = p.n_stages;
+    const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
+    const TileRange tr = cta_range(p);
+
+    if (tid == 0) {
+        for (int i = 0; i < kV4MaxStages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], kAggWarpsPerGroup);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_zfull[i], kAggWarpsPerGroup);
+            mbar_init(&bar_zempty[i], 1);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
+    {   // zero the B operand region: K / N padding must contribute exact zeros
+        const uint32_t n16 = (p.off_ystage - p.off_whi) >> 4;
+        const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t i = tid; i < n16; i += kBlock) sts_f<4>(base + p.off_whi + (i << 4), z4);
+    }
+    pdl_wait();   // everything above overlaps the previous kernel's tail
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == kWarpTma) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            for (int it = 0; it < tr.n_tiles; ++it) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(&bar_empty[s], ((it / S) - 1) & 1);
+                const int64_t g0 = tr.g_begin + static_cast<int64_t>(it) * p.G;
+                const int ng = min(p.G, tr.n_graphs_cta - it * p.G);
+                const int64_t r0 = g0 * C * N;
+                const int rows_csr = ng * C * N;
+                const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
+                const int64_t rp_lo = r0 & ~3ll;
+                const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
+                const int32_t e_lo = e_first & ~3;
+                const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
+                const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap);
+                unsigned char* st = gen + p.off_stage + static_cast<size_t>(s) * p.stage_bytes;
+                const uint32_t x_bytes = static_cast<uint32_t>(ng) * static_cast<uint32_t>(N) * pitch;
+                mbar_expect_tx(&bar_full[s], x_bytes + 4u * rp_cnt + ((staged && e_cnt) ? 8u * e_cnt : 0u));
+                bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, &bar_full[s]);
+                if (staged && e_cnt) {
+                    bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, &bar_full[s]);
+                    bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, &bar_full[s]);
+                }
+                bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, &bar_full[s]);
+            }
+        }
+    } else {
+        // B operand [W ; bias] -> (hi, lo), K-major SWIZZLE_128B: B row n = output column n, k = c * f_in + f for
+        // the weights, k = K + c for bias_c (it meets rowsum(A_c) in column K + c of Z).  All non-producer warps.
+        {
+            constexpr int kStagers = kBlock - 32;
+            const int kq = Kp >> 2;
+            for (int idx = tid; idx < kq * f_out; idx += kStagers) {
+                const int n = idx % f_out, k4 = (idx / f_out) << 2;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = k4 + j;
+                    float wv = 0.0f;
+                    if (kk < K) wv = __ldg(p.w + static_cast<size_t>(kk) * f_out + n);
+                    else if (kk - K < C && p.bias != nullptr) wv = __ldg(p.bias + static_cast<size_t>(kk - K) * f_out + n);
+                    hi[j] = tf32_hi(wv);
+                    lo[j] = wv - hi[j];
+                }
+                const uint32_t off = sw128_offset(n, k4, p.w_atom);
+                sts_f<4>(base + p.off_whi + off, hi);
+                sts_f<4>(base + p.off_wlo + off, lo);
+            }
+        }
+        fence_proxy_async_smem();   // B is read by the tensor core through the async proxy
+        if (warp < 4) {   // the unused row-sum columns K + C .. K + 7 of every Z buffer stay zero for the whole kernel
+            const uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int b = 0; b < p.zbufs; ++b) {
+                const uint32_t zc = tmem + (static_cast<uint32_t>(warp * 32) << 16) + p.tm_z + static_cast<uint32_t>(b * 2 * Kp);
+                tmem_st8(zc + K, z8);
+                tmem_st8(zc + Kp + K, z8);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kBlock - 32) : "memory");
+        tc_fence_after_sync();
+
+        if (warp < kAggWarps) {
+            // =============================== aggregation warps ===============================
+            const int grp = warp / kAggWarpsPerGroup;
+            const int wq = warp & 3;                               // TMEM lane quarter of this warp
+            const int phase = (warp % kAggWarpsPerGroup) >> 2;     // slab phase: slabs phase, phase + 2, ...
+            const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
+            const bool p1 = (s7 & 1u) != 0, p2 = (s7 & 2u) != 0, p4 = (s7 & 4u) != 0;
+            const int w = wq * 32 + lane;                          // tile row
+            const int gl = w / N, node = w - gl * N;
+            const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
+            for (int it = grp; it < tr.n_tiles; it += NG) {
+                const int s = it % S, b = it % p.zbufs;
+                const int ng = min(p.G, tr.n_graphs_cta - it * p.G);
+                const int rows = ng * N;
+                const int64_t r0 = (tr.g_begin + static_cast<int64_t>(it) * p.G) * C * N;
+                const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
+                mbar_wait(&bar_full[s], (it / S) & 1);
+                const uint32_t rp_addr = st + p.st_rp + 4u * static_cast<uint32_t>(r0 & 3);
+                const int e_first = static_cast<int>(lds_u32(rp_addr));
+                const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(ng * C * N)));
+                const int e_lo = e_first & ~3;
+                const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
+                const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);   // entry e at col_addr + 4 e
+                const uint32_t val_addr = st + p.st_val - 4u * static_cast<uint32_t>(e_lo);
+                if (it >= p.zbufs) mbar_wait(&bar_zempty[b], ((it / p.zbufs) - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t zc = tmem + lane_sel + p.tm_z + static_cast<uint32_t>(b * 2 * Kp);
+                const bool valid = w < rows;
+                for (int slab = phase; slab < p.n_slabs; slab += 2) {
+                    const int c = slab / p.slabs_per_ch, fs = slab - c * p.slabs_per_ch;
+                    int rs = e_first, re = e_first;   // rows beyond the tile: empty
+                    if (valid) {
+                        const uint32_t ra = rp_addr + 4u * static_cast<uint32_t>((gl * C + c) * N + node);
+                        rs = static_cast<int>(lds_u32(ra));
+                        re = static_cast<int>(lds_u32(ra + 4u));
+                    }
+                    const uint32_t xbase = st + static_cast<uint32_t>(gl * N) * pitch + static_cast<uint32_t>(fs) * 128u + (s7 << 4);
+                    float acc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+                    float deg = 0.0f;
+                    if (staged) gather_row<true>(acc, deg, rs, re, col_addr, val_addr, p.col, p.val, xbase, pitch);
+                    else gather_row<false>(acc, deg, rs, re, col_addr, val_addr, p.col, p.val, xbase, pitch);
+                    // undo the per-lane chunk rotation: block i holds chunk i ^ s7 -> three conditional butterflies
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float a0 = acc[4 * i + j], a1 = acc[4 * (i + 1) + j];
+                            acc[4 * i + j] = p1 ? a1 : a0;
+                            acc[4 * (i + 1) + j] = p1 ? a0 : a1;
+                        }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if ((i & 2) == 0)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float a0 = acc[4 * i + j], a1 = acc[4 * (i + 2) + j];
+                                acc[4 * i + j] = p2 ? a1 : a0;
+                                acc[4 * (i + 2) + j] = p2 ? a0 : a1;
+                            }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float a0 = acc[4 * i + j], a1 = acc[4 * (i + 4) + j];
+                            acc[4 * i + j] = p4 ? a1 : a0;
+                            acc[4 * (i + 4) + j] = p4 ? a0 : a1;
+                        }
+                    __syncwarp();   // the gather loop is divergent; tcgen05.st is warp-collective
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float h = tf32_hi(acc[i]);
+                        hi[i] = __float_as_uint(h);
+                        lo[i] = __float_as_uint(acc[i] - h);
+                    }
+                    tmem_st32(zc + static_cast<uint32_t>(slab * 32), hi);
+                    tmem_st32(zc + static_cast<uint32_t>(Kp + slab * 32), lo);
+                    if (fs == 0) {   // rowsum(A_c) rides in column K + c and meets bias_c in the contraction
+                        const float h = tf32_hi(deg);
+                        tmem_st1(zc + static_cast<uint32_t>(K + c), __float_as_uint(h));
+                        tmem_st1(zc + static_cast<uint32_t>(Kp + K + c), __float_as_uint(deg - h));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[s]);   // this warp is done reading the stage
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_zfull[b]);
+            }
+        } else if (warp == kWarpMma) {
+            // =============================== MMA issuer ===============================
+            if (lane == 0) {
+                const uint32_t idesc = umma_idesc_tf32(128, Np);
+                const uint64_t dwhi = umma_desc_sw128(base + p.off_whi), dwlo = umma_desc_sw128(base + p.off_wlo);
+                const uint32_t w_atom16 = p.w_atom >> 4;
+                const int ks = Kp >> 3;
+                for (int it = 0; it < tr.n_tiles; ++it) {
+                    const int b = it % p.zbufs, a = it & 1;
+                    mbar_wait(&bar_zfull[b], (it / p.zbufs) & 1);
+                    if (it >= 2) mbar_wait(&bar_tempty[a], ((it >> 1) - 1) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem + static_cast<uint32_t>(a * Np);
+                    const uint32_t zhi = tmem + p.tm_z + static_cast<uint32_t>(b * 2 * Kp), zlo = zhi + static_cast<uint32_t>(Kp);
+                    switch (ks) {
+                        case 5: issue_tile<5>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        case 9: issue_tile<9>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        case 13: issue_tile<13>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        case 17: issue_tile<17>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        default: issue_tile_loop(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16, ks);
+                    }
+                    umma_commit(&bar_zempty[b]);   // Z buffer b may be overwritten once these MMAs have read it
+                    umma_commit(&bar_tfull[a]);    // accumulator a is complete
+                }
+            }
+        } else {
+            // =============================== epilogue warps ===============================
+            const int wq = warp & 3;
+            const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
+            const uint32_t ys = base + p.off_ystage + static_cast<uint32_t>(warp - kWarpEpi0) * 4096u;   // 32 rows x 128 B
+            const uint32_t l7 = static_cast<uint32_t>(lane) & 7u;
+            const int n_cslabs = (f_out + 31) >> 5;
+            for (int it = 0; it < tr.n_tiles; ++it) {
+                const int a = it & 1;
+                const int ng = min(p.G, tr.n_graphs_cta - it * p.G);
+                const int rows = ng * N;
+                float* y_tile = p.y + (tr.g_begin + static_cast<int64_t>(it) * p.G) * N * f_out;
+                mbar_wait(&bar_tfull[a], (it >> 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(a * Np);
+                for (int cs = 0; cs < n_cslabs; ++cs) {
+                    float v0[16], v1[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
+                    tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
+                    if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
+                    tmem_ld_wait();
+                    tmem_ld_fence(v0);
+                    tmem_ld_fence(v1);
+                    if (cs == n_cslabs - 1) {   // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[a]);
+                    }
+                    act16_rt(v0, p.act);
+                    act16_rt(v1, p.act);
+                    // row `lane` of the warp's staging tile; 16-byte chunk c sits at position c ^ (lane & 7)
+                    const uint32_t yrow = ys + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
+                        const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
+                        sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
+                        sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                    }
+                    __syncwarp();
+                    // copy-out: each store instruction writes 4 rows x 128 contiguous bytes
+                    const uint32_t chunk = l7;
+                    const int colf = cs * 32 + static_cast<int>(chunk) * 4;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t row = static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3);
+                        float t[4];
+                        lds_f<4>(t, ys + row * 128u + ((chunk ^ (row & 7u)) << 4));
+                        const int wrow = wq * 32 + static_cast<int>(row);
+                        if (wrow < rows && colf < f_out)
+                            *reinterpret_cast<float4*>(y_tile + static_cast<size_t>(wrow) * f_out + colf) = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kWarpMma) tmem_dealloc(tmem, 512);
+}
+
+inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) shares the 227 KB
+
+bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
+    if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || f_out > 256 || C > 8) return false;
+    p.C = C; p.N = N; p.f_in = f_in; p.f_out = f_out; p.n_graphs = n_graphs;
+    p.K = C * f_in;
+    p.Kp = p.K + 8;
+    p.Np = static_cast<int>(up(f_out, 16));
+    p.n_slabs = p.K / 32;
+    p.slabs_per_ch = f_in / 32;
+    // TMEM: two accumulators + zbufs x (Zhi | Zlo)
+    p.tm_z = static_cast<uint32_t>(2 * p.Np);
+    if (2 * p.Np + 4 * p.Kp <= 512) p.zbufs = 2;
+    else if (2 * p.Np + 2 * p.Kp <= 512) p.zbufs = 1;
+    else return false;
+    p.G = std::max(1, 128 / N);
+    // contiguous graph ranges, one per CTA; small batches are spread over all SMs
+    const int64_t grid0 = std::min<int64_t>(kNumSMs, n_graphs);
+    const int64_t gpc = ceil_div<int64_t>(n_graphs, grid0);
+    if (gpc > (1 << 24)) return false;
+    p.graphs_per_cta = static_cast<int>(gpc);
+    if (p.G > p.graphs_per_cta) p.G = p.graphs_per_cta;
+    const uint32_t rows_max = static_cast<uint32_t>(p.G) * N;
+    const uint32_t n_watoms = (static_cast<uint32_t>(p.Kp) + 31) / 32;
+    p.w_atom = static_cast<uint32_t>(p.Np) * 128u;
+    uint32_t off = 0;
+    p.off_whi = off; off += n_watoms * p.w_atom;
+    p.off_wlo = off; off += n_watoms * p.w_atom;
+    p.off_ystage = off; off += kEpiWarps * 4096u;
+    p.off_stage = off;
+    p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C), 4));
+    p.st_rp = up(rows_max * f_in * 4u, 128);
+    p.st_col = p.st_rp + up((rows_max * C + 8) * 4u, 16);
+    p.st_val = p.st_col + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u;
+    p.stage_bytes = up(p.st_val + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u, 128);
+    p.n_stages = 0;
+    for (int st = kV4MaxStages; st >= 2; --st)
+        if (off + st * p.stage_bytes + 1024 <= static_cast<uint32_t>(kSmemMax)) { p.n_stages = st; break; }
+    if (p.n_stages == 0) return false;
+    p.smem_total = off + p.n_stages * p.stage_bytes + 1024;
+    return true;
+}
+
+}  // namespace
+
+bool fused_v4_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KGCN_FUSED_V4");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
+}
+
+bool fused_v4_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x, const float* y,
+                       const int32_t* rowptr, const int32_t* col, const float* val) {
+    V4Params p{};
+    if (!fused_v4_enabled() || !plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
+    return aligned16(x) && aligned16(y) && aligned16(rowptr) && aligned16(col) && aligned16(val) &&
+           n_graphs * static_cast<int64_t>(n_nodes) * channels < (1ll << 31);
+}
+
+static long long* g_dbg_v4 = nullptr;
+
+int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
+                              int n_nodes, const float* x, int f_in, const float* w, const float* bias, int f_out, int act,
+                              float* y, cudaStream_t st) {
+    V4Params p{};
+    KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: unsupported shape");
+    p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act;
+    p.dbg = g_dbg_v4;
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
+    static const int force_groups = [] {
+        const char* e = getenv("KGCN_V4_GROUPS");
+        return e ? atoi(e) : 0;
+    }();
+    const int groups = force_groups ? force_groups : (p.zbufs == 2 ? 2 : 1);
+    if (groups == 2 && p.zbufs == 2) {
+        auto kernel = graphconv_fused_v4_kernel<2>;
+        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
+        launch_pdl(kernel, grid, (2 * kAggWarpsPerGroup + kEpiWarps + 2) * 32, p.smem_total, st, p);
+    } else {
+        auto kernel = graphconv_fused_v4_kernel<1>;
+        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
+        launch_pdl(kernel, grid, (kAggWarpsPerGroup + kEpiWarps + 2) * 32, p.smem_total, st, p);
+    }
+    KGCN_LAUNCH_OK("graphconv_fused_v4_kernel");
+    return KGCN_OK;
+}
+
+}  // namespace kgcn
