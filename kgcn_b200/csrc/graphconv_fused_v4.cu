@@ -19,6 +19,8 @@
 //                    K + c and B carries bias_c in row K + c, so the epilogue is activation only.
 //   epilogue warps   tcgen05.ld the accumulator (double-buffered), activation, swizzled per-warp staging
 //                    tile, coalesced 16-byte global stores (four full 128-byte lines per store instruction).
+// 20 warps = 5 warpgroups (2 aggregation, 2 epilogue, 1 MMA + TMA); setmaxnreg moves registers from the
+// epilogue / MMA / TMA warpgroups to the aggregation threads (32 accumulators + 32 values in flight each).
 //
 // Z (in TMEM) and the accumulator are double-buffered, so aggregation of tile i+1, the contraction of
 // tile i and the epilogue of tile i-1 overlap; shared memory is left for a deep (3-4 tile) TMA ring.
@@ -35,8 +37,6 @@ namespace kgcn {
 namespace {
 
 constexpr int kV4MaxStages = 4;
-constexpr int kAggWarpsPerGroup = 8;    // 4 lane quarters x 2 slab phases
-constexpr int kEpiWarps = 4;
 
 struct V4Params {
     const int32_t* rowptr;
@@ -113,6 +113,21 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
     return r;
 }
+
+// tuning aid: per-role phase timers (lane 0 of the first warp of each role), enabled by kgcn_debug_v4_times
+struct PhaseTimer {
+    long long acc[6] = {0, 0, 0, 0, 0, 0};
+    long long last = 0;
+    bool on;
+    __device__ __forceinline__ explicit PhaseTimer(bool enabled) : on(enabled) { if (on) last = clock64(); }
+    __device__ __forceinline__ void mark(int ph) {
+        if (on) {
+            const long long now = clock64();
+            acc[ph] += now - last;
+            last = now;
+        }
+    }
+};
 
 // ---- tile bookkeeping shared by every role ----
 struct TileRange {
@@ -213,14 +228,41 @@ __device__ __noinline__ void issue_tile_loop(uint32_t d, uint32_t zhi, uint32_t 
     }
 }
 
-// NG aggregation groups of 8 warps (group g takes the tiles with index % NG == g)
-template <int NG>
-__global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32, 1) graphconv_fused_v4_kernel(const V4Params p) {
-    constexpr int kAggWarps = NG * kAggWarpsPerGroup;
-    constexpr int kWarpEpi0 = kAggWarps;
-    constexpr int kWarpMma = kAggWarps + kEpiWarps;
-    constexpr int kWarpTma = kWarpMma + 1;
-    constexpr int kBlock = (kWarpTma + 1) * 32;
+// Warp roles.  20 warps = 5 warpgroups; registers are re-balanced per warpgroup with setmaxnreg (the
+// gather threads hold a 32-float accumulator block plus 32 floats in flight).
+constexpr int kAggWarps = 8;      // warps 0-7   (warpgroups 0-1): 4 TMEM lane quarters x 2 slab phases
+constexpr int kEpiWarps = 8;      // warps 8-15  (warpgroups 2-3): 4 TMEM lane quarters x 2 column phases
+constexpr int kWarpEpi0 = 8;
+constexpr int kWarpMma = 16;      // warpgroup 4: MMA issuer, two idle warps, TMA producer
+constexpr int kWarpTma = 19;
+constexpr int kBlock = 20 * 32;
+constexpr int kRegsAgg = 128, kRegsEpi = 80, kRegsMisc = 56;
+
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// ring position + mbarrier phase bit of a role walking a ring of `n` slots
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1u;
+        }
+    }
+};
+// waits that are not latency-critical back off, so the polling does not take issue slots from the working warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {   // no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
     __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
@@ -232,14 +274,18 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
     const int C = p.C, N = p.N, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp, Np = p.Np, S = p.n_stages;
     const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
     const TileRange tr = cta_range(p);
+    const int n_tiles = tr.n_tiles;
+    const int last_ng = tr.n_graphs_cta - (n_tiles - 1) * p.G;   // graphs in the CTA's last tile
+    const long long t_start = p.dbg ? clock64() : 0;
+    long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
 
     if (tid == 0) {
         for (int i = 0; i < kV4MaxStages; ++i) {
             mbar_init(&bar_full[i], 1);
-            mbar_init(&bar_empty[i], kAggWarpsPerGroup);
+            mbar_init(&bar_empty[i], kAggWarps);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_zfull[i], kAggWarpsPerGroup);
+            mbar_init(&bar_zfull[i], kAggWarps);
             mbar_init(&bar_zempty[i], 1);
             mbar_init(&bar_tfull[i], 1);
             mbar_init(&bar_tempty[i], kEpiWarps);
@@ -260,52 +306,72 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
 
     if (warp == kWarpTma) {
         // =============================== TMA producer ===============================
+        reg_dec<kRegsMisc>();
         if (lane == 0) {
-            for (int it = 0; it < tr.n_tiles; ++it) {
-                const int s = it % S;
-                if (it >= S) mbar_wait(&bar_empty[s], ((it / S) - 1) & 1);
+            PhaseTimer pt(dbg != nullptr);
+            Ring rs;
+            for (int it = 0; it < n_tiles; ++it) {
+                pt.mark(1);
+                mbar_wait_relaxed(&bar_empty[rs.idx], rs.phase ^ 1u);   // a fresh barrier passes the parity-1 wait
+                pt.mark(0);
                 const int64_t g0 = tr.g_begin + static_cast<int64_t>(it) * p.G;
-                const int ng = min(p.G, tr.n_graphs_cta - it * p.G);
+                const int ng = (it == n_tiles - 1) ? last_ng : p.G;
                 const int64_t r0 = g0 * C * N;
                 const int rows_csr = ng * C * N;
-                const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
+                unsigned char* st = gen + p.off_stage + static_cast<size_t>(rs.idx) * p.stage_bytes;
+                uint64_t* full = &bar_full[rs.idx];
+                // the feature rows and the row extents do not depend on anything: they go first; the column / value
+                // slices need the tile's first and last entry index (one dependent global load)
                 const int64_t rp_lo = r0 & ~3ll;
                 const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
+                const uint32_t x_bytes = static_cast<uint32_t>(ng) * static_cast<uint32_t>(N) * pitch;
+                mbar_expect_tx_only(full, x_bytes + 4u * rp_cnt);
+                bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
+                bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
+                const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
                 const int32_t e_lo = e_first & ~3;
                 const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
-                const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap);
-                unsigned char* st = gen + p.off_stage + static_cast<size_t>(s) * p.stage_bytes;
-                const uint32_t x_bytes = static_cast<uint32_t>(ng) * static_cast<uint32_t>(N) * pitch;
-                mbar_expect_tx(&bar_full[s], x_bytes + 4u * rp_cnt + ((staged && e_cnt) ? 8u * e_cnt : 0u));
-                bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, &bar_full[s]);
-                if (staged && e_cnt) {
-                    bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, &bar_full[s]);
-                    bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, &bar_full[s]);
+                const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap) && e_cnt != 0;
+                mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the one arrival of the phase
+                if (staged) {
+                    bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
+                    bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
                 }
-                bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, &bar_full[s]);
+                rs.advance(S);
             }
+            if (dbg) dbg[10] = pt.acc[0];
         }
     } else {
         // B operand [W ; bias] -> (hi, lo), K-major SWIZZLE_128B: B row n = output column n, k = c * f_in + f for
         // the weights, k = K + c for bias_c (it meets rowsum(A_c) in column K + c of Z).  All non-producer warps.
         {
             constexpr int kStagers = kBlock - 32;
-            const int kq = Kp >> 2;
-            for (int idx = tid; idx < kq * f_out; idx += kStagers) {
-                const int n = idx % f_out, k4 = (idx / f_out) << 2;
-                float hi[4], lo[4];
+            const int nq_n = f_out >> 2, kq_n = Kp >> 2;   // one thread per 4 (k) x 4 (n) block: 4 coalesced 16-byte loads
+            for (int idx = tid; idx < kq_n * nq_n; idx += kStagers) {
+                const int n0 = (idx % nq_n) << 2, k4 = (idx / nq_n) << 2;
+                float4 r[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int kk = k4 + j;
-                    float wv = 0.0f;
-                    if (kk < K) wv = __ldg(p.w + static_cast<size_t>(kk) * f_out + n);
-                    else if (kk - K < C && p.bias != nullptr) wv = __ldg(p.bias + static_cast<size_t>(kk - K) * f_out + n);
-                    hi[j] = tf32_hi(wv);
-                    lo[j] = wv - hi[j];
+                    r[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (kk < K) r[j] = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(kk) * f_out + n0));
+                    else if (kk - K < C && p.bias != nullptr)
+                        r[j] = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(kk - K) * f_out + n0));
                 }
-                const uint32_t off = sw128_offset(n, k4, p.w_atom);
-                sts_f<4>(base + p.off_whi + off, hi);
-                sts_f<4>(base + p.off_wlo + off, lo);
+                const float t[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x}, {r[0].y, r[1].y, r[2].y, r[3].y},
+                                       {r[0].z, r[1].z, r[2].z, r[3].z}, {r[0].w, r[1].w, r[2].w, r[3].w}};
+#pragma unroll
+                for (int nn = 0; nn < 4; ++nn) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        hi[j] = tf32_hi(t[nn][j]);
+                        lo[j] = t[nn][j] - hi[j];
+                    }
+                    const uint32_t off = sw128_offset(n0 + nn, k4, p.w_atom);
+                    sts_f<4>(base + p.off_whi + off, hi);
+                    sts_f<4>(base + p.off_wlo + off, lo);
+                }
             }
         }
         fence_proxy_async_smem();   // B is read by the tensor core through the async proxy
@@ -324,47 +390,61 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
 
         if (warp < kAggWarps) {
             // =============================== aggregation warps ===============================
-            const int grp = warp / kAggWarpsPerGroup;
-            const int wq = warp & 3;                               // TMEM lane quarter of this warp
-            const int phase = (warp % kAggWarpsPerGroup) >> 2;     // slab phase: slabs phase, phase + 2, ...
+            reg_inc<kRegsAgg>();
+            const int wq = warp & 3;          // TMEM lane quarter of this warp
+            const int phase = warp >> 2;      // slab phase: slabs phase, phase + 2, ...
             const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
             const bool p1 = (s7 & 1u) != 0, p2 = (s7 & 2u) != 0, p4 = (s7 & 4u) != 0;
-            const int w = wq * 32 + lane;                          // tile row
+            const int w = wq * 32 + lane;     // tile row = TMEM lane
             const int gl = w / N, node = w - gl * N;
             const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
-            for (int it = grp; it < tr.n_tiles; it += NG) {
-                const int s = it % S, b = it % p.zbufs;
-                const int ng = min(p.G, tr.n_graphs_cta - it * p.G);
-                const int rows = ng * N;
-                const int64_t r0 = (tr.g_begin + static_cast<int64_t>(it) * p.G) * C * N;
-                const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
-                mbar_wait(&bar_full[s], (it / S) & 1);
-                const uint32_t rp_addr = st + p.st_rp + 4u * static_cast<uint32_t>(r0 & 3);
+            const int full_rows = p.G * N;
+            const uint32_t r0_step = static_cast<uint32_t>(p.G * C * N);
+            uint32_t r0_lo = static_cast<uint32_t>((tr.g_begin * C * N) & 3);
+            const uint32_t z_stride = static_cast<uint32_t>(2 * Kp);
+            const uint32_t row_rp_off = 4u * static_cast<uint32_t>(gl * C * N + node);
+            const uint32_t row_x_off = static_cast<uint32_t>(gl * N) * pitch + (s7 << 4);
+            Ring rs, rz;
+            PhaseTimer pt(dbg != nullptr && warp == 0 && lane == 0);
+            if (pt.on) dbg[12] = pt.last - t_start;
+            for (int it = 0; it < n_tiles; ++it) {
+                const bool last = it == n_tiles - 1;
+                const int rows = last ? last_ng * N : full_rows;
+                const int rows_csr = last ? last_ng * C * N : static_cast<int>(r0_step);
+                const uint32_t st = base + p.off_stage + static_cast<uint32_t>(rs.idx) * p.stage_bytes;
+                mbar_wait(&bar_full[rs.idx], rs.phase);
+                pt.mark(0);
+                const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
                 const int e_first = static_cast<int>(lds_u32(rp_addr));
-                const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(ng * C * N)));
+                const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
                 const int e_lo = e_first & ~3;
                 const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
                 const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);   // entry e at col_addr + 4 e
                 const uint32_t val_addr = st + p.st_val - 4u * static_cast<uint32_t>(e_lo);
-                if (it >= p.zbufs) mbar_wait(&bar_zempty[b], ((it / p.zbufs) - 1) & 1);
-                tc_fence_after_sync();
-                const uint32_t zc = tmem + lane_sel + p.tm_z + static_cast<uint32_t>(b * 2 * Kp);
                 const bool valid = w < rows;
+
+                mbar_wait(&bar_zempty[rz.idx], rz.phase ^ 1u);
+                tc_fence_after_sync();
+                pt.mark(1);
+                const uint32_t zc = tmem + lane_sel + p.tm_z + static_cast<uint32_t>(rz.idx) * z_stride;
+                const uint32_t row_rp = rp_addr + row_rp_off;
+                const uint32_t row_x = st + row_x_off;
+                int c = 0, fs = phase;
                 for (int slab = phase; slab < p.n_slabs; slab += 2) {
-                    const int c = slab / p.slabs_per_ch, fs = slab - c * p.slabs_per_ch;
-                    int rs = e_first, re = e_first;   // rows beyond the tile: empty
+                    while (fs >= p.slabs_per_ch) { fs -= p.slabs_per_ch; ++c; }
+                    int rs_ = e_first, re_ = e_first;   // rows beyond the tile: empty
                     if (valid) {
-                        const uint32_t ra = rp_addr + 4u * static_cast<uint32_t>((gl * C + c) * N + node);
-                        rs = static_cast<int>(lds_u32(ra));
-                        re = static_cast<int>(lds_u32(ra + 4u));
+                        const uint32_t ra = row_rp + 4u * static_cast<uint32_t>(c * N);
+                        rs_ = static_cast<int>(lds_u32(ra));
+                        re_ = static_cast<int>(lds_u32(ra + 4u));
                     }
-                    const uint32_t xbase = st + static_cast<uint32_t>(gl * N) * pitch + static_cast<uint32_t>(fs) * 128u + (s7 << 4);
+                    const uint32_t xbase = row_x + static_cast<uint32_t>(fs) * 128u;
                     float acc[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
                     float deg = 0.0f;
-                    if (staged) gather_row<true>(acc, deg, rs, re, col_addr, val_addr, p.col, p.val, xbase, pitch);
-                    else gather_row<false>(acc, deg, rs, re, col_addr, val_addr, p.col, p.val, xbase, pitch);
+                    if (staged) gather_row<true>(acc, deg, rs_, re_, col_addr, val_addr, p.col, p.val, xbase, pitch);
+                    else gather_row<false>(acc, deg, rs_, re_, col_addr, val_addr, p.col, p.val, xbase, pitch);
                     // undo the per-lane chunk rotation: block i holds chunk i ^ s7 -> three conditional butterflies
 #pragma unroll
                     for (int i = 0; i < 8; i += 2)
@@ -392,12 +472,14 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
                             acc[4 * (i + 4) + j] = p4 ? a0 : a1;
                         }
                     __syncwarp();   // the gather loop is divergent; tcgen05.st is warp-collective
+                    pt.mark(2);
+                    // tf32 split by truncation: hi keeps the top 19 bits, lo = x - hi is exact (|lo| < 2^-10 |x|) and is
+                    // itself read as tf32 by the tensor core -> 21 mantissa bits survive, 2 instructions per element
                     uint32_t hi[32], lo[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float h = tf32_hi(acc[i]);
-                        hi[i] = __float_as_uint(h);
-                        lo[i] = __float_as_uint(acc[i] - h);
+                        hi[i] = __float_as_uint(acc[i]) & 0xFFFFE000u;
+                        lo[i] = __float_as_uint(acc[i] - __uint_as_float(hi[i]));
                     }
                     tmem_st32(zc + static_cast<uint32_t>(slab * 32), hi);
                     tmem_st32(zc + static_cast<uint32_t>(Kp + slab * 32), lo);
@@ -406,55 +488,90 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
                         tmem_st1(zc + static_cast<uint32_t>(K + c), __float_as_uint(h));
                         tmem_st1(zc + static_cast<uint32_t>(Kp + K + c), __float_as_uint(deg - h));
                     }
+                    fs += 2;
                 }
+                pt.mark(3);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_empty[s]);   // this warp is done reading the stage
+                if (lane == 0) mbar_arrive(&bar_empty[rs.idx]);   // this warp is done reading the stage
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_zfull[b]);
+                if (lane == 0) mbar_arrive(&bar_zfull[rz.idx]);
+                pt.mark(4);
+                rs.advance(S);
+                rz.advance(p.zbufs);
+                r0_lo += r0_step;
             }
-        } else if (warp == kWarpMma) {
-            // =============================== MMA issuer ===============================
-            if (lane == 0) {
+            if (pt.on) {
+                for (int i = 0; i < 5; ++i) dbg[i] = pt.acc[i];
+                dbg[11] = clock64() - t_start;
+                dbg[13] = n_tiles;
+            }
+        } else if (warp >= kWarpMma) {
+            reg_dec<kRegsMisc>();
+            if (warp == kWarpMma) {
+                // =============================== MMA issuer ===============================
+                // the whole warp walks the tile loop converged; one elected lane issues (operands stay on the uniform datapath)
                 const uint32_t idesc = umma_idesc_tf32(128, Np);
                 const uint64_t dwhi = umma_desc_sw128(base + p.off_whi), dwlo = umma_desc_sw128(base + p.off_wlo);
                 const uint32_t w_atom16 = p.w_atom >> 4;
                 const int ks = Kp >> 3;
-                for (int it = 0; it < tr.n_tiles; ++it) {
-                    const int b = it % p.zbufs, a = it & 1;
-                    mbar_wait(&bar_zfull[b], (it / p.zbufs) & 1);
-                    if (it >= 2) mbar_wait(&bar_tempty[a], ((it >> 1) - 1) & 1);
+                Ring rz, ra;
+                PhaseTimer pt(dbg != nullptr && lane == 0);
+                for (int it = 0; it < n_tiles; ++it) {
+                    mbar_wait(&bar_zfull[rz.idx], rz.phase);
+                    pt.mark(0);
+                    mbar_wait(&bar_tempty[ra.idx], ra.phase ^ 1u);
                     tc_fence_after_sync();
-                    const uint32_t d = tmem + static_cast<uint32_t>(a * Np);
-                    const uint32_t zhi = tmem + p.tm_z + static_cast<uint32_t>(b * 2 * Kp), zlo = zhi + static_cast<uint32_t>(Kp);
-                    switch (ks) {
-                        case 5: issue_tile<5>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
-                        case 9: issue_tile<9>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
-                        case 13: issue_tile<13>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
-                        case 17: issue_tile<17>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
-                        default: issue_tile_loop(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16, ks);
+                    pt.mark(1);
+                    const uint32_t d = tmem + static_cast<uint32_t>(ra.idx * Np);
+                    const uint32_t zhi = tmem + p.tm_z + static_cast<uint32_t>(rz.idx * 2 * Kp), zlo = zhi + static_cast<uint32_t>(Kp);
+                    __syncwarp();
+                    if (elect_one()) {
+                        switch (ks) {
+                            case 5: issue_tile<5>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                            case 9: issue_tile<9>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                            case 13: issue_tile<13>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                            case 17: issue_tile<17>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                            default: issue_tile_loop(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16, ks);
+                        }
+                        umma_commit(&bar_zempty[rz.idx]);   // Z buffer may be overwritten once these MMAs have read it
+                        umma_commit(&bar_tfull[ra.idx]);    // accumulator is complete
                     }
-                    umma_commit(&bar_zempty[b]);   // Z buffer b may be overwritten once these MMAs have read it
-                    umma_commit(&bar_tfull[a]);    // accumulator a is complete
+                    __syncwarp();
+                    pt.mark(2);
+                    rz.advance(p.zbufs);
+                    ra.advance(2);
                 }
+                if (pt.on) for (int i = 0; i < 3; ++i) dbg[5 + i] = pt.acc[i];
             }
         } else {
             // =============================== epilogue warps ===============================
-            const int wq = warp & 3;
+            // warp (q, h): TMEM lanes 32 q .. 32 q + 31, 32-column slabs h, h + 2, ...  The activated 32 x 32 block goes
+            // through a swizzled per-warp staging tile and leaves as 16-byte stores, 128 contiguous bytes per row.
+            reg_dec<kRegsEpi>();
+            const int e = warp - kWarpEpi0;
+            const int wq = e & 3, h = e >> 2;
             const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
-            const uint32_t ys = base + p.off_ystage + static_cast<uint32_t>(warp - kWarpEpi0) * 4096u;   // 32 rows x 128 B
+            const uint32_t ys = base + p.off_ystage + static_cast<uint32_t>(e) * 4096u;   // 32 rows x 128 B
             const uint32_t l7 = static_cast<uint32_t>(lane) & 7u;
-            const int n_cslabs = (f_out + 31) >> 5;
-            for (int it = 0; it < tr.n_tiles; ++it) {
-                const int a = it & 1;
-                const int ng = min(p.G, tr.n_graphs_cta - it * p.G);
-                const int rows = ng * N;
-                float* y_tile = p.y + (tr.g_begin + static_cast<int64_t>(it) * p.G) * N * f_out;
-                mbar_wait(&bar_tfull[a], (it >> 1) & 1);
+            const int n_cslabs = (Np + 31) >> 5;
+            const int full_rows = p.G * N;
+            const uint32_t yrow = ys + static_cast<uint32_t>(lane) * 128u;   // this lane's staging row; chunk c at c ^ (lane & 7)
+            const uint32_t ysrc = ys + (static_cast<uint32_t>(lane) >> 3) * 128u;   // copy-out: rows 4 k + lane / 8, chunk lane & 7
+            const int colq = static_cast<int>(l7) * 4;
+            const int row0 = wq * 32 + (lane >> 3);   // first of the 8 tile rows (stride 4) this lane copies out
+            float* y_tile = p.y + tr.g_begin * N * f_out + static_cast<size_t>(row0) * f_out + colq;
+            const size_t y_step = static_cast<size_t>(full_rows) * f_out;
+            Ring ra;
+            PhaseTimer pt(dbg != nullptr && e == 0 && lane == 0);
+            for (int it = 0; it < n_tiles; ++it) {
+                const int rows = (it == n_tiles - 1) ? last_ng * N : full_rows;
+                mbar_wait_relaxed(&bar_tfull[ra.idx], ra.phase);
                 tc_fence_after_sync();
-                const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(a * Np);
-                for (int cs = 0; cs < n_cslabs; ++cs) {
+                pt.mark(0);
+                const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ra.idx * Np);
+                for (int cs = h; cs < n_cslabs; cs += 2) {
                     float v0[16], v1[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
@@ -463,15 +580,17 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
                     tmem_ld_wait();
                     tmem_ld_fence(v0);
                     tmem_ld_fence(v1);
-                    if (cs == n_cslabs - 1) {   // accumulator fully read: hand it back to the MMA warp
+                    pt.mark(2);
+                    if (cs + 2 >= n_cslabs) {   // this warp has read all its columns: hand the accumulator back
                         tc_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_tempty[a]);
+                        if (lane == 0) mbar_arrive(&bar_tempty[ra.idx]);
                     }
                     act16_rt(v0, p.act);
                     act16_rt(v1, p.act);
-                    // row `lane` of the warp's staging tile; 16-byte chunk c sits at position c ^ (lane & 7)
-                    const uint32_t yrow = ys + static_cast<uint32_t>(lane) * 128u;
+                    tmem_ld_fence(v0);
+                    tmem_ld_fence(v1);
+                    pt.mark(3);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
@@ -480,20 +599,32 @@ __global__ void __launch_bounds__((NG * kAggWarpsPerGroup + kEpiWarps + 2) * 32,
                         sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
                     }
                     __syncwarp();
+                    pt.mark(4);
                     // copy-out: each store instruction writes 4 rows x 128 contiguous bytes
-                    const uint32_t chunk = l7;
-                    const int colf = cs * 32 + static_cast<int>(chunk) * 4;
+                    const bool col_ok = cs * 32 + colq < f_out;
+                    float* ycs = y_tile + cs * 32;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const uint32_t row = static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3);
+                        const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
                         float t[4];
-                        lds_f<4>(t, ys + row * 128u + ((chunk ^ (row & 7u)) << 4));
-                        const int wrow = wq * 32 + static_cast<int>(row);
-                        if (wrow < rows && colf < f_out)
-                            *reinterpret_cast<float4*>(y_tile + static_cast<size_t>(wrow) * f_out + colf) = make_float4(t[0], t[1], t[2], t[3]);
+                        lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                        if (row0 + 4 * k < rows && col_ok)
+                            *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * f_out) = make_float4(t[0], t[1], t[2], t[3]);
                     }
                     __syncwarp();
+                    pt.mark(5);
                 }
+                if (h >= n_cslabs) {   // no columns for this warp (f_out <= 32): it still takes part in the hand-back
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[ra.idx]);
+                }
+                ra.advance(2);
+                y_tile += y_step;
+            }
+            if (pt.on) {
+                dbg[8] = pt.acc[0]; dbg[9] = pt.acc[1]; dbg[14] = pt.acc[2]; dbg[15] = pt.acc[3];
+                p.dbg[148 * 16 + blockIdx.x * 2] = pt.acc[4]; p.dbg[148 * 16 + blockIdx.x * 2 + 1] = pt.acc[5];
             }
         }
     }
@@ -559,10 +690,10 @@ bool fused_v4_enabled() {
 }
 
 bool fused_v4_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x, const float* y,
-                       const int32_t* rowptr, const int32_t* col, const float* val) {
+                       const int32_t* rowptr, const int32_t* col, const float* val, const float* w, const float* bias) {
     V4Params p{};
     if (!fused_v4_enabled() || !plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
-    return aligned16(x) && aligned16(y) && aligned16(rowptr) && aligned16(col) && aligned16(val) &&
+    return aligned16(x) && aligned16(y) && aligned16(rowptr) && aligned16(col) && aligned16(val) && aligned16(w) && aligned16(bias) &&
            n_graphs * static_cast<int64_t>(n_nodes) * channels < (1ll << 31);
 }
 
@@ -576,22 +707,14 @@ int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const f
     p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act;
     p.dbg = g_dbg_v4;
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
-    static const int force_groups = [] {
-        const char* e = getenv("KGCN_V4_GROUPS");
-        return e ? atoi(e) : 0;
-    }();
-    const int groups = force_groups ? force_groups : (p.zbufs == 2 ? 2 : 1);
-    if (groups == 2 && p.zbufs == 2) {
-        auto kernel = graphconv_fused_v4_kernel<2>;
-        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-        launch_pdl(kernel, grid, (2 * kAggWarpsPerGroup + kEpiWarps + 2) * 32, p.smem_total, st, p);
-    } else {
-        auto kernel = graphconv_fused_v4_kernel<1>;
-        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-        launch_pdl(kernel, grid, (kAggWarpsPerGroup + kEpiWarps + 2) * 32, p.smem_total, st, p);
-    }
+    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
+    launch_pdl(graphconv_fused_v4_kernel, grid, kBlock, p.smem_total, st, p);
     KGCN_LAUNCH_OK("graphconv_fused_v4_kernel");
     return KGCN_OK;
 }
 
 }  // namespace kgcn
+
+// Tuning hook (not part of the documented ABI): device buffer of [148][16] + [148][2] int64 phase cycle sums of the v4
+// kernel (aggregation warp 0, MMA warp, epilogue warp 0, producer; see tools/phase_times_v4.py for the slot names).
+extern "C" void kgcn_debug_v4_times(long long* device_buffer) { kgcn::g_dbg_v4 = device_buffer; }
