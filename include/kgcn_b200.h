@@ -196,6 +196,56 @@ int kgcn_gather_fwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32
 int kgcn_gather_bwd_f32(const float* dout, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GraphMaxPooling (kgcn/layers.py:122-153): per molecule, channel and feature the reference forms the sparse
+ * matrix A * x[:, k] (column j scaled by x[j, k]), densifies it (tf.sparse_tensor_to_dense: absent entries
+ * become 0) and takes tf.reduce_max over axis 1; channels are summed (tf.add_n):
+ *   y[g,i,k] = sum_c max( {A_c[i,j] * x[g,j,k] : (i,j) stored} U {0 if row i stores fewer than n_nodes entries} ).
+ * workspace (kgcn_maxpool_workspace_bytes; NULL for inference) receives the per-channel maxima and tie counts
+ * the backward needs.  Backward = TF's gradient of that op chain (ties share the gradient evenly, implicit
+ * zeros included) as a gather over the TRANSPOSED BatchedCSR: deterministic.  Square matrices (n_nodes x n_nodes).
+ */
+size_t kgcn_maxpool_workspace_bytes(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t feat);
+int kgcn_maxpool_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                         int32_t channels, int32_t n_nodes, const float* x, int32_t feat, float* y,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int kgcn_maxpool_bwd_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                         int32_t channels, int32_t n_nodes, const float* x, int32_t feat, const float* dy,
+                         const void* workspace, size_t workspace_bytes, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-molecule readout of the block-diagonal model (example_model/sparse.py:79-90: tf.scan of reduce_sum over
+ * the row range of every molecule): out[m,:] = sum of rows start[m] .. start[m]+size[m]-1 of x [rows, feat].
+ * start / size: device int64[n_segments].  Backward broadcasts dout[m,:] to those rows (rows outside every
+ * segment are left untouched).
+ */
+int kgcn_segment_sum_fwd_f32(const float* x, const int64_t* start, const int64_t* size, int64_t n_segments,
+                             int32_t feat, float* out, void* stream);
+int kgcn_segment_sum_bwd_f32(const float* dout, const int64_t* start, const int64_t* size, int64_t n_segments,
+                             int32_t feat, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GraphBatchNormalization (kgcn/layers.py:170-220, kgcn/legacy/layers.py:170-218): per-feature
+ *   y = gamma * (x - mean) / sqrt(var + eps) + beta   on the first enabled_node_nums[g] rows of molecule g,
+ * exact zeros on the rest (the extract / normalise / split / pad sequence of layers.py:202-214);
+ * enabled_node_nums == NULL: every row (layers.py:216-219).
+ * mode 0: mean / var are INPUTS (moving statistics -- what the Keras layer uses under the reference trainer);
+ * mode 1: mean / var are OUTPUTS, the batch statistics over the enabled rows (biased variance; the legacy
+ * tf.layers.batch_normalization(training=True) variant).  The legacy variant without enabled_node_nums
+ * normalises per (node, feature) pair over the batch: call with n_nodes = 1, feat = N * F.
+ * gamma / beta may be NULL (1 / 0).  Backward returns dx (may be NULL), dgamma, dbeta (may be NULL).
+ * workspace: kgcn_graph_bn_workspace_bytes (+ 2 * feat floats for the backward).
+ */
+size_t kgcn_graph_bn_workspace_bytes(int64_t n_graphs, int32_t feat);
+int kgcn_graph_bn_fwd_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat,
+                          const int32_t* enabled_node_nums, const float* gamma, const float* beta, float* mean,
+                          float* var, float eps, int32_t mode, float* y, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int kgcn_graph_bn_bwd_f32(const float* x, const float* dy, int64_t n_graphs, int32_t n_nodes, int32_t feat,
+                          const int32_t* enabled_node_nums, const float* gamma, const float* mean, const float* var,
+                          float eps, int32_t mode, float* dx, float* dgamma, float* dbeta, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Step-loop helpers (the minimal trainer around the layers; kgcn/core.py:121-127, 267-269).
  *
  * Readout head of the shipped classifiers (example_model/model.py:56-69):

@@ -76,6 +76,14 @@ SIGNATURES = {
     "kgcn_graphdense_bwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_gather_fwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "kgcn_gather_bwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "kgcn_maxpool_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "kgcn_maxpool_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "kgcn_maxpool_bwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp, _vp]),
+    "kgcn_segment_sum_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "kgcn_segment_sum_bwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "kgcn_graph_bn_workspace_bytes": (_sz, [_i64, _i32]),
+    "kgcn_graph_bn_fwd_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, _i32, _vp, _vp, _sz, _vp]),
+    "kgcn_graph_bn_bwd_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, ctypes.c_float, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_readout_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "kgcn_readout_xent_f32": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i64, ctypes.c_float, _vp, _vp]),

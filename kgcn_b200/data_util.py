@@ -134,3 +134,63 @@ def build_adjs(data, config):
     if config.get("normalize_adj_flag", False):
         adjs = normalize_adj(adjs)
     return adjs, np.array(enabled, dtype=np.int32), len(adjs[0])
+
+
+def construct_batched_adjacency_and_feature_matrices(size, adj_row, adj_column, adj_values, adj_elem_len, adj_degrees,
+                                                     feature_row, feature_column, feature_values, feature_elem_len,
+                                                     input_dim, max_degree=5, normalize=True, split_adj=False):
+    """Block-diagonal batch of the reference's tfrecords path (kgcn/data_util.py:698-845), as host numpy.
+
+    The reference builds this with a tf.scan per batch; here it is two prefix sums.  ``size[m]`` nodes per
+    molecule, ``adj_elem_len[m]`` stored entries per molecule, rows / columns local to their molecule.  Returns
+    ``(channels, features)``: ``channels`` is a list of ``(indices int64 [nnz, 2], values float32 [nnz],
+    [n, n])`` triples over the ``n = sum(size)`` rows of the batch (one triple; ``max_degree + 1`` with
+    ``split_adj``: entries whose ``adj_degrees`` clipped to ``[0, max_degree]`` equals 1..max_degree, then the
+    identity, :803-821), ``features`` the dense ``[n, input_dim]`` matrix of the stacked sparse feature entries
+    (:832-845).  ``normalize`` (:790-802): ``A[i, j] / sqrt(d[j]) / sqrt(d[i])`` with ``d`` = column sums, in
+    float32 like the TensorFlow ops."""
+    size = np.asarray(size, np.int64).reshape(-1)
+    adj_elem_len = np.asarray(adj_elem_len, np.int64).reshape(-1)
+    adj_row = np.asarray(adj_row, np.int64).reshape(-1)
+    adj_column = np.asarray(adj_column, np.int64).reshape(-1)
+    adj_values = np.asarray(adj_values, np.float32).reshape(-1)
+    if size.shape != adj_elem_len.shape or adj_elem_len.sum() != adj_row.shape[0] or adj_row.shape != adj_column.shape:
+        raise DataLoadError("block-diagonal batch: size / adj_elem_len / adj_row / adj_column are inconsistent")
+    n = int(size.sum())
+    offset = np.cumsum(size) - size                       # tf.cumsum(size, exclusive=True), :761
+    entry_off = np.repeat(offset, adj_elem_len)            # every entry of molecule m is shifted by offset[m], :764-789
+    diagonal_row, diagonal_col = adj_row + entry_off, adj_column + entry_off
+    if (adj_row < 0).any() or (adj_column < 0).any() or (adj_row >= np.repeat(size, adj_elem_len)).any() or \
+            (adj_column >= np.repeat(size, adj_elem_len)).any():
+        raise DataLoadError("block-diagonal batch: adjacency index outside its molecule")
+    shape = [n, n]
+    if normalize:
+        degree_hat = np.zeros(n, np.float32)
+        np.add.at(degree_hat, diagonal_col, adj_values)    # tf.sparse.reduce_sum(axis=0): column sums
+        root = np.sqrt(degree_hat, dtype=np.float32)
+        values = ((adj_values / root[diagonal_col]).astype(np.float32) / root[diagonal_row]).astype(np.float32)
+        channels = [(np.stack([diagonal_row, diagonal_col], 1), values, shape)]
+    elif split_adj:
+        deg = np.clip(np.asarray(adj_degrees, np.int64).reshape(-1), 0, max_degree)
+        channels = []
+        for degree in range(1, max_degree + 1):
+            keep = deg == degree
+            channels.append((np.stack([diagonal_row[keep], diagonal_col[keep]], 1), adj_values[keep], shape))
+        eye = np.arange(n, dtype=np.int64)
+        channels.append((np.stack([eye, eye], 1), np.ones(n, np.float32), shape))   # connection to self, :821
+    else:
+        channels = [(np.stack([diagonal_row, diagonal_col], 1), adj_values, shape)]
+
+    feature_elem_len = np.asarray(feature_elem_len, np.int64).reshape(-1)
+    feature_row = np.asarray(feature_row, np.int64).reshape(-1)
+    feature_column = np.asarray(feature_column, np.int64).reshape(-1)
+    feature_values = np.asarray(feature_values).reshape(-1)
+    stacked_row = feature_row + np.repeat(offset, feature_elem_len)
+    if (feature_column < 0).any() or (feature_column >= input_dim).any() or (stacked_row >= n).any():
+        raise DataLoadError("block-diagonal batch: feature index out of range")
+    flat = stacked_row * int(input_dim) + feature_column
+    if np.unique(flat).shape[0] != flat.shape[0]:      # tf.sparse_tensor_to_dense rejects repeated indices
+        raise DataLoadError("block-diagonal batch: repeated feature index")
+    features = np.zeros((n, int(input_dim)), feature_values.dtype)
+    features[stacked_row, feature_column] = feature_values
+    return channels, features

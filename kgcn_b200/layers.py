@@ -224,21 +224,25 @@ class GraphDense(Layer):
 
 
 class GraphBatchNormalization(Layer):
-    """Keras ``BatchNormalization`` over node rows as the reference trainer runs it (layers.py:170-220).
+    """Batch normalisation over node rows (kgcn/layers.py:170-220), kernels ``kgcn_graph_bn_{fwd,bwd}_f32``.
 
-    [TF-semantics, SURVEY.md Appendix A.10] The layer is called without ``training=`` in graph mode, so it
-    follows Keras' learning phase, which kgcn/core.py never feeds: it normalises with the MOVING
+    [TF-semantics, SURVEY.md Appendix A.10] The reference's Keras layer is called without ``training=`` in graph
+    mode, so it follows Keras' learning phase, which kgcn/core.py never feeds: it normalises with the MOVING
     statistics (initial mean 0 / variance 1, never updated) in training and inference alike, i.e.
-    ``y = gamma * x / sqrt(1 + 1e-3) + beta`` with trainable ``gamma`` (ones) and ``beta`` (zeros).  With
-    ``enabled_node_nums`` only the first ``n_b`` rows of graph ``b`` are normalised and the rest are exact
-    zeros (the extract / split / pad sequence of layers.py:202-214).  Plain torch elementwise ops: this
-    row is "next" in SURVEY.md section 8(f), not yet a fused kernel."""
+    ``y = gamma * x / sqrt(1 + 1e-3) + beta`` with trainable ``gamma`` (ones) and ``beta`` (zeros).  That is the
+    default here (``batch_statistics=False``).  ``batch_statistics=True`` gives the behaviour of
+    ``kgcn/legacy/layers.py:170-218`` (``tf.layers.batch_normalization(training=True)``): statistics of the
+    current batch over the enabled rows, moving averages updated with momentum 0.99.  With ``enabled_node_nums``
+    only the first ``n_b`` rows of graph ``b`` are normalised and the rest are exact zeros (the extract / split /
+    pad sequence of layers.py:202-214)."""
 
     EPS = 1e-3
+    MOMENTUM = 0.99
 
-    def __init__(self, bn_name=None, **kwargs):
+    def __init__(self, bn_name=None, batch_statistics=False, **kwargs):
         super().__init__(**kwargs)
         self.bn_name = bn_name
+        self.batch_statistics = batch_statistics
 
     def build(self, input_shape):
         f = int(input_shape[-1])
@@ -249,12 +253,35 @@ class GraphBatchNormalization(Layer):
         self.register_buffer("moving_variance", torch.ones(f, device=self._build_device))
 
     def call(self, inputs, enabled_node_nums=None, shape=None, max_node_num=None, training=True):
-        out = (inputs - self.moving_mean) * (self.gamma / torch.sqrt(self.moving_variance + self.EPS)) + self.beta
+        enabled = None
         if enabled_node_nums is not None:
-            n = torch.as_tensor(enabled_node_nums, device=inputs.device).reshape(-1)
-            keep = torch.arange(inputs.shape[1], device=inputs.device)[None, :] < n[:, None]
-            out = out * keep[:, :, None].to(out.dtype)
-        return out
+            enabled = torch.as_tensor(enabled_node_nums, device=inputs.device).reshape(-1).to(torch.int32).contiguous()
+        use_batch = bool(self.batch_statistics and training)
+        y, mean, var = ops.GraphBatchNormFunction.apply(inputs, self.gamma, self.beta, self.moving_mean, self.moving_variance,
+                                                        enabled, self.EPS, 1 if use_batch else 0)
+        if use_batch:
+            with torch.no_grad():
+                self.moving_mean.mul_(self.MOMENTUM).add_(mean, alpha=1.0 - self.MOMENTUM)
+                self.moving_variance.mul_(self.MOMENTUM).add_(var, alpha=1.0 - self.MOMENTUM)
+        return y
+
+    def compute_output_shape(self, input_shape):
+        return input_shape
+
+
+class GraphMaxPooling(Layer):
+    """``y[b,i,:] = sum_c max_j A[b][c][i,j] * x[b,j,:]`` over the densified rows (kgcn/layers.py:122-153): one
+    launch of ``kgcn_maxpool_fwd_f32`` instead of B * C * F TensorFlow op chains."""
+
+    def __init__(self, adj_channel_num, **kwargs):
+        super().__init__(**kwargs)
+        self.adj_channel_num = adj_channel_num
+
+    def call(self, inputs, adj=None):
+        csr = as_batched_csr(adj, inputs.device)
+        if csr.channels != self.adj_channel_num:
+            raise ValueError("GraphMaxPooling built for %d adjacency channels, got %d" % (self.adj_channel_num, csr.channels))
+        return ops.GraphMaxPoolFunction.apply(inputs, csr)
 
     def compute_output_shape(self, input_shape):
         return input_shape

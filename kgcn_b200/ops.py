@@ -228,3 +228,98 @@ class GraphGatherFunction(torch.autograd.Function):
         dx = torch.empty((B, N, F), dtype=torch.float32, device=dout.device)
         check(lib.kgcn_gather_bwd_f32(ptr(dout), B, N, F, ptr(dx), _stream()))
         return dx
+
+
+class GraphMaxPoolFunction(torch.autograd.Function):
+    """GraphMaxPooling (kgcn/layers.py:122-153) through kgcn_maxpool_{fwd,bwd}_f32."""
+
+    @staticmethod
+    def forward(ctx, x, csr):
+        x = _need_cuda("inputs", x)
+        B, N, F = x.shape
+        if csr.n_graphs != B or csr.n_rows != N or csr.n_cols != N:
+            raise ValueError("GraphMaxPooling: adjacency batch %s does not match inputs %s" % ((csr.n_graphs, csr.n_rows, csr.n_cols), (B, N, F)))
+        y = torch.empty_like(x)
+        ws = None
+        if x.requires_grad:
+            ws = torch.empty(int(lib.kgcn_maxpool_workspace_bytes(B, csr.channels, N, F)), dtype=torch.uint8, device=x.device)
+        check(lib.kgcn_maxpool_fwd_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), B, csr.channels, N, ptr(x), F, ptr(y),
+                                       ptr(ws), 0 if ws is None else ws.numel(), _stream()))
+        ctx.csr, ctx.ws = csr, ws
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        csr, ws = ctx.csr, ctx.ws
+        B, N, F = x.shape
+        dy = _need_cuda("dy", dy)
+        dx = torch.empty_like(x)
+        check(lib.kgcn_maxpool_bwd_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, csr.channels, N, ptr(x), F, ptr(dy),
+                                       ptr(ws), ws.numel(), ptr(dx), _stream()))
+        return dx, None
+
+
+class SegmentSumFunction(torch.autograd.Function):
+    """Per-molecule row-range sums of the block-diagonal model (example_model/sparse.py:79-90)."""
+
+    @staticmethod
+    def forward(ctx, x, start, size):
+        x = _need_cuda("inputs", x)
+        start = _need_cuda("start", start, torch.int64)
+        size = _need_cuda("size", size, torch.int64)
+        rows, F = x.shape
+        out = torch.empty((start.numel(), F), dtype=torch.float32, device=x.device)
+        check(lib.kgcn_segment_sum_fwd_f32(ptr(x), ptr(start), ptr(size), start.numel(), F, ptr(out), _stream()))
+        ctx.rows = rows
+        ctx.save_for_backward(start, size)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        start, size = ctx.saved_tensors
+        dout = _need_cuda("dout", dout)
+        dx = torch.zeros((ctx.rows, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        check(lib.kgcn_segment_sum_bwd_f32(ptr(dout), ptr(start), ptr(size), start.numel(), dout.shape[1], ptr(dx), _stream()))
+        return dx, None, None
+
+
+def segment_sum(x, sizes):
+    """out[m] = sum of the rows of molecule m; ``sizes`` = atoms per molecule (any integer sequence / tensor)."""
+    size = torch.as_tensor(sizes, dtype=torch.int64, device=x.device).reshape(-1).contiguous()
+    start = (torch.cumsum(size, 0) - size).contiguous()
+    return SegmentSumFunction.apply(x, start, size)
+
+
+class GraphBatchNormFunction(torch.autograd.Function):
+    """GraphBatchNormalization through kgcn_graph_bn_{fwd,bwd}_f32 (mode 0: given statistics, 1: batch statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, enabled, eps, mode):
+        x = _need_cuda("inputs", x)
+        B, N, F = x.shape
+        y = torch.empty_like(x)
+        if mode == 1:
+            mean = torch.empty(F, dtype=torch.float32, device=x.device)
+            var = torch.empty(F, dtype=torch.float32, device=x.device)
+        ws = workspace(int(lib.kgcn_graph_bn_workspace_bytes(B, F)) + 8 * F, x.device)
+        check(lib.kgcn_graph_bn_fwd_f32(ptr(x), B, N, F, ptr(enabled), ptr(gamma), ptr(beta), ptr(mean), ptr(var), eps, mode,
+                                        ptr(y), ptr(ws), ws.numel(), _stream()))
+        ctx.save_for_backward(x, gamma, mean, var)
+        ctx.enabled, ctx.eps, ctx.mode, ctx.has_beta = enabled, eps, mode, beta is not None
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _dvar):
+        x, gamma, mean, var = ctx.saved_tensors
+        B, N, F = x.shape
+        dy = _need_cuda("dy", dy)
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(F, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(F, dtype=torch.float32, device=x.device)
+        ws = workspace(int(lib.kgcn_graph_bn_workspace_bytes(B, F)) + 8 * F, x.device)
+        check(lib.kgcn_graph_bn_bwd_f32(ptr(x), ptr(dy), B, N, F, ptr(ctx.enabled), ptr(gamma), ptr(mean), ptr(var), ctx.eps,
+                                        ctx.mode, ptr(dx), ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), _stream()))
+        return dx, (dgamma if gamma is not None else None), (dbeta if ctx.has_beta else None), None, None, None, None, None

@@ -265,6 +265,63 @@ def bspmdt(sp_matrices, dense, adjoint_a=False, adjoint_b=False):
 # BatchNormalization/Dropout rows (both are inference-mode identities up to
 # a constant scale under the reference trainer, Appendix A.10).
 # --------------------------------------------------------------------------------------------
+def _dense_adj(triple):
+    idx, val, shape = triple
+    a = np.zeros(tuple(int(v) for v in shape), F32)
+    idx = np.asarray(idx).reshape(-1, 2)
+    a[idx[:, 0], idx[:, 1]] = np.asarray(val, F32)      # sparse_tensor_to_dense: unique, sorted indices only
+    return a
+
+
+def graph_max_pooling(x, adjs):
+    """GraphMaxPooling (kgcn/layers.py:122-153), literally: for every molecule b, channel c and feature k
+    ``d = to_dense(A[b][c] * x[b, :, k])`` (``A * v`` scales column j by v[j]; absent entries stay 0, :143-144),
+    ``el = reduce_max(d, axis=1)`` (:145), features stacked (:148), channels added (:149)."""
+    x = np.asarray(x, F32)
+    B, N, F = x.shape
+    out = np.zeros((B, N, F), F32)
+    for b in range(B):
+        for c in range(len(adjs[b])):
+            a = _dense_adj(adjs[b][c])
+            for k in range(F):
+                d = (a * x[b, :, k][None, :]).astype(F32)
+                out[b, :, k] += d.max(axis=1)
+    return out
+
+
+def graph_batch_normalization(x, gamma, beta, mean, var, enabled_node_nums=None, eps=1e-3, batch_statistics=False):
+    """GraphBatchNormalization (kgcn/layers.py:186-219): the first enabled_node_nums[b] rows of every molecule are
+    stacked (:202-204), normalised per feature (:205; moving statistics as the Keras layer does under the
+    reference trainer, or the batch's own statistics for the legacy tf.layers variant, legacy/layers.py:202),
+    split and zero-padded back (:206-211).  Returns (y, mean used, biased variance used)."""
+    x = np.asarray(x, F32)
+    B, N, F = x.shape
+    n = np.full(B, N, np.int64) if enabled_node_nums is None else np.asarray(enabled_node_nums, np.int64)
+    rows = np.concatenate([x[b, :n[b]] for b in range(B)], 0).astype(np.float64)
+    if batch_statistics:
+        mean = rows.mean(0) if rows.shape[0] else np.zeros(F)
+        var = rows.var(0) if rows.shape[0] else np.zeros(F)
+    mean, var = np.asarray(mean, np.float64), np.asarray(var, np.float64)
+    y = np.zeros((B, N, F), F32)
+    for b in range(B):
+        y[b, :n[b]] = ((x[b, :n[b]].astype(np.float64) - mean) / np.sqrt(var + eps) * np.asarray(gamma, np.float64)
+                       + np.asarray(beta, np.float64)).astype(F32)
+    return y, mean.astype(F32), var.astype(F32)
+
+
+def segment_sum(x, sizes):
+    """The per-molecule readout of the block-diagonal model (example_model/sparse.py:79-90)."""
+    x = np.asarray(x, F32)
+    out, pos = [], 0
+    for s in sizes:
+        acc = np.zeros(x.shape[1], F32)
+        for i in range(int(s)):
+            acc = acc + x[pos + i]
+        out.append(acc)
+        pos += int(s)
+    return np.stack(out) if out else np.zeros((0, x.shape[1]), F32)
+
+
 def glorot_uniform(rng, fan_in, fan_out):
     lim = np.sqrt(6.0 / (fan_in + fan_out))       # layers.py:54-57 'glorot_uniform'
     return rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(F32)
