@@ -28,6 +28,7 @@ WORKLOAD = {"name": "ring_graphs_b1024_n32_f64_2xGraphConv64", "batch_per_gpu": 
             "conv_dims": [64, 64], "channels": 1, "label_dim": 2, "act": "sigmoid"}
 N_ROT = 24          # distinct resident batches rotated through the timed loop (24 x 8.9 MB > 126 MB L2)
 METRIC, UNIT = "molecules/sec", "molecules/s"
+V4_TRAFFIC_BYTES = 9458176.0   # profiles/r01b_v4_B1024.txt: 9.46 MB read, writes still in the 126 MB L2 at kernel end
 
 
 def make_host_batches(n, seed, B=None):
@@ -235,24 +236,29 @@ def run_own(args):
         b = batches[i % N_ROT]
         ops.bspmm_raw(b.csr, b.features, N * F, 0, ys[i % N_ROT], N * F, 0, F)
 
-    g_spmm = torch.cuda.CUDAGraph()
-    for i in range(N_ROT):
-        spmm(i)
-    torch.cuda.synchronize()
-    with torch.cuda.graph(g_spmm):
-        for i in range(N_ROT):
-            spmm(i)
-    for _ in range(3):
-        g_spmm.replay()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = max(1, min(200, args.steps // 4))
-    s.record()
-    for _ in range(reps):
-        g_spmm.replay()
-    e.record()
-    torch.cuda.synchronize()
-    spmm_us = s.elapsed_time(e) * 1e3 / (reps * N_ROT)
+
+    def time_alone(fn):
+        """us per launch of fn(i), i over the rotating batches: graph-replayed back-to-back launches, CUDA events."""
+        g = torch.cuda.CUDAGraph()
+        for i in range(N_ROT):
+            fn(i)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            for i in range(N_ROT):
+                fn(i)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) * 1e3 / (reps * N_ROT)
+
+    spmm_us = time_alone(spmm)
     bytes_spmm = 4 * B * N * F * 2 + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1)
     achieved = bytes_spmm / spmm_us / 1e3
     roofline = {"kernel": "bspmm_tile_kernel (kgcn_bspmm_f32, Y[b]=A[b].X[b], B=%d N=%d F=%d)" % (B, N, F), "bound": "hbm",
@@ -271,27 +277,32 @@ def run_own(args):
         b = batches[i % N_ROT]
         ops.graphconv_fwd(b.csr, b.features, w0, b0, 2, 0, out=ys[i % N_ROT])
 
-    g_layer = torch.cuda.CUDAGraph()
-    for i in range(N_ROT):
-        layer(i)
-    torch.cuda.synchronize()
-    with torch.cuda.graph(g_layer):
-        for i in range(N_ROT):
-            layer(i)
-    for _ in range(3):
-        g_layer.replay()
-    torch.cuda.synchronize()
-    s.record()
-    for _ in range(reps):
-        g_layer.replay()
-    e.record()
-    torch.cuda.synchronize()
-    layer_us = s.elapsed_time(e) * 1e3 / (reps * N_ROT)
+    layer_us = time_alone(layer)
     bytes_layer = 4 * B * N * (F + F) + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1) + 4 * F * F + 4 * F
-    fused_roofline = {"kernel": "graphconv_fused_fwd_kernel (kgcn_graphconv_fwd_f32: TMA + aggregation + tcgen05 3xTF32 + bias/sigmoid)",
+    fused_roofline = {"kernel": "graphconv_fused_v4_kernel (kgcn_graphconv_fwd_f32: TMA ring -> thread-per-row aggregation into TMEM -> "
+                                "tcgen05 TS-mode 3xTF32 with the bias in the GEMM -> sigmoid epilogue)",
                       "bound": "hbm", "achieved": bytes_layer / layer_us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                       "frac": bytes_layer / layer_us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_layer,
-                      "us_per_launch": layer_us, "molecules_per_s_per_layer": B / layer_us * 1e6}
+                      "us_per_launch": layer_us, "molecules_per_s_per_layer": B / layer_us * 1e6,
+                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch (profiles/r01b_v4_B1024.txt)
+                      "traffic": V4_TRAFFIC_BYTES}
+
+    # ---- the fused GraphConv backward (dU, A^T.dU, dx, dW, dbias + the fixed-order partial reduce), the largest
+    # share of the step (profiles/r01b_bench_launches.csv), timed the same way on layer-2's shape with a dense dy ----
+    dys = [torch.randn(B, N, F, device=dev) for _ in range(4)]
+    acts = [torch.rand(B, N, F, device=dev) for _ in range(4)]
+
+    def layer_bwd(i):
+        b = batches[i % N_ROT]
+        ops.graphconv_bwd(b.csr, b.features, w0, 2, acts[i % 4], dys[i % 4])
+
+    bwd_us = time_alone(layer_bwd)
+    bytes_bwd = 4 * B * N * F * 4 + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1) + 2 * (4 * F * F + 4 * F)
+    bwd_roofline = {"kernel": "graphconv_fused_bwd_kernel + splitk_reduce_kernel (kgcn_graphconv_bwd_f32: x, y, dy read once, dx "
+                              "written once, dW/dbias per-CTA partials reduced in fixed order)",
+                    "bound": "hbm", "achieved": bytes_bwd / bwd_us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_bwd / bwd_us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_bwd,
+                    "us_per_launch": bwd_us}
 
     # ---- end to end from pinned host buffers through the public step call ----
     max_nnz = int(max(d["values"].shape[0] for d in host) * 1.1) + 64
@@ -337,7 +348,7 @@ def run_own(args):
                        "l2": "rotating %d resident batches (%.0f MB of inputs > 126 MB L2)" % (N_ROT, N_ROT * (B * N * F * 4 + 12 * nnz_mean) / 1e6),
                        "launch": "one CUDA graph replay per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "launches_per_step": int(launches_per_step), "roofline": roofline, "roofline_fused_layer": fused_roofline,
+            "launches_per_step": int(launches_per_step), "roofline": roofline, "roofline_fused_layer": fused_roofline, "roofline_fused_bwd": bwd_roofline,
             "cpu_baseline": cpu_baseline,
             "infer": {"value": mols * args.steps / (ms_infer * 1e-3), "unit": UNIT, "ms_per_step": ms_infer / args.steps,
                       "launches_per_step": int(launches_per_infer), "step": "forward only (layers + readout)"},

@@ -206,10 +206,21 @@ def _make_kgcn_alias():
     kgcn._kgcn_b200_facade = True
     legacy = types.ModuleType("kgcn.legacy")
     legacy.__path__ = []
-    legacy.layers = _layers
+    # kgcn/legacy/layers.py: same layers, but GraphBatchNormalization is tf.layers.batch_normalization(training=True),
+    # i.e. batch statistics (legacy/layers.py:202,213)
+    legacy_layers = types.ModuleType("kgcn.legacy.layers")
+    legacy_layers.__dict__.update({k: v for k, v in vars(_layers).items() if not k.startswith("__")})
+
+    class GraphBatchNormalization(_layers.GraphBatchNormalization):
+        def __init__(self, bn_name=None, **kwargs):
+            kwargs.setdefault("batch_statistics", True)
+            super().__init__(bn_name=bn_name, **kwargs)
+
+    legacy_layers.GraphBatchNormalization = GraphBatchNormalization
+    legacy.layers = legacy_layers
     kgcn.layers, kgcn.default_model, kgcn.legacy = _layers, _default_model, legacy
     return {"kgcn": kgcn, "kgcn.layers": _layers, "kgcn.default_model": _default_model, "kgcn.legacy": legacy,
-            "kgcn.legacy.layers": _layers}
+            "kgcn.legacy.layers": legacy_layers}
 
 
 _SAVED = {}

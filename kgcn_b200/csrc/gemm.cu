@@ -155,23 +155,38 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p
 }
 
 // out[r, n] = sum_z partial[z][r][n] (deterministic order); row M -> colsum output.
-// Block = 64 consecutive outputs x 4 interleaved split lanes, combined through shared memory.
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
-                                                            int has_colsum, float* __restrict__ out,
-                                                            float* __restrict__ colsum_out) {
+// Block = 32 consecutive outputs (one per lane, coalesced) x 32 warps; warp w adds the partials z = w, w + 32, ...
+// in that order with four independent loads in flight, then warp 0 adds the 32 warp sums in warp order.  The
+// reduction is a latency chain (a partial block is a few KB), so the width matters, not the bytes.
+__global__ void __launch_bounds__(1024) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
+                                                             int has_colsum, float* __restrict__ out,
+                                                             float* __restrict__ colsum_out) {
     pdl_prologue();
-    __shared__ float red[4][64];
+    __shared__ float red[32][33];
     const int64_t rows = M + (has_colsum ? 1 : 0);
     const int64_t total = rows * N;
-    const int o = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
-    const int64_t idx = static_cast<int64_t>(blockIdx.x) * 64 + o;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * 32 + lane;
     float s = 0.0f;
-    if (idx < total)
-        for (int z = lane4; z < splits; z += 4) s += partial[static_cast<int64_t>(z) * total + idx];
-    red[lane4][o] = s;
+    if (idx < total) {
+        const float* p = partial + idx;
+        int z = warp;
+        for (; z + 96 < splits; z += 128) {
+            const float v0 = p[static_cast<int64_t>(z) * total], v1 = p[static_cast<int64_t>(z + 32) * total];
+            const float v2 = p[static_cast<int64_t>(z + 64) * total], v3 = p[static_cast<int64_t>(z + 96) * total];
+            s += v0;
+            s += v1;
+            s += v2;
+            s += v3;
+        }
+        for (; z < splits; z += 32) s += p[static_cast<int64_t>(z) * total];
+    }
+    red[warp][lane] = s;
     __syncthreads();
-    if (lane4 == 0 && idx < total) {
-        s = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+    if (warp == 0 && idx < total) {
+        s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) s += red[w][lane];
         if (idx < M * N)
             out[idx] = s;
         else if (colsum_out != nullptr)
@@ -278,7 +293,7 @@ int launch_sgemm(bool trans_a, bool trans_b, int64_t M, int N, int K, const floa
 
 int launch_splitk_reduce(const float* partial, int splits, int64_t M, int N, float* out, float* colsum_out,
                          cudaStream_t st) {
-    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((M + 1) * N, 64)), 256, 0, st, partial, splits,
+    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((M + 1) * N, 32)), 1024, 0, st, partial, splits,
                M, N, 1, out, colsum_out);
     KGCN_LAUNCH_OK("splitk_reduce_kernel");
     return KGCN_OK;
@@ -306,7 +321,7 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
     dim3 grid(ceil_div(N, BN), ceil_div(Ka, BM), splits);
     launch_pdl(sgemm_kernel<true, false>, grid, GEMM_THREADS, 0, st, p);
     KGCN_LAUNCH_OK("sgemm_kernel(split-K)");
-    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((static_cast<int64_t>(Ka) + 1) * N, 64)), 256, 0, st, 
+    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((static_cast<int64_t>(Ka) + 1) * N, 32)), 1024, 0, st, 
         static_cast<const float*>(workspace), splits, Ka, N, 1, out, colsum_b);
     KGCN_LAUNCH_OK("splitk_reduce_kernel");
     return KGCN_OK;

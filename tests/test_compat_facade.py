@@ -42,8 +42,10 @@ def test_facade_exposes_reference_surface(facade):
                 "sigmoid_cross_entropy_with_logits", "weighted_cross_entropy_with_logits"):
         assert hasattr(tf.nn, sym), sym
     assert hasattr(K.layers, "Dense") and hasattr(K.layers, "Dropout")
-    for cls in ("GraphConv", "GraphDense", "GraphGather", "GraphBatchNormalization", "GINAggregate", "BatchGraphConv", "load_bspmm"):
+    for cls in ("GraphConv", "GraphDense", "GraphGather", "GraphBatchNormalization", "GINAggregate", "BatchGraphConv", "load_bspmm",
+                "GraphMaxPooling"):
         assert hasattr(kgcn.layers, cls) and hasattr(kgcn.legacy.layers, cls)
+    assert kgcn.legacy.layers.GraphBatchNormalization().batch_statistics and not kgcn.layers.GraphBatchNormalization().batch_statistics
     ph = DefaultModel().get_placeholders(make_info(C=2), {}, 3, ["adjs", "features", "labels", "mask", "enabled_node_nums"])
     assert len(ph["adjs"]) == 3 and len(ph["adjs"][0]) == 2 and ph["features"].shape == (3, 10, 3)
 
@@ -55,7 +57,8 @@ def test_tf_style_fixture_model_builds_placeholders(facade):
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "example_model")), reason="reference tree not present")
 @pytest.mark.parametrize("spec", ["example_model.model:GCN", "example_model.sparse_infer:GCN", "example_model.opt_param:GCN",
-                                  "example_model.model_multitask:GCN", "example_model.model_gin:GIN", "example_model.model_rxn_3layer:GCN"])
+                                  "example_model.model_multitask:GCN", "example_model.model_gin:GIN", "example_model.model_rxn_3layer:GCN",
+                                  "example_model.model_deepchem:GCN"])
 def test_reference_model_files_import_unchanged(facade, spec):
     """The reference's own model files import on the façade (authoring container only)."""
     import importlib

@@ -257,10 +257,11 @@ def test_integrated_gradients_completeness():
     from kgcn_b200 import bconv_call, layers, visualization
     from kgcn_b200.csr import BatchedCSR
     rng = np.random.default_rng(2)
+    torch.manual_seed(0)
     B, N, F = 6, 8, 5
     adjs = rand_unique_adjs(rng, B, N, 1, density=0.4, full_rows=False)
     csr = BatchedCSR.from_coo_lists(adjs)
-    x = rng.standard_normal((B, N, F)).astype(np.float32)
+    x = (0.3 * rng.standard_normal((B, N, F))).astype(np.float32)
     conv, gather = layers.GraphConv(4, 1, activation="tanh"), layers.GraphGather()
     xt = dev(x)
     conv(xt, adj=csr)
@@ -268,7 +269,7 @@ def test_integrated_gradients_completeness():
     def score(features, _values):
         return torch.tanh(gather(conv(features, adj=csr))).sum()
 
-    res = visualization.integrated_gradients(score, xt, None, divide_number=64, method="ig")
+    res = visualization.integrated_gradients(score, xt, None, divide_number=256, method="ig")
     with torch.no_grad():
         full, zero = score(xt, None).item(), score(torch.zeros_like(xt), None).item()
     assert abs(res["sum_of_IG"] - (full - zero)) < 0.05 * max(1.0, abs(full - zero))
