@@ -26,7 +26,6 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     float* __restrict__ logits, float* __restrict__ prediction, float* __restrict__ dlogits, float* __restrict__ dg,
     float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state) {
     pdl_prologue();
-    extern __shared__ float rd_smem[];   // g_s [slice][feat], w_s [feat][n_labels]: one global round trip for the whole head
     __shared__ float dz_s[kReadoutMaxSlice * kMaxLabels];
     __shared__ float cost_s[kReadoutMaxSlice], corr_s[kReadoutMaxSlice];
     __shared__ int is_last;
@@ -34,21 +33,16 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     const int64_t per = (n_graphs + gridDim.x - 1) / gridDim.x;
     const int64_t b0 = blockIdx.x * per;
     const int n_here = static_cast<int>(max(static_cast<int64_t>(0), min(n_graphs, b0 + per) - b0));
-    float* g_s = rd_smem;
-    float* w_s = rd_smem + static_cast<size_t>(per) * feat;
-    for (int i = threadIdx.x; i < n_here * feat; i += kReadoutThreads) g_s[i] = g[b0 * feat + i];
-    for (int i = threadIdx.x; i < feat * n_labels; i += kReadoutThreads) w_s[i] = w[i];
-    __syncthreads();
 
     // ---- phase 1 ----
     for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
         const int64_t b = b0 + i;
-        const float* gb = g_s + i * feat;
+        const float* gb = g + b * feat;
         float z[kMaxLabels];
 #pragma unroll 1
         for (int l = 0; l < n_labels; ++l) {
             float acc = 0.0f;
-            for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w_s[f * n_labels + l], acc);
+            for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w[static_cast<int64_t>(f) * n_labels + l], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             z[l] = acc + (bias ? bias[l] : 0.0f);
@@ -82,7 +76,7 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
         if (dg != nullptr)
             for (int f = lane; f < feat; f += 32) {
                 float acc = 0.0f;
-                for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w_s[f * n_labels + l], acc);
+                for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w[static_cast<int64_t>(f) * n_labels + l], acc);
                 dg[b * feat + f] = acc;
             }
         if (lane == 0) {
@@ -102,7 +96,7 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
             if (dw != nullptr) {
                 const int f = o / n_labels, l = o - f * n_labels;
                 if (f < feat)
-                    for (int i = 0; i < n_here; ++i) acc = fmaf(g_s[i * feat + f], dz_s[i * n_labels + l], acc);
+                    for (int i = 0; i < n_here; ++i) acc = fmaf(g[(b0 + i) * feat + f], dz_s[i * n_labels + l], acc);
                 else
                     for (int i = 0; i < n_here; ++i) acc += dz_s[i * n_labels + l];
             }
@@ -119,38 +113,17 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // Final sum over the block partials, fixed order: 8 lanes share one output (partials k = sub, sub + 8, ...
-    // summed in that order, then a fixed xor tree over the 8 lanes), so the dependent-load chain is gridDim/8 long.
-    const int sub = threadIdx.x & 7;
-    for (int o0 = 0; o0 < n_out; o0 += kReadoutThreads / 8) {
-        const int o = o0 + (threadIdx.x >> 3);
+    for (int o = threadIdx.x; o < n_out; o += kReadoutThreads) {
         float acc = 0.0f;
-        if (o < n_out) {
-            float v[4];
-            unsigned k = sub;
-            for (; k + 24 < gridDim.x; k += 32) {   // 4 independent loads in flight
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = partial[static_cast<size_t>(k + 8 * j) * n_out + o];
-                acc += v[0];
-                acc += v[1];
-                acc += v[2];
-                acc += v[3];
+        for (unsigned k = 0; k < gridDim.x; ++k) acc += partial[static_cast<size_t>(k) * n_out + o];
+        if (o < n_w) {
+            const int f = o / n_labels, l = o - f * n_labels;
+            if (dw != nullptr) {
+                if (f < feat) dw[o] = acc;
+                else if (dbias != nullptr) dbias[l] = acc;
             }
-            for (; k < gridDim.x; k += 8) acc += partial[static_cast<size_t>(k) * n_out + o];
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (o < n_out && sub == 0) {
-            if (o < n_w) {
-                const int f = o / n_labels, l = o - f * n_labels;
-                if (dw != nullptr) {
-                    if (f < feat) dw[o] = acc;
-                    else if (dbias != nullptr) dbias[l] = acc;
-                }
-            } else {
-                state[o - n_w] = acc;
-            }
+        } else {
+            state[o - n_w] = acc;
         }
     }
     if (threadIdx.x == 0) *ticket = 0;
@@ -254,10 +227,7 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
     const int nb = readout_blocks(n_graphs);
     KGCN_REQUIRE(ceil_div<int64_t>(n_graphs, nb) <= kReadoutMaxSlice, KGCN_ERR_UNSUPPORTED,
                  "readout_xent: batch too large for one launch (%lld graphs)", (long long)n_graphs);
-    const size_t dyn = (static_cast<size_t>(ceil_div<int64_t>(n_graphs, nb)) * feat + static_cast<size_t>(feat) * n_labels) * sizeof(float);
-    KGCN_REQUIRE(dyn <= 200 * 1024, KGCN_ERR_UNSUPPORTED, "readout_xent: feature width too large (%d)", feat);
-    KGCN_CUDA_OK(cudaFuncSetAttribute(readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(dyn, 48 * 1024))));
-    launch_pdl(readout_kernel, nb, kReadoutThreads, dyn, static_cast<cudaStream_t>(stream), g, n_graphs, feat, w, bias,
+    launch_pdl(readout_kernel, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), g, n_graphs, feat, w, bias,
                n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg, dw, dbias, static_cast<float*>(workspace),
                stats);
     KGCN_LAUNCH_OK("readout_kernel");
