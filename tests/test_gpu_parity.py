@@ -171,6 +171,46 @@ def test_graphconv_forward(K, B, N, C, fi, fo, act, flags):
         assert torch.all(y[B - 1] == float(R.activation(np.zeros(1, np.float32), act)[0]))
 
 
+# shapes the warp-specialised kernel (graphconv_fused_v4.cu: F_in % 32 == 0, F_out % 4 == 0, N <= 128) takes, with the
+# cases its pipeline has to get right: short last tiles, graphs that do not fill the 128 lanes, several slabs per
+# aggregation warp (K = C * F_in > 64), a single Z buffer (K large), dense tiles whose CSR slice does not fit the
+# stage (entries are then read from global memory), more CTAs than graphs per CTA, one graph only.
+V4_SHAPES = [  # B, N, C, F_in, F_out, max_nnz per matrix
+    (1, 32, 1, 64, 64, None),
+    (7, 32, 1, 64, 64, None),
+    (1024, 32, 1, 64, 64, None),     # C2 at full size
+    (149, 32, 1, 64, 64, None),      # 148 CTAs + 1 graph
+    (333, 50, 1, 32, 20, None),      # 2 graphs per tile, 100 of 128 lanes
+    (40, 128, 1, 64, 36, None),      # one graph per tile
+    (61, 17, 2, 32, 48, None),       # 7 graphs per tile, two channels
+    (90, 32, 3, 64, 64, None),       # K = 192: three slabs per aggregation warp, single Z buffer
+    (33, 16, 1, 32, 64, 16 * 16),    # dense graphs (~10 entries per row > stage capacity): un-staged CSR path
+    (20, 64, 1, 96, 128, None),      # three slabs, 4 column slabs in the epilogue
+    (12, 24, 1, 160, 8, None),       # five slabs, F_out < 32 (second epilogue column phase idle)
+]
+
+
+@pytest.mark.parametrize("B,N,C,fi,fo,max_nnz", V4_SHAPES)
+@pytest.mark.parametrize("act", ["none", "sigmoid"])
+def test_graphconv_forward_v4_pipeline(K, B, N, C, fi, fo, max_nnz, act):
+    rng = np.random.default_rng(B * 7 + N)
+    adjs, x = random_batch(rng, B, N, C, fi, max_nnz=max_nnz, empty_graphs=(B // 2,) if B > 2 else ())
+    w = [R.glorot_uniform(rng, fi, fo) for _ in range(C)]
+    b = [rng.uniform(-0.5, 0.5, (1, fo)).astype(np.float32) for _ in range(C)]
+    want = R.activation(R.graph_conv(x, adjs, w, b, fast=True), act)
+    csr = K["csr"].BatchedCSR.from_coo_lists(adjs)
+    xd, wd, bd = dev(x), dev(np.stack(w)), dev(np.concatenate(b))
+    y = K["ops"].graphconv_fwd(csr, xd, wd, bd, R.ACT_IDS[act], 0)
+    close(y, want)
+    # fused == decomposed reference-order path (exact-fp32 GEMM + SpMM) of the library itself
+    close(y, K["ops"].graphconv_fwd(csr, xd, wd, bd, R.ACT_IDS[act], 1).cpu().numpy())
+    # deterministic: bit-identical on a second launch
+    assert torch.equal(y, K["ops"].graphconv_fwd(csr, xd, wd, bd, R.ACT_IDS[act], 0))
+    # no bias
+    y0 = K["ops"].graphconv_fwd(csr, xd, wd, None, R.ACT_IDS[act], 0)
+    close(y0, R.activation(R.graph_conv(x, adjs, w, [np.zeros((1, fo), np.float32)] * C, fast=True), act))
+
+
 def test_graphconv_forward_faithful_order_small(K):
     """Against the slow O1 tier (per-nnz storage order) on a small case."""
     rng = np.random.default_rng(11)
