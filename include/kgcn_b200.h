@@ -267,6 +267,15 @@ int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const 
                           float* logits, float* prediction, float* stats, float* dlogits, float* dg,
                           float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
 
+/* GraphGather + the readout head in one launch: g [n_graphs, feat] is an OUTPUT here, formed from the node rows
+ * x [n_graphs, n_nodes, feat] exactly like kgcn_gather_fwd_f32 (rows added in index order); everything else as
+ * kgcn_readout_xent_f32.  Saves one launch and one pass over the last layer's activations per step. */
+int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
+                                 const float* w, const float* bias, int32_t n_labels, const float* labels,
+                                 const float* mask, float inv_batch, float* logits, float* prediction, float* stats,
+                                 float* dlogits, float* dg, float* dw, float* dbias, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 /* Adam with TensorFlow's formulation (tf.train.AdamOptimizer, kgcn/core.py:121-127):
  *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
  *   param -= lr * sqrt(1-b2^step)/(1-b1^step) * m / (sqrt(v) + eps);     step counts from 1.

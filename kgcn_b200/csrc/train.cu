@@ -20,8 +20,13 @@ constexpr int kMaxLabels = 32;
 constexpr int kReadoutThreads = 256;
 constexpr int kReadoutMaxSlice = 128;
 
+// FUSE_GATHER: the GraphGather sums (layers.py:164, rows added in index order exactly like gather_fwd_kernel) are formed
+// here from the node rows x_nodes [n_graphs, n_nodes, feat] and written to g (an OUTPUT then) -- one launch and one pass
+// over the last layer's activations less per step.
+template <bool FUSE_GATHER>
 __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
-    const float* __restrict__ g, int64_t n_graphs, int feat, const float* __restrict__ w, const float* __restrict__ bias,
+    const float* __restrict__ x_nodes, int n_nodes,
+    float* g, int64_t n_graphs, int feat, const float* __restrict__ w, const float* __restrict__ bias,
     int n_labels, const float* __restrict__ labels, const float* __restrict__ mask, float inv_batch,
     float* __restrict__ logits, float* __restrict__ prediction, float* __restrict__ dlogits, float* __restrict__ dg,
     float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state) {
@@ -37,7 +42,15 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     // ---- phase 1 ----
     for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
         const int64_t b = b0 + i;
-        const float* gb = g + b * feat;
+        float* gb = g + b * feat;
+        if (FUSE_GATHER) {   // lane owns features lane, lane + 32, ...: it writes gb[f] here and reads the same gb[f] below
+            const float* xb = x_nodes + b * n_nodes * feat;
+            for (int f = lane; f < feat; f += 32) {
+                float acc = 0.0f;
+                for (int r = 0; r < n_nodes; ++r) acc += xb[static_cast<int64_t>(r) * feat + f];
+                gb[f] = acc;
+            }
+        }
         float z[kMaxLabels];
 #pragma unroll 1
         for (int l = 0; l < n_labels; ++l) {
@@ -227,10 +240,30 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
     const int nb = readout_blocks(n_graphs);
     KGCN_REQUIRE(ceil_div<int64_t>(n_graphs, nb) <= kReadoutMaxSlice, KGCN_ERR_UNSUPPORTED,
                  "readout_xent: batch too large for one launch (%lld graphs)", (long long)n_graphs);
-    launch_pdl(readout_kernel, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), g, n_graphs, feat, w, bias,
-               n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg, dw, dbias, static_cast<float*>(workspace),
-               stats);
+    launch_pdl(readout_kernel<false>, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), static_cast<const float*>(nullptr), 0,
+               const_cast<float*>(g), n_graphs, feat, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg,
+               dw, dbias, static_cast<float*>(workspace), stats);
     KGCN_LAUNCH_OK("readout_kernel");
+    return KGCN_OK;
+}
+
+extern "C" int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
+                                            const float* w, const float* bias, int32_t n_labels, const float* labels,
+                                            const float* mask, float inv_batch, float* logits, float* prediction,
+                                            float* stats, float* dlogits, float* dg, float* dw, float* dbias,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    KGCN_REQUIRE(x && g && w && labels && stats, KGCN_ERR_NULL, "gather_readout_xent: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && n_nodes > 0 && feat > 0 && n_labels > 0 && n_labels <= kMaxLabels, KGCN_ERR_BAD_SHAPE,
+                 "gather_readout_xent: bad shape (n_labels <= %d)", kMaxLabels);
+    KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= kgcn_readout_workspace_bytes(n_graphs, feat, n_labels),
+                 KGCN_ERR_WORKSPACE, "gather_readout_xent: workspace too small");
+    const int nb = readout_blocks(n_graphs);
+    KGCN_REQUIRE(ceil_div<int64_t>(n_graphs, nb) <= kReadoutMaxSlice, KGCN_ERR_UNSUPPORTED,
+                 "gather_readout_xent: batch too large for one launch (%lld graphs)", (long long)n_graphs);
+    launch_pdl(readout_kernel<true>, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), x, static_cast<int>(n_nodes), g,
+               n_graphs, feat, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg, dw, dbias,
+               static_cast<float*>(workspace), stats);
+    KGCN_LAUNCH_OK("readout_kernel(gather)");
     return KGCN_OK;
 }
 

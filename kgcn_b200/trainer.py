@@ -149,14 +149,15 @@ class Trainer:
                                               ptr(self.views["graph_dense/bias"]), int(s.dense_dim), self.act, None,
                                               ptr(y), st))
             x, f = y, int(s.dense_dim)
-        check(lib.kgcn_gather_fwd_f32(ptr(x), B, N, f, ptr(self.gathered), st))
+        self._last_nodes = x      # GraphGather is fused into the readout head (kgcn_gather_readout_xent_f32)
         return f, n_launch
 
     def _head(self, batch, f, st, train):
         s, B = self.spec, self.B
         inv_batch = 1.0 / (B * self.world_size)
-        check(lib.kgcn_readout_xent_f32(
-            ptr(self.gathered), B, f, ptr(self.views["dense/kernel"]), ptr(self.views["dense/bias"]), s.label_dim,
+        check(lib.kgcn_gather_readout_xent_f32(
+            ptr(self._last_nodes), B, s.n_nodes, f, ptr(self.gathered), ptr(self.views["dense/kernel"]),
+            ptr(self.views["dense/bias"]), s.label_dim,
             ptr(batch.labels), ptr(batch.mask), inv_batch, ptr(self.logits), ptr(self.prediction), ptr(self.stats),
             ptr(self.dlogits) if train else None, ptr(self.dgathered) if train else None,
             ptr(self.gviews["dense/kernel"]) if train else None, ptr(self.gviews["dense/bias"]) if train else None,
