@@ -38,6 +38,11 @@ def head(i):
     check(lib.kgcn_readout_xent_f32(ptr(tr.gathered), B, 64, ptr(tr.views["dense/kernel"]), ptr(tr.views["dense/bias"]), 2, ptr(b.labels), ptr(b.mask),
                                     1.0 / B, ptr(tr.logits), ptr(tr.prediction), ptr(tr.stats), ptr(tr.dlogits), ptr(tr.dgathered),
                                     ptr(tr.gviews["dense/kernel"]), ptr(tr.gviews["dense/bias"]), ptr(ws), ws.numel(), st()))
+def gather_head(i):   # what the trainer launches: GraphGather fused into the readout head
+    b = batches[i]
+    check(lib.kgcn_gather_readout_xent_f32(ptr(acts2[i]), B, N, 64, ptr(tr.gathered), ptr(tr.views["dense/kernel"]), ptr(tr.views["dense/bias"]), 2,
+                                           ptr(b.labels), ptr(b.mask), 1.0 / B, ptr(tr.logits), ptr(tr.prediction), ptr(tr.stats), ptr(tr.dlogits),
+                                           ptr(tr.dgathered), ptr(tr.gviews["dense/kernel"]), ptr(tr.gviews["dense/bias"]), ptr(ws), ws.numel(), st()))
 def bwd2(i):   # last conv layer: dy broadcast from the gather gradient, dx needed
     b = batches[i]
     check(lib.kgcn_graphconv_bwd_f32(ptr(b.csr.rowptr_t), ptr(b.csr.col_t), ptr(b.csr.val_t), B, 1, N, ptr(acts1[i]), 64, ptr(tr.views["conv1/kernel"]), 64, 2,
@@ -51,7 +56,8 @@ def adam(i):
     tr._optimizer(st())
 
 total = 0.0
-for name, fn, mult in (("graphconv_fwd (fused)", fwd, 2), ("gather_fwd", gather, 1), ("readout_xent (+dW)", head, 1), ("graphconv_bwd L2 (dx, bcast)", bwd2, 1),
+for name, fn, mult in (("graphconv_fwd (fused)", fwd, 2), ("gather_fwd (layer API only)", gather, 0), ("readout_xent (layer API only)", head, 0),
+                       ("gather + readout_xent (+dW)", gather_head, 1), ("graphconv_bwd L2 (dx, bcast)", bwd2, 1),
                        ("graphconv_bwd L1 (no dx)", bwd1, 1), ("adam", adam, 1)):
     for i in range(ROT): fn(i)
     torch.cuda.synchronize()
