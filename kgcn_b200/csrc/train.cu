@@ -128,7 +128,19 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     __threadfence();
     for (int o = threadIdx.x; o < n_out; o += kReadoutThreads) {
         float acc = 0.0f;
-        for (unsigned k = 0; k < gridDim.x; ++k) acc += partial[static_cast<size_t>(k) * n_out + o];
+        {   // fixed order, 16 independent loads in flight (this loop is a chain of L2 round trips, nothing else)
+            const float* src = partial + o;
+            const unsigned nb = gridDim.x;
+            unsigned k = 0;
+            for (; k + 16 <= nb; k += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __ldcg(src + static_cast<size_t>(k + j) * n_out);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc += v[j];
+            }
+            for (; k < nb; ++k) acc += __ldcg(src + static_cast<size_t>(k) * n_out);
+        }
         if (o < n_w) {
             const int f = o / n_labels, l = o - f * n_labels;
             if (dw != nullptr) {
@@ -175,7 +187,19 @@ __global__ void __launch_bounds__(256) readout_dw_kernel(const float* __restrict
     __threadfence();
     for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
         float acc = 0.0f;
-        for (unsigned k = 0; k < gridDim.x; ++k) acc += partial[static_cast<size_t>(k) * n_out + o];
+        {   // fixed order, 16 independent loads in flight (this loop is a chain of L2 round trips, nothing else)
+            const float* src = partial + o;
+            const unsigned nb = gridDim.x;
+            unsigned k = 0;
+            for (; k + 16 <= nb; k += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __ldcg(src + static_cast<size_t>(k + j) * n_out);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc += v[j];
+            }
+            for (; k < nb; ++k) acc += __ldcg(src + static_cast<size_t>(k) * n_out);
+        }
         const int f = o / n_labels, l = o - f * n_labels;
         if (f < feat) dw[o] = acc;
         else if (dbias != nullptr) dbias[l] = acc;
