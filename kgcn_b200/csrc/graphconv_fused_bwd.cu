@@ -57,6 +57,7 @@ struct BwdParams {
     int64_t n_graphs;
     int n_nodes, f_in, f_out, act, dy_bcast;
     int graphs_per_tile, n_tiles;
+    int graphs_per_cta;      // every CTA owns a contiguous range of graphs (balanced: the last tile of a range may be short)
     int KGp;                 // f_out padded to 32: K of dx, N of dW
     int Fip;                 // f_in padded to 16: N of dx
     int cv_cap, lpr_log2, n_stages;
@@ -206,9 +207,9 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_bwd_kernel(const Bw
     const uint32_t graph_bytes_u = static_cast<uint32_t>(N) * row_pitch;
     const uint32_t graph_bytes_x = static_cast<uint32_t>(N) * static_cast<uint32_t>(f_in) * 4u;
 
-    auto tile_graphs = [&](int t) {
-        return static_cast<int>(min(static_cast<int64_t>(p.graphs_per_tile), p.n_graphs - static_cast<int64_t>(t) * p.graphs_per_tile));
-    };
+    const int64_t cta_g0 = static_cast<int64_t>(blockIdx.x) * p.graphs_per_cta;
+    const int cta_ng = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(p.graphs_per_cta), p.n_graphs - cta_g0)));
+    const int cta_tiles = (cta_ng + p.graphs_per_tile - 1) / p.graphs_per_tile;
 
     if (tid == 0) {
         for (int i = 0; i < kStagesMax; ++i) {
@@ -230,12 +231,11 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_bwd_kernel(const Bw
     if (warp == kConsumers / 32) {
         // =============================== TMA producer warp ===============================
         if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < cta_tiles; ++it) {
                 const int s = it % S;
                 if (it >= S) mbar_wait(&bar_empty[s], ((it / S) - 1) & 1);
-                const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
-                const int ng = tile_graphs(tile);
+                const int64_t g0 = cta_g0 + static_cast<int64_t>(it) * p.graphs_per_tile;
+                const int ng = min(p.graphs_per_tile, cta_ng - it * p.graphs_per_tile);
                 const int64_t r0 = g0 * N;
                 const int rows_csr = ng * N;
                 const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
@@ -306,11 +306,10 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_bwd_kernel(const Bw
         const int f4o = f_out >> 2, f4i = f_in >> 2;
         float csum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < cta_tiles; ++it) {
             const int s = it % S;
-            const int64_t g0 = static_cast<int64_t>(tile) * p.graphs_per_tile;
-            const int ng = tile_graphs(tile);
+            const int64_t g0 = cta_g0 + static_cast<int64_t>(it) * p.graphs_per_tile;
+            const int ng = min(p.graphs_per_tile, cta_ng - it * p.graphs_per_tile);
             const int rows = ng * N;
             const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
             const uint32_t us = st + p.st_u, ds = st + p.st_d;
@@ -602,7 +601,9 @@ int launch_graphconv_fused_bwd(const int32_t* rowptr_t, const int32_t* col_t, co
     BwdParams p{};
     KGCN_REQUIRE(plan_bwd(p, n_graphs, n_nodes, f_in, f_out, act, dy_bcast, dx != nullptr), KGCN_ERR_UNSUPPORTED,
                  "fused GraphConv backward: shape does not fit one SM's shared memory");
-    const unsigned grid = static_cast<unsigned>(std::min<int>(p.n_tiles, kNumSMs));
+    const int64_t grid0 = std::min<int64_t>(p.n_tiles, kNumSMs);
+    p.graphs_per_cta = static_cast<int>(ceil_div<int64_t>(n_graphs, grid0));
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));   // every CTA owns >= 1 graph
     const size_t need = static_cast<size_t>(grid) * (static_cast<size_t>(f_in) + 1) * f_out * sizeof(float);
     KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= need && aligned16(workspace), KGCN_ERR_WORKSPACE,
                  "fused GraphConv backward: workspace %zu < %zu bytes", workspace_bytes, need);
