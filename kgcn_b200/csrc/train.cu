@@ -13,11 +13,15 @@ namespace {
 constexpr int kMaxLabels = 32;
 
 // One kernel for the whole head.  Each block owns a contiguous slice of the batch:
+//   phase 0: w, labels, mask of the slice -> shared memory; the gathered rows g (either read, or formed here from the
+//            node rows: FUSE_GATHER) -> shared memory.  All of these loads are independent, so the head pays ONE
+//            global round trip for its inputs instead of a chain of dependent ones;
 //   phase 1 (warp per graph): logits, softmax, masked cross-entropy, d logits, d gathered;
 //   phase 2 (thread per weight): d out_w[f,l] / d out_b[l] over the slice, in graph order;
-// block partials go to `partial`; the last block to finish (ticket in state[2]) adds them in block
-// order, so every sum is deterministic and no memset / second launch is needed.
-constexpr int kReadoutThreads = 256;
+// block partials go to `partial`; the last block to finish (ticket in state[2]) adds them in a fixed order (R helper
+// threads per output over contiguous block ranges, then the R sums in helper order), so every sum is deterministic
+// and no memset / second launch is needed.
+constexpr int kReadoutThreads = 512;
 constexpr int kReadoutMaxSlice = 128;
 
 // FUSE_GATHER: the GraphGather sums (layers.py:164, rows added in index order exactly like gather_fwd_kernel) are formed
@@ -31,31 +35,49 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     float* __restrict__ logits, float* __restrict__ prediction, float* __restrict__ dlogits, float* __restrict__ dg,
     float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state) {
     pdl_prologue();
+    extern __shared__ float rd_smem[];   // g_s [slice][feat] | w_s [feat][n_labels] | y_s [slice][n_labels] | m_s [slice]
     __shared__ float dz_s[kReadoutMaxSlice * kMaxLabels];
     __shared__ float cost_s[kReadoutMaxSlice], corr_s[kReadoutMaxSlice];
+    __shared__ float red_s[kReadoutThreads];
     __shared__ int is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t per = (n_graphs + gridDim.x - 1) / gridDim.x;
     const int64_t b0 = blockIdx.x * per;
     const int n_here = static_cast<int>(max(static_cast<int64_t>(0), min(n_graphs, b0 + per) - b0));
+    float* g_s = rd_smem;
+    float* w_s = g_s + static_cast<size_t>(per) * feat;
+    float* y_s = w_s + static_cast<size_t>(feat) * n_labels;
+    float* m_s = y_s + static_cast<size_t>(per) * n_labels;
+
+    // ---- phase 0 ----
+    for (int i = threadIdx.x; i < feat * n_labels; i += kReadoutThreads) w_s[i] = w[i];
+    for (int i = threadIdx.x; i < n_here * n_labels; i += kReadoutThreads) y_s[i] = labels[b0 * n_labels + i];
+    for (int i = threadIdx.x; i < n_here; i += kReadoutThreads) m_s[i] = mask ? mask[b0 + i] : 1.0f;
+    if (FUSE_GATHER) {   // warp per graph, lane owns features lane, lane + 32, ...
+        for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
+            const float* xb = x_nodes + (b0 + i) * n_nodes * feat;
+            for (int f = lane; f < feat; f += 32) {
+                float acc = 0.0f;
+                for (int r = 0; r < n_nodes; ++r) acc += xb[static_cast<int64_t>(r) * feat + f];
+                g_s[i * feat + f] = acc;
+                g[(b0 + i) * feat + f] = acc;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_here * feat; i += kReadoutThreads) g_s[i] = g[b0 * feat + i];
+    }
+    __syncthreads();
 
     // ---- phase 1 ----
     for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
         const int64_t b = b0 + i;
-        float* gb = g + b * feat;
-        if (FUSE_GATHER) {   // lane owns features lane, lane + 32, ...: it writes gb[f] here and reads the same gb[f] below
-            const float* xb = x_nodes + b * n_nodes * feat;
-            for (int f = lane; f < feat; f += 32) {
-                float acc = 0.0f;
-                for (int r = 0; r < n_nodes; ++r) acc += xb[static_cast<int64_t>(r) * feat + f];
-                gb[f] = acc;
-            }
-        }
+        const float* gb = g_s + i * feat;
+        const float* yb = y_s + i * n_labels;
         float z[kMaxLabels];
 #pragma unroll 1
         for (int l = 0; l < n_labels; ++l) {
             float acc = 0.0f;
-            for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w[static_cast<int64_t>(f) * n_labels + l], acc);
+            for (int f = lane; f < feat; f += 32) acc = fmaf(gb[f], w_s[f * n_labels + l], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             z[l] = acc + (bias ? bias[l] : 0.0f);
@@ -65,20 +87,20 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
         float sum = 0.0f;
         for (int l = 0; l < n_labels; ++l) sum += expf(z[l] - zmax);
         const float lse = logf(sum) + zmax;
-        const float m = mask ? mask[b] : 1.0f;
+        const float m = m_s[i];
         float cost = 0.0f, ysum = 0.0f;
         int arg_p = 0, arg_y = 0;
         for (int l = 0; l < n_labels; ++l) {
-            const float y = labels[b * n_labels + l];
+            const float y = yb[l];
             cost -= y * (z[l] - lse);            // softmax cross-entropy with (possibly soft) labels
             ysum += y;
             if (z[l] > z[arg_p]) arg_p = l;
-            if (y > labels[b * n_labels + arg_y]) arg_y = l;
+            if (y > yb[arg_y]) arg_y = l;
         }
         float dz[kMaxLabels];
         for (int l = 0; l < n_labels; ++l) {
             const float pr = expf(z[l] - lse);
-            dz[l] = m * inv_batch * (pr * ysum - labels[b * n_labels + l]);
+            dz[l] = m * inv_batch * (pr * ysum - yb[l]);
             if (lane == 0) {
                 if (logits) logits[b * n_labels + l] = z[l];
                 if (prediction) prediction[b * n_labels + l] = pr;
@@ -89,7 +111,7 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
         if (dg != nullptr)
             for (int f = lane; f < feat; f += 32) {
                 float acc = 0.0f;
-                for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w[static_cast<int64_t>(f) * n_labels + l], acc);
+                for (int l = 0; l < n_labels; ++l) acc = fmaf(dz[l], w_s[f * n_labels + l], acc);
                 dg[b * feat + f] = acc;
             }
         if (lane == 0) {
@@ -109,7 +131,7 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
             if (dw != nullptr) {
                 const int f = o / n_labels, l = o - f * n_labels;
                 if (f < feat)
-                    for (int i = 0; i < n_here; ++i) acc = fmaf(g[(b0 + i) * feat + f], dz_s[i * n_labels + l], acc);
+                    for (int i = 0; i < n_here; ++i) acc = fmaf(g_s[i * feat + f], dz_s[i * n_labels + l], acc);
                 else
                     for (int i = 0; i < n_here; ++i) acc += dz_s[i * n_labels + l];
             }
@@ -126,30 +148,42 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int o = threadIdx.x; o < n_out; o += kReadoutThreads) {
+    // ---- final sum over the block partials: R helpers per output over contiguous block ranges, 16 loads in flight ----
+    const int nb = static_cast<int>(gridDim.x);
+    const int R = max(1, min(4, kReadoutThreads / n_out));
+    const int chunk = (nb + R - 1) / R;
+    for (int o0 = 0; o0 < n_out; o0 += kReadoutThreads / R) {
+        const int slot = threadIdx.x, h = slot / (kReadoutThreads / R), o = o0 + slot - h * (kReadoutThreads / R);
         float acc = 0.0f;
-        {   // fixed order, 16 independent loads in flight (this loop is a chain of L2 round trips, nothing else)
+        if (o < n_out && h < R) {
             const float* src = partial + o;
-            const unsigned nb = gridDim.x;
-            unsigned k = 0;
-            for (; k + 16 <= nb; k += 16) {
+            int k = h * chunk;
+            const int k_end = min(nb, k + chunk);
+            for (; k + 16 <= k_end; k += 16) {
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __ldcg(src + static_cast<size_t>(k + j) * n_out);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc += v[j];
             }
-            for (; k < nb; ++k) acc += __ldcg(src + static_cast<size_t>(k) * n_out);
+            for (; k < k_end; ++k) acc += __ldcg(src + static_cast<size_t>(k) * n_out);
         }
-        if (o < n_w) {
-            const int f = o / n_labels, l = o - f * n_labels;
-            if (dw != nullptr) {
-                if (f < feat) dw[o] = acc;
-                else if (dbias != nullptr) dbias[l] = acc;
+        red_s[slot] = acc;
+        __syncthreads();
+        if (h == 0 && o < n_out) {
+            acc = red_s[slot];
+            for (int r = 1; r < R; ++r) acc += red_s[slot + r * (kReadoutThreads / R)];
+            if (o < n_w) {
+                const int f = o / n_labels, l = o - f * n_labels;
+                if (dw != nullptr) {
+                    if (f < feat) dw[o] = acc;
+                    else if (dbias != nullptr) dbias[l] = acc;
+                }
+            } else {
+                state[o - n_w] = acc;
             }
-        } else {
-            state[o - n_w] = acc;
         }
+        __syncthreads();
     }
     if (threadIdx.x == 0) *ticket = 0;
 }
@@ -241,10 +275,15 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
 using namespace kgcn;
 
 static int readout_blocks(int64_t n_graphs) {
-    int64_t nb = ceil_div<int64_t>(n_graphs, 8);   // one graph per warp in phase 1
+    int64_t nb = ceil_div<int64_t>(n_graphs, kReadoutThreads / 32);   // one graph per warp in phase 1
     nb = std::min<int64_t>(nb, kNumSMs);
     nb = std::max<int64_t>(nb, ceil_div<int64_t>(n_graphs, kReadoutMaxSlice));
     return static_cast<int>(nb);
+}
+
+static size_t readout_dyn_smem(int64_t n_graphs, int nb, int feat, int n_labels) {
+    const size_t slice = static_cast<size_t>(ceil_div<int64_t>(n_graphs, nb));
+    return (slice * (static_cast<size_t>(feat) + n_labels + 1) + static_cast<size_t>(feat) * n_labels) * sizeof(float);
 }
 
 extern "C" size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels) {
@@ -264,7 +303,10 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
     const int nb = readout_blocks(n_graphs);
     KGCN_REQUIRE(ceil_div<int64_t>(n_graphs, nb) <= kReadoutMaxSlice, KGCN_ERR_UNSUPPORTED,
                  "readout_xent: batch too large for one launch (%lld graphs)", (long long)n_graphs);
-    launch_pdl(readout_kernel<false>, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), static_cast<const float*>(nullptr), 0,
+    const size_t dyn = readout_dyn_smem(n_graphs, nb, feat, n_labels);
+    KGCN_REQUIRE(dyn <= 160 * 1024, KGCN_ERR_UNSUPPORTED, "readout_xent: feature width %d too large for the staged head", feat);
+    KGCN_CUDA_OK(cudaFuncSetAttribute(readout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    launch_pdl(readout_kernel<false>, nb, kReadoutThreads, dyn, static_cast<cudaStream_t>(stream), static_cast<const float*>(nullptr), 0,
                const_cast<float*>(g), n_graphs, feat, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg,
                dw, dbias, static_cast<float*>(workspace), stats);
     KGCN_LAUNCH_OK("readout_kernel");
@@ -284,7 +326,10 @@ extern "C" int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, in
     const int nb = readout_blocks(n_graphs);
     KGCN_REQUIRE(ceil_div<int64_t>(n_graphs, nb) <= kReadoutMaxSlice, KGCN_ERR_UNSUPPORTED,
                  "gather_readout_xent: batch too large for one launch (%lld graphs)", (long long)n_graphs);
-    launch_pdl(readout_kernel<true>, nb, kReadoutThreads, 0, static_cast<cudaStream_t>(stream), x, static_cast<int>(n_nodes), g,
+    const size_t dyn = readout_dyn_smem(n_graphs, nb, feat, n_labels);
+    KGCN_REQUIRE(dyn <= 160 * 1024, KGCN_ERR_UNSUPPORTED, "gather_readout_xent: feature width %d too large for the staged head", feat);
+    KGCN_CUDA_OK(cudaFuncSetAttribute(readout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    launch_pdl(readout_kernel<true>, nb, kReadoutThreads, dyn, static_cast<cudaStream_t>(stream), x, static_cast<int>(n_nodes), g,
                n_graphs, feat, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg, dw, dbias,
                static_cast<float*>(workspace), stats);
     KGCN_LAUNCH_OK("readout_kernel(gather)");
