@@ -259,7 +259,7 @@ int kgcn_graph_bn_bwd_f32(const float* x, const float* dy, int64_t n_graphs, int
  *   dlogits [B,L], dg [B,F] = dlogits . w^T, dw [F,L] = g^T . dlogits, dbias [L].
  * g [n_graphs, feat]; w [feat, n_labels]; labels [n_graphs, n_labels] (one-hot or soft);
  * mask [n_graphs] or NULL.  Any output pointer except stats may be NULL.  n_labels <= 32;
- * n_graphs <= 75776 per launch.
+ * any n_graphs (every block stages a slice of <= 128 graphs in shared memory).
  */
 size_t kgcn_readout_workspace_bytes(int64_t n_graphs, int32_t feat, int32_t n_labels);
 int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t feat, const float* w, const float* bias,
