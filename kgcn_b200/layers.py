@@ -62,6 +62,19 @@ def _init_tensor(initializer, shape, fan_in, fan_out, device):
     raise ValueError("unsupported initializer %r" % (initializer,))
 
 
+def _shape_of(t):
+    """Static shape of one element of a list input: a tensor, a packed batch, or a SparseTensorValue-like triple
+    (the block-diagonal adjacency of BatchGraphConv, kgcn/layers.py:388-390)."""
+    if isinstance(t, BatchedCSR):
+        return (t.n_graphs * t.n_rows, t.n_graphs * t.n_cols)
+    if hasattr(t, "shape"):
+        return tuple(t.shape)
+    dense_shape = getattr(t, "dense_shape", None)
+    if dense_shape is None and isinstance(t, (list, tuple)) and len(t) == 3:
+        dense_shape = t[2]
+    return tuple(int(v) for v in dense_shape)
+
+
 class Layer(torch.nn.Module):
     """Keras-style lazily built layer: weights are created on the first call from the input shape."""
 
@@ -96,7 +109,7 @@ class Layer(torch.nn.Module):
         if not self.built:
             first = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
             self._build_device = first.device
-            self.build([tuple(t.shape) for t in inputs] if isinstance(inputs, (list, tuple)) else tuple(inputs.shape))
+            self.build([_shape_of(t) for t in inputs] if isinstance(inputs, (list, tuple)) else tuple(inputs.shape))
             self.built = True
         return self.call(inputs, *args, **kwargs)
 

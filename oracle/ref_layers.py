@@ -4,14 +4,18 @@ TEST INFRASTRUCTURE ONLY -- only ``tests/``, ``__graft_entry__.smoke()`` and ``b
 ``cpu_baseline`` / ``--impl reference`` legs may import this module.  The product path
 (``kgcn_b200/``) never does and fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED (arithmetic half): the reference ships no golden outputs, known-answer vectors
-or tests for these layers and its arithmetic lives in un-vendored
-TensorFlow 1.15.0 (requirements.yaml:84), which is not installable here.  What pins this file
-instead: (i) the hand-derived known-answer vectors KAT1-KAT3 of SURVEY.md Appendix B
-(``tests/test_oracle.py``), (ii) a slow "faithful" tier (O1) that follows the reference's
-operation order literally and a fast tier (O2, scipy CSR) cross-checked against it, and
-(iii) the integer/ingest half being pinned by the reference's *own* numpy code run under
-``oracle/tf_stub.py`` (``oracle/make_golden.py`` -> ``tests/golden/``).
+PARITY PIN (arithmetic half): the reference ships no golden outputs, known-answer vectors or tests for these layers
+ and its arithmetic primitives live in un-vendored TensorFlow 1.15.0 (requirements.yaml:84),
+which is not installable here.  What pins this file: (i) golden layer outputs produced by the reference's OWN
+``kgcn/layers.py`` / ``kgcn/legacy/layers.py`` imported and executed unchanged under ``oracle/tf_numpy.py`` (its
+loops, op order, indexing, bias placement, padding rules; only the ~25 TensorFlow primitives are numpy restatements)
+on batches ingested by the reference's own ``data_util`` / ``feed`` code -- ``oracle/make_layer_golden.py`` ->
+``tests/golden/layers_*.npz``, reproduced bit for bit by ``tests/test_reference_layers.py``; that run also confirms
+the hand-derived known-answer vectors KAT1-KAT3 of SURVEY.md Appendix B; (ii) a slow "faithful" tier (O1) that follows
+the reference's operation order literally and a fast tier (O2, scipy CSR) cross-checked against it; (iii) the
+integer/ingest half pinned by the reference's numpy code run under ``oracle/tf_stub.py`` (``oracle/make_golden.py``
+-> ``tests/golden/ingest_*.npz``).  What remains unpinned: TensorFlow's own kernels were never executed (summation
+order inside ``tf.matmul`` and Keras' BatchNormalization learning-phase behaviour are taken from documentation).
 
 All citations are relative to /root/reference (clinfo/kGCN @ 32328d5).  float32 throughout.
 """
