@@ -287,6 +287,42 @@ int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, int32_t n_nod
 int kgcn_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int64_t step, float grad_scale, int32_t* step_state, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Record IO for the block-diagonal ("sparse") ingest and the checkpoint reader.  HOST functions,
+ * HOST pointers, no CUDA.  They replace what the reference gets from TensorFlow's C++ runtime:
+ * tf.data.TFRecordDataset (task_sparse_gcn.py:119) and tf.io.parse_single_example with the
+ * feature_spec of task_sparse_gcn.py:153-166, over files written by
+ * kgcn/preprocessing/utils.py:178-226 (convert_to_example / save_tfrecords); and the CRC-32C
+ * (Castagnoli) that guards both TFRecord files and tensor-bundle checkpoints
+ * (model/reaction/model.best.ckpt.*, restored by kgcn/core.py's tf.train.Saver).
+ */
+/* CRC-32C of n_bytes at data (0 for an empty range); _masked applies TensorFlow's storage mask
+ * rotr(crc, 15) + 0xa282ead8. */
+uint32_t kgcn_crc32c(const void* data, size_t n_bytes);
+uint32_t kgcn_crc32c_masked(const void* data, size_t n_bytes);
+
+/* Walks a whole TFRecord file image (u64le length | u32le masked crc of the length | data |
+ * u32le masked crc of the data, repeated).  Writes the byte offset and length of each record's
+ * data into rec_off / rec_len (first `capacity` records) and the number of records found into
+ * *n_records; call with capacity 0 to count.  verify_crc != 0 checks both checksums of every
+ * record.  KGCN_ERR_BAD_SHAPE for a truncated or corrupted file (TF: DataLossError). */
+int kgcn_tfrecord_scan(const void* file, size_t n_bytes, int32_t verify_crc, int64_t* rec_off,
+                       int64_t* rec_len, int64_t capacity, int64_t* n_records);
+
+/* For each of n_rec serialized tensorflow.Example messages (file + rec_off[r], rec_len[r] bytes)
+ * extracts the feature stored under `key` and appends its values to `values`: kind 1 = float_list
+ * -> fp32, kind 2 = int64_list -> int64 (packed or unpacked encoding).  counts[r] (optional) = number of values record r
+ * contributed (0 if the key is absent: VarLenFeature semantics; the FixedLenFeature shape check is
+ * the caller's), *total = their sum.  `values` may be NULL (count only).  KGCN_ERR_WORKSPACE if
+ * `capacity` values are not enough (*total then says how many are needed), KGCN_ERR_BAD_SHAPE for
+ * a malformed message, KGCN_ERR_UNSUPPORTED if the feature holds another kind than requested
+ * (TF: InvalidArgumentError) or for kind 0 (bytes lists: not used by the feature_spec).
+ * This is exactly the concatenated layout construct_batched_adjacency_and_feature_matrices
+ * (kgcn/data_util.py:698-845) takes after tf.data batching + tf.sparse.to_dense flattening. */
+int kgcn_tfexample_gather(const void* file, const int64_t* rec_off, const int64_t* rec_len, int64_t n_rec,
+                          const char* key, int32_t kind, void* values, int64_t capacity, int64_t* counts,
+                          int64_t* total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,10 @@ SIGNATURES = {
     "kgcn_readout_xent_f32": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_gather_readout_xent_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i64, ctypes.c_float, _vp, _vp]),
+    "kgcn_crc32c": (ctypes.c_uint32, [_vp, _sz]),
+    "kgcn_crc32c_masked": (ctypes.c_uint32, [_vp, _sz]),
+    "kgcn_tfrecord_scan": (ctypes.c_int, [_vp, _sz, _i32, _vp, _vp, _i64, _vp]),
+    "kgcn_tfexample_gather": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_char_p, _i32, _vp, _i64, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
