@@ -17,24 +17,37 @@ from ..feed import SparseTensorValue
 # ------------------------------------------------------------------------------------------------
 class VariableStore:
     def __init__(self):
-        self.params = {}          # "graph_conv_1/kernel0" -> Parameter
+        self.params = {}          # "graph_conv_1/kernel0" -> Parameter (trainable or not)
+        self.initial_values = {}  # name -> numpy array waiting for its variable (restore before the first run)
         self._counts = {}
         self._scope = []
 
     def begin_pass(self):
         self._counts = {}
 
+    def scoped(self, name):
+        return "/".join(self._scope + [name])
+
     def layer_name(self, cls_name):
         base = re.sub(r"(?<!^)(?=[A-Z])", "_", cls_name).lower()        # GraphConv -> graph_conv (Keras naming)
         k = self._counts.get(base, 0)
         self._counts[base] = k + 1
-        name = base if k == 0 else "%s_%d" % (base, k)
-        return "/".join(self._scope + [name])
+        return self.scoped(base if k == 0 else "%s_%d" % (base, k))
 
     def get(self, key, make):
         if key not in self.params:
             self.params[key] = make()
+            if key in self.initial_values:
+                self.assign(key, self.initial_values.pop(key))
         return self.params[key]
+
+    def assign(self, key, value):
+        param = self.params[key]
+        value = np.asarray(value)
+        if tuple(value.shape) != tuple(param.shape):
+            raise ValueError("variable %s has shape %r, the checkpoint holds %r" % (key, tuple(param.shape), tuple(value.shape)))
+        with torch.no_grad():
+            param.copy_(torch.as_tensor(value, dtype=param.dtype))
 
 
 _STORE = None
@@ -268,13 +281,43 @@ class ModelRunner:
                 sys.path.remove(search_path)
         self.model = getattr(module, cls_name)() if cls_name else module
         self.store = VariableStore()
+        self._restore_strict, self._restored_names = None, set()
         self.placeholders = self.model.build_placeholders(info, config, self.batch_size)
 
     def parameters(self):
-        return list(self.store.params.values())
+        """Trainable variables (tf.trainable_variables())."""
+        return [p for p in self.store.params.values() if p.requires_grad]
 
     def named_parameters(self):
+        return {k: p for k, p in self.store.params.items() if p.requires_grad}
+
+    def named_variables(self):
+        """All variables incl. the non-trainable batch-normalisation statistics (tf.global_variables())."""
         return dict(self.store.params)
+
+    def restore(self, prefix, strict=True):
+        """``saver.restore(sess, prefix)`` (kgcn/core.py) from a TensorFlow V2 checkpoint, by variable name.
+
+        Variables that already exist are assigned now; the rest are assigned when the first ``run`` creates them
+        (eager mode has no build step).  Optimizer slots in the file (``.../Adam``, ``beta1_power``) are ignored.
+        ``strict``: a variable of the model that the checkpoint lacks raises KeyError on creation / now
+        (TF: NotFoundError).  Returns the names found in the file."""
+        from ..tf_checkpoint import load_checkpoint
+        values = load_checkpoint(prefix).tensors(skip_slots=True)
+        missing = [k for k in self.store.params if k not in values]
+        if strict and missing:
+            raise KeyError("%s: no value for variable(s) %s" % (prefix, ", ".join(sorted(missing))))
+        for k in self.store.params:
+            if k in values:
+                self.store.assign(k, values[k])
+        self.store.initial_values = {k: v for k, v in values.items() if k not in self.store.params}
+        self._restore_strict, self._restored_names = (prefix if strict else None), set(values)
+        return sorted(values)
+
+    def save(self, prefix):
+        """``saver.save(sess, prefix)``: all variables to ``prefix.index`` + ``prefix.data-00000-of-00001``."""
+        from ..tf_checkpoint import save_checkpoint
+        save_checkpoint(prefix, {k: p.detach().cpu().numpy() for k, p in self.store.params.items()})
 
     def _bind(self, feed):
         bound = {}
@@ -297,7 +340,12 @@ class ModelRunner:
     def run(self, feed):
         """One eager execution of ``build_model`` on this step's feed.  Returns a dict with the five
         values of the model-module protocol: model, prediction, cost_opt, cost_sum, metrics."""
+        before = set(self.store.params)
         with _use_store(self.store):
             out = self.model.build_model(self._bind(feed), self.info, self.config, self.batch_size)
+        if self._restore_strict:
+            fresh = sorted(k for k in set(self.store.params) - before if k not in self._restored_names)
+            if fresh:
+                raise KeyError("%s: no value for variable(s) %s" % (self._restore_strict, ", ".join(fresh)))
         model, prediction, cost_opt, cost_sum, metrics = out[:5]
         return {"model": model, "prediction": prediction, "cost_opt": cost_opt, "cost_sum": cost_sum, "metrics": metrics}

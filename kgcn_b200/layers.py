@@ -93,7 +93,8 @@ class Layer(torch.nn.Module):
         store = _active_store()
         if store is not None:   # eager re-execution of a TF-style build_model: reuse variables by TF-style name
             if self._store_name is None:
-                self._store_name = self._layer_name or store.layer_name(type(self).__name__)
+                self._store_name = store.scoped(self._layer_name) if self._layer_name else \
+                    store.layer_name(getattr(self, "TF_SCOPE_CLASS", None) or type(self).__name__)
             param = store.get(self._store_name + "/" + name, make)
             if tuple(param.shape) != tuple(shape):
                 raise ValueError("variable %s/%s has shape %r, layer wants %r" % (self._store_name, name, tuple(param.shape), tuple(shape)))
@@ -251,10 +252,17 @@ class GraphBatchNormalization(Layer):
 
     EPS = 1e-3
     MOMENTUM = 0.99
+    # The reference layer owns no variables itself: they belong to the tf.keras BatchNormalization /
+    # tf.layers.batch_normalization it instantiates inside call() (layers.py:205,215; legacy/layers.py:202,213), so
+    # TensorFlow names them ``[bn_name or batch_normalization(_k)]/{gamma,beta,moving_mean,moving_variance}`` -- the
+    # names in the shipped checkpoint (model/reaction/model.best.ckpt.index: rollout/batch_normalization_1/gamma ...).
+    TF_SCOPE_CLASS = "BatchNormalization"
 
     def __init__(self, bn_name=None, batch_statistics=False, **kwargs):
         super().__init__(**kwargs)
         self.bn_name = bn_name
+        if bn_name and not self._layer_name:
+            self._layer_name = bn_name
         self.batch_statistics = batch_statistics
 
     def build(self, input_shape):
@@ -262,8 +270,9 @@ class GraphBatchNormalization(Layer):
         self.data_shape = input_shape
         self.gamma = self.add_weight("gamma", (f,), "ones", device=self._build_device)
         self.beta = self.add_weight("beta", (f,), "zeros", device=self._build_device)
-        self.register_buffer("moving_mean", torch.zeros(f, device=self._build_device))
-        self.register_buffer("moving_variance", torch.ones(f, device=self._build_device))
+        # non-trainable variables (saved and restored with the rest, never touched by the optimizer)
+        self.moving_mean = self.add_weight("moving_mean", (f,), "zeros", trainable=False, device=self._build_device)
+        self.moving_variance = self.add_weight("moving_variance", (f,), "ones", trainable=False, device=self._build_device)
 
     def call(self, inputs, enabled_node_nums=None, shape=None, max_node_num=None, training=True):
         enabled = None

@@ -181,14 +181,25 @@ class BatchNormalization(Layer):
         return T(y)
 
 
+# Variables for the next tf.layers.batch_normalization calls, consumed in call order: dicts with gamma / beta /
+# moving_mean / moving_variance (what a restored checkpoint provides; oracle/make_ckpt_golden.py).  Empty = fresh
+# variables (gamma 1, beta 0, moving mean 0 / variance 1).
+BN_VARIABLES = []
+
+
 def _batch_normalization(inputs, training=False, name=None, epsilon=1e-3, **kwargs):
-    """tf.layers.batch_normalization with fresh variables (gamma 1, beta 0): training=True -> batch statistics."""
+    """tf.layers.batch_normalization: training=True -> batch statistics, else the moving ones; y = x_hat * gamma + beta."""
     x = np.asarray(inputs, np.float64)
+    f = x.shape[-1]
+    v = BN_VARIABLES.pop(0) if BN_VARIABLES else {}
     if training:
         mean, var = x.mean(0), x.var(0)
     else:
-        mean, var = np.zeros(x.shape[-1]), np.ones(x.shape[-1])
-    return T((x - mean) / np.sqrt(var + epsilon))
+        mean, var = np.asarray(v.get("moving_mean", np.zeros(f)), np.float64), np.asarray(v.get("moving_variance", np.ones(f)), np.float64)
+    y = (x - mean) / np.sqrt(var + epsilon)
+    if v:
+        y = y * np.asarray(v["gamma"], np.float64) + np.asarray(v["beta"], np.float64)
+    return T(y)
 
 
 def install():

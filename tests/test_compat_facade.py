@@ -87,12 +87,14 @@ def test_tf_style_model_runs_on_gpu_and_reuses_variables(facade):
     fd = feed.construct_feed(list(range(6)), runner.placeholders, data, batch_size=B, config={"task": "classification"})
     out1 = runner.run(fd)
     names = sorted(runner.named_parameters())
-    assert names == ["dense/bias", "dense/kernel", "graph_batch_normalization/beta", "graph_batch_normalization/gamma",
+    # TensorFlow's names: the normalisation variables belong to the BatchNormalization the layer instantiates inside call()
+    assert names == ["batch_normalization/beta", "batch_normalization/gamma", "dense/bias", "dense/kernel",
                      "graph_conv/bias0", "graph_conv/kernel0", "graph_conv_1/bias0", "graph_conv_1/kernel0",
                      "graph_dense/bias", "graph_dense/kernel"]
-    ids = {k: id(v) for k, v in runner.named_parameters().items()}
+    assert sorted(set(runner.named_variables()) - set(names)) == ["batch_normalization/moving_mean", "batch_normalization/moving_variance"]
+    ids = {k: id(v) for k, v in runner.named_variables().items()}
     out2 = runner.run(fd)
-    assert {k: id(v) for k, v in runner.named_parameters().items()} == ids          # variables reused, none created
+    assert {k: id(v) for k, v in runner.named_variables().items()} == ids           # variables reused, none created
     assert torch.equal(out1["prediction"], out2["prediction"])
     # numerics against the oracle with the same weights
     P = {k: v.detach().cpu().numpy() for k, v in runner.named_parameters().items()}
