@@ -112,11 +112,14 @@ def cpu_reference_run(steps, warmup, max_seconds=None):
             lim = np.sqrt(6.0 / (shape[-2] + shape[-1]))
             net.view(net.params, name)[...] = rng.uniform(-lim, lim, size=shape)
     mask = np.ones(B, np.float32)
-    threads = cref.max_threads()
+    # all the host cores this process may use -- stated explicitly, because torchrun exports OMP_NUM_THREADS=1 to its
+    # workers and the OpenMP default would then time the CPU arm on a single thread
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     def one(i):
         d = host[i % len(host)]
-        return net.train_step(d["counts"], d["indices"], d["values"], d["features"], d["labels"], mask, w["n_nodes"])
+        return net.train_step(d["counts"], d["indices"], d["values"], d["features"], d["labels"], mask, w["n_nodes"],
+                              n_threads=threads)
 
     for i in range(warmup):
         one(i)
