@@ -273,6 +273,17 @@ def run_own(args):
                 "traffic": 9386000.0,
                 "timing": "CUDA events around %d back-to-back launches (graph replay) over %d rotating batches" % (reps * N_ROT, N_ROT)}
 
+    # context for `frac` at this size: a plain device-to-device copy moving about the same bytes (8.4 MB read + 8.4 MB
+    # written), timed the same way.  MEASURED_PEAKS' copy figure is for 2 GiB transfers; at 17 MB a launch is a few
+    # microseconds long and its fill / drain is a large part of it.
+    def copy_same(i):
+        ys[i % N_ROT].copy_(batches[i % N_ROT].features)
+
+    copy_us = time_alone(copy_same)
+    copy_bytes = 2 * 4 * B * N * F
+    roofline["same_size_copy"] = {"bytes": copy_bytes, "us_per_launch": copy_us, "gbs": copy_bytes / copy_us / 1e3,
+                                  "spmm_vs_copy": (bytes_spmm / spmm_us) / (copy_bytes / copy_us)}
+
     # ---- the fused GraphConv layer kernel (x -> act(A.x.W + deg*b)) timed the same way ----
     w0, b0 = tr.views["conv0/kernel"], tr.views["conv0/bias"]
 

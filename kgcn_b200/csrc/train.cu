@@ -28,14 +28,14 @@ constexpr int kReadoutMaxSlice = 128;
 // here from the node rows x_nodes [n_graphs, n_nodes, feat] and written to g (an OUTPUT then) -- one launch and one pass
 // over the last layer's activations less per step.
 template <bool FUSE_GATHER>
-__global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
+__global__ void __launch_bounds__(kReadoutThreads, 1) readout_kernel(
     const float* __restrict__ x_nodes, int n_nodes,
     float* g, int64_t n_graphs, int feat, const float* __restrict__ w, const float* __restrict__ bias,
     int n_labels, const float* __restrict__ labels, const float* __restrict__ mask, float inv_batch,
     float* __restrict__ logits, float* __restrict__ prediction, float* __restrict__ dlogits, float* __restrict__ dg,
     float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state) {
     pdl_prologue();
-    extern __shared__ float rd_smem[];   // g_s [slice][feat] | w_s [feat][n_labels] | y_s [slice][n_labels] | m_s [slice]
+    extern __shared__ __align__(16) float rd_smem[];   // g_s [slice][feat] | w_s [feat][n_labels] | y_s [slice][n_labels] | m_s [slice]
     __shared__ float dz_s[kReadoutMaxSlice * kMaxLabels];
     __shared__ float cost_s[kReadoutMaxSlice], corr_s[kReadoutMaxSlice];
     __shared__ float red_s[kReadoutThreads];
@@ -53,14 +53,45 @@ __global__ void __launch_bounds__(kReadoutThreads) readout_kernel(
     for (int i = threadIdx.x; i < feat * n_labels; i += kReadoutThreads) w_s[i] = w[i];
     for (int i = threadIdx.x; i < n_here * n_labels; i += kReadoutThreads) y_s[i] = labels[b0 * n_labels + i];
     for (int i = threadIdx.x; i < n_here; i += kReadoutThreads) m_s[i] = mask ? mask[b0 + i] : 1.0f;
-    if (FUSE_GATHER) {   // warp per graph, lane owns features lane, lane + 32, ...
-        for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
-            const float* xb = x_nodes + (b0 + i) * n_nodes * feat;
-            for (int f = lane; f < feat; f += 32) {
-                float acc = 0.0f;
-                for (int r = 0; r < n_nodes; ++r) acc += xb[static_cast<int64_t>(r) * feat + f];
-                g_s[i * feat + f] = acc;
-                g[(b0 + i) * feat + f] = acc;
+    if (FUSE_GATHER) {
+        const int lpr = feat >> 2;   // lanes per node row when every lane owns 4 consecutive features
+        if ((feat & 3) == 0 && lpr <= 32 && (32 % lpr) == 0 && (reinterpret_cast<uintptr_t>(x_nodes) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            // 32 / lpr graphs per warp; a lane walks ALL node rows of its 4 features in index order (the sum stays
+            // bit-identical to gather_fwd_kernel), 16 independent 16-byte loads in flight per lane: the phase is one
+            // or two memory round trips instead of n_nodes / 4 dependent ones.
+            const int gpw = 32 / lpr, sub = lane / lpr, fl = (lane - sub * lpr) * 4;
+            for (int i0 = warp * gpw; i0 < n_here; i0 += (kReadoutThreads / 32) * gpw) {
+                const int i = i0 + sub;
+                if (i >= n_here) continue;
+                const float4* xb = reinterpret_cast<const float4*>(x_nodes + (b0 + i) * n_nodes * feat + fl);
+                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                int r = 0;
+                for (; r + 16 <= n_nodes; r += 16) {
+                    float4 v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = xb[static_cast<int64_t>(r + j) * lpr];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+                    }
+                }
+                for (; r < n_nodes; ++r) {
+                    const float4 v = xb[static_cast<int64_t>(r) * lpr];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                *reinterpret_cast<float4*>(g_s + i * feat + fl) = acc;
+                *reinterpret_cast<float4*>(g + (b0 + i) * feat + fl) = acc;
+            }
+        } else {   // any width: warp per graph, lane owns features lane, lane + 32, ...
+            for (int i = warp; i < n_here; i += kReadoutThreads / 32) {
+                const float* xb = x_nodes + (b0 + i) * n_nodes * feat;
+                for (int f = lane; f < feat; f += 32) {
+                    float acc = 0.0f;
+                    for (int r = 0; r < n_nodes; ++r) acc += xb[static_cast<int64_t>(r) * feat + f];
+                    g_s[i * feat + f] = acc;
+                    g[(b0 + i) * feat + f] = acc;
+                }
             }
         }
     } else {

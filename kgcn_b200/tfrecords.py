@@ -150,12 +150,24 @@ class SparseDataset:
     def __len__(self):
         return len(self.index)
 
-    def batches(self, batch_size, order=None):
-        """Yields parsed batches (dict as :func:`parse_examples`).  Records of one batch may span files."""
+    def batches(self, batch_size, order=None, rank=0, world_size=1):
+        """Yields parsed batches (dict as :func:`parse_examples`).  Records of one batch may span files.
+
+        Data-parallel runs: every rank walks the same global batches of ``batch_size`` records and
+        parses only its contiguous shard of each (molecules are independent, the block-diagonal matrix of a
+        shard is the corresponding diagonal block of the global one) -- no data-path collective."""
         order = range(len(self.index)) if order is None else order
         order = list(order)
         for lo in range(0, len(order), batch_size):
-            chunk = [self.index[i] for i in order[lo:lo + batch_size]]
+            picked = order[lo:lo + batch_size]
+            if world_size > 1:
+                from .trainer import shard_range
+                a, b = shard_range(len(picked), rank, world_size)
+                picked = picked[a:b]
+            chunk = [self.index[i] for i in picked]
+            if not chunk:
+                yield parse_examples(self.files[0], self.spec, [])
+                continue
             parts = []
             start = 0
             while start < len(chunk):          # runs of consecutive records from the same file

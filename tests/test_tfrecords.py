@@ -309,4 +309,4 @@ def test_tfrecords_to_block_diagonal_graphconv(tmp_path):
             for c in range(C):
                 conv.w[c].copy_(torch.as_tensor(w[c]).cuda()); conv.bias[c].copy_(torch.as_tensor(b[c]).cuda())
         out = ops.segment_sum(conv(xt, adj=csr)[0], sizes)
-        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
