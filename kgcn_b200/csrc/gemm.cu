@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p
 
 // out[r, n] = sum_z partial[z][r][n] (deterministic order); row M -> colsum output.
 // Block = 32 consecutive outputs (one per lane, coalesced) x 32 warps; warp w adds the partials z = w, w + 32, ...
-// in that order with four independent loads in flight, then warp 0 adds the 32 warp sums in warp order.  The
+// in that order with up to eight independent loads in flight, then warp 0 adds the 32 warp sums in warp order.  The
 // reduction is a latency chain (a partial block is a few KB), so the width matters, not the bytes.
 __global__ void __launch_bounds__(1024) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
                                                              int has_colsum, float* __restrict__ out,
@@ -170,16 +170,14 @@ __global__ void __launch_bounds__(1024) splitk_reduce_kernel(const float* __rest
     float s = 0.0f;
     if (idx < total) {
         const float* p = partial + idx;
-        int z = warp;
-        for (; z + 96 < splits; z += 128) {
-            const float v0 = p[static_cast<int64_t>(z) * total], v1 = p[static_cast<int64_t>(z + 32) * total];
-            const float v2 = p[static_cast<int64_t>(z + 64) * total], v3 = p[static_cast<int64_t>(z + 96) * total];
-            s += v0;
-            s += v1;
-            s += v2;
-            s += v3;
+        for (int z = warp; z < splits; z += 256) {   // predicated batches of 8: up to 256 partials in ONE round trip
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (z + 32 * j < splits) ? p[static_cast<int64_t>(z + 32 * j) * total] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (z + 32 * j < splits) s += v[j];
         }
-        for (; z < splits; z += 32) s += p[static_cast<int64_t>(z) * total];
     }
     red[warp][lane] = s;
     __syncthreads();

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kReadoutThreads, 1) readout_kernel(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // ---- final sum over the block partials: R helpers per output over contiguous block ranges, 16 loads in flight ----
+    // ---- final sum over the block partials: R helpers per output over contiguous block ranges ----
     const int nb = static_cast<int>(gridDim.x);
     const int R = max(1, min(4, kReadoutThreads / n_out));
     const int chunk = (nb + R - 1) / R;
@@ -188,16 +188,17 @@ __global__ void __launch_bounds__(kReadoutThreads, 1) readout_kernel(
         float acc = 0.0f;
         if (o < n_out && h < R) {
             const float* src = partial + o;
-            int k = h * chunk;
-            const int k_end = min(nb, k + chunk);
-            for (; k + 16 <= k_end; k += 16) {
-                float v[16];
+            const int k_end = min(nb, h * chunk + chunk);
+            // predicated batches of 32 independent loads, added in block order: a helper's whole range (<= 50 blocks
+            // at 148 CTAs and R = 3) costs one or two L2 round trips, never a chain of dependent ones
+            for (int k = h * chunk; k < k_end; k += 32) {
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __ldcg(src + static_cast<size_t>(k + j) * n_out);
+                for (int j = 0; j < 32; ++j) v[j] = (k + j < k_end) ? __ldcg(src + static_cast<size_t>(k + j) * n_out) : 0.0f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc += v[j];
+                for (int j = 0; j < 32; ++j)
+                    if (k + j < k_end) acc += v[j];
             }
-            for (; k < k_end; ++k) acc += __ldcg(src + static_cast<size_t>(k) * n_out);
         }
         red_s[slot] = acc;
         __syncthreads();
@@ -276,17 +277,34 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
                             float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
                             float grad_scale, int host_step, int* __restrict__ step_state) {
     pdl_prologue();
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // this thread's first element is requested BEFORE the step counter is needed, so the counter and the operands
+    // arrive in one memory round trip (the whole parameter buffer is a few KB: the kernel is that round trip)
+    float g0 = 0.0f, m0 = 0.0f, v0 = 0.0f, p0 = 0.0f;
+    if (i < n) {
+        g0 = grad[i];
+        m0 = m[i];
+        v0 = v[i];
+        p0 = param[i];
+    }
     const int t = step_state != nullptr ? step_state[0] + 1 : host_step;
     // TF AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
     const float lr_t = lr * sqrtf(1.0f - powf(beta2, static_cast<float>(t))) / (1.0f - powf(beta1, static_cast<float>(t)));
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float gr = grad[i] * grad_scale;
-        const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
-        const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+    for (; i < n; i += stride) {
+        const float gr = g0 * grad_scale;
+        const float mi = beta1 * m0 + (1.0f - beta1) * gr;
+        const float vi = beta2 * v0 + (1.0f - beta2) * gr * gr;
         m[i] = mi;
         v[i] = vi;
-        param[i] -= lr_t * mi / (sqrtf(vi) + eps);
+        param[i] = p0 - lr_t * mi / (sqrtf(vi) + eps);
+        const int64_t nx = i + stride;
+        if (nx < n) {
+            g0 = grad[nx];
+            m0 = m[nx];
+            v0 = v[nx];
+            p0 = param[nx];
+        }
     }
     if (step_state != nullptr) {
         __syncthreads();
