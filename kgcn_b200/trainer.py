@@ -78,10 +78,12 @@ class Trainer:
         self.adam_m = torch.zeros(total, **f32)
         self.adam_v = torch.zeros(total, **f32)
         self.step_state = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self.views, self.gviews = {}, {}
+        self.views, self.gviews, self.mviews, self.vviews = {}, {}, {}, {}
         for (name, shape), off, n in zip(shapes, offs, sizes):
             self.views[name] = self.params[off:off + n].view(shape)
             self.gviews[name] = self.grads[off:off + n].view(shape)
+            self.mviews[name] = self.adam_m[off:off + n].view(shape)
+            self.vviews[name] = self.adam_v[off:off + n].view(shape)
         self.init_params(np.random.default_rng(seed))
 
         s, B, N = spec, self.B, spec.n_nodes
@@ -129,6 +131,80 @@ class Trainer:
             self.views["graph_dense/bias"].copy_(t(p["gd_b"]))
         self.views["dense/kernel"].copy_(t(p["out_w"]))
         self.views["dense/bias"].copy_(t(p["out_b"]))
+
+    # -- checkpoints (tf.train.Saver, kgcn/core.py) ------------------------------------------------
+    BETA1, BETA2 = 0.9, 0.999
+
+    def _tf_names(self, scope=""):
+        """(our name, channel or None, TensorFlow variable name) for every variable, as TensorFlow names them when
+        example_model/model.py builds this network: ``graph_conv[_i]/kernel{c}`` ``[F_in, F_out]``, ``bias{c}``
+        ``[1, F_out]`` (kgcn/layers.py:54-61), ``graph_dense/{kernel,bias}``, ``dense/{kernel,bias}``."""
+        pre = scope.rstrip("/") + "/" if scope else ""
+        out = []
+        for i in range(len(self.spec.conv_dims)):
+            layer = pre + ("graph_conv" if i == 0 else "graph_conv_%d" % i)
+            for c in range(self.spec.channels):
+                out.append(("conv%d/kernel" % i, c, "%s/kernel%d" % (layer, c)))
+                out.append(("conv%d/bias" % i, c, "%s/bias%d" % (layer, c)))
+        if self.spec.dense_dim:
+            out += [("graph_dense/kernel", None, pre + "graph_dense/kernel"), ("graph_dense/bias", None, pre + "graph_dense/bias")]
+        out += [("dense/kernel", None, pre + "dense/kernel"), ("dense/bias", None, pre + "dense/bias")]
+        return out
+
+    def steps_done(self):
+        return int(self.step_state[0].item())
+
+    def save_checkpoint(self, prefix, scope="", with_slots=True):
+        """``saver.save(sess, prefix)``: a TensorFlow V2 checkpoint (kgcn_b200/tf_checkpoint.py) with TensorFlow's
+        variable names.  ``with_slots`` adds what tf.train.AdamOptimizer keeps -- ``<var>/Adam`` (m), ``<var>/Adam_1``
+        (v), ``beta1_power`` / ``beta2_power`` (= beta^(t+1) after t steps) -- plus ``global_step``, so training resumes
+        exactly where it stopped."""
+        from .tf_checkpoint import save_checkpoint
+        tensors = {}
+        for ours, c, tf_name in self._tf_names(scope):
+            for views, suffix in ((self.views, ""),) + (((self.mviews, "/Adam"), (self.vviews, "/Adam_1")) if with_slots else ()):
+                a = views[ours].detach().cpu().numpy()
+                if c is not None:
+                    a = a[c].reshape(1, -1) if ours.endswith("bias") else a[c]
+                tensors[tf_name + suffix] = np.ascontiguousarray(a)
+        if with_slots:
+            t = self.steps_done()
+            tensors["beta1_power"] = np.array(np.float32(self.BETA1) ** np.float32(t + 1), np.float32)
+            tensors["beta2_power"] = np.array(np.float32(self.BETA2) ** np.float32(t + 1), np.float32)
+            tensors["global_step"] = np.array(t, np.int64)
+        save_checkpoint(prefix, tensors)
+
+    def load_checkpoint(self, prefix, scope="", with_slots=True):
+        """``saver.restore(sess, prefix)``.  A missing variable is a KeyError (TF: NotFoundError).  Optimizer state is
+        restored when the file has it; the step count comes from ``global_step``, else from ``beta2_power``."""
+        from .tf_checkpoint import load_checkpoint
+        reader = load_checkpoint(prefix)
+        have_slots = with_slots
+        for ours, c, tf_name in self._tf_names(scope):
+            for views, suffix, required in ((self.views, "", True), (self.mviews, "/Adam", False), (self.vviews, "/Adam_1", False)):
+                if suffix and not with_slots:
+                    continue
+                if not reader.has_tensor(tf_name + suffix):
+                    if required:
+                        raise KeyError("%s: no variable named %r" % (prefix, tf_name + suffix))
+                    have_slots = False
+                    continue
+                a = torch.as_tensor(np.ascontiguousarray(reader.get_tensor(tf_name + suffix), np.float32))
+                dst = views[ours] if c is None else views[ours][c]
+                if a.numel() != dst.numel():
+                    raise ValueError("%s: %s has shape %r, the network needs %r" % (prefix, tf_name + suffix, tuple(a.shape), tuple(dst.shape)))
+                dst.copy_(a.reshape(dst.shape))
+        t = 0
+        if with_slots and have_slots:
+            if reader.has_tensor("global_step"):
+                t = int(reader.get_tensor("global_step"))
+            elif reader.has_tensor("beta2_power"):
+                t = max(0, int(round(math.log(float(reader.get_tensor("beta2_power"))) / math.log(self.BETA2))) - 1)
+        else:
+            self.adam_m.zero_()
+            self.adam_v.zero_()
+        self.step_state.copy_(torch.tensor([t, 0], dtype=torch.int32))
+        return t
 
     # -- one step, eager launch sequence --------------------------------------------------------
     def _forward(self, batch, st):

@@ -213,3 +213,75 @@ def test_tf_style_model_restored_from_checkpoint_matches_reference_layers(tmp_pa
         for name in [m for m in sys.modules if m.startswith("models")]:
             sys.modules.pop(name, None)
         compat.uninstall()
+
+
+def test_trainer_checkpoint_names_and_roundtrip(tmp_path):
+    """The step loop's flat buffers <-> a TensorFlow-format checkpoint with TensorFlow's names (host logic only)."""
+    import torch
+    from kgcn_b200.trainer import NetSpec, Trainer
+    spec = NetSpec(5, [6, 4], 7, channels=2, label_dim=3, dense_dim=8)
+    a = Trainer(spec, 4, device="cpu", seed=1)
+    g = torch.Generator().manual_seed(0)
+    a.adam_m.copy_(torch.randn(a.n_params, generator=g))
+    a.adam_v.copy_(torch.rand(a.n_params, generator=g))
+    a.step_state[0] = 37
+    prefix = str(tmp_path / "run" / "model.ckpt")
+    os.makedirs(os.path.dirname(prefix))
+    a.save_checkpoint(prefix, scope="net")
+    reader = ckpt.load_checkpoint(prefix)
+    shapes = reader.get_variable_to_shape_map()
+    assert shapes["net/graph_conv/kernel0"] == [5, 6] and shapes["net/graph_conv/bias1"] == [1, 6]      # layers.py:54-61
+    assert shapes["net/graph_conv_1/kernel1"] == [6, 4] and shapes["net/graph_dense/kernel"] == [4, 8]
+    assert shapes["net/dense/kernel"] == [8, 3] and shapes["net/dense/bias/Adam_1"] == [3] and shapes["global_step"] == []
+    assert len(shapes) == 3 * (2 * 2 * 2 + 4) + 3
+    np.testing.assert_allclose(reader.get_tensor("beta1_power"), 0.9 ** 38, rtol=1e-5)
+    np.testing.assert_array_equal(reader.get_tensor("net/graph_conv_1/kernel1"), a.views["conv1/kernel"][1].numpy())
+    b = Trainer(spec, 4, device="cpu", seed=2)
+    assert b.load_checkpoint(prefix, scope="net") == 37 and b.steps_done() == 37
+    for name in a.views:          # (the flat buffers also hold alignment padding, which is not a variable)
+        for x, y in ((a.views, b.views), (a.mviews, b.mviews), (a.vviews, b.vviews)):
+            assert torch.equal(x[name], y[name]), name
+    # weights only (e.g. a file written by tf.train.Saver(var_list=trainable)): moments and step start afresh
+    a.save_checkpoint(prefix + ".weights", scope="net", with_slots=False)
+    assert len(ckpt.load_checkpoint(prefix + ".weights").entries) == 2 * 2 * 2 + 4
+    c = Trainer(spec, 4, device="cpu", seed=3)
+    c.adam_m.fill_(1.0)
+    assert c.load_checkpoint(prefix + ".weights", scope="net") == 0
+    assert all(torch.equal(c.views[n], a.views[n]) for n in a.views) and float(c.adam_m.abs().sum()) == 0.0 and c.steps_done() == 0
+    # without global_step the count is recovered from beta2_power (what TensorFlow's own Adam slots provide)
+    tensors = {n: reader.get_tensor(n) for n in reader.entries if n != "global_step"}
+    ckpt.save_checkpoint(prefix + ".tf", tensors)
+    assert Trainer(spec, 4, device="cpu").load_checkpoint(prefix + ".tf", scope="net") == 37
+    with pytest.raises(KeyError, match="other/graph_conv/kernel0"):
+        b.load_checkpoint(prefix, scope="other")
+
+
+@pytest.mark.gpu
+def test_trainer_resumes_bit_exactly_from_checkpoint(tmp_path):
+    """3 steps, save, 2 more steps == 3 steps, save | new process state: load, 2 steps -- bit for bit (the kernels are
+    deterministic and the Adam step counter, moments and weights all travel through the file)."""
+    import torch
+    from kgcn_b200 import synth
+    from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
+    rng = np.random.default_rng(4)
+    B, N, F = 64, 32, 64
+    spec = NetSpec(F, [64, 64], N)
+    batches = []
+    for _ in range(5):
+        d = synth.ring_graphs(rng, B, N, F)
+        batches.append(DeviceBatch.from_host(d["counts"], d["indices"], d["values"], d["features"], d["labels"], N))
+    a = Trainer(spec, B, seed=7)
+    for b in batches[:3]:
+        a.step_eager(b)
+    prefix = str(tmp_path / "model.ckpt")
+    a.save_checkpoint(prefix)
+    for b in batches[3:]:
+        a.step_eager(b)
+    r = Trainer(spec, B, seed=99)
+    assert r.load_checkpoint(prefix) == 3
+    for b in batches[3:]:
+        r.step_eager(b)
+    torch.cuda.synchronize()
+    assert r.steps_done() == a.steps_done() == 5
+    assert torch.equal(r.params, a.params) and torch.equal(r.adam_m, a.adam_m) and torch.equal(r.adam_v, a.adam_v)
+    assert not torch.equal(r.params, Trainer(spec, B, seed=7).params)
