@@ -323,9 +323,9 @@ class GINAggregate(Layer):
 
     def call(self, inputs, adj=None):
         csr = as_batched_csr(adj, inputs.device)
-        agg = ops.BspmmFunction.apply(inputs, None, csr, "shared_sum")
-        eps = torch.stack(list(self.epsilon)).sum()
-        return agg + eps * inputs
+        if csr.channels != self.adj_channel_num:
+            raise ValueError("GINAggregate built for %d adjacency channels, got %d" % (self.adj_channel_num, csr.channels))
+        return ops.GinAggregateFunction.apply(inputs, torch.stack(list(self.epsilon)).reshape(-1), csr)
 
     def compute_output_shape(self, input_shape):
         return input_shape

@@ -124,6 +124,65 @@ class BspmmFunction(torch.autograd.Function):
         return d_rhs, d_values, None, None
 
 
+_IDENTITY_CSR = {}
+
+
+def _identity_rows(B, N, device):
+    """rowptr / col of B identity matrices [N, N] (one stored entry per row), cached per shape and device."""
+    key = (B, N, device.index)
+    if key not in _IDENTITY_CSR:
+        rowptr = torch.arange(B * N + 1, dtype=torch.int32, device=device)
+        col = torch.arange(N, dtype=torch.int32, device=device).repeat(B).contiguous()
+        _IDENTITY_CSR[key] = (rowptr, col)
+    return _IDENTITY_CSR[key]
+
+
+def dot_all(a, b):
+    """sum(a * b) over [B, N, F] operands through the library, deterministic: per-row dot products with the
+    gather-dot kernel of the sparse-values gradient (kgcn_bspmm_dvalues_f32 on an identity pattern), then node sums
+    (kgcn_gather_fwd_f32) folded 32 at a time.  Returns a 0-d device tensor."""
+    a, b = _need_cuda("a", a), _need_cuda("b", b)
+    B, N, F = a.shape
+    rowptr, col = _identity_rows(B, N, a.device)
+    rows = torch.empty(B * N, dtype=torch.float32, device=a.device)
+    check(lib.kgcn_bspmm_dvalues_f32(ptr(rowptr), ptr(col), None, B, 1, N, N, F, ptr(a), N * F, 0, ptr(b), N * F, 0,
+                                     ptr(rows), _stream()))
+    cur, n, width = rows, B * N, N
+    while n > 1:
+        groups = (n + width - 1) // width
+        if groups * width != n:                       # zero padding does not change the sum
+            padded = torch.zeros(groups * width, dtype=torch.float32, device=a.device)
+            padded[:n].copy_(cur[:n])
+            cur = padded
+        out = torch.empty(groups, dtype=torch.float32, device=a.device)
+        check(lib.kgcn_gather_fwd_f32(ptr(cur), groups, width, 1, ptr(out), _stream()))
+        cur, n, width = out, groups, 32
+    return cur.reshape(())
+
+
+class GinAggregateFunction(torch.autograd.Function):
+    """``y[b] = sum_c (eps_c * x[b] + A[b][c] . x[b])`` (kgcn/layers.py:459-471) in ONE launch: the epsilon term is the
+    ``self_scale`` argument of kgcn_bspmm_f32.  Backward: ``dx = sum_c (eps_c * dy + A_c^T . dy)`` is the same launch on
+    the transposed batch; ``d eps_c = <x, dy>`` for every channel."""
+
+    @staticmethod
+    def forward(ctx, x, eps, csr):
+        x, eps = _need_cuda("inputs", x), _need_cuda("epsilon", eps)
+        if eps.numel() != csr.channels:
+            raise ValueError("GINAggregate has %d epsilons, the adjacency batch %d channels" % (eps.numel(), csr.channels))
+        ctx.csr = csr
+        ctx.save_for_backward(x, eps)
+        return bspmm(csr, x, "shared_sum", self_scale=eps)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, eps = ctx.saved_tensors
+        dout = _need_cuda("dout", dout)
+        d_x = bspmm(ctx.csr.transposed(), dout, "shared_sum", self_scale=eps) if ctx.needs_input_grad[0] else None
+        d_eps = dot_all(x, dout).expand(eps.numel()) if ctx.needs_input_grad[1] else None
+        return d_x, d_eps, None
+
+
 def graphconv_workspace_bytes(B, C, N, f_in, f_out):
     return int(lib.kgcn_graphconv_workspace_bytes(B, C, N, f_in, f_out))
 

@@ -292,3 +292,44 @@ def test_integrated_gradients_completeness():
     res = visualization.integrated_gradients(score_adj, xt, flat, divide_number=4, method="ig")
     want = np.concatenate([np.asarray(a[0][1]) * h[b].cpu().numpy().sum(1)[a[0][0][:, 1]] for b, a in enumerate(adjs)])
     np.testing.assert_allclose(res["adjs"].cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,C,F", [(5, 3, 1, 4), (7, 10, 2, 3), (33, 32, 1, 64), (9, 50, 3, 50), (6, 64, 2, 128), (2, 300, 1, 48),
+                                     (40, 32, 2, 64)])
+def test_gin_aggregate_fused_epsilon_forward_backward(B, N, C, F):
+    """GINAggregate (kgcn/layers.py:459-471) with the epsilon term inside the SpMM launch (tile kernel flat / general
+    paths and the row kernel, by shape): forward against the oracle, gradients (x and every epsilon) against
+    torch-CPU autograd of the dense formula."""
+    from kgcn_b200 import layers, ops
+    from kgcn_b200.csr import BatchedCSR
+    rng = np.random.default_rng(B * 100 + N + C)
+    adjs = rand_unique_adjs(rng, B, N, C, density=min(0.3, 6.0 / N), full_rows=False)
+    x = rng.standard_normal((B, N, F)).astype(np.float32)
+    eps = rng.uniform(-0.7, 0.7, C).astype(np.float32)
+    csr = BatchedCSR.from_coo_lists(adjs)
+    gin = layers.GINAggregate(C)
+    xt = dev(x).requires_grad_(True)
+    gin(xt, adj=csr)
+    with torch.no_grad():
+        for c in range(C):
+            gin.epsilon[c].fill_(float(eps[c]))
+    y = gin(xt, adj=csr)
+    ref = R.gin_aggregate(x, adjs, eps)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    dy = rng.standard_normal((B, N, F)).astype(np.float32)
+    y.backward(dev(dy))
+    a = torch.tensor(dense_of(adjs, B, C, N), dtype=torch.float64)
+    xc = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    ec = torch.tensor(eps, dtype=torch.float64, requires_grad=True)
+    yc = sum(ec[c] * xc + torch.einsum("bij,bjf->bif", a[:, c], xc) for c in range(C))
+    yc.backward(torch.tensor(dy, dtype=torch.float64))
+    want = xc.grad.numpy()
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    got_eps = np.array([float(gin.epsilon[c].grad) for c in range(C)])
+    np.testing.assert_allclose(got_eps, ec.grad.numpy(), rtol=2e-4, atol=2e-4 * max(1.0, float(np.abs(ec.grad.numpy()).max())))
+    # the reduction helper on its own: odd sizes exercise the zero-padded folding
+    for shape in ((1, 1, 1), (3, 5, 7), (33, 37, 9)):
+        p, q = rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape).astype(np.float32)
+        got = float(ops.dot_all(dev(p), dev(q)))
+        assert abs(got - float((p.astype(np.float64) * q).sum())) <= 1e-4 * max(1.0, float(np.abs(p * q).sum()))
