@@ -1,7 +1,8 @@
 """Host-side ingest: ``.jbl``-style dictionaries -> per-graph / per-channel COO adjacency lists.
 
-Mirror of the adjacency half of ``kgcn/data_util.py`` (clinfo/kGCN @ 32328d5): same function names,
-same outputs bit for bit (checked against vectors produced by the reference's own code,
+Mirror of ``kgcn/data_util.py`` (clinfo/kGCN @ 32328d5) for the graph path -- the adjacency builders,
+``build_data`` / ``load_data`` (``all_data`` members and ``info`` fields), shuffling and the train / validation
+split: same function names, same outputs bit for bit (checked against vectors produced by the reference's own code,
 ``tests/golden/ingest_*.npz``), rewritten on vectorised numpy.  One-time preprocessing, so it
 stays on the host; the per-step work (batching + CSR packing + upload) is in ``feed.py``/``csr.py``.
 """
@@ -134,6 +135,206 @@ def build_adjs(data, config):
     if config.get("normalize_adj_flag", False):
         adjs = normalize_adj(adjs)
     return adjs, np.array(enabled, dtype=np.int32), len(adjs[0])
+
+
+class dotdict(dict):
+    """``d.key`` access with ``None`` for a missing key -- the container ``build_data`` returns (data_util.py:14-18)."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+
+# per-sample members of ``all_data`` that shuffling / splitting permutes (data_util.py:155-179, 622-643)
+_PER_SAMPLE = ("features", "nodes", "adjs", "labels", "mask_label", "node_label", "mask_node_label", "label_list", "sequences",
+               "sequences_vec", "sequences_vec_range", "sequences_len", "enabled_node_nums")
+_MODAL_NAMES = ("vector_modal", "profeat", "dragon", "chemical_fp")
+_POS_WEIGHT_EPS = 0.01
+
+
+def _say(verbose, *args):
+    if verbose:
+        print(*args)
+
+
+def build_data(config, data, prohibit_shuffle=False, verbose=True, test_mode=False):
+    """``.jbl`` dictionary -> ``(all_data, info)`` with the members and ``info`` fields of ``kgcn/data_util.py:374-561``
+    (what ``kgcn/core.py``, ``kgcn/feed.py`` and the model files read).  The adjacency block is :func:`build_adjs`."""
+    features = data["feature"] if ("feature" in data and config["with_feature"]) else None
+    if features is not None and len(features) == 0:
+        features = None
+    nodes = np.array(data["node"], np.int32) if ("node" in data and config["with_node_embedding"]) else None
+    if nodes is not None and len(nodes) == 0:
+        nodes = None
+    try:
+        adjs, enabled_node_nums, adj_channel_num = build_adjs(data, config)
+    except DataLoadError:
+        _say(verbose, "[INFO] no graph")
+        adjs, enabled_node_nums, adj_channel_num = None, None, 1
+
+    labels = data.get("label")
+    mask_label = data.get("mask_label")
+    if "label_sparse" in data:
+        labels = np.array(data["label_sparse"].todense())
+    if "mask_label_sparse" in data:
+        mask_label = np.array(data["mask_label_sparse"].todense())
+    label_list = None
+    if "label_list" in data:
+        label_list = data["test_label_list"] if test_mode else data["label_list"]
+    vector_modal, vector_modal_name = [], {}
+    for name in _MODAL_NAMES:
+        if name in data:
+            vector_modal_name[name] = len(vector_modal)
+            vector_modal.append(data[name])
+
+    all_data = dotdict(
+        features=features, nodes=nodes, adjs=adjs, labels=np.array(labels) if labels is not None else None,
+        mask_label=mask_label, node_label=data.get("node_label"), mask_node_label=data.get("mask_node_label"),
+        label_list=label_list, num=len(adjs) if adjs is not None else max(len(v) for v in vector_modal),
+        sequences=data.get("sequence"), sequences_vec=data.get("sequence_vec"), sequences_vec_range=data.get("sequence_vec_range"),
+        sequences_len=np.array(data["sequence_length"], np.int32) if "sequence" in data else None,
+        sequence_symbol=np.array(data["sequence_symbol"]) if "sequence_symbol" in data else None,
+        vector_modal=vector_modal, enabled_node_nums=enabled_node_nums)
+    if config["shuffle_data"] and not prohibit_shuffle:
+        _say(verbose, "[INFO] data_shuffle is done")
+        all_data = shuffle_data(all_data)
+
+    info = dotdict(all_node_num=None)
+    if features is not None:      # features: #graphs x #nodes(graph) x #features
+        info.feature_dim, info.graph_node_num, info.feature_enabled = features.shape[2], features.shape[1], True
+    elif nodes is not None:       # nodes: #graphs x #nodes(graph)
+        info.feature_dim, info.graph_node_num, info.feature_enabled = 0, nodes.shape[1], False
+        info.all_node_num = data["node_num"]
+    elif adjs is not None:
+        raise DataLoadError("feature or node are required: please confirm input data and configuration")
+    sequences, sequences_vec = all_data.sequences, all_data.sequences_vec
+    info.sequence_max_length = sequences.shape[1] if sequences is not None else 0
+    info.sequence_symbol_num = data["sequence_symbol_num"] if sequences is not None else 0
+    info.sequences_vec_dim = 0
+    if sequences_vec is not None:
+        info.sequence_max_length, info.sequences_vec_dim = sequences_vec.shape[1], sequences_vec.shape[2]
+    if all_data.sequences_vec_range is not None:
+        info.sequences_vec_dim = len(data["sequence_vec_name"])
+    info.graph_num = len(adjs) if adjs is not None else 0
+    info.adj_channel_num = adj_channel_num
+    if labels is not None:
+        shape = np.shape(labels)
+        info.label_dim = data["label_dim"] if "label_dim" in data else (shape[1] if len(shape) >= 2 else 1)
+        expected = info.graph_num if adjs is not None else all_data.num
+        if shape[0] != expected:
+            _say(True, "[ERROR] %d labels for %d samples" % (shape[0], expected))
+    elif all_data.node_label is not None:      # node_label: graph_num x node_num x label_dim
+        info.label_dim = np.shape(all_data.node_label)[2]
+        _say(verbose, "[INFO] node centric mode")
+    else:
+        info.label_dim = data.get("label_dim")
+    if (features is not None and features.shape[0] != info.graph_num) or (nodes is not None and nodes.shape[0] != info.graph_num):
+        raise DataLoadError("the numbers of feature matrices, node lists and adjacency matrices differ: please confirm input data")
+    _say(verbose, "[OK] checking #graphs")
+    info.vector_modal_dim = [modal.shape[1] for modal in vector_modal]
+    info.vector_modal_name = vector_modal_name
+    info.graph_index_list = data.get("graph_index_list")
+    if all_data.mask_label is not None and all_data.labels is not None:      # class balance for weighted losses
+        positive = np.nansum(all_data.labels, axis=0)
+        negative = np.nansum(all_data.mask_label, axis=0) - positive
+        info.pos_weight = (negative + _POS_WEIGHT_EPS) / (positive + _POS_WEIGHT_EPS)
+    if "class_weight" in data:
+        info.class_weight = data["class_weight"]
+    elif all_data.labels is not None:      # labels: #data x #class
+        info.class_weight = (np.nansum(all_data.labels) + _POS_WEIGHT_EPS) / (np.nansum(all_data.labels, axis=0) + _POS_WEIGHT_EPS)
+    if "mol_info" in data:
+        info.mol_info = data["mol_info"]
+    _say(verbose, "graphs=%s feature_dim=%s graph_node_num=%s all_node_num=%s label_dim=%s adj_channel_num=%s"
+         % (info.graph_num, info.feature_dim, info.graph_node_num, info.all_node_num, info.label_dim, info.adj_channel_num))
+    return all_data, info
+
+
+def load_data(config, filename="data.jbl", prohibit_shuffle=False, test_mode=False, verbose=True):
+    """``joblib.load`` + :func:`build_data` (data_util.py:368-371)."""
+    import joblib
+    _say(verbose, "[LOAD]", filename)
+    return build_data(config, joblib.load(filename), prohibit_shuffle=prohibit_shuffle, test_mode=test_mode, verbose=verbose)
+
+
+def shuffle_data(data):
+    """One permutation from numpy's GLOBAL generator applied to every per-sample member (data_util.py:155-179): the
+    same ``np.random.seed`` gives the same order as the reference."""
+    idx = list(range(data.num))
+    np.random.shuffle(idx)
+    if data.adjs is not None:
+        data.adjs = _object_array(data.adjs)
+    for key in _PER_SAMPLE:
+        if data[key] is not None:
+            data[key] = data[key][idx]
+    if data.vector_modal is not None:
+        data.vector_modal = [m[idx] for m in data.vector_modal]
+    return data
+
+
+def _object_array(items):
+    """``np.array(list of per-graph channel lists)`` without numpy trying to broadcast ragged triples."""
+    out = np.empty(len(items), dtype=object)
+    for i, item in enumerate(items):
+        out[i] = item
+    return out
+
+
+def _take(value, indices):
+    if isinstance(value, np.ndarray):
+        return value[indices]
+    picked = [value[i] for i in indices]
+    try:
+        return np.array(picked)
+    except ValueError:          # ragged per-graph adjacency lists: keep them as an object array
+        return _object_array(picked)
+
+
+def split_data(all_data, valid_data_rate=0.2, indices_for_train_data=None, indices_for_valid_data=None):
+    """Train / validation split of ``all_data`` (data_util.py:597-644): ``int(num * rate)`` validation samples taken
+    from the tail of one global-generator shuffle of ``arange(num)``, unless both index lists are given."""
+    if all_data.get("label_list") is not None:
+        return split_label_list(all_data, valid_data_rate, indices_for_train_data, indices_for_valid_data)
+    if indices_for_train_data is None or indices_for_valid_data is None:
+        valid_num = int(all_data.num * valid_data_rate)
+        indices = np.arange(all_data.num)
+        np.random.shuffle(indices)
+        indices_for_train_data, indices_for_valid_data = indices[:all_data.num - valid_num], indices[all_data.num - valid_num:]
+    train_data, valid_data = dotdict(), dotdict()
+    for key in all_data.keys() - {"sequence_symbol", "num"}:
+        value = all_data[key]
+        for part, indices in ((train_data, indices_for_train_data), (valid_data, indices_for_valid_data)):
+            if value is None:
+                part[key] = None
+            elif key == "vector_modal":
+                part[key] = [np.array([modal[i] for i in indices]) for modal in value]
+            else:
+                part[key] = _take(value, indices)
+    train_data.num, valid_data.num = len(indices_for_train_data), len(indices_for_valid_data)
+    return train_data, valid_data
+
+
+def split_label_list(all_data, valid_data_rate=0.2, indices_for_train_data=None, indices_for_valid_data=None):
+    """Node / edge prediction data: only ``label_list [tasks, items, fields]`` is split, along its second axis
+    (data_util.py:662-695)."""
+    if indices_for_train_data is None or indices_for_valid_data is None:
+        n = len(all_data.label_list[0])
+        valid_num = int(n * valid_data_rate)
+        nid = np.array(list(range(n)))
+        np.random.shuffle(nid)
+        indices_for_train_data, indices_for_valid_data = nid[:n - valid_num], nid[n - valid_num:]
+    train_data, valid_data = dotdict(all_data), dotdict(all_data)
+    train_data["label_list"] = all_data["label_list"][:, indices_for_train_data, :]
+    valid_data["label_list"] = all_data["label_list"][:, indices_for_valid_data, :]
+    return train_data, valid_data
+
+
+def load_and_split_data(config, filename="data.jbl", valid_data_rate=0.2):
+    all_data, info = load_data(config, filename)
+    return (all_data,) + split_data(all_data, valid_data_rate) + (info,)
+
+
+def build_and_split_data(config, data, valid_data_rate=0.2):
+    all_data, info = build_data(config, data)
+    return (all_data,) + split_data(all_data, valid_data_rate) + (info,)
 
 
 def construct_batched_adjacency_and_feature_matrices(size, adj_row, adj_column, adj_values, adj_elem_len, adj_degrees,

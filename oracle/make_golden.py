@@ -94,6 +94,73 @@ def run_feed(all_data, info, batch_idx, batch_size):
     return out
 
 
+def object_array(items):
+    out = np.empty(len(items), dtype=object)
+    for i, item in enumerate(items):
+        out[i] = item
+    return out
+
+
+def build_data_goldens(out_dir):
+    """``build_data`` beyond the adjacency block -- the ``info`` fields, labels / masks / class weights -- and the
+    reference's ``split_data`` / ``shuffle_data`` under a fixed ``np.random.seed``  ->  tests/golden/build_data_*.npz.
+
+    With the installed numpy (2.x) the reference's ``np.array(list of ragged adjacency triples)`` raises, so its own
+    split / shuffle cannot run on the list ``build_data`` returns; they are run unchanged on the same data with
+    ``adjs`` pre-wrapped in a 1-D object array (the ``isinstance(..., np.ndarray)`` branch of data_util.py:636-638)."""
+    import json
+    fixtures = [("sample", "sample.jbl", {}), ("sample_multiadj", "sample_multiadj.jbl", {}), ("sample_multitask", "sample_multitask.jbl", {}),
+                ("sample_node_label", "sample_node_label.jbl", {}), ("synthetic", "synthetic.jbl", {}),
+                ("synthetic_norm", "synthetic.jbl", {"normalize_adj_flag": True})]
+    for name, fname, extra in fixtures:
+        raw = joblib.load(os.path.join(REF, "example_jbl", fname))
+        cfg = dict(BASE_CFG, **extra)
+        all_data, info = quiet(du.build_data, cfg, raw, prohibit_shuffle=True)
+        rec = {"raw_keys": np.array(sorted(raw.keys()))}
+        for k, v in raw.items():
+            rec["in_" + k] = np.asarray(v)
+        scalars = {k: (None if info[k] is None else (bool(info[k]) if isinstance(info[k], (bool, np.bool_)) else int(info[k])))
+                   for k in ("all_node_num", "feature_dim", "graph_node_num", "feature_enabled", "sequence_max_length",
+                             "sequence_symbol_num", "sequences_vec_dim", "graph_num", "adj_channel_num", "label_dim")}
+        scalars["vector_modal_dim"], scalars["vector_modal_name"] = list(info.vector_modal_dim), dict(info.vector_modal_name)
+        scalars["info_keys"] = sorted(info.keys())
+        scalars["all_data_keys"] = sorted(all_data.keys())
+        scalars["none_members"] = sorted(k for k in all_data if all_data[k] is None)
+        rec["info_json"] = np.array(json.dumps(scalars, sort_keys=True))
+        for k in ("pos_weight", "class_weight"):
+            if info.get(k) is not None:
+                rec["info_" + k] = np.asarray(info[k])
+        for k in ("labels", "mask_label", "node_label", "mask_node_label", "sequences", "sequences_len", "enabled_node_nums", "features"):
+            if all_data[k] is not None:
+                rec["all_" + k] = np.asarray(all_data[k])
+        rec["all_num"] = np.int64(all_data.num)
+        # split_data, seed 7, 40 % validation
+        all_data.adjs = object_array(all_data.adjs)
+        np.random.seed(7)
+        train, valid = quiet(du.split_data, all_data, 0.4)
+        for tag, part in (("train", train), ("valid", valid)):
+            rec["split_%s_num" % tag] = np.int64(part.num)
+            for k in ("features", "labels", "mask_label", "node_label", "enabled_node_nums", "sequences_len"):
+                if part[k] is not None:
+                    rec["split_%s_%s" % (tag, k)] = np.asarray(part[k])
+            for k, v in flatten_adjs(list(part.adjs)).items():
+                rec["split_%s_adj_%s" % (tag, k)] = v
+        # explicit index lists
+        tr2, va2 = quiet(du.split_data, all_data, 0.4, indices_for_train_data=[2, 0], indices_for_valid_data=[1, 3])
+        rec["split_explicit_train_enabled"], rec["split_explicit_valid_enabled"] = np.asarray(tr2.enabled_node_nums), np.asarray(va2.enabled_node_nums)
+        # shuffle_data, seed 3
+        np.random.seed(3)
+        shuffled = quiet(du.shuffle_data, all_data)
+        for k in ("features", "labels", "mask_label", "node_label", "enabled_node_nums", "sequences_len"):
+            if shuffled[k] is not None:
+                rec["shuffle_" + k] = np.asarray(shuffled[k])
+        for k, v in flatten_adjs(list(shuffled.adjs)).items():
+            rec["shuffle_adj_" + k] = v
+        path = os.path.join(out_dir, "build_data_%s.npz" % name)
+        np.savez_compressed(path, **rec)
+        print("wrote", os.path.relpath(path, ROOT), scalars["graph_num"], "graphs, label_dim", scalars["label_dim"])
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -161,4 +228,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "build_data":      # only the build_data_*.npz files
+        build_data_goldens(os.path.join(ROOT, "tests", "golden"))
+    else:
+        main()
+        build_data_goldens(os.path.join(ROOT, "tests", "golden"))
