@@ -16,8 +16,8 @@ from .csr import BatchedCSR, pack_host
 
 SparseTensorValue = collections.namedtuple("SparseTensorValue", ["indices", "values", "dense_shape"])
 
-GRAPH_KEYS = ("adjs", "features", "nodes", "labels", "mask", "mask_label", "dropout_rate", "is_train",
-              "enabled_node_nums")
+GRAPH_KEYS = ("adjs", "features", "nodes", "labels", "mask", "mask_label", "mask_node", "node_label", "mask_node_label",
+              "dropout_rate", "is_train", "enabled_node_nums")
 
 
 def construct_feed(batch_idx, placeholders, data, batch_size=None, dropout_rate=0.0, is_train=False, info=None,
@@ -70,6 +70,24 @@ def construct_feed(batch_idx, placeholders, data, batch_size=None, dropout_rate=
             ml = ml[:, None] if ml.ndim == 1 else ml
             tmp = np.zeros((batch_size, ml.shape[1]), np.float32)
             tmp[:n_real] = ml[batch_idx]
+            feed[key] = tmp
+        elif key == "node_label" and get("node_label") is not None:          # feed.py:160-163 (node-centric models)
+            nl = np.asarray(get("node_label"))
+            tmp = np.zeros((batch_size, nl.shape[1], nl.shape[2]), np.float32)
+            tmp[:n_real] = nl[batch_idx]
+            feed[key] = tmp
+        elif key == "mask_node_label" and get("mask_node_label") is not None:  # feed.py:164-170
+            # the reference allocates [batch, nodes] and assigns [n, nodes, labels] rows into it, which only works for a
+            # mask without a label axis; a mask that carries one (the shipped sample_node_label.jbl) keeps it here
+            ml = np.asarray(get("mask_node_label"))
+            tmp = np.zeros((batch_size,) + ml.shape[1:], np.float32)
+            tmp[:n_real] = ml[batch_idx]
+            feed[key] = tmp
+        elif key == "mask_node" and get("enabled_node_nums") is not None:      # feed.py:209-214: 1 for the real atoms
+            n_nodes = int(info.graph_node_num) if info is not None else int(np.asarray(get("features")).shape[1])
+            tmp = np.zeros((batch_size, n_nodes), np.float32)
+            lengths = np.asarray(get("enabled_node_nums"))[batch_idx].reshape(-1)
+            tmp[:n_real] = np.arange(n_nodes)[None, :] < lengths[:, None]
             feed[key] = tmp
         elif key == "dropout_rate":
             feed[key] = dropout_rate

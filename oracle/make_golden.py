@@ -134,6 +134,13 @@ def build_data_goldens(out_dir):
             if all_data[k] is not None:
                 rec["all_" + k] = np.asarray(all_data[k])
         rec["all_num"] = np.int64(all_data.num)
+        # node-level feed keys (feed.py:160-163, 209-214) and the label mask, short batch (padded by one)
+        bi = [2, 0, 1]
+        keys = ["mask_node", "enabled_node_nums"] + [k for k in ("node_label", "mask_label") if all_data[k] is not None]
+        fd = rfeed.construct_feed(bi, {k: k for k in keys}, all_data, batch_size=len(bi) + 1, info=info, config={"task": "classification"})
+        rec["feed_keys"], rec["feed_batch_idx"] = np.array(keys), np.asarray(bi, np.int64)
+        for k in keys:
+            rec["feed_" + k] = np.asarray(fd[k])
         # split_data, seed 7, 40 % validation
         all_data.adjs = object_array(all_data.adjs)
         np.random.seed(7)

@@ -98,6 +98,25 @@ def test_split_and_shuffle_follow_the_reference_generator(name, extra):
     same_members(kept, rec, "all_", ("labels", "enabled_node_nums"))                     # prohibit_shuffle wins
 
 
+@pytest.mark.parametrize("name,extra", FIXTURES)
+def test_node_level_feed_keys_match_reference(name, extra):
+    """``mask_node`` (1 for a graph's real atoms), ``node_label``, ``mask_label`` of a short batch, as the reference's
+    construct_feed builds them (feed.py:148-163, 209-218) from what build_data returned."""
+    from kgcn_b200 import feed
+    rec = load_golden("build_data_" + name)
+    all_data, info = data_util.build_data(dict(BASE_CFG, **extra), raw_dict(rec), prohibit_shuffle=True, verbose=False)
+    keys, bi = rec["feed_keys"].tolist(), rec["feed_batch_idx"].tolist()
+    fd = feed.construct_feed(bi, keys, all_data, batch_size=len(bi) + 1, info=info, config={"task": "classification"})
+    for k in keys:
+        assert fd[k].dtype == rec["feed_" + k].dtype and fd[k].shape == rec["feed_" + k].shape, k
+        assert fd[k].tobytes() == rec["feed_" + k].tobytes(), k
+    assert (fd["mask_node"].sum(1) == fd["enabled_node_nums"]).all() and fd["mask_node"][-1].sum() == 0
+    if all_data.mask_node_label is not None:      # the reference itself raises on its 3-D fixture mask (see feed.py here)
+        got = feed.construct_feed(bi, ["mask_node_label"], all_data, batch_size=len(bi) + 1, info=info)["mask_node_label"]
+        assert got.shape == (len(bi) + 1,) + np.shape(all_data.mask_node_label)[1:] and (got[-1] == 0).all()
+        np.testing.assert_array_equal(got[:len(bi)], np.asarray(all_data.mask_node_label)[bi])
+
+
 def test_build_data_without_graph_and_error_paths():
     rec = load_golden("build_data_sample")
     raw = raw_dict(rec)
