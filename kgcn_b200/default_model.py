@@ -28,5 +28,19 @@ class DefaultModel:
             "is_train": _ph("bool", name="is_train"),
         }
         placeholders["features"] = _ph("float32", (batch_size, N, g("feature_dim", 0)), "feature") if g("feature_enabled", True) else None
+        # the remaining names of the reference's table (default_model.py:22-39): inputs of the multimodal / sequence /
+        # link-prediction model families.  Declared so that any model file's key list resolves; the graph path feeds none.
+        seq_len = g("sequence_max_length", 0)
+        placeholders.update({
+            "sequences": _ph("int32", (batch_size, seq_len), "sequences"),
+            "sequences_vec": _ph("float32", (batch_size, seq_len, g("sequences_vec_dim", 0)), "sequences_vec"),
+            "sequences_len": _ph("int32", (batch_size, 2), "sequences_len"),
+            "preference_label_list": _ph("int64", (batch_size, None, 6), "preference_label_list"),
+            "label_list": _ph("int64", (batch_size, None, 2), "label_list"),
+            "embedded_layer": _ph("float32", (batch_size, seq_len, (config or {}).get("embedding_dim")), "embedded_layer"),
+        })
+        modal_dims = g("vector_modal_dim", None) or []
+        for name, j in (g("vector_modal_name", None) or {}).items():
+            placeholders[name] = _ph("float32", (batch_size, modal_dims[j]), name)
         self.placeholders = {name: placeholders[name] for name in placeholder_names}
         return self.placeholders

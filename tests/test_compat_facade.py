@@ -111,3 +111,21 @@ def test_tf_style_model_runs_on_gpu_and_reuses_variables(facade):
     # gradients flow to every variable through the C-ABI autograd functions
     out2["cost_opt"].backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in runner.parameters())
+
+
+def test_default_model_declares_the_whole_placeholder_table(facade):
+    """Every name of kgcn/default_model.py:9-39 resolves (shapes as declared there), with ``info`` as the dotdict
+    build_data returns; 'features' is None when the data has no feature matrix."""
+    from kgcn.default_model import DefaultModel
+    from kgcn_b200.data_util import dotdict
+    info = dotdict(adj_channel_num=2, graph_node_num=5, feature_dim=3, label_dim=2, feature_enabled=True, sequence_max_length=7,
+                   sequences_vec_dim=0, vector_modal_name={"profeat": 0}, vector_modal_dim=[11])
+    names = ["adjs", "nodes", "node_label", "mask_node_label", "labels", "mask", "mask_label", "mask_node", "dropout_rate",
+             "enabled_node_nums", "is_train", "sequences", "sequences_vec", "sequences_len", "profeat", "preference_label_list",
+             "label_list", "features", "embedded_layer"]
+    ph = DefaultModel().get_placeholders(info, {"embedding_dim": 4}, 3, names)
+    assert sorted(ph) == sorted(names)
+    assert ph["mask_node_label"].shape == (3, 5, 2) and ph["mask_node"].shape == (3, 5) and ph["profeat"].shape == (3, 11)
+    assert ph["embedded_layer"].shape == (3, 7, 4) and ph["label_list"].shape == (3, None, 2) and ph["features"].shape == (3, 5, 3)
+    assert len(ph["adjs"]) == 3 and len(ph["adjs"][0]) == 2 and ph["adjs"][1][0].sparse
+    assert DefaultModel().get_placeholders(dotdict(info, feature_enabled=False), {}, 3, ["features"])["features"] is None
