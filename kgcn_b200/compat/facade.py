@@ -29,7 +29,8 @@ class VariableStore:
         return "/".join(self._scope + [name])
 
     def layer_name(self, cls_name):
-        base = re.sub(r"(?<!^)(?=[A-Z])", "_", cls_name).lower()        # GraphConv -> graph_conv (Keras naming)
+        # Keras' to_snake_case (two passes): GraphConv -> graph_conv, GINAggregate -> gin_aggregate
+        base = re.sub(r"([a-z])([A-Z])", r"\1_\2", re.sub(r"(.)([A-Z][a-z0-9]+)", r"\1_\2", cls_name)).lower()
         k = self._counts.get(base, 0)
         self._counts[base] = k + 1
         return self.scoped(base if k == 0 else "%s_%d" % (base, k))

@@ -300,7 +300,7 @@ class GraphMaxPoolFunction(torch.autograd.Function):
             raise ValueError("GraphMaxPooling: adjacency batch %s does not match inputs %s" % ((csr.n_graphs, csr.n_rows, csr.n_cols), (B, N, F)))
         y = torch.empty_like(x)
         ws = None
-        if x.requires_grad:
+        if ctx.needs_input_grad[0]:   # not x.requires_grad: .contiguous() inside forward returns a no-grad copy
             ws = torch.empty(int(lib.kgcn_maxpool_workspace_bytes(B, csr.channels, N, F)), dtype=torch.uint8, device=x.device)
         check(lib.kgcn_maxpool_fwd_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), B, csr.channels, N, ptr(x), F, ptr(y),
                                        ptr(ws), 0 if ws is None else ws.numel(), _stream()))
@@ -312,6 +312,8 @@ class GraphMaxPoolFunction(torch.autograd.Function):
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         csr, ws = ctx.csr, ctx.ws
+        if ws is None:
+            raise RuntimeError("GraphMaxPooling backward: the forward pass kept no workspace (input did not require grad)")
         B, N, F = x.shape
         dy = _need_cuda("dy", dy)
         dx = torch.empty_like(x)

@@ -440,6 +440,12 @@ class HostFedPipeline:
         if nnz > self.max_nnz:
             raise _lib.KgcnError(1, "batch has %d nnz, pipeline capacity is %d" % (nnz, self.max_nnz))
         B = features.shape[0]
+        # range check on the host (TF: InvalidArgumentError at the sparse op; the host packer: KgcnIndexError).  The
+        # device packer only raises a flag, so a bad index must never reach it silently.
+        idx_chk = np.asarray(indices)
+        if idx_chk.size and (int(idx_chk.min()) < 0 or int(idx_chk.max()) >= self.trainer.spec.n_nodes):
+            raise _lib.KgcnIndexError(3, "adjacency index out of range [0, %d): min %d, max %d"
+                                      % (self.trainer.spec.n_nodes, int(idx_chk.min()), int(idx_chk.max())))
         packed = np.zeros(self.layout["bytes"], np.uint8)
         sec = lambda name, dt: packed[self.layout[name][0]:self.layout[name][1]].view(dt)
         off = sec("off", np.int64)

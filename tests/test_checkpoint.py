@@ -155,6 +155,9 @@ def test_variable_store_restores_by_name_before_and_after_creation():
     store._scope.append("rollout")
     assert store.layer_name("GraphConv") == "rollout/graph_conv" and store.layer_name("GraphConv") == "rollout/graph_conv_1"
     assert store.layer_name("BatchNormalization") == "rollout/batch_normalization" and store.scoped("my_bn") == "rollout/my_bn"
+    # Keras' to_snake_case keeps acronyms together: TF names example_model/model_gin.py's layer scope "gin_aggregate"
+    assert store.layer_name("GINAggregate") == "rollout/gin_aggregate" and store.layer_name("GINAggregate") == "rollout/gin_aggregate_1"
+    assert store.layer_name("GraphBatchNormalization") == "rollout/graph_batch_normalization"
     store.initial_values = {"rollout/graph_conv/kernel0": np.arange(6, dtype=np.float32).reshape(2, 3)}
     p = store.get("rollout/graph_conv/kernel0", make)                            # created -> pending value applied
     assert p.detach().numpy().tolist() == [[0, 1, 2], [3, 4, 5]] and not store.initial_values
