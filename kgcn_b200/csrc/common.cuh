@@ -120,6 +120,9 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
 // out[M, N] (+ colsum_out[N], may be null) = sum over `splits` partial blocks of (M + 1) * N floats, fixed order.
 int launch_splitk_reduce(const float* partial, int splits, int64_t M, int N, float* out, float* colsum_out,
                          cudaStream_t st);
+// same for partial blocks of (M + 1) x (channels * n_per_ch): out is channel-major [channels][M][n_per_ch]
+int launch_splitk_reduce_ch(const float* partial, int splits, int64_t M, int n_per_ch, int channels, float* out,
+                            float* colsum_out, cudaStream_t st);
 
 // du = dy * act'(y) (elementwise), optional row mask by enabled_node_nums.
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act,

@@ -158,9 +158,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const SgemmParams p
 // Block = 32 consecutive outputs (one per lane, coalesced) x 32 warps; warp w adds the partials z = w, w + 32, ...
 // in that order with up to eight independent loads in flight, then warp 0 adds the 32 warp sums in warp order.  The
 // reduction is a latency chain (a partial block is a few KB), so the width matters, not the bytes.
+// `n_per_ch` < N: the N columns are C = N / n_per_ch channel blocks and `out` is channel-major [C][M][n_per_ch]
+// (dW of a multi-channel GraphConv: the partial blocks hold X^T.[G_0 | G_1 | ..]).
 __global__ void __launch_bounds__(1024) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
                                                              int has_colsum, float* __restrict__ out,
-                                                             float* __restrict__ colsum_out) {
+                                                             float* __restrict__ colsum_out, int n_per_ch) {
     pdl_prologue();
     __shared__ float red[32][33];
     const int64_t rows = M + (has_colsum ? 1 : 0);
@@ -185,10 +187,17 @@ __global__ void __launch_bounds__(1024) splitk_reduce_kernel(const float* __rest
         s = 0.0f;
 #pragma unroll
         for (int w = 0; w < 32; ++w) s += red[w][lane];
-        if (idx < M * N)
-            out[idx] = s;
-        else if (colsum_out != nullptr)
+        if (idx < M * N) {
+            if (n_per_ch == N) {
+                out[idx] = s;
+            } else {
+                const int64_t m = idx / N;
+                const int cn = static_cast<int>(idx - m * N), c = cn / n_per_ch;
+                out[(static_cast<int64_t>(c) * M + m) * n_per_ch + (cn - c * n_per_ch)] = s;
+            }
+        } else if (colsum_out != nullptr) {
             colsum_out[idx - M * N] = s;
+        }
     }
 }
 
@@ -292,7 +301,16 @@ int launch_sgemm(bool trans_a, bool trans_b, int64_t M, int N, int K, const floa
 int launch_splitk_reduce(const float* partial, int splits, int64_t M, int N, float* out, float* colsum_out,
                          cudaStream_t st) {
     launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((M + 1) * N, 32)), 1024, 0, st, partial, splits,
-               M, N, 1, out, colsum_out);
+               M, N, 1, out, colsum_out, N);
+    KGCN_LAUNCH_OK("splitk_reduce_kernel");
+    return KGCN_OK;
+}
+
+int launch_splitk_reduce_ch(const float* partial, int splits, int64_t M, int n_per_ch, int channels, float* out,
+                            float* colsum_out, cudaStream_t st) {
+    const int N = n_per_ch * channels;
+    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((M + 1) * N, 32)), 1024, 0, st, partial, splits,
+               M, N, 1, out, colsum_out, n_per_ch);
     KGCN_LAUNCH_OK("splitk_reduce_kernel");
     return KGCN_OK;
 }
@@ -320,7 +338,7 @@ int launch_reduce_gemm_tn(int64_t M, int Ka, int N, const float* A, int64_t lda,
     launch_pdl(sgemm_kernel<true, false>, grid, GEMM_THREADS, 0, st, p);
     KGCN_LAUNCH_OK("sgemm_kernel(split-K)");
     launch_pdl(splitk_reduce_kernel, static_cast<unsigned>(ceil_div<int64_t>((static_cast<int64_t>(Ka) + 1) * N, 32)), 1024, 0, st, 
-        static_cast<const float*>(workspace), splits, Ka, N, 1, out, colsum_b);
+        static_cast<const float*>(workspace), splits, Ka, N, 1, out, colsum_b, N);
     KGCN_LAUNCH_OK("splitk_reduce_kernel");
     return KGCN_OK;
 }

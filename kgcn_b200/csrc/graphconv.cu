@@ -25,7 +25,15 @@ bool fused_v4_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, in
                        const int32_t* rowptr, const int32_t* col, const float* val, const float* w, const float* bias);
 int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                               int n_nodes, const float* x, int f_in, const float* w, const float* bias, int f_out, int act,
-                              float* y, cudaStream_t st);
+                              float* y, cudaStream_t st, bool w_transposed = false);
+
+// implemented in graphconv_fused_dw.cu (weight / bias gradient of a layer, all channels, one launch + the partial reduce)
+bool fused_dw_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x, const float* du,
+                       const int32_t* rowptr, const int32_t* col, const float* val);
+size_t fused_dw_partial_bytes(int f_in, int n_total);
+int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs, int channels,
+                              int n_nodes, const float* x, int f_in, const float* du, int f_out, float* dw, float* dbias,
+                              void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 bool fused_bwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int act, bool dy_bcast,
                         const float* x, const float* w, const float* y, const float* dy, const float* dx,
@@ -50,8 +58,8 @@ extern "C" size_t kgcn_graphconv_workspace_bytes(int64_t n_graphs, int32_t chann
     const size_t act_elems = static_cast<size_t>(n_graphs) * n_nodes * f_out;
     // forward: H[C][B*N][f_out]; backward: du[B*N][f_out] + G[C][B*N][f_out] + split-K partials
     return align_up((1 + static_cast<size_t>(channels)) * act_elems * sizeof(float), 256) +
-           align_up(std::max(reduce_gemm_workspace_bytes(n_graphs * n_nodes, f_in, f_out),
-                             fused_bwd_partial_bytes(f_in, f_out)), 256);
+           align_up(std::max({reduce_gemm_workspace_bytes(n_graphs * n_nodes, f_in, f_out), fused_bwd_partial_bytes(f_in, f_out),
+                              fused_dw_partial_bytes(f_in, channels * f_out)}), 256);
 }
 
 extern "C" int kgcn_graphconv_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
@@ -115,6 +123,39 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
     const size_t used = align_up((1 + static_cast<size_t>(channels)) * act_elems * sizeof(float), 256);
     void* ws2 = static_cast<char*>(workspace) + used;
     const size_t ws2_bytes = workspace_bytes - used;
+
+    // Two streaming launches with concurrent roles (feature widths that are multiples of 32, any channel count):
+    //   dx = sum_c (A_c^T.dU).W_c^T  = the fused layer kernel on (A^T, dU, W^T);   dW_c, dbias_c = graphconv_fused_dw.cu
+    if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && ws2_bytes >= fused_dw_partial_bytes(f_in, channels * f_out)) {
+        const bool need_du = act != KGCN_ACT_NONE || dy_bcast;
+        const float* du_in = need_du ? du : dy;
+        if (fused_dw_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, du_in, rowptr_t, col_t, val_t)) {
+            if (need_du) {
+                int rc = launch_act_grad(act != KGCN_ACT_NONE ? y : nullptr, dy, du, static_cast<int64_t>(act_elems), f_out, act,
+                                         nullptr, n_nodes, dy_bcast, st);
+                if (rc) return rc;
+            }
+            if (dx != nullptr && fused_v4_eligible(n_graphs, channels, n_nodes, f_out, f_in, du_in, dx, rowptr_t, col_t, val_t, w, nullptr)) {
+                int rc = launch_graphconv_fused_v4(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, du_in, f_out, w, nullptr, f_in,
+                                                   KGCN_ACT_NONE, dx, st, /*w_transposed=*/true);
+                if (rc) return rc;
+            } else if (dx != nullptr) {   // K = C * f_out too wide for tensor memory: G through HBM, exact-fp32 GEMMs
+                int rc = launch_bspmm(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, n_nodes, f_out, du_in,
+                                      static_cast<int64_t>(n_nodes) * f_out, 0, gbuf, static_cast<int64_t>(n_nodes) * f_out,
+                                      static_cast<int64_t>(act_elems), nullptr, KGCN_ACT_NONE, st);
+                if (rc) return rc;
+                for (int c = 0; c < channels; ++c) {
+                    GemmEpilogue ep;
+                    ep.accumulate = c > 0;
+                    rc = launch_sgemm(false, true, rows, f_in, f_out, gbuf + static_cast<size_t>(c) * act_elems, f_out,
+                                      w + static_cast<size_t>(c) * f_in * f_out, f_out, dx, f_in, ep, st);
+                    if (rc) return rc;
+                }
+            }
+            return launch_graphconv_fused_dw(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, x, f_in, du_in, f_out, dw, dbias,
+                                             ws2, ws2_bytes, st);
+        }
+    }
 
     // fused single-kernel backward (graphconv_fused_bwd.cu) when the shape is eligible
     if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && ws2_bytes >= fused_bwd_partial_bytes(f_in, f_out) &&

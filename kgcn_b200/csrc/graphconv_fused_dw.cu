@@ -1,0 +1,502 @@
+// Fused GraphConv weight gradient for sm_100a: ONE kernel computes, for all adjacency channels c of a layer,
+//
+//     G_c   = A_c^T . dU                      (adjoint_a=True of bspmm_call.py:44 / bconv_call.py:46-57; transposed CSR)
+//     dW_c  = X^T . G_c ,  dbias_c = column sums of G_c            (backward of kgcn/layers.py:112-115)
+//
+// where dU = dy (.) act'(y) comes from the caller.  The input gradient dx = sum_c G_c . W_c^T of the same layer is
+// the fused layer kernel (graphconv_fused_v4.cu) run on (A^T, dU, W^T), so the backward of a layer is two streaming
+// launches that share the concurrent-role design: no phase of a CTA waits for another phase of the same tile.
+//
+// Per persistent CTA (one per SM, contiguous graph range), roles on different chunks at once:
+//   TMA producer warp   ring of stages: the tile's x rows, dU rows and transposed-CSR slices (cp.async.bulk)
+//   8 worker warps      one THREAD per (tile row, 32-column slab): G rows by a gather over the row's CSR entries (8 LDS.128
+//                       per entry, 16-byte chunk order rotated per lane -> conflict-free although every dU row starts at
+//                       the same bank), x rows by a plain copy; both are split into tf32 hi / lo and written MN-major
+//                       (SWIZZLE_128B, 32-byte base: the contraction index of X^T.G is the ROW index, so both operands are
+//                       "transposed" tiles that tcgen05 reads without a transposition pass).  Double-buffered operands.
+//   MMA warp            3xTF32 into ONE fp32 accumulator [f_in x C*f_out] in tensor memory that lives across all tiles of
+//                       the CTA; a second accumulator takes ones^T.[Ghi|Glo] = the column sums of G (dbias).
+// At the end the CTA writes one partial block [(f_in + 1), C*f_out] (last row = dbias); a fixed-order reduction over
+// CTAs follows (splitk_reduce_kernel / the fused reduce + Adam tail).
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace kgcn {
+namespace {
+
+constexpr int kWorkWarps = 8;
+constexpr int kWarpMma = kWorkWarps, kWarpTma = kWorkWarps + 1;
+constexpr int kBlock = (kWorkWarps + 2) * 32;
+constexpr int kStagesMax = 4;
+
+struct DwParams {
+    const int32_t* rowptr;   // transposed BatchedCSR
+    const int32_t* col;
+    const float* val;
+    const float* x;          // [B, N, f_in]
+    const float* du;         // [B, N, f_out]
+    float* partial;          // [grid][(f_in + 1) * Ng]
+    int64_t n_graphs;
+    int C, N, f_in, f_out, Ng;
+    int G, graphs_per_cta;
+    int R;                   // operand chunk: rows (= K of one MMA batch), multiple of 8, <= 64
+    int stacked;             // f_in <= 64: [Xhi ; Xlo] is one M = 128 operand
+    int n_xs, n_gs, spc;     // 32-column slabs of x, of G = [G_0 | G_1 | ..], slabs per channel
+    int n_stages, opbufs, cv_cap;
+    uint32_t off_ones, off_op, op_bytes, op_g, lbo, off_stage, stage_bytes, st_du, st_rp, st_col, st_val, smem_total;
+    uint32_t tmem_cols;
+};
+
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {   // no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+
+// 32 values of one (row, slab) -> tf32 hi / lo, MN-major: the row's 128-byte line of slab `chunk`; inside the line the
+// 32-byte granule g sits at g ^ (row & 3).  acc block i holds 16-byte chunk q = i ^ s7 of the slab (the gather's rotation),
+// so no un-rotation is needed: the 8 lanes of a store phase hit 8 different 16-byte positions (bijective in lane & 7).
+__device__ __forceinline__ void store_split(uint32_t line_hi, uint32_t line_lo, uint32_t row, uint32_t s7, const float (&acc)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t q = static_cast<uint32_t>(i) ^ s7;
+        const uint32_t pos = ((((q >> 1) ^ (row & 3u)) << 1) | (q & 1u)) << 4;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __uint_as_float(__float_as_uint(acc[4 * i + j]) & 0xFFFFE000u);   // truncation: lo = x - hi is exact
+            lo[j] = acc[4 * i + j] - hi[j];
+        }
+        sts_f<4>(line_hi + pos, hi);
+        sts_f<4>(line_lo + pos, lo);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[kStagesMax], bar_empty[kStagesMax], bar_opfull[2], bar_opempty[2], bar_done;
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = p.C, N = p.N, f_in = p.f_in, f_out = p.f_out, Ng = p.Ng, S = p.n_stages, R = p.R;
+    const uint32_t pitch_x = static_cast<uint32_t>(f_in) * 4u, pitch_u = static_cast<uint32_t>(f_out) * 4u;
+
+    const int64_t g_begin = static_cast<int64_t>(blockIdx.x) * p.graphs_per_cta;
+    const int64_t left = p.n_graphs - g_begin;
+    const int n_graphs_cta = static_cast<int>(left < p.graphs_per_cta ? (left > 0 ? left : 0) : p.graphs_per_cta);
+    const int n_tiles = (n_graphs_cta + p.G - 1) / p.G;
+    const int last_ng = n_graphs_cta - (n_tiles - 1) * p.G;
+
+    if (tid == 0) {
+        for (int i = 0; i < kStagesMax; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], kWorkWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_opfull[i], kWorkWarps);
+            mbar_init(&bar_opempty[i], 1);
+        }
+        mbar_init(&bar_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == kWarpMma) tmem_alloc(&tmem_slot, p.tmem_cols);
+    {   // operand regions start as exact zeros (M / K padding must never contribute garbage); the ones operand: column 0
+        // of every K row is 1.0 (element m = 0 sits in granule 0 -> position (row & 3) << 5 of the row's line)
+        const uint32_t n16 = (p.off_stage - p.off_ones) >> 4;
+        const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t i = tid; i < n16; i += kBlock) sts_f<4>(base + p.off_ones + (i << 4), z4);
+    }
+    __syncthreads();
+    if (tid < R) {
+        const float one[1] = {1.0f};
+        sts_f<1>(base + p.off_ones + static_cast<uint32_t>(tid) * 128u + ((static_cast<uint32_t>(tid) & 3u) << 5), one);
+    }
+    fence_proxy_async_smem();
+    pdl_wait();   // everything above overlaps the previous kernel's tail
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == kWarpTma) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            Ring rs;
+            for (int it = 0; it < n_tiles; ++it) {
+                mbar_wait_relaxed(&bar_empty[rs.idx], rs.phase ^ 1u);
+                const int64_t g0 = g_begin + static_cast<int64_t>(it) * p.G;
+                const int ng = (it == n_tiles - 1) ? last_ng : p.G;
+                const int64_t r0 = g0 * C * N;
+                const int rows_csr = ng * C * N;
+                unsigned char* st = gen + p.off_stage + static_cast<size_t>(rs.idx) * p.stage_bytes;
+                uint64_t* full = &bar_full[rs.idx];
+                const int64_t rp_lo = r0 & ~3ll;
+                const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
+                const uint32_t x_bytes = static_cast<uint32_t>(ng * N) * pitch_x, u_bytes = static_cast<uint32_t>(ng * N) * pitch_u;
+                mbar_expect_tx_only(full, x_bytes + u_bytes + 4u * rp_cnt);
+                bulk_g2s(st + p.st_du, p.du + g0 * N * f_out, u_bytes, full);
+                bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
+                bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
+                const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
+                const int32_t e_lo = e_first & ~3;
+                const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
+                const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap) && e_cnt != 0;
+                mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the one arrival of the phase
+                if (staged) {
+                    bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
+                    bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
+                }
+                rs.advance(S);
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // =============================== MMA issuer ===============================
+        const uint32_t idesc_w = umma_idesc_tf32(128, Ng) | kUmmaMajorMnA | kUmmaMajorMnB;
+        const uint32_t idesc_b = umma_idesc_tf32(64, Ng) | kUmmaMajorMnA | kUmmaMajorMnB;
+        const uint32_t d_w = tmem, d_b = tmem + static_cast<uint32_t>(Ng);
+        const uint64_t desc_ones = umma_desc_mn32(base + p.off_ones, p.lbo, 512u);
+        const uint32_t lbo16 = p.lbo >> 4;
+        Ring ro;
+        uint32_t acc = 0;
+        for (int it = 0; it < n_tiles; ++it) {
+            const int rows_t = ((it == n_tiles - 1) ? last_ng : p.G) * N;
+            for (int c0 = 0; c0 < rows_t; c0 += R) {
+                const int ksteps = (min(R, rows_t - c0) + 7) >> 3;
+                mbar_wait(&bar_opfull[ro.idx], ro.phase);
+                tc_fence_after_sync();
+                __syncwarp();
+                if (elect_one()) {
+                    const uint32_t op = base + p.off_op + static_cast<uint32_t>(ro.idx) * p.op_bytes;
+                    const uint64_t dxh = umma_desc_mn32(op, p.lbo, 512u);                         // Xhi (stacked: [Xhi ; Xlo])
+                    const uint64_t dxl = dxh + static_cast<uint64_t>(4u * lbo16);                 // Xlo (not stacked)
+                    const uint64_t dgh = umma_desc_mn32(op + p.op_g, p.lbo, 512u);                // Ghi
+                    const uint64_t dgl = dgh + static_cast<uint64_t>(static_cast<uint32_t>(p.n_gs) * lbo16);   // Glo
+                    for (int ks = 0; ks < ksteps; ++ks) {   // 8 rows (1024 B) per K step
+                        const uint64_t o = static_cast<uint64_t>(64 * ks);
+                        umma_tf32(d_w, dxh + o, dgh + o, idesc_w, acc);
+                        umma_tf32(d_b, desc_ones + o, dgh + o, idesc_b, acc);
+                        acc = 1;
+                        umma_tf32(d_w, dxh + o, dgl + o, idesc_w, 1);
+                        umma_tf32(d_b, desc_ones + o, dgl + o, idesc_b, 1);
+                        if (!p.stacked) umma_tf32(d_w, dxl + o, dgh + o, idesc_w, 1);
+                    }
+                    umma_commit(&bar_opempty[ro.idx]);   // the operand buffer may be overwritten once these MMAs have read it
+                }
+                __syncwarp();
+                ro.advance(p.opbufs);
+            }
+        }
+        if (elect_one()) umma_commit(&bar_done);
+        __syncwarp();
+    } else {
+        // =============================== worker warps ===============================
+        const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
+        const int n_cs = p.n_gs + p.n_xs;
+        const uint32_t lo_x = (p.stacked ? 2u : 4u) * p.lbo, lo_g = static_cast<uint32_t>(p.n_gs) * p.lbo;
+        const uint32_t r0_step = static_cast<uint32_t>(p.G * C * N);
+        uint32_t r0_lo = static_cast<uint32_t>((g_begin * C * N) & 3);
+        Ring rs, ro;
+        for (int it = 0; it < n_tiles; ++it) {
+            const bool last = it == n_tiles - 1;
+            const int rows_t = (last ? last_ng : p.G) * N;
+            const int rows_csr = last ? last_ng * C * N : static_cast<int>(r0_step);
+            const uint32_t st = base + p.off_stage + static_cast<uint32_t>(rs.idx) * p.stage_bytes;
+            mbar_wait(&bar_full[rs.idx], rs.phase);
+            const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
+            const int e_first = static_cast<int>(lds_u32(rp_addr));
+            const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
+            const int e_lo = e_first & ~3;
+            const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
+            const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);   // entry e at col_addr + 4 e
+            const uint32_t val_addr = st + p.st_val - 4u * static_cast<uint32_t>(e_lo);
+
+            for (int c0 = 0; c0 < rows_t; c0 += R) {
+                const int rc8 = (min(R, rows_t - c0) + 7) & ~7;   // rows the MMAs of this chunk read (zero rows past the tile)
+                const int n_rb = (rc8 + 31) >> 5;
+                mbar_wait(&bar_opempty[ro.idx], ro.phase ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t op = base + p.off_op + static_cast<uint32_t>(ro.idx) * p.op_bytes;
+                for (int j = warp; j < n_cs * n_rb; j += kWorkWarps) {
+                    const int cs = j / n_rb, rb = j - cs * n_rb;
+                    const int rl = rb * 32 + lane;          // row inside the chunk
+                    const int r = c0 + rl;                  // row inside the tile
+                    const bool valid = r < rows_t;
+                    float acc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+                    uint32_t line_hi, line_lo;
+                    if (cs < p.n_gs) {
+                        // ---- G slab: gather over the row's entries of channel c ----
+                        const int c = cs / p.spc, s = cs - c * p.spc;
+                        const int gl = r / N, node = r - gl * N;
+                        int e = e_first, e_end = e_first;
+                        if (valid) {
+                            const uint32_t ra = rp_addr + 4u * static_cast<uint32_t>((gl * C + c) * N + node);
+                            e = static_cast<int>(lds_u32(ra));
+                            e_end = static_cast<int>(lds_u32(ra + 4u));
+                        }
+                        const uint32_t ubase = st + p.st_du + static_cast<uint32_t>(gl * N) * pitch_u + static_cast<uint32_t>(s) * 128u + (s7 << 4);
+                        if (staged) {
+                            uint32_t ce = col_addr + 4u * static_cast<uint32_t>(e), ve = val_addr + 4u * static_cast<uint32_t>(e);
+                            const uint32_t cend = col_addr + 4u * static_cast<uint32_t>(e_end);
+                            uint32_t cn = lds_u32(ce);   // one entry of look-ahead; reading one past the row is harmless (slack)
+                            float vn = lds_f32(ve);
+#pragma unroll 1
+                            while (ce < cend) {
+                                const uint32_t ua = ubase + cn * pitch_u;
+                                const float v = vn;
+                                ce += 4;
+                                ve += 4;
+                                cn = lds_u32(ce);
+                                vn = lds_f32(ve);
+                                float uv[8][4];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) lds_f<4>(uv[i], ua ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = fmaf(v, uv[i][jj], acc[4 * i + jj]);
+                            }
+                        } else {   // unusually dense tile: the CSR slice did not fit the stage, entries come from global memory
+                            for (; e < e_end; ++e) {
+                                const uint32_t ua = ubase + static_cast<uint32_t>(__ldg(p.col + e)) * pitch_u;
+                                const float v = __ldg(p.val + e);
+                                float uv[8][4];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) lds_f<4>(uv[i], ua ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = fmaf(v, uv[i][jj], acc[4 * i + jj]);
+                            }
+                        }
+                        line_hi = op + p.op_g + static_cast<uint32_t>(cs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
+                        line_lo = line_hi + lo_g;
+                    } else {
+                        // ---- x slab: the row's 128 bytes, same rotated chunk order ----
+                        const int xs = cs - p.n_gs;
+                        if (valid) {
+                            const uint32_t xa = st + static_cast<uint32_t>(r) * pitch_x + static_cast<uint32_t>(xs) * 128u + (s7 << 4);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float t[4];
+                                lds_f<4>(t, xa ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = t[jj];
+                            }
+                        }
+                        line_hi = op + static_cast<uint32_t>(xs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
+                        line_lo = line_hi + lo_x;
+                    }
+                    __syncwarp();
+                    if (rl < rc8) store_split(line_hi, line_lo, static_cast<uint32_t>(rl), s7, acc);
+                }
+                fence_proxy_async_smem();   // operands are read by the tensor core through the async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_opfull[ro.idx]);
+                ro.advance(p.opbufs);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[rs.idx]);   // this warp is done reading the stage
+            rs.advance(S);
+            r0_lo += r0_step;
+        }
+
+        // ---- per-CTA partial: accumulator rows -> [(f_in + 1), Ng] (last row = column sums of G = dbias partial) ----
+        mbar_wait(&bar_done, 0);
+        tc_fence_after_sync();
+        float* part_out = p.partial + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(f_in) + 1) * Ng;
+        const int q = warp & 3, h = warp >> 2;            // TMEM lane quarter, column phase
+        const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+        const int row = q * 32 + lane;                    // accumulator row = TMEM lane
+        const uint32_t scratch = base + p.off_op;         // operands are dead now: [64][Ng + 4] floats for the Xlo half
+        const uint32_t spitch = static_cast<uint32_t>(Ng + 4) * 4u;
+        if (p.stacked) {
+            if (q >= 2) {
+                for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                    float v[16];
+                    tmem_ld16(tmem + lane_bits + static_cast<uint32_t>(j * 16), v);
+                    tmem_ld_wait();
+                    tmem_ld_fence(v);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float o[4] = {v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]};
+                        sts_f<4>(scratch + static_cast<uint32_t>(row - 64) * spitch + 4u * static_cast<uint32_t>(j * 16 + 4 * qd), o);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kWorkWarps * 32) : "memory");
+            if (q < 2) {
+                for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                    float v[16];
+                    tmem_ld16(tmem + lane_bits + static_cast<uint32_t>(j * 16), v);
+                    tmem_ld_wait();
+                    tmem_ld_fence(v);
+                    if (row < f_in) {
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            float l4[4];
+                            lds_f<4>(l4, scratch + static_cast<uint32_t>(row) * spitch + 4u * static_cast<uint32_t>(j * 16 + 4 * qd));
+                            *reinterpret_cast<float4*>(part_out + static_cast<size_t>(row) * Ng + j * 16 + 4 * qd) =
+                                make_float4(v[4 * qd] + l4[0], v[4 * qd + 1] + l4[1], v[4 * qd + 2] + l4[2], v[4 * qd + 3] + l4[3]);
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                float v[16];
+                tmem_ld16(tmem + lane_bits + static_cast<uint32_t>(j * 16), v);
+                tmem_ld_wait();
+                tmem_ld_fence(v);
+                if (row < f_in) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd)
+                        *reinterpret_cast<float4*>(part_out + static_cast<size_t>(row) * Ng + j * 16 + 4 * qd) =
+                            make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                }
+            }
+        }
+        if (q == 0) {   // dbias accumulator: row 0 of the M = 64 block = TMEM lane 0
+            for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                float v[16];
+                tmem_ld16(tmem + static_cast<uint32_t>(Ng + j * 16), v);
+                tmem_ld_wait();
+                tmem_ld_fence(v);
+                if (lane == 0) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd)
+                        *reinterpret_cast<float4*>(part_out + static_cast<size_t>(f_in) * Ng + j * 16 + 4 * qd) =
+                            make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kWarpMma) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) shares the 227 KB
+
+bool plan_dw_try(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int G, int R, int opbufs, int min_stages) {
+    p.C = C; p.N = N; p.f_in = f_in; p.f_out = f_out; p.Ng = C * f_out; p.n_graphs = n_graphs;
+    p.stacked = f_in <= 64 ? 1 : 0;
+    p.n_xs = f_in / 32;
+    p.spc = f_out / 32;
+    p.n_gs = p.Ng / 32;
+    p.G = G; p.R = R; p.opbufs = opbufs;
+    const int64_t grid0 = std::min<int64_t>(kNumSMs, n_graphs);
+    const int64_t gpc = ceil_div<int64_t>(n_graphs, grid0);
+    if (gpc > (1 << 24)) return false;
+    p.graphs_per_cta = static_cast<int>(gpc);
+    if (p.G > p.graphs_per_cta) p.G = p.graphs_per_cta;
+    const uint32_t rows_max = static_cast<uint32_t>(p.G) * N;
+    if (static_cast<uint32_t>(R) > up(rows_max, 8)) p.R = static_cast<int>(up(rows_max, 8));
+    p.lbo = static_cast<uint32_t>(p.R) * 128u;
+    uint32_t off = 0;
+    p.off_ones = off; off += 2u * p.lbo;                              // M = 64: two 32-row chunks (the second stays zero)
+    p.off_op = off;
+    p.op_g = (p.stacked ? 4u : 8u) * p.lbo;                           // X operand: M = 128 (4 chunks), hi | lo
+    p.op_bytes = p.op_g + 2u * static_cast<uint32_t>(p.n_gs) * p.lbo;  // G operand: Ghi | Glo
+    off += static_cast<uint32_t>(opbufs) * p.op_bytes;
+    if (p.stacked && 64u * (static_cast<uint32_t>(p.Ng) + 4u) * 4u > static_cast<uint32_t>(opbufs) * p.op_bytes) return false;   // end-of-kernel scratch
+    p.off_stage = off;
+    p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C), 4));
+    p.st_du = up(rows_max * f_in * 4u, 128);
+    p.st_rp = p.st_du + up(rows_max * f_out * 4u, 128);
+    p.st_col = p.st_rp + up((rows_max * C + 8) * 4u, 16);
+    p.st_val = p.st_col + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u;
+    p.stage_bytes = up(p.st_val + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u, 128);
+    p.n_stages = 0;
+    for (int st = kStagesMax; st >= min_stages; --st)
+        if (off + st * p.stage_bytes + 1024 <= static_cast<uint32_t>(kSmemMax)) { p.n_stages = st; break; }
+    if (p.n_stages == 0) return false;
+    p.smem_total = off + p.n_stages * p.stage_bytes + 1024;
+    uint32_t cols = 32;
+    while (cols < 2u * static_cast<uint32_t>(p.Ng)) cols <<= 1;
+    p.tmem_cols = cols;
+    return cols <= 512;
+}
+
+bool plan_dw(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
+    if (n_graphs <= 0 || C < 1 || C > 8 || N < 1 || N > 128) return false;
+    if (f_in % 32 != 0 || f_out % 32 != 0 || f_in > 128 || f_in < 32 || C * f_out > 256) return false;
+    // preference: double-buffered operands and >= 2 stages; tiles of whole graphs up to 64 rows, chunks of up to 64 rows
+    const int g_max = std::max(1, 64 / N);
+    for (int opbufs = 2; opbufs >= 1; --opbufs)
+        for (int R = 64; R >= 16; R /= 2)
+            for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
+                if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, R, opbufs, 2)) return true;
+    return plan_dw_try(p, n_graphs, C, N, f_in, f_out, 1, 32, 1, 1);
+}
+
+}  // namespace
+
+bool fused_dw_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KGCN_FUSED_DW");   // tuning / A-B knob: 0 forces the older backward paths
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
+
+size_t fused_dw_partial_bytes(int f_in, int n_total) {
+    return static_cast<size_t>(kNumSMs) * (static_cast<size_t>(f_in) + 1) * n_total * sizeof(float);
+}
+
+bool fused_dw_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x, const float* du,
+                       const int32_t* rowptr, const int32_t* col, const float* val) {
+    if (!fused_dw_enabled()) return false;
+    DwParams p{};
+    if (!plan_dw(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
+    if (n_graphs * static_cast<int64_t>(n_nodes) * channels >= (1ll << 31)) return false;
+    return aligned16(x) && aligned16(du) && aligned16(rowptr) && aligned16(col) && aligned16(val);
+}
+
+int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs, int channels,
+                              int n_nodes, const float* x, int f_in, const float* du, int f_out, float* dw, float* dbias,
+                              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    DwParams p{};
+    KGCN_REQUIRE(plan_dw(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED,
+                 "fused GraphConv weight gradient: unsupported shape");
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
+    const size_t need = static_cast<size_t>(grid) * (static_cast<size_t>(f_in) + 1) * p.Ng * sizeof(float);
+    KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= need && aligned16(workspace), KGCN_ERR_WORKSPACE,
+                 "fused GraphConv weight gradient: workspace %zu < %zu bytes", workspace_bytes, need);
+    p.rowptr = rowptr_t; p.col = col_t; p.val = val_t; p.x = x; p.du = du;
+    p.partial = static_cast<float*>(workspace);
+    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
+    launch_pdl(graphconv_fused_dw_kernel, grid, kBlock, p.smem_total, st, p);
+    KGCN_LAUNCH_OK("graphconv_fused_dw_kernel");
+    return launch_splitk_reduce_ch(p.partial, static_cast<int>(grid), f_in, f_out, channels, dw, dbias, st);
+}
+
+}  // namespace kgcn

@@ -54,6 +54,11 @@ struct V4Params {
     int n_slabs, slabs_per_ch;
     int n_stages, cv_cap;
     int zbufs;            // Z buffers in TMEM (2 when they fit, else 1)
+    int abufs;            // accumulators in TMEM (2 when they fit, else 1)
+    int w_trans;          // 0: w[c][k][n] (+ bias) -- the forward layer;  1: w[c][n][k], no bias -- dx = G . W^T of the backward
+    int w_ld, w_cstride;  // row pitch and channel stride of w (floats)
+    int y_ld;             // row pitch of y (floats)
+    int n_split;          // output-column slices (blockIdx.y): slice s computes columns [s * f_out, (s + 1) * f_out) of y_ld
     uint32_t off_whi, off_wlo, off_ystage, off_stage, stage_bytes, st_rp, st_col, st_val, smem_total;
     uint32_t w_atom;      // bytes between K atoms of the B operand
     uint32_t tm_z;        // first TMEM column of Z buffer 0 (accumulators at columns 0 and Np)
@@ -342,33 +347,58 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
             if (dbg) dbg[10] = pt.acc[0];
         }
     } else {
-        // B operand [W ; bias] -> (hi, lo), K-major SWIZZLE_128B: B row n = output column n, k = c * f_in + f for
+        // B operand [W ; bias] -> (hi, lo), K-major SWIZZLE_128B: B row n = output column col0 + n, k = c * f_in + f for
         // the weights, k = K + c for bias_c (it meets rowsum(A_c) in column K + c of Z).  All non-producer warps.
         {
             constexpr int kStagers = kBlock - 32;
-            const int nq_n = f_out >> 2, kq_n = Kp >> 2;   // one thread per 4 (k) x 4 (n) block: 4 coalesced 16-byte loads
-            for (int idx = tid; idx < kq_n * nq_n; idx += kStagers) {
-                const int n0 = (idx % nq_n) << 2, k4 = (idx / nq_n) << 2;
-                float4 r[4];
+            const int col0 = static_cast<int>(blockIdx.y) * f_out;
+            if (p.w_trans == 0) {
+                const int nq_n = f_out >> 2, kq_n = Kp >> 2;   // one thread per 4 (k) x 4 (n) block: 4 coalesced 16-byte loads
+                for (int idx = tid; idx < kq_n * nq_n; idx += kStagers) {
+                    const int n0 = (idx % nq_n) << 2, k4 = (idx / nq_n) << 2;
+                    float4 r[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int kk = k4 + j;
-                    r[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (kk < K) r[j] = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(kk) * f_out + n0));
-                    else if (kk - K < C && p.bias != nullptr)
-                        r[j] = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(kk - K) * f_out + n0));
+                    for (int j = 0; j < 4; ++j) {
+                        const int kk = k4 + j;
+                        r[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (kk < K) {
+                            const int c = kk / f_in, f = kk - c * f_in;
+                            r[j] = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride +
+                                                                         static_cast<size_t>(f) * p.w_ld + col0 + n0));
+                        } else if (kk - K < C && p.bias != nullptr) {
+                            r[j] = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(kk - K) * p.w_ld + col0 + n0));
+                        }
+                    }
+                    const float t[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x}, {r[0].y, r[1].y, r[2].y, r[3].y},
+                                           {r[0].z, r[1].z, r[2].z, r[3].z}, {r[0].w, r[1].w, r[2].w, r[3].w}};
+#pragma unroll
+                    for (int nn = 0; nn < 4; ++nn) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            hi[j] = tf32_hi(t[nn][j]);
+                            lo[j] = t[nn][j] - hi[j];
+                        }
+                        const uint32_t off = sw128_offset(n0 + nn, k4, p.w_atom);
+                        sts_f<4>(base + p.off_whi + off, hi);
+                        sts_f<4>(base + p.off_wlo + off, lo);
+                    }
                 }
-                const float t[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x}, {r[0].y, r[1].y, r[2].y, r[3].y},
-                                       {r[0].z, r[1].z, r[2].z, r[3].z}, {r[0].w, r[1].w, r[2].w, r[3].w}};
-#pragma unroll
-                for (int nn = 0; nn < 4; ++nn) {
+            } else {
+                // transposed weights (dx = G . W^T): B(n, c * f_in + f) = w[c][col0 + n][f] -- k is the contiguous index
+                const int kq = f_in >> 2;
+                for (int idx = tid; idx < f_out * C * kq; idx += kStagers) {
+                    const int n = idx / (C * kq), r = idx - n * (C * kq), c = r / kq, f4 = (r - c * kq) << 2;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride +
+                                                                           static_cast<size_t>(col0 + n) * p.w_ld + f4));
+                    const float t[4] = {v.x, v.y, v.z, v.w};
                     float hi[4], lo[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        hi[j] = tf32_hi(t[nn][j]);
-                        lo[j] = t[nn][j] - hi[j];
+                        hi[j] = tf32_hi(t[j]);
+                        lo[j] = t[j] - hi[j];
                     }
-                    const uint32_t off = sw128_offset(n0 + nn, k4, p.w_atom);
+                    const uint32_t off = sw128_offset(n, c * f_in + f4, p.w_atom);
                     sts_f<4>(base + p.off_whi + off, hi);
                     sts_f<4>(base + p.off_wlo + off, lo);
                 }
@@ -541,7 +571,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                     __syncwarp();
                     pt.mark(2);
                     rz.advance(p.zbufs);
-                    ra.advance(2);
+                    ra.advance(p.abufs);
                 }
                 if (pt.on) for (int i = 0; i < 3; ++i) dbg[5 + i] = pt.acc[i];
             }
@@ -561,8 +591,9 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
             const uint32_t ysrc = ys + (static_cast<uint32_t>(lane) >> 3) * 128u;   // copy-out: rows 4 k + lane / 8, chunk lane & 7
             const int colq = static_cast<int>(l7) * 4;
             const int row0 = wq * 32 + (lane >> 3);   // first of the 8 tile rows (stride 4) this lane copies out
-            float* y_tile = p.y + tr.g_begin * N * f_out + static_cast<size_t>(row0) * f_out + colq;
-            const size_t y_step = static_cast<size_t>(full_rows) * f_out;
+            const size_t y_ld = static_cast<size_t>(p.y_ld);
+            float* y_tile = p.y + (tr.g_begin * N + row0) * y_ld + static_cast<size_t>(blockIdx.y) * f_out + colq;
+            const size_t y_step = static_cast<size_t>(full_rows) * y_ld;
             Ring ra;
             PhaseTimer pt(dbg != nullptr && e == 0 && lane == 0);
             for (int it = 0; it < n_tiles; ++it) {
@@ -609,7 +640,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                         float t[4];
                         lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
                         if (row0 + 4 * k < rows && col_ok)
-                            *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * f_out) = make_float4(t[0], t[1], t[2], t[3]);
+                            *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
                     }
                     __syncwarp();
                     pt.mark(5);
@@ -619,7 +650,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_tempty[ra.idx]);
                 }
-                ra.advance(2);
+                ra.advance(p.abufs);
                 y_tile += y_step;
             }
             if (pt.on) {
@@ -638,22 +669,27 @@ inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) shares the 227 KB
 
-bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
-    if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || f_out > 256 || C > 8) return false;
-    p.C = C; p.N = N; p.f_in = f_in; p.f_out = f_out; p.n_graphs = n_graphs;
+// One candidate plan: `n_split` output-column slices of f_out_total / n_split columns (each slice is its own CTA row of
+// the grid with its own [W ; bias] slice resident in shared memory), G graphs per tile.
+bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G) {
+    if (f_out_total % n_split != 0) return false;
+    const int f_out = f_out_total / n_split;
+    if (f_out % 4 != 0 || f_out > 256 || (n_split > 1 && f_out % 32 != 0)) return false;
+    p.C = C; p.N = N; p.f_in = f_in; p.f_out = f_out; p.n_graphs = n_graphs; p.n_split = n_split;
     p.K = C * f_in;
     p.Kp = p.K + 8;
     p.Np = static_cast<int>(up(f_out, 16));
     p.n_slabs = p.K / 32;
     p.slabs_per_ch = f_in / 32;
-    // TMEM: two accumulators + zbufs x (Zhi | Zlo)
-    p.tm_z = static_cast<uint32_t>(2 * p.Np);
-    if (2 * p.Np + 4 * p.Kp <= 512) p.zbufs = 2;
-    else if (2 * p.Np + 2 * p.Kp <= 512) p.zbufs = 1;
+    // TMEM: abufs accumulators + zbufs x (Zhi | Zlo)
+    if (2 * p.Np + 4 * p.Kp <= 512) { p.abufs = 2; p.zbufs = 2; }
+    else if (2 * p.Np + 2 * p.Kp <= 512) { p.abufs = 2; p.zbufs = 1; }
+    else if (p.Np + 2 * p.Kp <= 512) { p.abufs = 1; p.zbufs = 1; }
     else return false;
-    p.G = std::max(1, 128 / N);
-    // contiguous graph ranges, one per CTA; small batches are spread over all SMs
-    const int64_t grid0 = std::min<int64_t>(kNumSMs, n_graphs);
+    p.tm_z = static_cast<uint32_t>(p.abufs * p.Np);
+    p.G = G;
+    // contiguous graph ranges, one per CTA of a slice; small batches are spread over all SMs
+    const int64_t grid0 = std::min<int64_t>(std::max(1, kNumSMs / n_split), n_graphs);
     const int64_t gpc = ceil_div<int64_t>(n_graphs, grid0);
     if (gpc > (1 << 24)) return false;
     p.graphs_per_cta = static_cast<int>(gpc);
@@ -679,6 +715,17 @@ bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
     return true;
 }
 
+// Preference: whole output width in one CTA and full 128-row tiles; wide layers (F = 128: [W ; bias] hi / lo alone is
+// 160 KB) fall back to column slices -- each slice aggregates the tile again (the second reader hits L2) -- and to
+// fewer graphs per tile until at least two TMA stages fit.
+bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
+    if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || C > 8 || C < 1) return false;
+    for (int n_split = 1; n_split <= 4; n_split *= 2)
+        for (int G = std::max(1, 128 / N); G >= 1; G = (G > 1 ? G / 2 : 0))
+            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G)) return true;
+    return false;
+}
+
 }  // namespace
 
 bool fused_v4_enabled() {
@@ -701,12 +748,17 @@ static long long* g_dbg_v4 = nullptr;
 
 int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                               int n_nodes, const float* x, int f_in, const float* w, const float* bias, int f_out, int act,
-                              float* y, cudaStream_t st) {
+                              float* y, cudaStream_t st, bool w_transposed) {
     V4Params p{};
     KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: unsupported shape");
-    p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = bias; p.y = y; p.act = act;
+    p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = w_transposed ? nullptr : bias; p.y = y; p.act = act;
+    p.y_ld = f_out;
+    p.w_trans = w_transposed ? 1 : 0;
+    // forward: w[c][f_in][f_out];  transposed (backward dx): the layer's w[c][f_out (= this call's n)][f_in (= this call's k)]
+    p.w_ld = w_transposed ? f_in : f_out;
+    p.w_cstride = f_in * f_out;
     p.dbg = g_dbg_v4;
-    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
+    const dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta)), static_cast<unsigned>(p.n_split));
     KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
     launch_pdl(graphconv_fused_v4_kernel, grid, kBlock, p.smem_total, st, p);
     KGCN_LAUNCH_OK("graphconv_fused_v4_kernel");

@@ -187,6 +187,11 @@ V4_SHAPES = [  # B, N, C, F_in, F_out, max_nnz per matrix
     (33, 16, 1, 32, 64, 16 * 16),    # dense graphs (~10 entries per row > stage capacity): un-staged CSR path
     (20, 64, 1, 96, 128, None),      # three slabs, 4 column slabs in the epilogue
     (12, 24, 1, 160, 8, None),       # five slabs, F_out < 32 (second epilogue column phase idle)
+    (9, 64, 1, 128, 128, None),      # C5 width: [W ; bias] hi / lo is 160 KB -> two output-column slices (grid.y = 2), 1 graph per tile
+    (300, 64, 1, 128, 128, None),    # the same with several tiles per CTA (74 CTAs per slice)
+    (11, 50, 3, 64, 64, None),       # C4 hidden layer: K = 192 -> one accumulator + one Z buffer in tensor memory
+    (11, 50, 1, 96, 64, None),       # C3 first layer after padding 75 -> 96
+    (5, 32, 1, 256, 128, None),      # K = 256: column slices with a single Z buffer
 ]
 
 
@@ -273,6 +278,51 @@ def test_graphconv_backward_fused(K, B, N, fi, fo, max_nnz, act, bcast):
     gdx, gdw, gdb = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), flags=base)
     rdx, rdw, rdb = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), flags=base | 1)
     scale = max(1.0, float(np.abs(dw[0]).max()))
+    close(gdx, dx, 1e-4)
+    close(gdx, rdx.cpu().numpy(), 1e-4)
+    np.testing.assert_allclose(gdw.cpu().numpy(), np.stack(dw), rtol=1e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(gdw.cpu().numpy(), rdw.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(gdb.cpu().numpy(), np.concatenate(db), rtol=1e-4, atol=2e-5 * scale)
+    _, gdw2, gdb2 = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), need_dx=False,
+                                           flags=base)
+    assert torch.equal(gdw, gdw2) and torch.equal(gdb, gdb2)   # same tiles, same accumulation order
+
+
+SPLIT_BWD_SHAPES = [  # B, N, C, fi, fo, max_nnz: widths that are multiples of 32 -> dx by the fused layer kernel on
+    # (A^T, dU, W^T) + dW / dbias by graphconv_fused_dw_kernel (concurrent roles, all channels in one launch)
+    (24, 32, 1, 64, 64, None),      # C2
+    (700, 32, 1, 64, 64, None),     # more tiles than CTAs: the dW accumulator lives across tiles
+    (9, 50, 3, 64, 64, None),       # C4 hidden layer: three channels, 50-row graphs (56-row operand chunks)
+    (9, 50, 3, 96, 64, None),       # C4 first layer after padding (dx falls back: K = 3 * 64 fits, N = 96)
+    (9, 50, 1, 96, 64, None),       # C3 first layer after padding 75 -> 96: Xhi / Xlo as separate operands
+    (7, 64, 1, 128, 128, None),     # C5 width: 32-row operand chunks, dx in two column slices
+    (300, 64, 1, 128, 128, None),   # several tiles per CTA at C5 width
+    (33, 16, 1, 32, 128, None),     # 4 graphs per tile, last tile short
+    (6, 32, 1, 64, 64, 900),        # more entries per tile than the stage holds (entries read from global memory)
+    (5, 128, 1, 64, 32, None),      # 128-node graphs: two operand chunks per tile
+    (3, 1, 2, 32, 32, 1),           # degenerate
+]
+
+
+@pytest.mark.parametrize("B,N,C,fi,fo,max_nnz", SPLIT_BWD_SHAPES)
+@pytest.mark.parametrize("act", ["none", "sigmoid", "relu"])
+@pytest.mark.parametrize("bcast", [False, True])
+def test_graphconv_backward_split(K, B, N, C, fi, fo, max_nnz, act, bcast):
+    """Backward as two streaming launches vs the oracle and vs the decomposed exact-fp32 path (REFERENCE_ORDER flag)."""
+    rng = np.random.default_rng(B * 7 + fo + C)
+    adjs, x = random_batch(rng, B, N, C, fi, max_nnz=max_nnz, empty_graphs=(0,))
+    w = [R.glorot_uniform(rng, fi, fo) for _ in range(C)]
+    b = [rng.uniform(-0.5, 0.5, (1, fo)).astype(np.float32) for _ in range(C)]
+    y = R.activation(R.graph_conv(x, adjs, w, b, fast=True), act)
+    dy = rng.standard_normal((B, fo) if bcast else y.shape).astype(np.float32)
+    dy_full = np.broadcast_to(dy[:, None, :], y.shape) if bcast else dy
+    du = dy_full * R.activation_grad_from_output(y, act)
+    dx, dw, db = R.graph_conv_grad(x, adjs, w, b, du)
+    csr = K["csr"].BatchedCSR.from_coo_lists(adjs)
+    base = 2 if bcast else 0   # KGCN_FLAG_DY_BROADCAST
+    gdx, gdw, gdb = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), flags=base)
+    rdx, rdw, rdb = K["ops"].graphconv_bwd(csr, dev(x), dev(np.stack(w)), R.ACT_IDS[act], dev(y), dev(dy), flags=base | 1)
+    scale = max(1.0, float(np.abs(np.stack(dw)).max()))
     close(gdx, dx, 1e-4)
     close(gdx, rdx.cpu().numpy(), 1e-4)
     np.testing.assert_allclose(gdw.cpu().numpy(), np.stack(dw), rtol=1e-4, atol=2e-5 * scale)
