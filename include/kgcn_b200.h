@@ -276,6 +276,82 @@ int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, int32_t n_nod
                                  float* dlogits, float* dg, float* dw, float* dbias, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* Forward of a layer whose feature widths were padded to multiples of 32 by the caller (zero columns in x, zero rows /
+ * columns in w, zero bias entries) so that Tox21-style widths (75 -> 50) run on the tcgen05 layer kernel: output columns
+ * >= f_out_valid are written as exact zeros whatever the activation (sigmoid(0) = 0.5 would otherwise leak into the
+ * gradients of the next layer's zero rows).  Same mathematics as kgcn_graphconv_fwd_f32 on the un-padded problem.
+ * kgcn_graphconv_fwd_fused(shape) != 0 says the fused layer kernel takes the (padded) shape. */
+int32_t kgcn_graphconv_fwd_fused(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in, int32_t f_out);
+int kgcn_graphconv_fwd_padded_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                                  int32_t channels, int32_t n_nodes, const float* x, int32_t f_in, const float* w,
+                                  const float* bias, int32_t f_out, int32_t f_out_valid, int32_t act, float* y,
+                                  void* stream);
+
+/* kgcn_gather_readout_xent_f32 that also emits the dU of the last graph layer for the step loop:
+ *   du_nodes[b, r, :] = dg[b, :] (.) act'(x[b, r, :])      (the GraphGather gradient of layers.py:164 -- a broadcast over the
+ * node rows -- times the gradient of the activation `act` that produced x), so the layer's backward
+ * (kgcn_graphconv_bwd_partial_f32) needs no separate activation-gradient pass.  du_nodes and dg are required. */
+int kgcn_gather_readout_xent_du_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
+                                    const float* w, const float* bias, int32_t n_labels, const float* labels,
+                                    const float* mask, float inv_batch, float* logits, float* prediction, float* stats,
+                                    float* dlogits, float* dg, float* dw, float* dbias, int32_t act, float* du_nodes,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Step-loop form of the GraphConv backward (same mathematics as kgcn_graphconv_bwd_f32; kgcn/layers.py:105-116 with the
+ * registered gradients of bspmm_call.py:28-52 / bconv_call.py:28-70), two launches:
+ *   dx      = sum_c (A_c^T . du) . W_c^T              the fused layer kernel on (A^T, du, W^T); skipped when dx == NULL.
+ *             With act_below != KGCN_ACT_NONE the result is multiplied by act_below'(x) in the epilogue: x is the output
+ *             of the layer below, so dx then IS that layer's dU and the chain needs no activation-gradient launches.
+ *   partial = per-CTA blocks [(f_in + 1), channels * f_out] of X^T . [A_0^T.du | A_1^T.du | ..] (last row: column sums =
+ *             dbias) -- NOT reduced: kgcn_reduce_adam_f32 sums them in fixed order inside the optimizer launch.
+ * du [n_graphs, n_nodes, f_out] = dy (.) act'(y) of this layer (from the head, or the dx of the layer above).
+ * kgcn_graphconv_bwd_splits returns the number of partial blocks for a shape (0: shape not supported by the fused
+ * kernels -- feature widths must be multiples of 32, f_in <= 128, channels * f_out <= 256; use kgcn_graphconv_bwd_f32);
+ * partial must hold splits * (f_in + 1) * channels * f_out floats. */
+int32_t kgcn_graphconv_bwd_splits(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in, int32_t f_out,
+                                  int32_t need_dx);
+int kgcn_graphconv_bwd_partial_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                   int32_t channels, int32_t n_nodes, const float* x, int32_t f_in, const float* w,
+                                   int32_t f_out, const float* du, float* dx, int32_t act_below, float* partial,
+                                   size_t partial_bytes, void* stream);
+
+/* The reduction alone (gradient checks, the NCCL cross-check path): dw [channels][f_in][f_out] and dbias [channels][f_out]
+ * (may be NULL) from `splits` partial blocks, summed in split order (deterministic). */
+int kgcn_reduce_partials_f32(const float* partial, int32_t splits, int32_t f_in, int32_t f_out, int32_t channels,
+                             float* dw, float* dbias, void* stream);
+
+/* The tail of a training step in ONE launch: fixed-order reduction of the weight-gradient partials -> (data parallel:
+ * one-shot all-reduce over NVLink peer memory) -> Adam (kgcn_adam_f32's formulation, device-side step counter).
+ * `segments` (HOST array) says which ranges of the flat buffers are fed from partial blocks: kernel [channels][rows][cols]
+ * at kernel_off, bias [channels][cols] at bias_off (-1: none), partial [splits][(rows + 1)][channels * cols].  Every other
+ * element takes its gradient from grad[i] as it is.  The reduced (and, with a group, all-reduced) gradient is written back
+ * to grad.  `group` (HOST struct, may be NULL = single GPU): rank r's exchange buffer xg[r] holds 2 * n_pad floats and
+ * flags[r] n_flags uint32 (n_pad >= n rounded up to 32, n_flags >= ceil(n / 32)), zero-initialised, all W of them mapped
+ * into this process (kgcn_p2p_alloc on the owning rank, kgcn_p2p_open on the others); sums are formed in rank order,
+ * so all ranks hold bit-identical gradients and parameters.  Every rank must enqueue the call once per step; a rank
+ * that waits ~2 s for a peer sets *error_flag (device int32, may be NULL) and skips the exchange instead of hanging. */
+typedef struct kgcn_grad_segment {
+    int64_t kernel_off, bias_off;
+    const float* partial;
+    int32_t splits, rows, cols, channels;
+} kgcn_grad_segment;
+typedef struct kgcn_p2p_group {
+    int32_t rank, world;
+    int64_t n_pad, n_flags;
+    float* xg[8];
+    uint32_t* flags[8];
+    int32_t* error_flag;
+} kgcn_p2p_group;
+int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* v, int64_t n, const kgcn_grad_segment* segments,
+                         int32_t n_segments, float lr, float beta1, float beta2, float eps, float grad_scale,
+                         int32_t* step_state, const kgcn_p2p_group* group, void* stream);
+/* Peer-mapped device buffers for the exchange above (cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the 64-byte
+ * handle travels between the ranks' processes through any host channel, e.g. torch.distributed.all_gather).  HOST calls. */
+int kgcn_p2p_alloc(size_t n_bytes, void** device_ptr, unsigned char* handle64);
+int kgcn_p2p_open(const unsigned char* handle64, void** device_ptr);
+int kgcn_p2p_close(void* device_ptr);
+int kgcn_p2p_free(void* device_ptr);
+
 /* Adam with TensorFlow's formulation (tf.train.AdamOptimizer, kgcn/core.py:121-127):
  *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
  *   param -= lr * sqrt(1-b2^step)/(1-b1^step) * m / (sqrt(v) + eps);     step counts from 1.

@@ -87,12 +87,37 @@ SIGNATURES = {
     "kgcn_readout_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "kgcn_readout_xent_f32": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kgcn_gather_readout_xent_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "kgcn_graphconv_fwd_fused": (_i32, [_i64, _i32, _i32, _i32, _i32]),
+    "kgcn_graphconv_fwd_padded_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "kgcn_gather_readout_xent_du_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "kgcn_graphconv_bwd_splits": (_i32, [_i64, _i32, _i32, _i32, _i32, _i32]),
+    "kgcn_graphconv_bwd_partial_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "kgcn_reduce_partials_f32": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "kgcn_reduce_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
+    "kgcn_p2p_alloc": (ctypes.c_int, [_sz, _vp, _vp]),
+    "kgcn_p2p_open": (ctypes.c_int, [_vp, _vp]),
+    "kgcn_p2p_close": (ctypes.c_int, [_vp]),
+    "kgcn_p2p_free": (ctypes.c_int, [_vp]),
     "kgcn_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i64, ctypes.c_float, _vp, _vp]),
     "kgcn_crc32c": (ctypes.c_uint32, [_vp, _sz]),
     "kgcn_crc32c_masked": (ctypes.c_uint32, [_vp, _sz]),
     "kgcn_tfrecord_scan": (ctypes.c_int, [_vp, _sz, _i32, _vp, _vp, _i64, _vp]),
     "kgcn_tfexample_gather": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_char_p, _i32, _vp, _i64, _vp, _vp]),
 }
+
+
+
+class GradSegment(ctypes.Structure):
+    """kgcn_grad_segment (include/kgcn_b200.h)."""
+    _fields_ = [("kernel_off", _i64), ("bias_off", _i64), ("partial", _vp), ("splits", _i32), ("rows", _i32), ("cols", _i32),
+                ("channels", _i32)]
+
+
+class P2PGroup(ctypes.Structure):
+    """kgcn_p2p_group (include/kgcn_b200.h)."""
+    _fields_ = [("rank", _i32), ("world", _i32), ("n_pad", _i64), ("n_flags", _i64), ("xg", _vp * 8), ("flags", _vp * 8),
+                ("error_flag", _vp)]
+
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync: fail loudly

@@ -25,7 +25,8 @@ bool fused_v4_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, in
                        const int32_t* rowptr, const int32_t* col, const float* val, const float* w, const float* bias);
 int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                               int n_nodes, const float* x, int f_in, const float* w, const float* bias, int f_out, int act,
-                              float* y, cudaStream_t st, bool w_transposed = false);
+                              float* y, cudaStream_t st, bool w_transposed = false, const float* mul_src = nullptr,
+                              int mul_act = KGCN_ACT_NONE, int f_out_valid = 0);
 
 // implemented in graphconv_fused_dw.cu (weight / bias gradient of a layer, all channels, one launch + the partial reduce)
 bool fused_dw_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x, const float* du,
@@ -34,6 +35,11 @@ size_t fused_dw_partial_bytes(int f_in, int n_total);
 int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs, int channels,
                               int n_nodes, const float* x, int f_in, const float* du, int f_out, float* dw, float* dbias,
                               void* workspace, size_t workspace_bytes, cudaStream_t st);
+int fused_dw_splits(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
+int launch_graphconv_fused_dw_partial(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                      int channels, int n_nodes, const float* x, int f_in, const float* du, int f_out,
+                                      float* partial, size_t partial_bytes, int* splits_out, cudaStream_t st);
+bool fused_v4_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 
 bool fused_bwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int act, bool dy_bcast,
                         const float* x, const float* w, const float* y, const float* dy, const float* dx,
@@ -189,4 +195,62 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
         }
     }
     return KGCN_OK;
+}
+
+// ---- step-loop form of the backward: dU in, dU of the layer below out, weight-gradient partials left for the fused tail ----
+extern "C" int32_t kgcn_graphconv_bwd_splits(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in, int32_t f_out,
+                                             int32_t need_dx) {
+    if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || f_in <= 0 || f_out <= 0) return 0;
+    if (need_dx && !fused_v4_plannable(n_graphs, channels, n_nodes, f_out, f_in)) return 0;
+    return fused_dw_splits(n_graphs, channels, n_nodes, f_in, f_out);
+}
+
+extern "C" int kgcn_graphconv_bwd_partial_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                              int32_t channels, int32_t n_nodes, const float* x, int32_t f_in, const float* w,
+                                              int32_t f_out, const float* du, float* dx, int32_t act_below, float* partial,
+                                              size_t partial_bytes, void* stream) {
+    KGCN_REQUIRE(rowptr_t && col_t && val_t && x && w && du && partial, KGCN_ERR_NULL, "graphconv_bwd_partial: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && f_in > 0 && f_out > 0, KGCN_ERR_BAD_SHAPE, "graphconv_bwd_partial: bad shape");
+    KGCN_REQUIRE(act_below >= KGCN_ACT_NONE && act_below <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "graphconv_bwd_partial: unknown act %d", act_below);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KGCN_REQUIRE(fused_dw_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, du, rowptr_t, col_t, val_t), KGCN_ERR_UNSUPPORTED,
+                 "graphconv_bwd_partial: shape / alignment not supported by the fused weight-gradient kernel (see kgcn_graphconv_bwd_splits)");
+    if (dx != nullptr) {
+        KGCN_REQUIRE(fused_v4_eligible(n_graphs, channels, n_nodes, f_out, f_in, du, dx, rowptr_t, col_t, val_t, w, nullptr),
+                     KGCN_ERR_UNSUPPORTED, "graphconv_bwd_partial: shape / alignment not supported by the fused layer kernel");
+        int rc = launch_graphconv_fused_v4(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, du, f_out, w, nullptr, f_in,
+                                           KGCN_ACT_NONE, dx, st, /*w_transposed=*/true, x, act_below);
+        if (rc) return rc;
+    }
+    return launch_graphconv_fused_dw_partial(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, x, f_in, du, f_out, partial,
+                                             partial_bytes, nullptr, st);
+}
+
+// Forward of a layer whose output width is padded (feature dims rounded up to the next multiple of 32 so that the
+// tcgen05 kernels take Tox21-style widths such as 75 -> 50): columns >= f_out_valid are written as exact zeros whatever
+// the activation, so the zero rows / columns of the padded weights never receive a gradient.
+extern "C" int kgcn_graphconv_fwd_padded_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                                             int32_t channels, int32_t n_nodes, const float* x, int32_t f_in, const float* w,
+                                             const float* bias, int32_t f_out, int32_t f_out_valid, int32_t act, float* y,
+                                             void* stream) {
+    KGCN_REQUIRE(rowptr && col && val && x && w && y, KGCN_ERR_NULL, "graphconv_fwd_padded: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && f_in > 0 && f_out > 0 && f_out_valid > 0 && f_out_valid <= f_out,
+                 KGCN_ERR_BAD_SHAPE, "graphconv_fwd_padded: bad shape");
+    KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "graphconv_fwd_padded: unknown act %d", act);
+    KGCN_REQUIRE(fused_v4_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y, rowptr, col, val, w, bias), KGCN_ERR_UNSUPPORTED,
+                 "graphconv_fwd_padded: shape / alignment not supported by the fused layer kernel");
+    return launch_graphconv_fused_v4(rowptr, col, val, n_graphs, channels, n_nodes, x, f_in, w, bias, f_out, act, y,
+                                     static_cast<cudaStream_t>(stream), false, nullptr, KGCN_ACT_NONE, f_out_valid);
+}
+
+extern "C" int32_t kgcn_graphconv_fwd_fused(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in, int32_t f_out) {
+    if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || f_in <= 0 || f_out <= 0) return 0;
+    return fused_v4_plannable(n_graphs, channels, n_nodes, f_in, f_out) ? 1 : 0;
+}
+
+extern "C" int kgcn_reduce_partials_f32(const float* partial, int32_t splits, int32_t f_in, int32_t f_out, int32_t channels,
+                                        float* dw, float* dbias, void* stream) {
+    KGCN_REQUIRE(partial && dw, KGCN_ERR_NULL, "reduce_partials: NULL pointer argument");
+    KGCN_REQUIRE(splits > 0 && f_in > 0 && f_out > 0 && channels > 0, KGCN_ERR_BAD_SHAPE, "reduce_partials: bad shape");
+    return launch_splitk_reduce_ch(partial, splits, f_in, f_out, channels, dw, dbias, static_cast<cudaStream_t>(stream));
 }

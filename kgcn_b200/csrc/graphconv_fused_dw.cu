@@ -481,22 +481,41 @@ bool fused_dw_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, in
     return aligned16(x) && aligned16(du) && aligned16(rowptr) && aligned16(col) && aligned16(val);
 }
 
-int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs, int channels,
-                              int n_nodes, const float* x, int f_in, const float* du, int f_out, float* dw, float* dbias,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// number of partial blocks the kernel writes for this shape (= its grid), 0 when the shape is not supported
+int fused_dw_splits(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    DwParams p{};
+    if (!fused_dw_enabled() || !plan_dw(p, n_graphs, channels, n_nodes, f_in, f_out)) return 0;
+    return static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
+}
+
+// partial[grid][(f_in + 1)][channels * f_out]; no reduction
+int launch_graphconv_fused_dw_partial(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                      int channels, int n_nodes, const float* x, int f_in, const float* du, int f_out,
+                                      float* partial, size_t partial_bytes, int* splits_out, cudaStream_t st) {
     DwParams p{};
     KGCN_REQUIRE(plan_dw(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED,
                  "fused GraphConv weight gradient: unsupported shape");
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
     const size_t need = static_cast<size_t>(grid) * (static_cast<size_t>(f_in) + 1) * p.Ng * sizeof(float);
-    KGCN_REQUIRE(workspace != nullptr && workspace_bytes >= need && aligned16(workspace), KGCN_ERR_WORKSPACE,
-                 "fused GraphConv weight gradient: workspace %zu < %zu bytes", workspace_bytes, need);
+    KGCN_REQUIRE(partial != nullptr && partial_bytes >= need && aligned16(partial), KGCN_ERR_WORKSPACE,
+                 "fused GraphConv weight gradient: workspace %zu < %zu bytes", partial_bytes, need);
     p.rowptr = rowptr_t; p.col = col_t; p.val = val_t; p.x = x; p.du = du;
-    p.partial = static_cast<float*>(workspace);
+    p.partial = partial;
     KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
     launch_pdl(graphconv_fused_dw_kernel, grid, kBlock, p.smem_total, st, p);
     KGCN_LAUNCH_OK("graphconv_fused_dw_kernel");
-    return launch_splitk_reduce_ch(p.partial, static_cast<int>(grid), f_in, f_out, channels, dw, dbias, st);
+    if (splits_out != nullptr) *splits_out = static_cast<int>(grid);
+    return KGCN_OK;
+}
+
+int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs, int channels,
+                              int n_nodes, const float* x, int f_in, const float* du, int f_out, float* dw, float* dbias,
+                              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    int splits = 0;
+    const int rc = launch_graphconv_fused_dw_partial(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, x, f_in, du, f_out,
+                                                     static_cast<float*>(workspace), workspace_bytes, &splits, st);
+    if (rc) return rc;
+    return launch_splitk_reduce_ch(static_cast<const float*>(workspace), splits, f_in, f_out, channels, dw, dbias, st);
 }
 
 }  // namespace kgcn

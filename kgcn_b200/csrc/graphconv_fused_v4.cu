@@ -59,6 +59,11 @@ struct V4Params {
     int w_ld, w_cstride;  // row pitch and channel stride of w (floats)
     int y_ld;             // row pitch of y (floats)
     int n_split;          // output-column slices (blockIdx.y): slice s computes columns [s * f_out, (s + 1) * f_out) of y_ld
+    int C_csr, c_begin;   // the CSR holds C_csr channels per graph; this launch contracts channels [c_begin, c_begin + C)
+    int acc_in;           // add the existing y before the activation (second launch of a layer split over channel groups)
+    int f_valid;          // output columns >= f_valid (of this slice) are written as exact zeros: feature padding stays inert
+    const float* mul_src; // optional [rows, y_ld]: the output is multiplied by act'(mul_src) of activation mul_act (backward:
+    int mul_act;          // dx . act'(x) = the dU of the layer below, so no separate activation-gradient pass is needed)
     uint32_t off_whi, off_wlo, off_ystage, off_stage, stage_bytes, st_rp, st_col, st_val, smem_total;
     uint32_t w_atom;      // bytes between K atoms of the B operand
     uint32_t tm_z;        // first TMEM column of Z buffer 0 (accumulators at columns 0 and Np)
@@ -267,6 +272,9 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// EPI: 0 = activation epilogue; 1 = multiply by act'(mul_src) (backward dx -> dU of the layer below);
+//      2 = add the existing y, then activation (second launch of a layer split over channel groups)
+template <int EPI>
 __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
@@ -321,8 +329,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                 pt.mark(0);
                 const int64_t g0 = tr.g_begin + static_cast<int64_t>(it) * p.G;
                 const int ng = (it == n_tiles - 1) ? last_ng : p.G;
-                const int64_t r0 = g0 * C * N;
-                const int rows_csr = ng * C * N;
+                const int64_t r0 = g0 * p.C_csr * N;
+                const int rows_csr = ng * p.C_csr * N;
                 unsigned char* st = gen + p.off_stage + static_cast<size_t>(rs.idx) * p.stage_bytes;
                 uint64_t* full = &bar_full[rs.idx];
                 // the feature rows and the row extents do not depend on anything: they go first; the column / value
@@ -429,10 +437,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
             const int gl = w / N, node = w - gl * N;
             const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
             const int full_rows = p.G * N;
-            const uint32_t r0_step = static_cast<uint32_t>(p.G * C * N);
-            uint32_t r0_lo = static_cast<uint32_t>((tr.g_begin * C * N) & 3);
+            const uint32_t r0_step = static_cast<uint32_t>(p.G * p.C_csr * N);
+            uint32_t r0_lo = static_cast<uint32_t>((tr.g_begin * p.C_csr * N) & 3);
             const uint32_t z_stride = static_cast<uint32_t>(2 * Kp);
-            const uint32_t row_rp_off = 4u * static_cast<uint32_t>(gl * C * N + node);
+            const uint32_t row_rp_off = 4u * static_cast<uint32_t>((gl * p.C_csr + p.c_begin) * N + node);
             const uint32_t row_x_off = static_cast<uint32_t>(gl * N) * pitch + (s7 << 4);
             Ring rs, rz;
             PhaseTimer pt(dbg != nullptr && warp == 0 && lane == 0);
@@ -440,7 +448,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
             for (int it = 0; it < n_tiles; ++it) {
                 const bool last = it == n_tiles - 1;
                 const int rows = last ? last_ng * N : full_rows;
-                const int rows_csr = last ? last_ng * C * N : static_cast<int>(r0_step);
+                const int rows_csr = last ? last_ng * p.C_csr * N : static_cast<int>(r0_step);
                 const uint32_t st = base + p.off_stage + static_cast<uint32_t>(rs.idx) * p.stage_bytes;
                 mbar_wait(&bar_full[rs.idx], rs.phase);
                 pt.mark(0);
@@ -617,8 +625,17 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_tempty[ra.idx]);
                     }
-                    act16_rt(v0, p.act);
-                    act16_rt(v1, p.act);
+                    if (EPI != 2) {
+                        act16_rt(v0, p.act);
+                        act16_rt(v1, p.act);
+                    }
+                    if (EPI != 2 && cs * 32 + 32 > p.f_valid) {   // padded output columns: act(0) may be non-zero (sigmoid) -- force exact zeros
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                            if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                        }
+                    }
                     tmem_ld_fence(v0);
                     tmem_ld_fence(v1);
                     pt.mark(3);
@@ -634,13 +651,61 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                     // copy-out: each store instruction writes 4 rows x 128 contiguous bytes
                     const bool col_ok = cs * 32 + colq < f_out;
                     float* ycs = y_tile + cs * 32;
+                    if (EPI == 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
-                        float t[4];
-                        lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
-                        if (row0 + 4 * k < rows && col_ok)
-                            *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                            float t[4];
+                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                            if (row0 + 4 * k < rows && col_ok)
+                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                        }
+                    } else if (EPI == 2) {
+                        float4 ov[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            ov[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (row0 + 4 * k < rows && col_ok) ov[k] = *reinterpret_cast<const float4*>(ycs + static_cast<size_t>(4 * k) * y_ld);
+                        }
+                        const int cbase = cs * 32 + colq;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                            float t[4];
+                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                            const float o[4] = {ov[k].x, ov[k].y, ov[k].z, ov[k].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                t[j] += o[j];
+                                switch (p.act) {
+                                    case KGCN_ACT_RELU: t[j] = fast_act<KGCN_ACT_RELU>(t[j]); break;
+                                    case KGCN_ACT_SIGMOID: t[j] = fast_act<KGCN_ACT_SIGMOID>(t[j]); break;
+                                    case KGCN_ACT_TANH: t[j] = fast_act<KGCN_ACT_TANH>(t[j]); break;
+                                    default: break;
+                                }
+                                if (cbase + j >= p.f_valid) t[j] = 0.0f;
+                            }
+                            if (row0 + 4 * k < rows && col_ok)
+                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                        }
+                    } else {
+                        const float* mcs = p.mul_src + (ycs - p.y);   // same [rows, y_ld] layout as the output
+                        float4 mv[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            mv[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (row0 + 4 * k < rows && col_ok) mv[k] = __ldg(reinterpret_cast<const float4*>(mcs + static_cast<size_t>(4 * k) * y_ld));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                            float t[4];
+                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                            if (row0 + 4 * k < rows && col_ok)
+                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) =
+                                    make_float4(t[0] * act_grad_from_output(mv[k].x, p.mul_act), t[1] * act_grad_from_output(mv[k].y, p.mul_act),
+                                                t[2] * act_grad_from_output(mv[k].z, p.mul_act), t[3] * act_grad_from_output(mv[k].w, p.mul_act));
+                        }
                     }
                     __syncwarp();
                     pt.mark(5);
@@ -671,7 +736,7 @@ constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) sh
 
 // One candidate plan: `n_split` output-column slices of f_out_total / n_split columns (each slice is its own CTA row of
 // the grid with its own [W ; bias] slice resident in shared memory), G graphs per tile.
-bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G) {
+bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G, int C_csr) {
     if (f_out_total % n_split != 0) return false;
     const int f_out = f_out_total / n_split;
     if (f_out % 4 != 0 || f_out > 256 || (n_split > 1 && f_out % 32 != 0)) return false;
@@ -702,9 +767,10 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     p.off_wlo = off; off += n_watoms * p.w_atom;
     p.off_ystage = off; off += kEpiWarps * 4096u;
     p.off_stage = off;
-    p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C), 4));
+    p.C_csr = C_csr;
+    p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C_csr), 4));
     p.st_rp = up(rows_max * f_in * 4u, 128);
-    p.st_col = p.st_rp + up((rows_max * C + 8) * 4u, 16);
+    p.st_col = p.st_rp + up((rows_max * C_csr + 8) * 4u, 16);
     p.st_val = p.st_col + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u;
     p.stage_bytes = up(p.st_val + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u, 128);
     p.n_stages = 0;
@@ -718,12 +784,21 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
 // Preference: whole output width in one CTA and full 128-row tiles; wide layers (F = 128: [W ; bias] hi / lo alone is
 // 160 KB) fall back to column slices -- each slice aggregates the tile again (the second reader hits L2) -- and to
 // fewer graphs per tile until at least two TMA stages fit.
-bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
-    if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || C > 8 || C < 1) return false;
+bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int C_csr) {
+    if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || C_csr > 8 || C < 1 || C > C_csr) return false;
     for (int n_split = 1; n_split <= 4; n_split *= 2)
         for (int G = std::max(1, 128 / N); G >= 1; G = (G > 1 ? G / 2 : 0))
-            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G)) return true;
+            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G, C_csr)) return true;
     return false;
+}
+
+// A layer whose K = C * f_in does not fit tensor memory (three bond types x 96 features) is run as several launches over
+// channel groups: the first writes the partial pre-activation, the following ones add to it and the last activates.
+// Returns the largest group size that has a plan (0: none).
+int plan_v4_group(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
+    for (int cg = C; cg >= 1; --cg)
+        if (plan_v4(p, n_graphs, cg, N, f_in, f_out, C)) return (cg == C || p.n_split == 1) ? cg : 0;
+    return 0;
 }
 
 }  // namespace
@@ -739,29 +814,59 @@ bool fused_v4_enabled() {
 bool fused_v4_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x, const float* y,
                        const int32_t* rowptr, const int32_t* col, const float* val, const float* w, const float* bias) {
     V4Params p{};
-    if (!fused_v4_enabled() || !plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
+    if (!fused_v4_enabled() || plan_v4_group(p, n_graphs, channels, n_nodes, f_in, f_out) == 0) return false;
     return aligned16(x) && aligned16(y) && aligned16(rowptr) && aligned16(col) && aligned16(val) && aligned16(w) && aligned16(bias) &&
            n_graphs * static_cast<int64_t>(n_nodes) * channels < (1ll << 31);
+}
+
+bool fused_v4_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    V4Params p{};
+    return fused_v4_enabled() && plan_v4_group(p, n_graphs, channels, n_nodes, f_in, f_out) > 0;
 }
 
 static long long* g_dbg_v4 = nullptr;
 
 int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                               int n_nodes, const float* x, int f_in, const float* w, const float* bias, int f_out, int act,
-                              float* y, cudaStream_t st, bool w_transposed) {
-    V4Params p{};
-    KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: unsupported shape");
-    p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.w = w; p.bias = w_transposed ? nullptr : bias; p.y = y; p.act = act;
-    p.y_ld = f_out;
-    p.w_trans = w_transposed ? 1 : 0;
-    // forward: w[c][f_in][f_out];  transposed (backward dx): the layer's w[c][f_out (= this call's n)][f_in (= this call's k)]
-    p.w_ld = w_transposed ? f_in : f_out;
-    p.w_cstride = f_in * f_out;
-    p.dbg = g_dbg_v4;
-    const dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta)), static_cast<unsigned>(p.n_split));
-    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-    launch_pdl(graphconv_fused_v4_kernel, grid, kBlock, p.smem_total, st, p);
-    KGCN_LAUNCH_OK("graphconv_fused_v4_kernel");
+                              float* y, cudaStream_t st, bool w_transposed, const float* mul_src, int mul_act, int f_out_valid) {
+    V4Params p0{};
+    const int cg = plan_v4_group(p0, n_graphs, channels, n_nodes, f_in, f_out);
+    KGCN_REQUIRE(cg > 0, KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: unsupported shape");
+    const bool want_mul = mul_act != KGCN_ACT_NONE && mul_src != nullptr;
+    for (int c0 = 0; c0 < channels; c0 += cg) {
+        const int cn = std::min(cg, channels - c0);
+        const bool first = c0 == 0, last = c0 + cn == channels;
+        KGCN_REQUIRE(!(want_mul && !(first && last)), KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: act' epilogue with channel groups");
+        V4Params p{};
+        KGCN_REQUIRE(plan_v4(p, n_graphs, cn, n_nodes, f_in, f_out, channels), KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: unsupported shape");
+        p.c_begin = c0;
+        p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.y = y;
+        p.act = last ? act : KGCN_ACT_NONE;
+        p.acc_in = first ? 0 : 1;
+        p.y_ld = f_out;
+        p.w_trans = w_transposed ? 1 : 0;
+        // forward: w[c][f_in][f_out];  transposed (backward dx): the layer's w[c][f_out (= this call's n)][f_in (= this call's k)]
+        p.w_ld = w_transposed ? f_in : f_out;
+        p.w_cstride = f_in * f_out;
+        p.w = w + static_cast<size_t>(c0) * p.w_cstride;
+        p.bias = (w_transposed || bias == nullptr) ? nullptr : bias + static_cast<size_t>(c0) * f_out;
+        // columns >= f_valid are written as exact zeros by the launch that activates (feature padding stays inert); only
+        // supported without column slices (F = 128 layers are never padded)
+        p.f_valid = (last && f_out_valid > 0 && f_out_valid < f_out) ? f_out_valid : p.f_out;
+        KGCN_REQUIRE(p.f_valid == p.f_out || p.n_split == 1, KGCN_ERR_UNSUPPORTED, "fused GraphConv v4: padded outputs with column slices");
+        p.mul_src = want_mul ? mul_src : nullptr;
+        p.mul_act = mul_act;
+        p.dbg = g_dbg_v4;
+        const dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta)), static_cast<unsigned>(p.n_split));
+        auto go = [&](auto kernel) -> int {
+            KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
+            launch_pdl(kernel, grid, kBlock, p.smem_total, st, p);
+            KGCN_LAUNCH_OK("graphconv_fused_v4_kernel");
+            return KGCN_OK;
+        };
+        const int rc = p.acc_in ? go(graphconv_fused_v4_kernel<2>) : (p.mul_src != nullptr ? go(graphconv_fused_v4_kernel<1>) : go(graphconv_fused_v4_kernel<0>));
+        if (rc) return rc;
+    }
     return KGCN_OK;
 }
 

@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(kReadoutThreads, 1) readout_kernel(
     float* g, int64_t n_graphs, int feat, const float* __restrict__ w, const float* __restrict__ bias,
     int n_labels, const float* __restrict__ labels, const float* __restrict__ mask, float inv_batch,
     float* __restrict__ logits, float* __restrict__ prediction, float* __restrict__ dlogits, float* __restrict__ dg,
-    float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state) {
+    float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ state,
+    float* __restrict__ du_nodes, int act) {
     pdl_prologue();
     extern __shared__ __align__(16) float rd_smem[];   // g_s [slice][feat] | w_s [feat][n_labels] | y_s [slice][n_labels] | m_s [slice]
     __shared__ float dz_s[kReadoutMaxSlice * kMaxLabels];
@@ -151,6 +152,35 @@ __global__ void __launch_bounds__(kReadoutThreads, 1) readout_kernel(
         }
     }
     __syncthreads();
+
+    // ---- phase 1b (training step): dU of the last graph layer, du[b, r, :] = dg[b, :] (.) act'(x[b, r, :]) -- the
+    // GraphGather gradient (layers.py:164, a broadcast over the node rows) times the activation gradient, so the layer's
+    // backward needs no separate activation-gradient pass.  The rows were read a moment ago by the gather phase (L2 hits).
+    if (FUSE_GATHER && du_nodes != nullptr && dg != nullptr) {
+        const int64_t row_elems = static_cast<int64_t>(n_nodes) * feat;
+        if ((feat & 3) == 0 && (reinterpret_cast<uintptr_t>(x_nodes) & 15) == 0 && (reinterpret_cast<uintptr_t>(du_nodes) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(dg) & 15) == 0) {
+            const int f4 = feat >> 2;
+            const int64_t n4 = static_cast<int64_t>(n_here) * n_nodes * f4;
+            const float4* xs = reinterpret_cast<const float4*>(x_nodes + b0 * row_elems);
+            float4* us = reinterpret_cast<float4*>(du_nodes + b0 * row_elems);
+            const float4* dgs = reinterpret_cast<const float4*>(dg + b0 * feat);
+            for (int64_t idx = threadIdx.x; idx < n4; idx += kReadoutThreads) {
+                const int64_t row = idx / f4;
+                const int c4 = static_cast<int>(idx - row * f4), i = static_cast<int>(row / n_nodes);
+                const float4 xv = xs[idx], gv = dgs[i * f4 + c4];
+                us[idx] = make_float4(gv.x * act_grad_from_output(xv.x, act), gv.y * act_grad_from_output(xv.y, act),
+                                      gv.z * act_grad_from_output(xv.z, act), gv.w * act_grad_from_output(xv.w, act));
+            }
+        } else {
+            const int64_t n1 = static_cast<int64_t>(n_here) * row_elems;
+            for (int64_t idx = threadIdx.x; idx < n1; idx += kReadoutThreads) {
+                const int64_t row = idx / feat;
+                const int f = static_cast<int>(idx - row * feat), i = static_cast<int>(row / n_nodes);
+                du_nodes[b0 * row_elems + idx] = dg[(b0 + i) * feat + f] * act_grad_from_output(x_nodes[b0 * row_elems + idx], act);
+            }
+        }
+    }
 
     // ---- phase 2: block partials, graph order inside the slice ----
     const int n_w = (feat + 1) * n_labels;      // row `feat` is the bias gradient
@@ -357,16 +387,16 @@ extern "C" int kgcn_readout_xent_f32(const float* g, int64_t n_graphs, int32_t f
     KGCN_CUDA_OK(cudaFuncSetAttribute(readout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     launch_pdl(readout_kernel<false>, nb, kReadoutThreads, dyn, static_cast<cudaStream_t>(stream), static_cast<const float*>(nullptr), 0,
                const_cast<float*>(g), n_graphs, feat, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg,
-               dw, dbias, static_cast<float*>(workspace), stats);
+               dw, dbias, static_cast<float*>(workspace), stats, static_cast<float*>(nullptr), 0);
     KGCN_LAUNCH_OK("readout_kernel");
     return KGCN_OK;
 }
 
-extern "C" int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
+static int gather_readout_impl(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
                                             const float* w, const float* bias, int32_t n_labels, const float* labels,
                                             const float* mask, float inv_batch, float* logits, float* prediction,
                                             float* stats, float* dlogits, float* dg, float* dw, float* dbias,
-                                            void* workspace, size_t workspace_bytes, void* stream) {
+                                            void* workspace, size_t workspace_bytes, void* stream, int32_t act, float* du_nodes) {
     KGCN_REQUIRE(x && g && w && labels && stats, KGCN_ERR_NULL, "gather_readout_xent: NULL pointer argument");
     KGCN_REQUIRE(n_graphs > 0 && n_nodes > 0 && feat > 0 && n_labels > 0 && n_labels <= kMaxLabels, KGCN_ERR_BAD_SHAPE,
                  "gather_readout_xent: bad shape (n_labels <= %d)", kMaxLabels);
@@ -380,9 +410,29 @@ extern "C" int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, in
     KGCN_CUDA_OK(cudaFuncSetAttribute(readout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     launch_pdl(readout_kernel<true>, nb, kReadoutThreads, dyn, static_cast<cudaStream_t>(stream), x, static_cast<int>(n_nodes), g,
                n_graphs, feat, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, dlogits, dg, dw, dbias,
-               static_cast<float*>(workspace), stats);
+               static_cast<float*>(workspace), stats, du_nodes, static_cast<int>(act));
     KGCN_LAUNCH_OK("readout_kernel(gather)");
     return KGCN_OK;
+}
+
+extern "C" int kgcn_gather_readout_xent_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
+                                            const float* w, const float* bias, int32_t n_labels, const float* labels,
+                                            const float* mask, float inv_batch, float* logits, float* prediction,
+                                            float* stats, float* dlogits, float* dg, float* dw, float* dbias,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    return gather_readout_impl(x, n_graphs, n_nodes, feat, g, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, stats,
+                               dlogits, dg, dw, dbias, workspace, workspace_bytes, stream, KGCN_ACT_NONE, nullptr);
+}
+
+extern "C" int kgcn_gather_readout_xent_du_f32(const float* x, int64_t n_graphs, int32_t n_nodes, int32_t feat, float* g,
+                                               const float* w, const float* bias, int32_t n_labels, const float* labels,
+                                               const float* mask, float inv_batch, float* logits, float* prediction,
+                                               float* stats, float* dlogits, float* dg, float* dw, float* dbias, int32_t act,
+                                               float* du_nodes, void* workspace, size_t workspace_bytes, void* stream) {
+    KGCN_REQUIRE(du_nodes != nullptr && dg != nullptr, KGCN_ERR_NULL, "gather_readout_xent_du: du_nodes and dg are required");
+    KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "gather_readout_xent_du: unknown act %d", act);
+    return gather_readout_impl(x, n_graphs, n_nodes, feat, g, w, bias, n_labels, labels, mask, inv_batch, logits, prediction, stats,
+                               dlogits, dg, dw, dbias, workspace, workspace_bytes, stream, act, du_nodes);
 }
 
 extern "C" int kgcn_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,

@@ -12,7 +12,9 @@ buffer each, so data-parallel training over molecules needs exactly one all-redu
 the flat gradient buffer per step; the loss scale ``1/B_global`` is folded
 into the head's gradient so the sum over ranks is the global ``reduce_mean`` gradient.
 """
+import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -43,6 +45,65 @@ class NetSpec:
         return shapes
 
 
+def pad_features(features, width):
+    """[B, N, F] -> [B, N, width] with zero columns (no copy when F == width)."""
+    features = np.asarray(features, np.float32)
+    if width is None or features.shape[-1] == width:
+        return features
+    out = np.zeros(features.shape[:-1] + (int(width),), np.float32)
+    out[..., :features.shape[-1]] = features
+    return out
+
+
+class PeerExchange:
+    """Peer-mapped exchange buffers of the ranks of one node (cudaIpc through kgcn_p2p_*): rank r allocates
+    ``xg[2][n_pad]`` floats + ``flags[n_blocks]`` and every rank maps all of them; the 64-byte handles travel through
+    ``torch.distributed.all_gather`` (plumbing).  Consumed by kgcn_reduce_adam_f32."""
+
+    def __init__(self, n_params, rank, world, pg, device):
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        n_pad = (n_params + 31) // 32 * 32
+        n_flags = n_pad // 32
+        self.own, handles = [], []
+        for nbytes in (2 * n_pad * 4, n_flags * 4):
+            p_own, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            check(lib.kgcn_p2p_alloc(nbytes, ctypes.byref(p_own), h))
+            self.own.append(p_own.value)
+            handles.append(bytes(h))
+        mine = torch.tensor(list(handles[0] + handles[1]), dtype=torch.uint8, device=device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=pg)
+        self.mapped = []
+        g = _lib.P2PGroup()
+        g.rank, g.world, g.n_pad, g.n_flags = rank, world, n_pad, n_flags
+        for r in range(world):
+            if r == rank:
+                g.xg[r], g.flags[r] = self.own
+                continue
+            raw = bytes(every[r].cpu().tolist())
+            ptrs = []
+            for k in range(2):
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(raw[64 * k:64 * k + 64])
+                q = ctypes.c_void_p()
+                check(lib.kgcn_p2p_open(h, ctypes.byref(q)))
+                ptrs.append(q.value)
+                self.mapped.append(q.value)
+            g.xg[r], g.flags[r] = ptrs
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        g.error_flag = self.error.data_ptr()
+        self.group = g
+        dist.barrier(group=pg)
+
+    def close(self):
+        for q in self.mapped:
+            lib.kgcn_p2p_close(q)
+        self.mapped = []
+        for q in self.own:
+            lib.kgcn_p2p_free(q)
+        self.own = []
+
+
 class DeviceBatch:
     """Static device buffers for one batch (CUDA-graph friendly: pointers never change)."""
 
@@ -50,44 +111,82 @@ class DeviceBatch:
         self.csr, self.features, self.labels, self.mask = csr, features, labels, mask
 
     @classmethod
-    def from_host(cls, counts, indices, values, features, labels, n_nodes, mask=None, device="cuda"):
+    def from_host(cls, counts, indices, values, features, labels, n_nodes, mask=None, device="cuda", pad_to=None):
+        """``pad_to``: store the features zero-padded to this width (``Trainer.dims[0]``, see Trainer ``pad_features``)."""
         csr = BatchedCSR.from_flat(counts, indices, values, n_nodes, n_nodes, device=device)
         B = features.shape[0]
+        features = pad_features(features, pad_to)
         mask = np.ones(B, np.float32) if mask is None else mask
         up = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).to(device)
         return cls(csr, up(features), up(labels), up(mask))
 
 
+def _pad32(d):
+    return (int(d) + 31) // 32 * 32
+
+
 class Trainer:
+    """``pad_features`` (default on): feature widths that are not multiples of 32 (Tox21: 75 -> 50 -> 50 -> 50) are stored
+    zero-padded to the next multiple of 32 -- features ``[B, N, 96]``, kernels ``[C, 96, 64]`` with zero rows / columns,
+    padded activations kept at exact zero by the layer kernel -- so every GraphConv runs on the fused tcgen05 kernels.
+    ``views`` / ``gviews`` are the LOGICAL tensors (strided views into the padded storage): checkpoints, tests and the
+    oracle never see the padding.  ``p2p`` (data parallel only, default on): gradients are all-reduced inside the
+    optimizer launch over NVLink peer memory (kgcn_reduce_adam_f32); ``p2p=False`` keeps the NCCL all-reduce between
+    two graph replays as the cross-check."""
+
     def __init__(self, spec, batch_size, device="cuda", lr=0.01, world_size=1, seed=1234, flags=_lib.FLAG_DEFAULT,
-                 process_group=None):
+                 process_group=None, pad_features=True, p2p=None, rank=0):
         self.spec, self.B, self.device, self.lr = spec, int(batch_size), torch.device(device), float(lr)
-        self.world_size, self.flags, self.pg = int(world_size), flags, process_group
+        self.world_size, self.flags, self.pg, self.rank = int(world_size), flags, process_group, int(rank)
         self.act = act_id(spec.act)
-        shapes = spec.param_shapes()
-        sizes = [int(np.prod(s)) for _, s in shapes]
+        s, B, N, C = spec, self.B, spec.n_nodes, spec.channels
+        # ---- padded widths: only when the fused layer kernel then takes every GraphConv of the network ----
+        ldims = [s.feature_dim] + s.conv_dims
+        pdims = [_pad32(d) for d in ldims]
+        ref_order = bool(flags & _lib.FLAG_REFERENCE_ORDER)
+        fused_ok = lambda dims: all(lib.kgcn_graphconv_fwd_fused(B, C, N, dims[i], dims[i + 1]) for i in range(len(s.conv_dims)))
+        self.padded = bool(pad_features) and not ref_order and pdims != ldims and fused_ok(pdims)
+        self.dims = pdims if self.padded else ldims          # what the kernels see
+        self.ldims = ldims
+        lshapes = spec.param_shapes()
+        pshape = {}
+        for i in range(len(s.conv_dims)):
+            pshape["conv%d/kernel" % i] = (C, self.dims[i], self.dims[i + 1])
+            pshape["conv%d/bias" % i] = (C, self.dims[i + 1])
+        f_last = self.dims[-1]
+        if s.dense_dim:
+            pshape["graph_dense/kernel"] = (f_last, int(s.dense_dim))
+            f_last = int(s.dense_dim)
+        pshape["dense/kernel"] = (f_last, s.label_dim)
+        self.f_head = f_last
         # 16-byte align every tensor inside the flat buffers
-        offs, total = [], 0
-        for n in sizes:
-            offs.append(total)
-            total += (n + 3) // 4 * 4
-        self.n_params = total
+        offs, total = {}, 0
+        for name, shape in lshapes:
+            shape = pshape.get(name, shape)
+            offs[name] = total
+            total += (int(np.prod(shape)) + 3) // 4 * 4
+        self.n_params, self.offs = total, offs
         f32 = dict(dtype=torch.float32, device=self.device)
         self.params = torch.zeros(total, **f32)
         self.grads = torch.zeros(total, **f32)
         self.adam_m = torch.zeros(total, **f32)
         self.adam_v = torch.zeros(total, **f32)
         self.step_state = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self.views, self.gviews, self.mviews, self.vviews = {}, {}, {}, {}
-        for (name, shape), off, n in zip(shapes, offs, sizes):
-            self.views[name] = self.params[off:off + n].view(shape)
-            self.gviews[name] = self.grads[off:off + n].view(shape)
-            self.mviews[name] = self.adam_m[off:off + n].view(shape)
-            self.vviews[name] = self.adam_v[off:off + n].view(shape)
+        self.views, self.gviews, self.mviews, self.vviews = {}, {}, {}, {}   # logical tensors
+        self.pviews, self.pgviews = {}, {}                                   # padded storage (what the C ABI is given)
+        for name, lshape in lshapes:
+            shape = pshape.get(name, lshape)
+            off, n = offs[name], int(np.prod(shape))
+            sl = tuple(slice(0, d) for d in lshape)
+            for flat, logical, padded in ((self.params, self.views, self.pviews), (self.grads, self.gviews, self.pgviews),
+                                          (self.adam_m, self.mviews, None), (self.adam_v, self.vviews, None)):
+                full = flat[off:off + n].view(shape)
+                logical[name] = full[sl]
+                if padded is not None:
+                    padded[name] = full
         self.init_params(np.random.default_rng(seed))
 
-        s, B, N = spec, self.B, spec.n_nodes
-        dims = [s.feature_dim] + s.conv_dims + ([int(s.dense_dim)] if s.dense_dim else [])
+        dims = self.dims + ([int(s.dense_dim)] if s.dense_dim else [])
         self.acts = [None] + [torch.empty(B, N, d, **f32) for d in dims[1:]]
         self.dact = [torch.empty(B, N, max(dims), **f32) for _ in range(2)]
         self.gathered = torch.empty(B, dims[-1], **f32)
@@ -97,15 +196,30 @@ class Trainer:
         self.dlogits = torch.empty(B, s.label_dim, **f32)
         self.stats = torch.zeros(4, **f32)   # [cost_sum, correct_count, block ticket, reserved]
         ws = 0
-        f = s.feature_dim
-        for d in s.conv_dims:
-            ws = max(ws, int(lib.kgcn_graphconv_workspace_bytes(B, s.channels, N, f, d)))
-            f = d
+        for i in range(len(s.conv_dims)):
+            ws = max(ws, int(lib.kgcn_graphconv_workspace_bytes(B, C, N, self.dims[i], self.dims[i + 1])))
         if s.dense_dim:
-            ws = max(ws, int(lib.kgcn_graphdense_workspace_bytes(B, N, f, int(s.dense_dim))))
-            f = int(s.dense_dim)
-        ws = max(ws, int(lib.kgcn_readout_workspace_bytes(B, f, s.label_dim)))
+            ws = max(ws, int(lib.kgcn_graphdense_workspace_bytes(B, N, self.dims[-1], int(s.dense_dim))))
+        ws = max(ws, int(lib.kgcn_readout_workspace_bytes(B, dims[-1], s.label_dim)))
         self.ws = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
+        # ---- fused step: head emits the last layer's dU, each layer's backward leaves weight-gradient partials, one
+        # tail launch reduces them, all-reduces across ranks and applies Adam ----
+        self.splits = [int(lib.kgcn_graphconv_bwd_splits(B, C, N, self.dims[i], self.dims[i + 1], 1 if i > 0 else 0))
+                       for i in range(len(s.conv_dims))]
+        self.fused_step = (not ref_order and not s.dense_dim and all(n > 0 for n in self.splits) and fused_ok(self.dims) and
+                           os.environ.get("KGCN_FUSED_STEP", "1") != "0")
+        self.partials, self._segments = [], None
+        if self.fused_step:
+            segs = (_lib.GradSegment * len(s.conv_dims))()
+            for i, n in enumerate(self.splits):
+                buf = torch.empty(n * (self.dims[i] + 1) * C * self.dims[i + 1], **f32)
+                self.partials.append(buf)
+                segs[i] = _lib.GradSegment(offs["conv%d/kernel" % i], offs["conv%d/bias" % i], buf.data_ptr(), n, self.dims[i],
+                                           self.dims[i + 1], C)
+            self._segments = segs
+        self.p2p = None
+        if self.world_size > 1 and (p2p if p2p is not None else os.environ.get("KGCN_P2P", "1") != "0"):
+            self.p2p = PeerExchange(self.n_params, self.rank, self.world_size, self.pg, self.device)
         self.graphs = {}
         self.launches_per_step = None
 
@@ -210,34 +324,60 @@ class Trainer:
     def _forward(self, batch, st):
         s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
         csr = batch.csr
-        x, f = batch.features, s.feature_dim
+        x = batch.features
+        if x.shape[-1] != self.dims[0]:
+            raise ValueError("batch features are %d wide, the trainer stores %d (DeviceBatch.from_host(..., pad_to=trainer.dims[0]))"
+                             % (x.shape[-1], self.dims[0]))
         self.acts[0] = x
-        n_launch = 0
-        for i, d in enumerate(s.conv_dims):
-            y = self.acts[i + 1]
-            check(lib.kgcn_graphconv_fwd_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), B, C, N, ptr(x), f,
-                                             ptr(self.views["conv%d/kernel" % i]), ptr(self.views["conv%d/bias" % i]),
-                                             d, self.act, ptr(y), self.flags, ptr(self.ws), self.ws.numel(), st))
-            x, f = y, d
+        for i in range(len(s.conv_dims)):
+            y, f, d = self.acts[i + 1], self.dims[i], self.dims[i + 1]
+            w, b = self.pviews["conv%d/kernel" % i], self.pviews["conv%d/bias" % i]
+            if self.padded:
+                check(lib.kgcn_graphconv_fwd_padded_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), B, C, N, ptr(x), f, ptr(w), ptr(b),
+                                                        d, self.ldims[i + 1], self.act, ptr(y), st))
+            else:
+                check(lib.kgcn_graphconv_fwd_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), B, C, N, ptr(x), f, ptr(w), ptr(b),
+                                                 d, self.act, ptr(y), self.flags, ptr(self.ws), self.ws.numel(), st))
+            x = y
+        f = self.dims[-1]
         if s.dense_dim:
             y = self.acts[len(s.conv_dims) + 1]
-            check(lib.kgcn_graphdense_fwd_f32(ptr(x), B, N, f, ptr(self.views["graph_dense/kernel"]),
-                                              ptr(self.views["graph_dense/bias"]), int(s.dense_dim), self.act, None,
+            check(lib.kgcn_graphdense_fwd_f32(ptr(x), B, N, f, ptr(self.pviews["graph_dense/kernel"]),
+                                              ptr(self.pviews["graph_dense/bias"]), int(s.dense_dim), self.act, None,
                                               ptr(y), st))
             x, f = y, int(s.dense_dim)
         self._last_nodes = x      # GraphGather is fused into the readout head (kgcn_gather_readout_xent_f32)
-        return f, n_launch
+        return f, 0
 
     def _head(self, batch, f, st, train):
         s, B = self.spec, self.B
         inv_batch = 1.0 / (B * self.world_size)
-        check(lib.kgcn_gather_readout_xent_f32(
-            ptr(self._last_nodes), B, s.n_nodes, f, ptr(self.gathered), ptr(self.views["dense/kernel"]),
-            ptr(self.views["dense/bias"]), s.label_dim,
-            ptr(batch.labels), ptr(batch.mask), inv_batch, ptr(self.logits), ptr(self.prediction), ptr(self.stats),
-            ptr(self.dlogits) if train else None, ptr(self.dgathered) if train else None,
-            ptr(self.gviews["dense/kernel"]) if train else None, ptr(self.gviews["dense/bias"]) if train else None,
-            ptr(self.ws), self.ws.numel(), st))
+        args = (ptr(self._last_nodes), B, s.n_nodes, f, ptr(self.gathered), ptr(self.pviews["dense/kernel"]),
+                ptr(self.pviews["dense/bias"]), s.label_dim, ptr(batch.labels), ptr(batch.mask), inv_batch, ptr(self.logits),
+                ptr(self.prediction), ptr(self.stats), ptr(self.dlogits) if train else None, ptr(self.dgathered) if train else None,
+                ptr(self.pgviews["dense/kernel"]) if train else None, ptr(self.pgviews["dense/bias"]) if train else None)
+        if train and self.fused_step:   # + dU of the last graph layer (dgathered broadcast over the nodes, times act')
+            check(lib.kgcn_gather_readout_xent_du_f32(*args, self.act, ptr(self.dact[0]), ptr(self.ws), self.ws.numel(), st))
+        else:
+            check(lib.kgcn_gather_readout_xent_f32(*args, ptr(self.ws), self.ws.numel(), st))
+
+    def _backward_fused(self, batch, st):
+        """dU chain: the head wrote dU of the last layer into dact[0]; every layer's dx launch multiplies by the activation
+        gradient of the layer below, so dact[cur] always holds a ready dU; weight gradients stay as per-CTA partials."""
+        s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
+        csr = batch.csr
+        cur = 0
+        for i in range(len(s.conv_dims) - 1, -1, -1):
+            fin, fout = self.dims[i], self.dims[i + 1]
+            du = self.dact[cur].view(-1)[:B * N * fout]
+            dx = None
+            if i > 0:
+                cur ^= 1
+                dx = self.dact[cur].view(-1)[:B * N * fin]
+            part = self.partials[i]
+            check(lib.kgcn_graphconv_bwd_partial_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, ptr(self.acts[i]), fin,
+                                                     ptr(self.pviews["conv%d/kernel" % i]), fout, ptr(du), ptr(dx), self.act,
+                                                     ptr(part), part.numel() * 4, st))
 
     def _backward(self, batch, f, st):
         s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
@@ -249,37 +389,59 @@ class Trainer:
         if s.dense_dim:
             dy = self.dact[0].view(-1)[:B * N * f].view(B, N, f)
             check(lib.kgcn_gather_bwd_f32(ptr(self.dgathered), B, N, f, ptr(dy), st))
-            fin = s.conv_dims[-1]
+            fin = self.dims[-1]
             dx = self.dact[1].view(-1)[:B * N * fin].view(B, N, fin)
-            check(lib.kgcn_graphdense_bwd_f32(ptr(self.acts[k - 1]), B, N, fin, ptr(self.views["graph_dense/kernel"]),
+            check(lib.kgcn_graphdense_bwd_f32(ptr(self.acts[k - 1]), B, N, fin, ptr(self.pviews["graph_dense/kernel"]),
                                               int(s.dense_dim), self.act, None, ptr(self.acts[k]), ptr(dy), ptr(dx),
-                                              ptr(self.gviews["graph_dense/kernel"]), ptr(self.gviews["graph_dense/bias"]),
+                                              ptr(self.pgviews["graph_dense/kernel"]), ptr(self.pgviews["graph_dense/bias"]),
                                               ptr(self.ws), self.ws.numel(), st))
             dy, cur, k, f = dx, 1, k - 1, fin
         else:
             # the GraphGather gradient ([B, F] broadcast over nodes) is consumed directly by the last conv layer
             dy, bcast = self.dgathered, _lib.FLAG_DY_BROADCAST
         for i in range(n_conv - 1, -1, -1):
-            fin = s.conv_dims[i - 1] if i > 0 else s.feature_dim
+            fin = self.dims[i]
             dx = None
             if i > 0:
                 cur ^= 1
                 dx = self.dact[cur].view(-1)[:B * N * fin].view(B, N, fin)
             check(lib.kgcn_graphconv_bwd_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N,
-                                             ptr(self.acts[i]), fin, ptr(self.views["conv%d/kernel" % i]), f, self.act,
-                                             ptr(self.acts[i + 1]), ptr(dy), ptr(dx), ptr(self.gviews["conv%d/kernel" % i]),
-                                             ptr(self.gviews["conv%d/bias" % i]), self.flags | bcast, ptr(self.ws),
+                                             ptr(self.acts[i]), fin, ptr(self.pviews["conv%d/kernel" % i]), f, self.act,
+                                             ptr(self.acts[i + 1]), ptr(dy), ptr(dx), ptr(self.pgviews["conv%d/kernel" % i]),
+                                             ptr(self.pgviews["conv%d/bias" % i]), self.flags | bcast, ptr(self.ws),
                                              self.ws.numel(), st))
             dy, f, bcast = dx, fin, 0
 
     def _optimizer(self, st):
-        check(lib.kgcn_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
-                                self.lr, 0.9, 0.999, 1e-8, 1, 1.0, ptr(self.step_state), st))
+        """The step's tail.  Fused step / peer exchange: ONE launch reduces the weight-gradient partials, all-reduces over
+        NVLink peer memory and applies Adam; otherwise plain Adam on the (already NCCL-reduced) flat gradient buffer."""
+        if self.fused_step or self.p2p is not None:
+            segs, n_seg = (self._segments, len(self._segments)) if self.fused_step else (None, 0)
+            group = ctypes.byref(self.p2p.group) if self.p2p is not None else None
+            check(lib.kgcn_reduce_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
+                                           segs, n_seg, self.lr, 0.9, 0.999, 1e-8, 1.0, ptr(self.step_state), group, st))
+        else:
+            check(lib.kgcn_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
+                                    self.lr, 0.9, 0.999, 1e-8, 1, 1.0, ptr(self.step_state), st))
+
+    def _reduce_only(self, st):
+        """Fused step without the update (tests / gradient checks): reduce the partials into ``grads``."""
+        s, C = self.spec, self.spec.channels
+        for i, n in enumerate(self.splits):
+            f, d = self.dims[i], self.dims[i + 1]
+            # X^T.[G_0 | G_1 | ..] partial blocks -> channel-major kernel gradient + bias gradient
+            check(lib.kgcn_reduce_partials_f32(ptr(self.partials[i]), n, f, d, C, ptr(self.pgviews["conv%d/kernel" % i]),
+                                               ptr(self.pgviews["conv%d/bias" % i]), st))
 
     def _allreduce(self):
-        if self.world_size > 1:
+        if self.world_size > 1 and self.p2p is None:
             import torch.distributed as dist
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+
+    @property
+    def single_graph(self):
+        """True when the whole step (collective included) is one capturable launch sequence."""
+        return self.world_size == 1 or self.p2p is not None
 
     def forward_eager(self, batch):
         st = torch.cuda.current_stream().cuda_stream
@@ -290,22 +452,44 @@ class Trainer:
         st = torch.cuda.current_stream().cuda_stream
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=True)
-        self._backward(batch, f, st)
+        if self.fused_step:
+            self._backward_fused(batch, st)
+            if not self.single_graph:      # NCCL cross-check path: the all-reduce needs the reduced gradients
+                self._reduce_only(st)
+        else:
+            self._backward(batch, f, st)
 
     def step_eager(self, batch, apply_update=True):
         self._fwd_bwd(batch)
-        self._allreduce()
-        if apply_update:
-            self._optimizer(torch.cuda.current_stream().cuda_stream)
+        st = torch.cuda.current_stream().cuda_stream
+        if not apply_update:
+            if self.fused_step and self.single_graph:
+                self._reduce_only(st)
+            self._allreduce()
+            return
+        if self.single_graph:
+            self._optimizer(st)
+        else:
+            self._allreduce()
+            if self.fused_step:
+                check(lib.kgcn_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
+                                        self.lr, 0.9, 0.999, 1e-8, 1, 1.0, ptr(self.step_state), st))
+            else:
+                self._optimizer(st)
 
     # -- CUDA-graph replay ------------------------------------------------------------------------
-    def _capture_fn(self, fn):
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):      # warm-up outside capture (lazy cudaFuncSetAttribute calls)
-                fn()
-        torch.cuda.current_stream().wait_stream(side)
+    def _capture_fn(self, fn, warm_fn="same"):
+        """Warm-up outside capture (lazy cudaFuncSetAttribute calls) runs ``warm_fn`` -- by default ``fn`` itself, for a
+        training step the forward + backward WITHOUT the optimizer launch: warm-up must neither move the parameters (the
+        number of Adam updates would then depend on how many graphs were captured) nor wait for other ranks."""
+        warm_fn = fn if warm_fn == "same" else warm_fn
+        if warm_fn is not None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    warm_fn()
+            torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -315,19 +499,22 @@ class Trainer:
     def capture(self, key, batch, train=True):
         """Capture the step for ``batch``'s static buffers; replay with :meth:`replay`.
 
-        Single GPU: the whole step (forward, head, backward, Adam) is ONE graph.  Data parallel:
-        forward+backward is one graph and Adam another, with the NCCL all-reduce of the flat
-        gradient buffer issued eagerly between the two replays (collectives are kept out of graph
-        capture on purpose: the eager call is the plain, always-supported ``torch.distributed`` path)."""
+        The whole step (forward, head, backward, reduce + all-reduce + Adam) is ONE graph -- also data parallel, where the
+        gradient exchange is peer-memory loads inside the optimizer launch.  Only the NCCL cross-check path (``p2p=False``)
+        splits it: forward+backward graph, eager ``dist.all_reduce``, optimizer graph."""
         if not train:
             self.graphs[key] = (self._capture_fn(lambda: self.forward_eager(batch)),)
-        elif self.world_size == 1:
-            self.graphs[key] = (self._capture_fn(lambda: self.step_eager(batch)),)
+        elif self.single_graph:
+            self.graphs[key] = (self._capture_fn(lambda: self.step_eager(batch), warm_fn=lambda: self._fwd_bwd(batch)),)
         else:
             if getattr(self, "_opt_graph", None) is None:
-                self._opt_graph = self._capture_fn(lambda: self._optimizer(torch.cuda.current_stream().cuda_stream))
+                self._opt_graph = self._capture_fn(lambda: self._plain_adam(), warm_fn=None)
             self.graphs[key] = (self._capture_fn(lambda: self._fwd_bwd(batch)), "allreduce", self._opt_graph)
         return self.graphs[key]
+
+    def _plain_adam(self):
+        check(lib.kgcn_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
+                                self.lr, 0.9, 0.999, 1e-8, 1, 1.0, ptr(self.step_state), torch.cuda.current_stream().cuda_stream))
 
     def replay(self, key):
         for g in self.graphs[key]:
@@ -368,7 +555,7 @@ class _Slot:
         rp, col, val = mk()
         rpt, colt, valt = mk()
         self.batch = DeviceBatch(BatchedCSR(B, C, N, N, rp, col, val, rpt, colt, valt),
-                                 torch.zeros(B, N, s.feature_dim, **f32), labels, mask)
+                                 torch.zeros(B, N, t.dims[0], **f32), labels, mask)
         self.h_stats = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.copied, self.done = torch.cuda.Event(), torch.cuda.Event()
         self.graph = None
@@ -421,15 +608,15 @@ class HostFedPipeline:
     def capture(self):
         t = self.trainer
         for slot in self.slots:
-            if self.train and t.world_size > 1:   # collectives stay outside graph capture (see Trainer.capture)
-                def fb(slot=slot):
-                    self._pack(slot)
-                    t._fwd_bwd(slot.batch)
+            def fb(slot=slot):
+                self._pack(slot)
+                t._fwd_bwd(slot.batch)
+            if self.train and not t.single_graph:   # NCCL cross-check path: the collective stays outside graph capture
                 if getattr(t, "_opt_graph", None) is None:
-                    t._opt_graph = t._capture_fn(lambda: t._optimizer(torch.cuda.current_stream().cuda_stream))
+                    t._opt_graph = t._capture_fn(lambda: t._plain_adam(), warm_fn=None)
                 slot.graph = (t._capture_fn(fb), "allreduce", t._opt_graph)
             else:
-                slot.graph = (t._capture_fn(lambda slot=slot: self._device_part(slot)),)
+                slot.graph = (t._capture_fn(lambda slot=slot: self._device_part(slot), warm_fn=fb if self.train else "same"),)
 
     # -- host side ------------------------------------------------------------------------------
     def pin_host_batch(self, counts, indices, values, features, labels, mask=None):
@@ -456,8 +643,9 @@ class HostFedPipeline:
         sec("labels", np.float32)[:] = np.asarray(labels, np.float32).reshape(-1)
         sec("mask", np.float32)[:] = np.ones(B, np.float32) if mask is None else np.asarray(mask, np.float32)
         used = self.layout["idx"][0] + 8 * nnz   # the idx section is copied only up to the entries in use
+        feats = np.ascontiguousarray(pad_features(features, self.trainer.dims[0]), np.float32)   # padded on the host: one plain copy
         return {"packed": torch.from_numpy(packed).pin_memory(), "nnz": nnz, "idx_used_end": used,
-                "features": torch.from_numpy(np.ascontiguousarray(features, np.float32)).pin_memory()}
+                "features": torch.from_numpy(feats).pin_memory()}
 
     def h2d_bytes(self, host):
         return int(host["packed"].numel() + host["features"].numel() * 4)

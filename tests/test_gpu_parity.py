@@ -192,6 +192,8 @@ V4_SHAPES = [  # B, N, C, F_in, F_out, max_nnz per matrix
     (11, 50, 3, 64, 64, None),       # C4 hidden layer: K = 192 -> one accumulator + one Z buffer in tensor memory
     (11, 50, 1, 96, 64, None),       # C3 first layer after padding 75 -> 96
     (5, 32, 1, 256, 128, None),      # K = 256: column slices with a single Z buffer
+    (11, 50, 3, 96, 64, None),       # C4 first layer after padding: K = 288 exceeds tensor memory -> channel groups {0,1} + {2}
+    (300, 50, 3, 96, 64, None),      # the same with several tiles per CTA
 ]
 
 
@@ -293,7 +295,7 @@ SPLIT_BWD_SHAPES = [  # B, N, C, fi, fo, max_nnz: widths that are multiples of 3
     (24, 32, 1, 64, 64, None),      # C2
     (700, 32, 1, 64, 64, None),     # more tiles than CTAs: the dW accumulator lives across tiles
     (9, 50, 3, 64, 64, None),       # C4 hidden layer: three channels, 50-row graphs (56-row operand chunks)
-    (9, 50, 3, 96, 64, None),       # C4 first layer after padding (dx falls back: K = 3 * 64 fits, N = 96)
+    (9, 50, 3, 96, 64, None),       # C4 first layer after padding (X as separate hi / lo operands, N = 192)
     (9, 50, 1, 96, 64, None),       # C3 first layer after padding 75 -> 96: Xhi / Xlo as separate operands
     (7, 64, 1, 128, 128, None),     # C5 width: 32-row operand chunks, dx in two column slices
     (300, 64, 1, 128, 128, None),   # several tiles per CTA at C5 width

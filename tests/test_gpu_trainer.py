@@ -47,6 +47,8 @@ def numpy_adam(p, g, lr=0.01, b1=0.9, b2=0.999, eps=1e-8, t=1):
     (16, 10, 1, 3, [50, 50, 50], 50),     # C1 network (example_model/model.py without BN/Dropout)
     (24, 32, 1, 64, [64, 64], None),      # C2
     (10, 50, 3, 75, [50, 50, 50], None),  # C4
+    (12, 50, 1, 75, [50, 50, 50], None),  # C3
+    (6, 64, 1, 128, [128, 128], None),    # C5 (per-GPU network)
 ])
 @pytest.mark.parametrize("flags", [0, 1])
 def test_step_matches_oracle(B, N, C, F, conv_dims, dense_dim, flags):
@@ -56,7 +58,9 @@ def test_step_matches_oracle(B, N, C, F, conv_dims, dense_dim, flags):
     spec = NetSpec(F, conv_dims, N, channels=C, label_dim=2, dense_dim=dense_dim, act="sigmoid")
     tr = Trainer(spec, B, lr=0.01, flags=flags)
     tr.load_oracle_params(p)
-    batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask)
+    batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=tr.dims[0])
+    assert tr.padded == (flags == 0 and any(d % 32 for d in [F] + conv_dims))   # Tox21-style widths run zero-padded to 32s
+    assert tr.fused_step == (flags == 0 and dense_dim is None)
     tr.forward_eager(batch)
     close(tr.logits, fw["logits"], 1e-4)
     close(tr.prediction, fw["prediction"], 1e-4)
@@ -87,15 +91,14 @@ def test_graph_replay_equals_eager():
     batch = DeviceBatch.from_host(counts, idx, val, x, labels, 32, mask=mask)
     a, b = Trainer(spec, 32), Trainer(spec, 32)
     a.load_oracle_params(p); b.load_oracle_params(p)
-    b.capture("k", batch)                      # two warm-up steps happen inside capture()
-    for _ in range(2):
-        a.step_eager(batch)
+    b.capture("k", batch)                      # warm-up inside capture() runs forward + backward only: no update
+    assert int(b.step_state[0].item()) == 0
     for _ in range(3):
         a.step_eager(batch)
         b.replay("k")
     torch.cuda.synchronize()
     assert torch.equal(a.params, b.params)     # same kernels, same order, deterministic reductions
-    assert int(b.step_state[0].item()) == 5
+    assert int(b.step_state[0].item()) == 3
     sa, sb = a.read_stats(), b.read_stats()      # cost_sum is accumulated with float atomics: order-dependent last bits
     assert abs(sa[0] - sb[0]) <= 1e-5 * abs(sa[0]) and sa[1] == sb[1]
 
