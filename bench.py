@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- molecules/sec of the batched graph-convolution hot path on N B200s (one node).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): synthetic ring graphs (data_generator/synth_generator_ring.py
-scaled to 32 nodes), batch 1024 molecules per GPU, 64-dim features, 2 x GraphConv(64) + sigmoid ->
-GraphGather -> Dense(2) -> softmax cross-entropy.  One "step" = one training pass over one batch:
-forward + backward + (N>1: one NCCL all-reduce of the flat gradient buffer) + Adam.  Weak scaling:
-the per-GPU batch is fixed, the global batch is 1024 * N.
+Primary line (the driver's command, no --workload): BASELINE.json configs[1] = "c2", synthetic ring graphs
+(data_generator/synth_generator_ring.py scaled to 32 nodes), batch 1024 molecules per GPU, 64-dim features,
+2 x GraphConv(64) + sigmoid -> GraphGather -> Dense(2) -> softmax cross-entropy.  One "step" = one training pass over one
+batch: forward + backward + ONE tail launch (weight-gradient reduce + peer-memory all-reduce over NVLink + Adam), the
+whole step one CUDA-graph replay at every N.  Weak scaling: the per-GPU batch is fixed.
 
-Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how each field is measured.
+The other BASELINE configs ride in the same JSON line under "workloads" (each with its own value / roofline / e2e /
+cpu_baseline): c3 Tox21-scale (8192 molecules <= 50 atoms, 75 atom features, 3 x GraphConv(50) + GraphGather, batch 512),
+c4 the multi-adjacency shape (3 bond types per layer), c5 config 5's per-GPU shard (batch 512 of 64-atom molecules with
+128 features, generated on the device with seed 1234 + rank; at --gpus 8 the global batch is 4096).  --workload X makes X
+the primary line.  Prints ONE JSON line (rank 0).  DESIGN.md section 6 says how each field is measured.
 """
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -24,21 +29,48 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = {"name": "ring_graphs_b1024_n32_f64_2xGraphConv64", "batch_per_gpu": 1024, "n_nodes": 32, "feature_dim": 64,
-            "conv_dims": [64, 64], "channels": 1, "label_dim": 2, "act": "sigmoid"}
-N_ROT = 24          # distinct resident batches rotated through the timed loop (24 x 8.9 MB > 126 MB L2)
+WORKLOADS = {
+    "c2": {"name": "ring_graphs_b1024_n32_f64_2xGraphConv64", "batch_per_gpu": 1024, "n_nodes": 32, "feature_dim": 64,
+           "conv_dims": [64, 64], "channels": 1, "label_dim": 2, "act": "sigmoid", "gen": "ring", "n_rot": 24},
+    "c3": {"name": "tox21_scale_8k_molecules_b512_n50_f75_3xGraphConv50_gather", "batch_per_gpu": 512, "n_nodes": 50,
+           "feature_dim": 75, "conv_dims": [50, 50, 50], "channels": 1, "label_dim": 2, "act": "sigmoid", "gen": "mol", "n_rot": 16},
+    "c4": {"name": "multiadj_3_bond_types_b512_n50_f75_3xGraphConv50_gather", "batch_per_gpu": 512, "n_nodes": 50,
+           "feature_dim": 75, "conv_dims": [50, 50, 50], "channels": 3, "label_dim": 2, "act": "sigmoid", "gen": "mol", "n_rot": 16},
+    "c5": {"name": "1M_molecules_n64_f128_2xGraphConv128_b512_per_gpu_device_generated", "batch_per_gpu": 512, "n_nodes": 64,
+           "feature_dim": 128, "conv_dims": [128, 128], "channels": 1, "label_dim": 2, "act": "sigmoid", "gen": "device", "n_rot": 16},
+}
 METRIC, UNIT = "molecules/sec", "molecules/s"
-V4_TRAFFIC_BYTES = 9458176.0   # profiles/r01b_v4_B1024.txt: 9.46 MB read, writes still in the 126 MB L2 at kernel end
+ACT_ID = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 
 
-def make_host_batches(n, seed, B=None):
-    from kgcn_b200 import synth
-    w = WORKLOAD
+def load_synth():
+    """kgcn_b200/synth.py by FILE PATH: numpy-only generators, importable without the package (the reference arm must not
+    load the CUDA library)."""
+    spec = importlib.util.spec_from_file_location("_kgcn_synth", os.path.join(ROOT, "kgcn_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_host_batches(w, n, seed, B=None):
+    """n host batches of workload w: dict(counts [B,C], indices [nnz,2] i32, values, features [B,N,F], labels [B,2])."""
+    synth = load_synth()
     B = B or w["batch_per_gpu"]
+    N, F, C = w["n_nodes"], w["feature_dim"], w["channels"]
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n):
-        out.append(synth.ring_graphs(rng, B, w["n_nodes"], w["feature_dim"]))
+        if w["gen"] == "ring":
+            out.append(synth.ring_graphs(rng, B, N, F))
+            continue
+        if w["gen"] == "mol":     # Tox21-like molecules: spanning tree + ring closures, diag 1, one-hot block features
+            counts, indices, values, n_atoms = synth.random_molecule_coo(rng, B, N, C, return_sizes=True)
+            feats = synth.atom_like_features(rng, B, N, n_atoms)
+        else:                     # CPU stand-in of the device generator (reference arm / cpu_baseline only)
+            counts, indices, values = synth.random_molecule_coo(rng, B, N, C, min_atoms=N)
+            feats = rng.standard_normal((B, N, F)).astype(np.float32)
+        labels = np.eye(2, dtype=np.float32)[rng.integers(0, 2, B)]
+        out.append({"counts": counts, "indices": indices, "values": values, "features": feats, "labels": labels})
     return out
 
 
@@ -100,12 +132,14 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU restatement of the reference's per-molecule path (oracle/graphconv_ref.c)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, max_seconds=None):
+def cpu_reference_run(w, steps, warmup, max_seconds=None, warm_seconds=3.0):
+    """Times oracle/graphconv_ref.c (per-molecule port of layers.py:105-116 + autodiff + Adam, OpenMP over molecules) on
+    all host cores this process may use.  At least `warm_seconds` of untimed steps first, so the figure does not depend
+    on how many steps were asked for (thread pool start-up, page faults, clock ramp)."""
     from oracle import cref
-    w = WORKLOAD
     B = w["batch_per_gpu"]
-    host = make_host_batches(min(4, max(1, steps)), seed=1234)
-    net = cref.RefNet(w["feature_dim"], w["conv_dims"], w["channels"], w["label_dim"], act=2)
+    host = make_host_batches(w, min(4, max(1, steps)), seed=1234)
+    net = cref.RefNet(w["feature_dim"], w["conv_dims"], w["channels"], w["label_dim"], act=ACT_ID[w["act"]])
     rng = np.random.default_rng(1234)
     for name, (off, shape) in net.offsets.items():
         if name.endswith("kernel"):
@@ -121,8 +155,11 @@ def cpu_reference_run(steps, warmup, max_seconds=None):
         return net.train_step(d["counts"], d["indices"], d["values"], d["features"], d["labels"], mask, w["n_nodes"],
                               n_threads=threads)
 
-    for i in range(warmup):
+    t0 = time.perf_counter()
+    i = 0
+    while i < warmup or time.perf_counter() - t0 < warm_seconds:
         one(i)
+        i += 1
     t0 = time.perf_counter()
     done = 0
     for i in range(steps):
@@ -138,17 +175,17 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup)
-    w = WORKLOAD
+    w = WORKLOADS[args.workload or "c2"]
+    r = cpu_reference_run(w, args.steps, args.warmup, max_seconds=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "step": "train: fwd+bwd+Adam", "batch_per_step": w["batch_per_gpu"],
                    "note": "CPU port of the reference's per-molecule GraphConv path (oracle/graphconv_ref.c, OpenMP over "
-                           "molecules); TensorFlow itself is not installable here (BASELINE.md section 2)"},
+                           "molecules, >= 3 s of untimed warm-up steps); TensorFlow itself is not installable here (BASELINE.md section 2)"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": "%d full steps of %d molecules" % (r["steps"], w["batch_per_gpu"])},
+                         "sample": "%d full steps of %d molecules (%.1f s)" % (r["steps"], w["batch_per_gpu"], r["seconds"])},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -158,97 +195,65 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------
-def run_own(args):
-    import torch
-    import torch.distributed as dist
-    from kgcn_b200 import _lib, ops
-    from kgcn_b200.trainer import DeviceBatch, HostFedPipeline, NetSpec, Trainer
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank, self.local_rank, self.world = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: kgcn_b200 has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peaks, self.peak_kind = measured_peaks()
 
-    rank, local_rank, world = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: kgcn_b200 has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOAD
-    B, N, F = w["batch_per_gpu"], w["n_nodes"], w["feature_dim"]
-    spec = NetSpec(F, w["conv_dims"], N, channels=w["channels"], label_dim=w["label_dim"], act=w["act"])
-    tr = Trainer(spec, B, device=dev, lr=0.01, world_size=world, seed=1234)
-    host = make_host_batches(N_ROT, seed=1234 + rank)
-    batches = [DeviceBatch.from_host(d["counts"], d["indices"], d["values"], d["features"], d["labels"], N, device=dev)
-               for d in host]
-    nnz_mean = float(np.mean([b.csr.nnz for b in batches]))
+    def note(self, msg):
+        if self.args.verbose:
+            print("[bench rank %d] %s" % (self.rank, msg), file=sys.stderr, flush=True)
 
-    def note(msg):
-        if args.verbose:
-            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # ---- launches of this library's kernels per step (counted on one eager step) ----
-    c0 = _lib.lib.kgcn_launch_count()
-    tr.step_eager(batches[0])
-    launches_per_step = _lib.lib.kgcn_launch_count() - c0
-    c0 = _lib.lib.kgcn_launch_count()
-    tr.forward_eager(batches[0])
-    launches_per_infer = _lib.lib.kgcn_launch_count() - c0
-    torch.cuda.synchronize()
-    note("eager step ok, %d launches" % launches_per_step)
-    # ---- capture one CUDA graph per resident batch (train) + one inference graph per batch ----
-    for i in range(N_ROT):
-        tr.capture(("train", i), batches[i])
-    for i in range(N_ROT):
-        tr.capture(("infer", i), batches[i], train=False)
-    note("graphs captured")
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- data ----
+    def make_batches(self, w):
+        """(device batches, host batches or None).  c5: generated on the device, seed 1234 + rank."""
+        torch = self.torch
+        from kgcn_b200.trainer import DeviceBatch
+        N, n_rot, B = w["n_nodes"], w["n_rot"], w["batch_per_gpu"]
+        if w["gen"] == "device":
+            from kgcn_b200 import synth_device
+            raw = synth_device.device_batches(1234 + self.rank, n_rot, B, N, w["feature_dim"], device=self.dev)
+            batches = [DeviceBatch(r["csr"], r["features"], r["labels"], r["mask"]) for r in raw]
+            host = []
+            for r in raw[:4]:      # host copies of a few batches for the end-to-end (host-fed) measurement
+                E = r["idx"].shape[1]
+                host.append({"counts": np.full((B, 1), E, np.int64), "indices": r["idx"].reshape(-1, 2).cpu().numpy(),
+                             "values": r["vals"].reshape(-1).cpu().numpy(), "features": r["features"].cpu().numpy(),
+                             "labels": r["labels"].cpu().numpy()})
+            return batches, host
+        host = make_host_batches(w, n_rot, seed=1234 + self.rank)
+        return None, host
 
-    def timed(kind, steps, warmup):
-        for i in range(warmup):
-            tr.replay((kind, i % N_ROT))
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(steps):
-            tr.replay((kind, i % N_ROT))
-        e.record()
-        barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms_train = timed("train", args.steps, args.warmup)
-    clocks = sampler.result()
-    note("train timed %.3f ms" % ms_train)
-    ms_infer = timed("infer", args.steps, args.warmup)
-    note("infer timed")
-    cost_sum, correct = tr.read_stats()
-
-    # ---- dominant-kernel roofline: the batched SpMM  Y = A.X  on the step's own shape, timed alone ----
-    peaks, peak_kind = measured_peaks()
-    ys = [torch.empty(B, N, F, device=dev) for _ in range(N_ROT)]
-    st = torch.cuda.current_stream()
-
-    def spmm(i):
-        b = batches[i % N_ROT]
-        ops.bspmm_raw(b.csr, b.features, N * F, 0, ys[i % N_ROT], N * F, 0, F)
-
-    reps = max(1, min(200, args.steps // 4))
-
-    def time_alone(fn):
+    def time_alone(self, fn, n_rot, reps):
         """us per launch of fn(i), i over the rotating batches: graph-replayed back-to-back launches, CUDA events."""
+        torch = self.torch
         g = torch.cuda.CUDAGraph()
-        for i in range(N_ROT):
+        for i in range(n_rot):
             fn(i)
         torch.cuda.synchronize()
         with torch.cuda.graph(g):
-            for i in range(N_ROT):
+            for i in range(n_rot):
                 fn(i)
         for _ in range(3):
             g.replay()
@@ -259,118 +264,314 @@ def run_own(args):
             g.replay()
         e.record()
         torch.cuda.synchronize()
-        return s.elapsed_time(e) * 1e3 / (reps * N_ROT)
+        return s.elapsed_time(e) * 1e3 / (reps * n_rot)
 
-    spmm_us = time_alone(spmm)
-    bytes_spmm = 4 * B * N * F * 2 + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1)
-    achieved = bytes_spmm / spmm_us / 1e3
-    roofline = {"kernel": "bspmm_tile_kernel (kgcn_bspmm_f32, Y[b]=A[b].X[b], B=%d N=%d F=%d)" % (B, N, F), "bound": "hbm",
-                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "peak_source": peak_kind + " copy bandwidth (burst)", "frac_of_8TBs_spec": achieved / 8000.0,
-                "algorithmic_bytes_per_launch": bytes_spmm, "us_per_launch": spmm_us,
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full launch of this kernel on this
-                # shape (profiles/r01_spmm_tile_c2.txt): the 8.4 MB output was still in the 126 MB L2 at kernel end
-                "traffic": 9386000.0,
-                "timing": "CUDA events around %d back-to-back launches (graph replay) over %d rotating batches" % (reps * N_ROT, N_ROT)}
+    # ---- one workload ----
+    def measure(self, key, primary):
+        torch, dist, args, world, rank, dev = self.torch, self.dist, self.args, self.world, self.rank, self.dev
+        from kgcn_b200 import _lib, ops
+        from kgcn_b200._lib import check, lib, ptr
+        from kgcn_b200.trainer import DeviceBatch, HostFedPipeline, NetSpec, Trainer
+        w = WORKLOADS[key]
+        B, N, F, C, n_rot = w["batch_per_gpu"], w["n_nodes"], w["feature_dim"], w["channels"], w["n_rot"]
+        steps = args.steps if primary else max(50, args.steps // 4)
+        warmup = args.warmup
+        spec = NetSpec(F, w["conv_dims"], N, channels=C, label_dim=w["label_dim"], act=w["act"])
+        tr = Trainer(spec, B, device=dev, lr=0.01, world_size=world, seed=1234, rank=rank)
+        batches, host = self.make_batches(w)
+        if batches is None:
+            batches = [DeviceBatch.from_host(d["counts"], d["indices"], d["values"], d["features"], d["labels"], N, device=dev,
+                                             pad_to=tr.dims[0]) for d in host]
+        nnz_mean = float(np.mean([b.csr.nnz for b in batches]))
+        res = {"workload": w["name"]}
 
-    # context for `frac` at this size: a plain device-to-device copy moving about the same bytes (8.4 MB read + 8.4 MB
-    # written), timed the same way.  MEASURED_PEAKS' copy figure is for 2 GiB transfers; at 17 MB a launch is a few
-    # microseconds long and its fill / drain is a large part of it.
-    def copy_same(i):
-        ys[i % N_ROT].copy_(batches[i % N_ROT].features)
+        # ---- data-parallel correctness on the hardware: N shards + peer-memory all-reduce == one GPU on the global batch ----
+        if world > 1 and primary:
+            res["dp_check"] = self.dp_check(w, tr, batches[0])
 
-    copy_us = time_alone(copy_same)
-    copy_bytes = 2 * 4 * B * N * F
-    roofline["same_size_copy"] = {"bytes": copy_bytes, "us_per_launch": copy_us, "gbs": copy_bytes / copy_us / 1e3,
-                                  "spmm_vs_copy": (bytes_spmm / spmm_us) / (copy_bytes / copy_us)}
+        # ---- launches of this library's kernels per step (counted on one eager forward+backward, no update) ----
+        c0 = lib.kgcn_launch_count()
+        tr._fwd_bwd(batches[0])
+        launches_per_step = lib.kgcn_launch_count() - c0 + 1          # + the reduce/all-reduce/Adam tail
+        c0 = lib.kgcn_launch_count()
+        tr.forward_eager(batches[0])
+        launches_per_infer = lib.kgcn_launch_count() - c0
+        torch.cuda.synchronize()
+        for i in range(n_rot):
+            tr.capture(("train", i), batches[i])
+        for i in range(n_rot):
+            tr.capture(("infer", i), batches[i], train=False)
+        self.note("%s: graphs captured, %d launches/step" % (key, launches_per_step))
 
-    # ---- the fused GraphConv layer kernel (x -> act(A.x.W + deg*b)) timed the same way ----
-    w0, b0 = tr.views["conv0/kernel"], tr.views["conv0/bias"]
+        def timed(kind, k, wu):
+            for i in range(wu):
+                tr.replay((kind, i % n_rot))
+            self.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(k):
+                tr.replay((kind, i % n_rot))
+            e.record()
+            self.barrier()
+            return self.max_over_ranks(s.elapsed_time(e))
 
-    def layer(i):
-        b = batches[i % N_ROT]
-        ops.graphconv_fwd(b.csr, b.features, w0, b0, 2, 0, out=ys[i % N_ROT])
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
+        ms_train = timed("train", steps, warmup)
+        clocks = sampler.result()
+        self.note("%s: train timed, %.4f ms/step" % (key, ms_train / steps))
+        ms_infer = timed("infer", steps, warmup)
+        self.note("%s: infer timed" % key)
+        cost_sum, correct = tr.read_stats()
+        adam_steps = tr.steps_done()
+        mols = B * world
+        res.update({"value": mols * steps / (ms_train * 1e-3), "unit": UNIT, "ms_per_step": ms_train / steps, "steps": steps,
+                    "launches_per_step": int(launches_per_step), "clocks": clocks,
+                    "infer": {"value": mols * steps / (ms_infer * 1e-3), "unit": UNIT, "ms_per_step": ms_infer / steps,
+                              "launches_per_step": int(launches_per_infer), "step": "forward only (layers + readout)"},
+                    "last_step": {"cost_sum": cost_sum, "correct_count": correct, "adam_updates": adam_steps,
+                                  "cost_per_molecule": cost_sum / B},
+                    "padded_dims": tr.dims if tr.padded else None, "fused_step": bool(tr.fused_step)})
 
-    layer_us = time_alone(layer)
-    bytes_layer = 4 * B * N * (F + F) + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1) + 4 * F * F + 4 * F
-    fused_roofline = {"kernel": "graphconv_fused_v4_kernel (kgcn_graphconv_fwd_f32: TMA ring -> thread-per-row aggregation into TMEM -> "
-                                "tcgen05 TS-mode 3xTF32 with the bias in the GEMM -> sigmoid epilogue)",
-                      "bound": "hbm", "achieved": bytes_layer / layer_us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                      "frac": bytes_layer / layer_us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_layer,
-                      "us_per_launch": layer_us, "molecules_per_s_per_layer": B / layer_us * 1e6,
-                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch (profiles/r01b_v4_B1024.txt)
-                      "traffic": V4_TRAFFIC_BYTES}
+        # ---- per-kernel timings on the step's own shapes, each timed alone (graph-replayed back to back over the rotating
+        # batches, CUDA events on the launching stream), against the measured copy bandwidth ----
+        reps = max(1, min(100, steps // 8))
+        hbm = self.peaks["hbm_gbs"]
+        dims, act = tr.dims, tr.act
+        L = len(w["conv_dims"])
+        st = lambda: torch.cuda.current_stream().cuda_stream
+        kernels = []   # (name, count per step, us, algorithmic bytes)
+        csr_bytes = 8 * nnz_mean + 4 * C * B * (N + 1)
 
-    # ---- the fused GraphConv backward (dU, A^T.dU, dx, dW, dbias + the fixed-order partial reduce), the largest
-    # share of the step (profiles/r01b_bench_launches.csv), timed the same way on layer-2's shape with a dense dy ----
-    dys = [torch.randn(B, N, F, device=dev) for _ in range(4)]
-    acts = [torch.rand(B, N, F, device=dev) for _ in range(4)]
+        def add(name, count, fn, nbytes):
+            us = self.time_alone(fn, n_rot, reps)
+            kernels.append({"kernel": name, "launches_per_step": count, "us_per_launch": us, "algorithmic_bytes_per_launch": nbytes,
+                            "achieved": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / hbm})
 
-    def layer_bwd(i):
-        b = batches[i % N_ROT]
-        ops.graphconv_bwd(b.csr, b.features, w0, 2, acts[i % 4], dys[i % 4])
+        for li in sorted(set([0, L - 1])):   # first and last layer shapes (the middle layers repeat the last one's)
+            fi, fo = dims[li], dims[li + 1]
+            lfi, lfo = tr.ldims[li], tr.ldims[li + 1]
+            xs = [b.features for b in batches] if li == 0 else [torch.rand(B, N, fi, device=dev) for _ in range(min(n_rot, 8))]
+            ys = [torch.empty(B, N, fo, device=dev) for _ in range(min(n_rot, 8))]
+            wk, bk = tr.pviews["conv%d/kernel" % li], tr.pviews["conv%d/bias" % li]
 
-    bwd_us = time_alone(layer_bwd)
-    bytes_bwd = 4 * B * N * F * 4 + 8 * nnz_mean + 4 * w["channels"] * B * (N + 1) + 2 * (4 * F * F + 4 * F)
-    bwd_roofline = {"kernel": "graphconv_fused_bwd_kernel + splitk_reduce_kernel (kgcn_graphconv_bwd_f32: x, y, dy read once, dx "
-                              "written once, dW/dbias per-CTA partials reduced in fixed order)",
-                    "bound": "hbm", "achieved": bytes_bwd / bwd_us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": bytes_bwd / bwd_us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_bwd,
-                    "us_per_launch": bwd_us}
+            def fwd(i, xs=xs, ys=ys, wk=wk, bk=bk, fi=fi, fo=fo, lfo=lfo):
+                b = batches[i % n_rot]
+                if tr.padded:
+                    check(lib.kgcn_graphconv_fwd_padded_f32(ptr(b.csr.rowptr), ptr(b.csr.col), ptr(b.csr.val), B, C, N, ptr(xs[i % len(xs)]), fi,
+                                                            ptr(wk), ptr(bk), fo, lfo, act, ptr(ys[i % len(ys)]), st()))
+                else:
+                    check(lib.kgcn_graphconv_fwd_f32(ptr(b.csr.rowptr), ptr(b.csr.col), ptr(b.csr.val), B, C, N, ptr(xs[i % len(xs)]), fi,
+                                                     ptr(wk), ptr(bk), fo, act, ptr(ys[i % len(ys)]), 0, ptr(tr.ws), tr.ws.numel(), st()))
 
-    # ---- end to end from pinned host buffers through the public step call ----
-    max_nnz = int(max(d["values"].shape[0] for d in host) * 1.1) + 64
-    pipe = HostFedPipeline(tr, max_nnz, train=True, depth=2)
-    pinned = [pipe.pin_host_batch(d["counts"], d["indices"], d["values"], d["features"], d["labels"]) for d in host]
-    pipe.capture()
-    note("e2e pipeline captured")
-    e2e_steps = max(10, min(args.steps, 300))
-    for _ in pipe.run_many(pinned[i % N_ROT] for i in range(6)):
-        pass
-    barrier()
-    t0 = time.perf_counter()
-    e2e_last = None
-    for e2e_last in pipe.run_many(pinned[i % N_ROT] for i in range(e2e_steps)):   # every step's stats are read on the host
-        pass
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    h2d = int(np.mean([pipe.h2d_bytes(p) for p in pinned]))
-    e2e = {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-           "path": "pinned host COO+labels (1 packed copy) + features -> H2D (copy stream, 2 slots) -> device CSR pack -> "
-                   "train step (CUDA graph) -> D2H cost_sum/correct_count, every step"}
+            n_same = (L - 1 if li == L - 1 and L > 1 else 1) if L > 1 else 1
+            count = 1 if li == 0 else L - 1
+            # algorithmic bytes on the LOGICAL widths (x once, y once, CSR once, W once): padding is this library's cost
+            add("graphconv_fused_v4_kernel fwd layer %d (%d->%d%s)" % (li, lfi, lfo, ", stored %d->%d" % (fi, fo) if tr.padded else ""), count, fwd,
+                4 * B * N * (lfi + lfo) + csr_bytes + 4 * C * lfi * lfo + 4 * C * lfo)
+            if tr.fused_step:
+                dus = [torch.randn(B, N, fo, device=dev) for _ in range(min(n_rot, 8))]
+                part = tr.partials[li]
+
+                def dw(i, xs=xs, dus=dus, wk=wk, fi=fi, fo=fo, part=part):
+                    b = batches[i % n_rot]
+                    check(lib.kgcn_graphconv_bwd_partial_f32(ptr(b.csr.rowptr_t), ptr(b.csr.col_t), ptr(b.csr.val_t), B, C, N, ptr(xs[i % len(xs)]),
+                                                             fi, ptr(wk), fo, ptr(dus[i % len(dus)]), None, act, ptr(part), part.numel() * 4, st()))
+
+                add("graphconv_fused_dw_kernel layer %d (dW, dbias partials)" % li, count, dw,
+                    4 * B * N * (lfi + lfo) + csr_bytes + 4 * tr.splits[li] * (lfi + 1) * C * lfo)
+                if li > 0:
+                    dxs = [torch.empty(B, N, fi, device=dev) for _ in range(min(n_rot, 8))]
+                    c_before = lib.kgcn_launch_count()
+
+                    def dxdw(i, xs=xs, dus=dus, dxs=dxs, wk=wk, fi=fi, fo=fo, part=part):
+                        b = batches[i % n_rot]
+                        check(lib.kgcn_graphconv_bwd_partial_f32(ptr(b.csr.rowptr_t), ptr(b.csr.col_t), ptr(b.csr.val_t), B, C, N,
+                                                                 ptr(xs[i % len(xs)]), fi, ptr(wk), fo, ptr(dus[i % len(dus)]), ptr(dxs[i % len(dxs)]),
+                                                                 act, ptr(part), part.numel() * 4, st()))
+
+                    us_both = self.time_alone(dxdw, n_rot, reps)
+                    us_dw = kernels[-1]["us_per_launch"]
+                    nb = 4 * B * N * (lfo + 2 * lfi) + csr_bytes + 4 * C * lfi * lfo   # dU in, x (act') in, dU below out
+                    us = max(us_both - us_dw, 1e-3)
+                    kernels.append({"kernel": "graphconv_fused_v4_kernel dx layer %d (A^T, dU, W^T) x act'(x)" % li, "launches_per_step": count,
+                                    "us_per_launch": us, "algorithmic_bytes_per_launch": nb, "achieved": nb / us / 1e3, "frac": nb / us / 1e3 / hbm,
+                                    "note": "timed as (dx + dW pair) - (dW alone)"})
+
+        def head(i):
+            b = batches[i % n_rot]
+            tr._last_nodes = tr.acts[L]
+            tr._head(b, tr.f_head, st(), train=True)
+
+        add("readout_kernel (GraphGather + Dense + softmax-xent + dU of the last layer)", 1, head,
+            4 * B * N * tr.ldims[-1] * (2 if tr.fused_step else 1))
+
+        def tail(i):
+            tr._optimizer(st())
+
+        if world == 1:
+            nb_tail = sum(4 * tr.splits[l] * (tr.dims[l] + 1) * C * tr.dims[l + 1] for l in range(L)) if tr.fused_step else 0
+            add("reduce_adam_kernel (partials -> gradient -> Adam)", 1, tail, nb_tail + 16 * tr.n_params)
+            torch.cuda.synchronize()
+        self.note("%s: kernels timed" % key)
+        total_us = sum(k["us_per_launch"] * k["launches_per_step"] for k in kernels)
+        for k in kernels:
+            k["share_of_step"] = k["us_per_launch"] * k["launches_per_step"] / total_us
+        dom = max(kernels, key=lambda k: k["share_of_step"])
+        res["kernels"] = kernels
+        res["roofline"] = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": hbm, "unit": "GB/s",
+                           "frac": dom["frac"], "peak_source": self.peak_kind + " copy bandwidth (burst)",
+                           "frac_of_8TBs_spec": dom["achieved"] / 8000.0, "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                           "us_per_launch": dom["us_per_launch"], "share_of_step": dom["share_of_step"],
+                           "traffic": None, "traffic_source": "see the ncu --set full summaries under profiles/ (r02*) for dram__bytes_read/write of this kernel",
+                           "timing": "CUDA events around %d back-to-back launches (graph replay) over %d rotating batches" % (reps * n_rot, n_rot)}
+        whole = 0.0
+        for l in range(L):
+            lfi, lfo = tr.ldims[l], tr.ldims[l + 1]
+            whole += 4 * B * N * (lfi + lfo) + csr_bytes                                   # forward
+            whole += 4 * B * N * (lfi + lfo) + csr_bytes                                   # dW: x, dU
+            if l > 0:
+                whole += 4 * B * N * (lfo + 2 * lfi) + csr_bytes                           # dx: dU, x, dU below
+        whole += 8 * B * N * tr.ldims[-1]
+        res["roofline_step"] = {"algorithmic_bytes_per_step": whole, "achieved": whole / (ms_train / steps * 1e3) / 1e3, "peak": hbm,
+                                "unit": "GB/s", "frac": whole / (ms_train / steps * 1e3) / 1e3 / hbm}
+
+        # ---- the batched SpMM alone (the metric's named kernel), on the first layer's logical shape ----
+        if primary:
+            Fs = tr.dims[0]
+            ys = [torch.empty(B, N, Fs, device=dev) for _ in range(min(n_rot, 8))]
+
+            def spmm(i):
+                b = batches[i % n_rot]
+                ops.bspmm_raw(b.csr, b.features, N * Fs, 0, ys[i % len(ys)], N * Fs, 0, Fs)
+
+            us = self.time_alone(spmm, n_rot, reps)
+            nb = 4 * B * N * Fs * 2 + csr_bytes
+
+            def copy_same(i):
+                ys[i % len(ys)].copy_(batches[i % n_rot].features)
+
+            cus = self.time_alone(copy_same, n_rot, reps)
+            res["roofline_spmm"] = {"kernel": "bspmm_tile_kernel (kgcn_bspmm_f32, Y[b]=A[b].X[b], B=%d N=%d F=%d; not part of the step)" % (B, N, Fs),
+                                    "bound": "hbm", "achieved": nb / us / 1e3, "peak": hbm, "unit": "GB/s", "frac": nb / us / 1e3 / hbm,
+                                    "us_per_launch": us, "algorithmic_bytes_per_launch": nb,
+                                    "same_size_copy": {"bytes": 8 * B * N * Fs, "us_per_launch": cus, "gbs": 8 * B * N * Fs / cus / 1e3}}
+
+        # ---- end to end from pinned host buffers through the public step call ----
+        if host is not None:
+            max_nnz = int(max(d["values"].shape[0] for d in host) * 1.1) + 64
+            pipe = HostFedPipeline(tr, max_nnz, train=True, depth=2)
+            pinned = [pipe.pin_host_batch(d["counts"], d["indices"], d["values"], d["features"], d["labels"]) for d in host]
+            pipe.capture()
+            e2e_steps = max(10, min(steps, 300))
+            for _ in pipe.run_many(pinned[i % len(pinned)] for i in range(6)):
+                pass
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in pipe.run_many(pinned[i % len(pinned)] for i in range(e2e_steps)):   # every step's stats are read on the host
+                pass
+            self.barrier()
+            e2e_s = self.max_over_ranks(time.perf_counter() - t0)
+            h2d = int(np.mean([pipe.h2d_bytes(p) for p in pinned]))
+            res["e2e"] = {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                          "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                          "path": "pinned host COO+labels (1 packed copy) + features -> H2D (copy stream, 2 slots) -> device CSR pack -> "
+                                  "train step (CUDA graph) -> D2H cost_sum/correct_count, every step"}
+            del pipe
+        if tr.p2p is not None:
+            res["p2p_error_flag"] = int(tr.p2p.error.item())
+        res["config"] = {"workload": w["name"], "step": "train: fwd+bwd+%sAdam (tail: ONE launch)" % ("peer-memory grad all-reduce+" if world > 1 else ""),
+                         "batch_per_gpu": B, "global_batch": mols, "n_nodes": N, "feature_dim": F, "conv_dims": w["conv_dims"], "channels": C,
+                         "nnz_per_graph": nnz_mean / B, "parallelism": "dp%d" % world,
+                         "l2": "rotating %d resident batches (%.0f MB of inputs > 126 MB L2)" % (n_rot, n_rot * (B * N * tr.dims[0] * 4 + 12 * nnz_mean) / 1e6),
+                         "launch": "one CUDA graph replay per step", "data_seed": "1234 + rank",
+                         "data": "generated on the device (torch device RNG + kgcn_pack_coo_device)" if w["gen"] == "device" else "host numpy generator"}
+        return res, tr
+
+    def dp_check(self, w, tr, batch):
+        """One step on `world` shards with the peer-memory all-reduce vs ONE GPU (rank 0) on the concatenated global batch:
+        gradients agree to 1e-5 of max, all ranks' parameters are bit-identical after Adam."""
+        torch, dist, world, rank, dev = self.torch, self.dist, self.world, self.rank, self.dev
+        from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
+        B, N = w["batch_per_gpu"], w["n_nodes"]
+        Bc = 128                                               # per-rank shard of the check
+        host = make_host_batches(w, 1, seed=4321, B=Bc * world)[0]   # same global batch on every rank
+        off = np.zeros(Bc * world + 1, np.int64)
+        np.cumsum(host["counts"].reshape(-1), out=off[1:])
+        lo, hi = rank * Bc, (rank + 1) * Bc
+        spec = NetSpec(w["feature_dim"], w["conv_dims"], N, channels=w["channels"], label_dim=w["label_dim"], act=w["act"])
+        sh = Trainer(spec, Bc, device=dev, lr=0.01, world_size=world, seed=99, rank=rank)
+        shard = DeviceBatch.from_host(host["counts"][lo:hi], host["indices"][off[lo]:off[hi]], host["values"][off[lo]:off[hi]],
+                                      host["features"][lo:hi], host["labels"][lo:hi], N, device=dev, pad_to=sh.dims[0])
+        sh.step_eager(shard)
+        torch.cuda.synchronize()
+        params = sh.params.clone()
+        gathered = [torch.empty_like(params) for _ in range(world)]
+        dist.all_gather(gathered, params)
+        identical = all(torch.equal(gathered[0], g) for g in gathered)
+        out = {"params_identical": bool(identical), "shard": Bc, "p2p_error_flag": int(sh.p2p.error.item()) if sh.p2p is not None else None}
+        if rank == 0:
+            one = Trainer(spec, Bc * world, device=dev, lr=0.01, world_size=1, seed=99)
+            full = DeviceBatch.from_host(host["counts"], host["indices"], host["values"], host["features"], host["labels"], N, device=dev,
+                                         pad_to=one.dims[0])
+            one.step_eager(full)
+            torch.cuda.synchronize()
+            scale = float(one.grads.abs().max())
+            out["max_rel_err"] = float((one.grads - sh.grads).abs().max()) / max(scale, 1e-30)
+            out["param_max_abs_diff"] = float((one.params - sh.params).abs().max())
+            out["grad_ok"] = out["max_rel_err"] <= 1e-5
+        if sh.p2p is not None:
+            dist.barrier()
+            sh.p2p.close()
+        return out
+
+
+def run_own(args):
+    bench = Bench(args)
+    rank, world = bench.rank, bench.world
+    primary_key = args.workload or "c2"
+    res, tr = bench.measure(primary_key, primary=True)
+    others = {}
+    if args.workload is None and not args.only_primary:
+        del tr
+        bench.torch.cuda.empty_cache()
+        for key in ("c3", "c4", "c5"):
+            r, t = bench.measure(key, primary=False)
+            others[key] = r
+            del t
+            bench.torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(10 ** 6, 2, max_seconds=12.0)
+        r = cpu_reference_run(WORKLOADS[primary_key], 10 ** 6, 2, max_seconds=12.0)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                        "sample": "%d training steps of %d molecules (%.1f s) of the same workload, oracle/graphconv_ref.c"
-                                  % (r["steps"], B, r["seconds"])}
+                        "sample": "%d training steps of %d molecules (%.1f s, after >= 3 s of warm-up steps) of the same workload, oracle/graphconv_ref.c"
+                                  % (r["steps"], WORKLOADS[primary_key]["batch_per_gpu"], r["seconds"])}
+        for key, o in others.items():
+            r = cpu_reference_run(WORKLOADS[key], 10 ** 6, 1, max_seconds=4.0, warm_seconds=2.0)
+            o["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": "%d training steps of %d molecules (%.1f s)" % (r["steps"], WORKLOADS[key]["batch_per_gpu"], r["seconds"])}
 
     if rank == 0:
-        mols = B * world
+        steps = res["steps"]
         line = {
-            "metric": METRIC, "value": mols * args.steps / (ms_train * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_train / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "step": "train: fwd+bwd+%sAdam" % ("NCCL grad all-reduce+" if world > 1 else ""),
-                       "batch_per_gpu": B, "global_batch": mols, "n_nodes": N, "feature_dim": F, "conv_dims": w["conv_dims"],
-                       "nnz_per_graph": nnz_mean / B, "parallelism": "dp%d" % world,
-                       "l2": "rotating %d resident batches (%.0f MB of inputs > 126 MB L2)" % (N_ROT, N_ROT * (B * N * F * 4 + 12 * nnz_mean) / 1e6),
-                       "launch": "one CUDA graph replay per step"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "launches_per_step": int(launches_per_step), "roofline": roofline, "roofline_fused_layer": fused_roofline, "roofline_fused_bwd": bwd_roofline,
-            "cpu_baseline": cpu_baseline,
-            "infer": {"value": mols * args.steps / (ms_infer * 1e-3), "unit": UNIT, "ms_per_step": ms_infer / args.steps,
-                      "launches_per_step": int(launches_per_infer), "step": "forward only (layers + readout)"},
-            "last_step": {"cost_sum": cost_sum, "correct_count": correct},
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res.get("e2e"),
+            "gpu_launches": int(res["launches_per_step"] * steps), "launches_per_step": res["launches_per_step"],
+            "roofline": res["roofline"], "roofline_step": res["roofline_step"], "roofline_spmm": res.get("roofline_spmm"),
+            "kernels": res["kernels"], "cpu_baseline": cpu_baseline, "infer": res["infer"], "last_step": res["last_step"],
+            "padded_dims": res["padded_dims"], "fused_step": res["fused_step"],
         }
+        if "dp_check" in res:
+            line["dp_check"] = res["dp_check"]
+        if "p2p_error_flag" in res:
+            line["p2p_error_flag"] = res["p2p_error_flag"]
+        if others:
+            line["workloads"] = others
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        bench.dist.destroy_process_group()
 
 
 def main():
@@ -379,6 +580,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--only-primary", action="store_true", help="skip the c3 / c4 / c5 sub-measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

@@ -325,11 +325,13 @@ int kgcn_reduce_partials_f32(const float* partial, int32_t splits, int32_t f_in,
  * `segments` (HOST array) says which ranges of the flat buffers are fed from partial blocks: kernel [channels][rows][cols]
  * at kernel_off, bias [channels][cols] at bias_off (-1: none), partial [splits][(rows + 1)][channels * cols].  Every other
  * element takes its gradient from grad[i] as it is.  The reduced (and, with a group, all-reduced) gradient is written back
- * to grad.  `group` (HOST struct, may be NULL = single GPU): rank r's exchange buffer xg[r] holds 2 * n_pad floats and
- * flags[r] n_flags uint32 (n_pad >= n rounded up to 32, n_flags >= ceil(n / 32)), zero-initialised, all W of them mapped
- * into this process (kgcn_p2p_alloc on the owning rank, kgcn_p2p_open on the others); sums are formed in rank order,
- * so all ranks hold bit-identical gradients and parameters.  Every rank must enqueue the call once per step; a rank
- * that waits ~2 s for a peer sets *error_flag (device int32, may be NULL) and skips the exchange instead of hanging. */
+ * to grad.  n, every segment offset and every segment width must be multiples of 4 (16-byte vector accesses).
+ * `group` (HOST struct, may be NULL = single GPU): rank r owns a mailbox of 2 * world * n_pad 8-byte slots {fp32 value,
+ * step tag} (n_pad >= n), zero-initialised, and all W mailboxes are mapped into this process (kgcn_p2p_alloc on the owning
+ * rank, kgcn_p2p_open on the others).  Each rank PUSHES its tagged sums into every peer's mailbox (posted NVLink stores) and
+ * spins on its own, local one; sums are formed in rank order, so all ranks hold bit-identical gradients and parameters.
+ * Every rank must enqueue the call once per step; a rank that waits ~2 s for a peer sets *error_flag (device int32, may be
+ * NULL) instead of hanging the GPU. */
 typedef struct kgcn_grad_segment {
     int64_t kernel_off, bias_off;
     const float* partial;
@@ -337,9 +339,8 @@ typedef struct kgcn_grad_segment {
 } kgcn_grad_segment;
 typedef struct kgcn_p2p_group {
     int32_t rank, world;
-    int64_t n_pad, n_flags;
-    float* xg[8];
-    uint32_t* flags[8];
+    int64_t n_pad;
+    void* mailbox[8];
     int32_t* error_flag;
 } kgcn_p2p_group;
 int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* v, int64_t n, const kgcn_grad_segment* segments,

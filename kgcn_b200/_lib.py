@@ -115,8 +115,7 @@ class GradSegment(ctypes.Structure):
 
 class P2PGroup(ctypes.Structure):
     """kgcn_p2p_group (include/kgcn_b200.h)."""
-    _fields_ = [("rank", _i32), ("world", _i32), ("n_pad", _i64), ("n_flags", _i64), ("xg", _vp * 8), ("flags", _vp * 8),
-                ("error_flag", _vp)]
+    _fields_ = [("rank", _i32), ("world", _i32), ("n_pad", _i64), ("mailbox", _vp * 8), ("error_flag", _vp)]
 
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1,15 +1,18 @@
 // The tail of a training step in ONE launch: fixed-order reduction of the per-CTA weight-gradient partials of every
 // GraphConv layer -> (data parallel: one-shot all-reduce over NVLink peer memory) -> Adam.
 //
-//   reduce     graphconv_fused_dw_kernel leaves one partial block [(f_in + 1), C * f_out] per CTA; element i of the flat
-//              parameter buffer sums its `splits` partials in split order (32 warps take splits w, w + 32, ..; the 32 warp
-//              sums are then added in warp order), exactly like splitk_reduce_kernel, so the result is deterministic.
+//   reduce     graphconv_fused_dw_kernel leaves one partial block [(f_in + 1), C * f_out] per CTA; a lane owns 4 consecutive
+//              elements of the flat parameter buffer (one 16-byte load per partial), the 32 warps of a block take splits
+//              w, w + 32, .. and the 32 warp sums are added in warp order, so the result is deterministic.
 //              Parameters outside every segment (readout head, GraphDense) already have their gradient in `grad`.
-//   all-reduce every rank owns a peer-mapped exchange buffer (cudaIpc, kgcn_p2p_*): block b writes its 32 local sums,
-//              publishes flag[b] = step (release, system scope), then lanes 0..W-1 poll the W ranks' flag[b] and all lanes
-//              read the W ranks' values in ONE NVLink round trip and add them in rank order -- every rank computes
-//              bit-identical sums.  The buffer is double-buffered by step parity: a rank passes the wait of step t only
-//              after every peer has published step t, i.e. has finished reading step t - 1.
+//   all-reduce low-latency PUSH over peer-mapped memory (cudaIpc, kgcn_p2p_*): every rank owns a mailbox
+//              ll[2][W][n_pad] of 8-byte slots {fp32 value, step}.  A lane stores its 4 local sums, tagged with the step
+//              number, straight into slot [step & 1][my rank] of every PEER's mailbox (posted NVLink writes, no fence, no
+//              flag: an aligned 8-byte store is single-copy atomic, so value and tag arrive together -- NCCL's LL idea),
+//              then spins on its OWN mailbox (local memory) until the W - 1 peers' slots carry this step's tag and adds
+//              the values in rank order: every rank computes bit-identical sums in one NVLink one-way latency.
+//              Double-buffered by step parity: a rank can reach step t + 2 only after it consumed every peer's step t + 1
+//              slot, which that peer wrote after finishing its step t -- so nobody still reads what is overwritten.
 //              The reference has no counterpart (single process); this replaces the NCCL all-reduce between two
 //              graph replays of round 1 (kgcn/core.py:121-127 is the optimizer it feeds).
 //   Adam       TensorFlow's formulation (kgcn_adam_f32), step counter on the device so the launch replays from a CUDA graph.
@@ -24,6 +27,7 @@ namespace {
 constexpr int kMaxSegments = 16;
 constexpr int kMaxWorld = 8;
 constexpr int kTailThreads = 1024;
+constexpr int kTailElems = 128;   // elements per block: 32 lanes x 4
 
 struct TailSegment {
     long long kernel_off, bias_off;   // offsets into the flat buffers; kernel [C][rows][cols], bias [C][cols] (-1: none)
@@ -42,34 +46,28 @@ struct TailParams {
     int n_segments;
     TailSegment seg[kMaxSegments];
     int rank, world;
-    float* xg[kMaxWorld];             // peer-mapped exchange buffers [2][n_pad]
-    unsigned* flags[kMaxWorld];       // peer-mapped flags [n_blocks]
+    unsigned long long* ll[kMaxWorld];   // peer-mapped mailboxes [2][world][n_pad] of {value, step}
     long long n_pad;
     int* error_flag;                  // set when a peer never shows up (bounded spin)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
 __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailParams p) {
     pdl_prologue();
-    __shared__ float red[32][33];
+    __shared__ float4 red[32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
+    const long long i = (static_cast<long long>(blockIdx.x) * 32 + lane) * 4;   // first of this lane's 4 elements
     const int t = p.step_state[0] + 1;
 
-    // ---- which gradient is element i? ----
+    // ---- which gradient are elements i .. i + 3?  (segment offsets and widths are multiples of 4) ----
     const float* src = nullptr;
     long long stride = 0;
     int splits = 0;
@@ -94,77 +92,90 @@ __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailPar
         }
     }
     // Adam operands are requested before anything is waited for
-    float m0 = 0.0f, v0 = 0.0f, p0 = 0.0f, gdirect = 0.0f;
+    float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = m0, p0 = m0, gd = m0;
     if (warp == 0 && i < p.n) {
-        m0 = p.m[i];
-        v0 = p.v[i];
-        p0 = p.param[i];
-        if (src == nullptr) gdirect = p.grad[i];
+        m0 = *reinterpret_cast<const float4*>(p.m + i);
+        v0 = *reinterpret_cast<const float4*>(p.v + i);
+        p0 = *reinterpret_cast<const float4*>(p.param + i);
+        if (src == nullptr) gd = *reinterpret_cast<const float4*>(p.grad + i);
     }
-    float s = 0.0f;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (src != nullptr) {
         for (int z = warp; z < splits; z += 256) {   // predicated batches of 8: up to 256 partials in ONE round trip
-            float val[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) val[j] = (z + 32 * j < splits) ? __ldcg(src + static_cast<long long>(z + 32 * j) * stride) : 0.0f;
+            float4 val[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (z + 32 * j < splits) s += val[j];
+                val[j] = (z + 32 * j < splits) ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(z + 32 * j) * stride))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (z + 32 * j < splits) { s.x += val[j].x; s.y += val[j].y; s.z += val[j].z; s.w += val[j].w; }
         }
     }
     red[warp][lane] = s;
     __syncthreads();
     if (warp == 0) {
-        float g = gdirect;
+        float4 g4 = gd;
         if (src != nullptr) {
-            g = 0.0f;
+            g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int w = 0; w < 32; ++w) g += red[w][lane];
+            for (int w = 0; w < 32; ++w) { const float4 r = red[w][lane]; g4.x += r.x; g4.y += r.y; g4.z += r.z; g4.w += r.w; }
         }
-        if (p.world > 1) {
-            // ---- one-shot all-reduce over peer memory ----
-            float* mine = p.xg[p.rank] + static_cast<long long>(t & 1) * p.n_pad;
-            if (i < p.n_pad) mine[i] = (i < p.n) ? g : 0.0f;
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) st_release_sys(p.flags[p.rank] + blockIdx.x, static_cast<unsigned>(t));
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        if (p.world > 1 && i < p.n) {
+            // ---- one-shot all-reduce: push {value, step} into every peer's mailbox, spin on the own one ----
+            const long long slot = (static_cast<long long>(t & 1) * p.world) * p.n_pad + i;
+            const unsigned long long tag = static_cast<unsigned long long>(static_cast<unsigned>(t)) << 32;
+#pragma unroll
+            for (int r = 0; r < kMaxWorld; ++r)
+                if (r < p.world && r != p.rank) {
+                    unsigned long long* dst = p.ll[r] + slot + static_cast<long long>(p.rank) * p.n_pad;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st_relaxed_sys_u64(dst + j, tag | __float_as_uint(g[j]));
+                }
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
             bool ok = true;
-            if (lane < p.world && lane != p.rank) {
-                const unsigned* f = p.flags[lane] + blockIdx.x;
-                const long long t0 = clock64();
-                while (static_cast<int>(ld_acquire_sys(f)) < t) {
-                    if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer never launched its step; fail instead of hanging the GPU
-                        ok = false;
-                        break;
+            const long long t0 = clock64();
+#pragma unroll 1
+            for (int r = 0; r < p.world; ++r) {
+                if (r == p.rank) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tot[j] += g[j];
+                    continue;
+                }
+                const unsigned long long* mine = p.ll[p.rank] + slot + static_cast<long long>(r) * p.n_pad;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned long long w;
+                    while (((w = ld_relaxed_sys_u64(mine + j)) >> 32) != static_cast<unsigned>(t)) {
+                        if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer never launched its step; fail instead of hanging the GPU
+                            ok = false;
+                            break;
+                        }
                     }
+                    tot[j] += __uint_as_float(static_cast<unsigned>(w));
                 }
             }
-            ok = __all_sync(0xffffffffu, ok);
-            __threadfence_system();
-            if (!ok) {
-                if (lane == 0 && p.error_flag != nullptr) atomicExch(p.error_flag, 1);
-            } else if (i < p.n) {
-                float pv[kMaxWorld];
+            if (!ok && p.error_flag != nullptr) atomicExch(p.error_flag, 1);
 #pragma unroll
-                for (int r = 0; r < kMaxWorld; ++r)
-                    pv[r] = (r < p.world && r != p.rank) ? ld_relaxed_sys(p.xg[r] + static_cast<long long>(t & 1) * p.n_pad + i) : 0.0f;
-                float tot = 0.0f;
-#pragma unroll
-                for (int r = 0; r < kMaxWorld; ++r)
-                    if (r < p.world) tot += (r == p.rank) ? g : pv[r];
-                g = tot;
-            }
+            for (int j = 0; j < 4; ++j) g[j] = tot[j];
         }
         if (i < p.n) {
-            p.grad[i] = g;
+            *reinterpret_cast<float4*>(p.grad + i) = make_float4(g[0], g[1], g[2], g[3]);
             // TF AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
             const float lr_t = p.lr * sqrtf(1.0f - powf(p.beta2, static_cast<float>(t))) / (1.0f - powf(p.beta1, static_cast<float>(t)));
-            const float gr = g * p.grad_scale;
-            const float mi = p.beta1 * m0 + (1.0f - p.beta1) * gr;
-            const float vi = p.beta2 * v0 + (1.0f - p.beta2) * gr * gr;
-            p.m[i] = mi;
-            p.v[i] = vi;
-            p.param[i] = p0 - lr_t * mi / (sqrtf(vi) + p.eps);
+            const float mo[4] = {m0.x, m0.y, m0.z, m0.w}, vo[4] = {v0.x, v0.y, v0.z, v0.w}, po[4] = {p0.x, p0.y, p0.z, p0.w};
+            float mn[4], vn[4], pn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float gr = g[j] * p.grad_scale;
+                mn[j] = p.beta1 * mo[j] + (1.0f - p.beta1) * gr;
+                vn[j] = p.beta2 * vo[j] + (1.0f - p.beta2) * gr * gr;
+                pn[j] = po[j] - lr_t * mn[j] / (sqrtf(vn[j]) + p.eps);
+            }
+            *reinterpret_cast<float4*>(p.m + i) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            *reinterpret_cast<float4*>(p.v + i) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+            *reinterpret_cast<float4*>(p.param + i) = make_float4(pn[0], pn[1], pn[2], pn[3]);
         }
     }
     __syncthreads();
@@ -186,8 +197,10 @@ extern "C" int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* 
                                     int32_t n_segments, float lr, float beta1, float beta2, float eps, float grad_scale,
                                     int32_t* step_state, const kgcn_p2p_group* group, void* stream) {
     KGCN_REQUIRE(param && grad && m && v && step_state, KGCN_ERR_NULL, "reduce_adam: NULL pointer argument");
-    KGCN_REQUIRE(n >= 0 && n_segments >= 0 && n_segments <= kMaxSegments && (n_segments == 0 || segments != nullptr), KGCN_ERR_BAD_SHAPE,
-                 "reduce_adam: bad n / n_segments (at most %d segments)", kMaxSegments);
+    KGCN_REQUIRE(n >= 0 && n % 4 == 0 && n_segments >= 0 && n_segments <= kMaxSegments && (n_segments == 0 || segments != nullptr),
+                 KGCN_ERR_BAD_SHAPE, "reduce_adam: bad n (a multiple of 4) / n_segments (at most %d segments)", kMaxSegments);
+    KGCN_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v), KGCN_ERR_MISALIGNED,
+                 "reduce_adam: flat buffers must be 16-byte aligned");
     if (n == 0) return KGCN_OK;
     TailParams p{};
     p.param = param; p.grad = grad; p.m = m; p.v = v; p.n = n;
@@ -200,24 +213,24 @@ extern "C" int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* 
                          g.kernel_off + static_cast<int64_t>(g.channels) * g.rows * g.cols <= n &&
                          (g.bias_off < 0 || g.bias_off + static_cast<int64_t>(g.channels) * g.cols <= n),
                      KGCN_ERR_BAD_SHAPE, "reduce_adam: segment %d is out of range", s);
+        KGCN_REQUIRE(g.cols % 4 == 0 && g.kernel_off % 4 == 0 && (g.bias_off < 0 || g.bias_off % 4 == 0) && aligned16(g.partial),
+                     KGCN_ERR_MISALIGNED, "reduce_adam: segment %d: offsets and width must be multiples of 4 floats", s);
         p.seg[s] = TailSegment{g.kernel_off, g.bias_off, g.partial, g.splits, g.rows, g.cols, g.channels};
     }
-    const unsigned blocks = static_cast<unsigned>(ceil_div<int64_t>(n, 32));
+    const unsigned blocks = static_cast<unsigned>(ceil_div<int64_t>(n, kTailElems));
     p.rank = 0;
     p.world = 1;
     if (group != nullptr && group->world > 1) {
         KGCN_REQUIRE(group->world <= kMaxWorld && group->rank >= 0 && group->rank < group->world, KGCN_ERR_BAD_SHAPE,
                      "reduce_adam: bad rank %d / world %d (at most %d ranks)", group->rank, group->world, kMaxWorld);
-        KGCN_REQUIRE(group->n_pad >= n && group->n_flags >= static_cast<int64_t>(blocks), KGCN_ERR_WORKSPACE,
-                     "reduce_adam: exchange buffers too small (%lld floats, %lld flags)", (long long)group->n_pad, (long long)group->n_flags);
+        KGCN_REQUIRE(group->n_pad >= n, KGCN_ERR_WORKSPACE, "reduce_adam: mailboxes too small (%lld slots per rank)", (long long)group->n_pad);
         p.rank = group->rank;
         p.world = group->world;
         p.n_pad = group->n_pad;
         p.error_flag = group->error_flag;
         for (int r = 0; r < group->world; ++r) {
-            KGCN_REQUIRE(group->xg[r] != nullptr && group->flags[r] != nullptr, KGCN_ERR_NULL, "reduce_adam: peer %d is not mapped", r);
-            p.xg[r] = group->xg[r];
-            p.flags[r] = group->flags[r];
+            KGCN_REQUIRE(group->mailbox[r] != nullptr, KGCN_ERR_NULL, "reduce_adam: peer %d is not mapped", r);
+            p.ll[r] = reinterpret_cast<unsigned long long*>(group->mailbox[r]);
         }
     }
     launch_pdl(reduce_adam_kernel, blocks, kTailThreads, 0, static_cast<cudaStream_t>(stream), p);

@@ -56,40 +56,32 @@ def pad_features(features, width):
 
 
 class PeerExchange:
-    """Peer-mapped exchange buffers of the ranks of one node (cudaIpc through kgcn_p2p_*): rank r allocates
-    ``xg[2][n_pad]`` floats + ``flags[n_blocks]`` and every rank maps all of them; the 64-byte handles travel through
+    """Peer-mapped mailboxes of the ranks of one node (cudaIpc through kgcn_p2p_*): rank r allocates
+    ``ll[2][world][n_pad]`` 8-byte slots and every rank maps all of them; the 64-byte handles travel through
     ``torch.distributed.all_gather`` (plumbing).  Consumed by kgcn_reduce_adam_f32."""
 
     def __init__(self, n_params, rank, world, pg, device):
         import torch.distributed as dist
         self.rank, self.world = rank, world
-        n_pad = (n_params + 31) // 32 * 32
-        n_flags = n_pad // 32
-        self.own, handles = [], []
-        for nbytes in (2 * n_pad * 4, n_flags * 4):
-            p_own, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
-            check(lib.kgcn_p2p_alloc(nbytes, ctypes.byref(p_own), h))
-            self.own.append(p_own.value)
-            handles.append(bytes(h))
-        mine = torch.tensor(list(handles[0] + handles[1]), dtype=torch.uint8, device=device)
+        n_pad = (n_params + 127) // 128 * 128
+        p_own, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        check(lib.kgcn_p2p_alloc(2 * world * n_pad * 8, ctypes.byref(p_own), h))
+        self.own = p_own.value
+        mine = torch.tensor(list(bytes(h)), dtype=torch.uint8, device=device)
         every = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(every, mine, group=pg)
         self.mapped = []
         g = _lib.P2PGroup()
-        g.rank, g.world, g.n_pad, g.n_flags = rank, world, n_pad, n_flags
+        g.rank, g.world, g.n_pad = rank, world, n_pad
         for r in range(world):
             if r == rank:
-                g.xg[r], g.flags[r] = self.own
+                g.mailbox[r] = self.own
                 continue
-            raw = bytes(every[r].cpu().tolist())
-            ptrs = []
-            for k in range(2):
-                h = (ctypes.c_ubyte * 64).from_buffer_copy(raw[64 * k:64 * k + 64])
-                q = ctypes.c_void_p()
-                check(lib.kgcn_p2p_open(h, ctypes.byref(q)))
-                ptrs.append(q.value)
-                self.mapped.append(q.value)
-            g.xg[r], g.flags[r] = ptrs
+            hr = (ctypes.c_ubyte * 64).from_buffer_copy(bytes(every[r].cpu().tolist()))
+            q = ctypes.c_void_p()
+            check(lib.kgcn_p2p_open(hr, ctypes.byref(q)))
+            g.mailbox[r] = q.value
+            self.mapped.append(q.value)
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         g.error_flag = self.error.data_ptr()
         self.group = g
@@ -99,9 +91,9 @@ class PeerExchange:
         for q in self.mapped:
             lib.kgcn_p2p_close(q)
         self.mapped = []
-        for q in self.own:
-            lib.kgcn_p2p_free(q)
-        self.own = []
+        if self.own is not None:
+            lib.kgcn_p2p_free(self.own)
+            self.own = None
 
 
 class DeviceBatch:
