@@ -315,6 +315,34 @@ int kgcn_graphconv_bwd_partial_f32(const int32_t* rowptr_t, const int32_t* col_t
                                    int32_t f_out, const float* du, float* dx, int32_t act_below, float* partial,
                                    size_t partial_bytes, void* stream);
 
+/* Chained launches for the step loop: ALL GraphConv layers of a network in one launch.  A CTA owns the same graph range in
+ * every layer and the aggregation never leaves a graph, so layer l + 1 starts on a CTA as soon as that CTA has finished layer l
+ * (CTA-local barrier + proxy fence; no grid-wide dependency, no launch / drain / fill per layer).  dims[n_layers + 1] are the
+ * STORED widths (multiples of 32), dims_valid the logical ones (NULL = same; columns beyond are written as exact zeros).
+ *   kgcn_graphconv_chain_fwd_f32   y[l] = act(GraphConv_l(y[l - 1])), y[-1] = x;  w / bias / y are HOST arrays of n_layers
+ *                                  device pointers (w[l] [C][dims[l]][dims[l+1]], bias[l] [C][dims[l+1]] or bias == NULL).
+ *   kgcn_graphconv_chain_dx_f32    du[l - 1] = (sum_c A_c^T . du[l] . W_l,c^T) (.) act'(x[l]) for l = n_layers - 1 .. 1, where
+ *                                  x[l] is the input of layer l (= y[l - 1]); du[n_layers - 1] is the input (from the head),
+ *                                  du[l] is [B, N, dims[l + 1]].  x, w, du are HOST arrays of n_layers device pointers
+ *                                  (x[0] is not read).  Same mathematics as kgcn_graphconv_bwd_partial_f32's dx, layer by layer.
+ * kgcn_graphconv_chain_supported(...) != 0: every layer (and every dx) has a single-CTA plan on these widths (<= 4 layers). */
+int32_t kgcn_graphconv_chain_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims);
+int kgcn_graphconv_chain_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                                 int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                 const int32_t* dims_valid, const float* x, const float* const* w, const float* const* bias,
+                                 float* const* y, int32_t act, void* stream);
+int kgcn_graphconv_chain_dx_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                const float* const* x, const float* const* w, float* const* du, int32_t act, void* stream);
+
+/* Weight-gradient partials of ALL layers (kgcn_graphconv_bwd_partial_f32 with dx == NULL, layer by layer) in as few launches
+ * as tensor memory allows (2 * channels * dims[l + 1] accumulator columns per layer, 512 per launch): x[l] = input of layer l,
+ * du[l] = its dU, partial[l] / partial_bytes[l] its partial blocks.  HOST arrays of n_layers entries. */
+int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                const float* const* x, const float* const* du, float* const* partial,
+                                const size_t* partial_bytes, void* stream);
+
 /* The reduction alone (gradient checks, the NCCL cross-check path): dw [channels][f_in][f_out] and dbias [channels][f_out]
  * (may be NULL) from `splits` partial blocks, summed in split order (deterministic). */
 int kgcn_reduce_partials_f32(const float* partial, int32_t splits, int32_t f_in, int32_t f_out, int32_t channels,

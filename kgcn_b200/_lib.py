@@ -92,6 +92,10 @@ SIGNATURES = {
     "kgcn_gather_readout_xent_du_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "kgcn_graphconv_bwd_splits": (_i32, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "kgcn_graphconv_bwd_partial_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "kgcn_graphconv_chain_supported": (_i32, [_i64, _i32, _i32, _i32, _vp]),
+    "kgcn_graphconv_chain_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "kgcn_graphconv_chain_dx_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "kgcn_graphconv_chain_dw_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kgcn_reduce_partials_f32": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "kgcn_reduce_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "kgcn_p2p_alloc": (ctypes.c_int, [_sz, _vp, _vp]),

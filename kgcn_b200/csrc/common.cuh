@@ -128,6 +128,37 @@ int launch_splitk_reduce_ch(const float* partial, int splits, int64_t M, int n_p
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act,
                     const int32_t* enabled, int n_nodes, bool dy_bcast, cudaStream_t st);
 
+// One job of a chained fused-layer launch (graphconv_fused_v4.cu): y = epilogue((A . x) . W) on the job's own widths.
+struct V4ChainJob {
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* val;
+    const float* x;         // [B, N, f_in]
+    const float* w;         // forward: [C][f_in][f_out]; w_transposed (backward dx): the layer's [C][f_out][f_in]
+    const float* bias;      // [C][f_out] or NULL (ignored when w_transposed)
+    float* y;               // [B, N, f_out]
+    int f_in, f_out, act, w_transposed;
+    const float* mul_src;   // y *= act'(mul_src) of activation mul_act (all jobs of a chain or none)
+    int mul_act, f_out_valid;
+};
+bool fused_v4_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
+int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);
+
+// One job of a multi-layer weight-gradient launch (graphconv_fused_dw.cu)
+struct DwJob {
+    const int32_t* rowptr_t;
+    const int32_t* col_t;
+    const float* val_t;
+    const float* x;        // [B, N, f_in]   input of the layer
+    const float* du;       // [B, N, f_out]  dU of the layer
+    float* partial;        // [splits][(f_in + 1)][channels * f_out]
+    size_t partial_bytes;
+    int f_in, f_out;
+};
+int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, int* splits_out,
+                                   cudaStream_t st);
+int fused_dw_jobs_per_launch(int channels, const int* f_out, int n_jobs);
+
 int launch_bspmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                  int n_rows, int n_cols, int feat, const float* rhs, int64_t rs_g, int64_t rs_c, float* out,
                  int64_t os_g, int64_t os_c, const float* self_scale, int act, cudaStream_t st);

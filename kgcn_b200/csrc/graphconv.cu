@@ -254,3 +254,87 @@ extern "C" int kgcn_reduce_partials_f32(const float* partial, int32_t splits, in
     KGCN_REQUIRE(splits > 0 && f_in > 0 && f_out > 0 && channels > 0, KGCN_ERR_BAD_SHAPE, "reduce_partials: bad shape");
     return launch_splitk_reduce_ch(partial, splits, f_in, f_out, channels, dw, dbias, static_cast<cudaStream_t>(stream));
 }
+
+// ---- chained launches for the step loop: all forward layers / all dx layers of a network in ONE launch each ----
+extern "C" int32_t kgcn_graphconv_chain_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
+                                                  const int32_t* dims) {
+    if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || n_layers < 1 || n_layers > 4 || dims == nullptr) return 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (!fused_v4_chainable(n_graphs, channels, n_nodes, dims[l], dims[l + 1])) return 0;            // forward layer l
+        if (l > 0 && !fused_v4_chainable(n_graphs, channels, n_nodes, dims[l + 1], dims[l])) return 0;    // dx of layer l
+    }
+    return 1;
+}
+
+extern "C" int kgcn_graphconv_chain_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
+                                            int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                            const int32_t* dims_valid, const float* x, const float* const* w,
+                                            const float* const* bias, float* const* y, int32_t act, void* stream) {
+    KGCN_REQUIRE(rowptr && col && val && dims && x && w && y, KGCN_ERR_NULL, "graphconv_chain_fwd: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 4, KGCN_ERR_BAD_SHAPE,
+                 "graphconv_chain_fwd: bad shape (1..4 layers)");
+    KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "graphconv_chain_fwd: unknown act %d", act);
+    V4ChainJob jobs[4];
+    const float* in = x;
+    for (int l = 0; l < n_layers; ++l) {
+        KGCN_REQUIRE(w[l] && y[l], KGCN_ERR_NULL, "graphconv_chain_fwd: NULL weight / output of layer %d", l);
+        KGCN_REQUIRE(aligned16(in) && aligned16(y[l]) && aligned16(w[l]) && (!bias || aligned16(bias[l])) && aligned16(rowptr) &&
+                         aligned16(col) && aligned16(val), KGCN_ERR_MISALIGNED, "graphconv_chain_fwd: 16-byte alignment required");
+        jobs[l] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, y[l], dims[l], dims[l + 1], act, 0, nullptr,
+                             KGCN_ACT_NONE, dims_valid ? dims_valid[l + 1] : dims[l + 1]};
+        in = y[l];
+    }
+    return launch_graphconv_fused_v4_chain(jobs, n_layers, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kgcn_graphconv_chain_dx_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                           int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                           const float* const* x, const float* const* w, float* const* du, int32_t act,
+                                           void* stream) {
+    KGCN_REQUIRE(rowptr_t && col_t && val_t && dims && x && w && du, KGCN_ERR_NULL, "graphconv_chain_dx: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 2 && n_layers <= 5, KGCN_ERR_BAD_SHAPE,
+                 "graphconv_chain_dx: bad shape (2..5 layers)");
+    KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "graphconv_chain_dx: unknown act %d", act);
+    // du[l] = dU of layer l ([B, N, dims[l + 1]]); du[n_layers - 1] is the input, du[n_layers - 2] .. du[0] are outputs:
+    // du[l - 1] = (sum_c A_c^T . du[l] . W_l,c^T) (.) act'(x[l]),  x[l] = input of layer l = output of layer l - 1
+    V4ChainJob jobs[4];
+    int k = 0;
+    for (int l = n_layers - 1; l >= 1; --l, ++k) {
+        KGCN_REQUIRE(x[l] && w[l] && du[l] && du[l - 1], KGCN_ERR_NULL, "graphconv_chain_dx: NULL pointer at layer %d", l);
+        KGCN_REQUIRE(aligned16(x[l]) && aligned16(w[l]) && aligned16(du[l]) && aligned16(du[l - 1]) && aligned16(rowptr_t) &&
+                         aligned16(col_t) && aligned16(val_t), KGCN_ERR_MISALIGNED, "graphconv_chain_dx: 16-byte alignment required");
+        jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
+                             x[l], act == KGCN_ACT_NONE ? KGCN_ACT_NONE : act, 0};
+    }
+    return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                           int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                           const float* const* x, const float* const* du, float* const* partial,
+                                           const size_t* partial_bytes, void* stream) {
+    KGCN_REQUIRE(rowptr_t && col_t && val_t && dims && x && du && partial && partial_bytes, KGCN_ERR_NULL,
+                 "graphconv_chain_dw: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 8, KGCN_ERR_BAD_SHAPE,
+                 "graphconv_chain_dw: bad shape (1..8 layers)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int l = 0;
+    while (l < n_layers) {   // as many consecutive layers per launch as tensor memory holds accumulators for
+        int f_out[4], n_try = std::min(4, n_layers - l);
+        for (int k = 0; k < n_try; ++k) f_out[k] = dims[l + k + 1];
+        const int n = std::max(1, fused_dw_jobs_per_launch(channels, f_out, n_try));
+        DwJob jobs[4];
+        for (int k = 0; k < n; ++k) {
+            const int i = l + k;
+            KGCN_REQUIRE(x[i] && du[i] && partial[i], KGCN_ERR_NULL, "graphconv_chain_dw: NULL pointer at layer %d", i);
+            KGCN_REQUIRE(fused_dw_eligible(n_graphs, channels, n_nodes, dims[i], dims[i + 1], x[i], du[i], rowptr_t, col_t, val_t),
+                         KGCN_ERR_UNSUPPORTED, "graphconv_chain_dw: layer %d (%d -> %d) is not supported by the fused weight-gradient kernel",
+                         i, dims[i], dims[i + 1]);
+            jobs[k] = DwJob{rowptr_t, col_t, val_t, x[i], du[i], partial[i], partial_bytes[i], dims[i], dims[i + 1]};
+        }
+        const int rc = launch_graphconv_fused_dw_jobs(jobs, n, n_graphs, channels, n_nodes, nullptr, st);
+        if (rc) return rc;
+        l += n;
+    }
+    return KGCN_OK;
+}

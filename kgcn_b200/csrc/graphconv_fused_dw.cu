@@ -50,6 +50,7 @@ struct DwParams {
     int n_stages, opbufs, cv_cap;
     uint32_t off_ones, off_op, op_bytes, op_g, lbo, off_stage, stage_bytes, st_du, st_rp, st_col, st_val, smem_total;
     uint32_t tmem_cols;
+    uint32_t tm_off;         // first tensor-memory column of this job's accumulators (dW at tm_off, dbias at tm_off + Ng)
 };
 
 struct Ring {
@@ -94,7 +95,19 @@ __device__ __forceinline__ void store_split(uint32_t line_hi, uint32_t line_lo, 
     }
 }
 
-__global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwParams p) {
+// Several layers' weight gradients in ONE launch ("jobs"): after the dx chain every layer's dU exists, so the CTA walks
+// its graph range once per layer, each job with its own accumulators in tensor memory (columns tm_off .. tm_off + 2 Ng).
+// Job boundary: the MMA warp waits for its last MMAs, then one CTA barrier -- shared-memory layouts may differ per job.
+constexpr int kDwMaxJobs = 4;
+struct DwBatch {
+    int n_jobs;
+    uint32_t tmem_cols;
+    DwParams job[kDwMaxJobs];
+};
+
+__device__ __forceinline__ void bar_cta_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
+
+__global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwBatch b) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kStagesMax], bar_empty[kStagesMax], bar_opfull[2], bar_opempty[2], bar_done;
     __shared__ uint32_t tmem_slot;
@@ -102,14 +115,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwP
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int C = p.C, N = p.N, f_in = p.f_in, f_out = p.f_out, Ng = p.Ng, S = p.n_stages, R = p.R;
-    const uint32_t pitch_x = static_cast<uint32_t>(f_in) * 4u, pitch_u = static_cast<uint32_t>(f_out) * 4u;
-
-    const int64_t g_begin = static_cast<int64_t>(blockIdx.x) * p.graphs_per_cta;
-    const int64_t left = p.n_graphs - g_begin;
-    const int n_graphs_cta = static_cast<int>(left < p.graphs_per_cta ? (left > 0 ? left : 0) : p.graphs_per_cta);
-    const int n_tiles = (n_graphs_cta + p.G - 1) / p.G;
-    const int last_ng = n_graphs_cta - (n_tiles - 1) * p.G;
+    const int n_jobs = b.n_jobs;
 
     if (tid == 0) {
         for (int i = 0; i < kStagesMax; ++i) {
@@ -123,275 +129,320 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwP
         mbar_init(&bar_done, 1);
         fence_mbar_init();
     }
-    if (warp == kWarpMma) tmem_alloc(&tmem_slot, p.tmem_cols);
-    {   // operand regions start as exact zeros (M / K padding must never contribute garbage); the ones operand: column 0
-        // of every K row is 1.0 (element m = 0 sits in granule 0 -> position (row & 3) << 5 of the row's line)
-        const uint32_t n16 = (p.off_stage - p.off_ones) >> 4;
-        const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (uint32_t i = tid; i < n16; i += kBlock) sts_f<4>(base + p.off_ones + (i << 4), z4);
-    }
-    __syncthreads();
-    if (tid < R) {
-        const float one[1] = {1.0f};
-        sts_f<1>(base + p.off_ones + static_cast<uint32_t>(tid) * 128u + ((static_cast<uint32_t>(tid) & 3u) << 5), one);
-    }
-    fence_proxy_async_smem();
+    if (warp == kWarpMma) tmem_alloc(&tmem_slot, b.tmem_cols);
     pdl_wait();   // everything above overlaps the previous kernel's tail
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == kWarpTma) {
-        // =============================== TMA producer ===============================
-        if (lane == 0) {
-            Ring rs;
-            for (int it = 0; it < n_tiles; ++it) {
-                mbar_wait_relaxed(&bar_empty[rs.idx], rs.phase ^ 1u);
-                const int64_t g0 = g_begin + static_cast<int64_t>(it) * p.G;
-                const int ng = (it == n_tiles - 1) ? last_ng : p.G;
-                const int64_t r0 = g0 * C * N;
-                const int rows_csr = ng * C * N;
-                unsigned char* st = gen + p.off_stage + static_cast<size_t>(rs.idx) * p.stage_bytes;
-                uint64_t* full = &bar_full[rs.idx];
-                const int64_t rp_lo = r0 & ~3ll;
-                const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
-                const uint32_t x_bytes = static_cast<uint32_t>(ng * N) * pitch_x, u_bytes = static_cast<uint32_t>(ng * N) * pitch_u;
-                mbar_expect_tx_only(full, x_bytes + u_bytes + 4u * rp_cnt);
-                bulk_g2s(st + p.st_du, p.du + g0 * N * f_out, u_bytes, full);
-                bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
-                bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
-                const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
-                const int32_t e_lo = e_first & ~3;
-                const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
-                const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap) && e_cnt != 0;
-                mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the one arrival of the phase
-                if (staged) {
-                    bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
-                    bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
-                }
-                rs.advance(S);
-            }
-        }
-    } else if (warp == kWarpMma) {
-        // =============================== MMA issuer ===============================
-        const uint32_t idesc_w = umma_idesc_tf32(128, Ng) | kUmmaMajorMnA | kUmmaMajorMnB;
-        const uint32_t idesc_b = umma_idesc_tf32(64, Ng) | kUmmaMajorMnA | kUmmaMajorMnB;
-        const uint32_t d_w = tmem, d_b = tmem + static_cast<uint32_t>(Ng);
-        const uint64_t desc_ones = umma_desc_mn32(base + p.off_ones, p.lbo, 512u);
-        const uint32_t lbo16 = p.lbo >> 4;
-        Ring ro;
-        uint32_t acc = 0;
-        for (int it = 0; it < n_tiles; ++it) {
-            const int rows_t = ((it == n_tiles - 1) ? last_ng : p.G) * N;
-            for (int c0 = 0; c0 < rows_t; c0 += R) {
-                const int ksteps = (min(R, rows_t - c0) + 7) >> 3;
-                mbar_wait(&bar_opfull[ro.idx], ro.phase);
-                tc_fence_after_sync();
-                __syncwarp();
-                if (elect_one()) {
-                    const uint32_t op = base + p.off_op + static_cast<uint32_t>(ro.idx) * p.op_bytes;
-                    const uint64_t dxh = umma_desc_mn32(op, p.lbo, 512u);                         // Xhi (stacked: [Xhi ; Xlo])
-                    const uint64_t dxl = dxh + static_cast<uint64_t>(4u * lbo16);                 // Xlo (not stacked)
-                    const uint64_t dgh = umma_desc_mn32(op + p.op_g, p.lbo, 512u);                // Ghi
-                    const uint64_t dgl = dgh + static_cast<uint64_t>(static_cast<uint32_t>(p.n_gs) * lbo16);   // Glo
-                    for (int ks = 0; ks < ksteps; ++ks) {   // 8 rows (1024 B) per K step
-                        const uint64_t o = static_cast<uint64_t>(64 * ks);
-                        umma_tf32(d_w, dxh + o, dgh + o, idesc_w, acc);
-                        umma_tf32(d_b, desc_ones + o, dgh + o, idesc_b, acc);
-                        acc = 1;
-                        umma_tf32(d_w, dxh + o, dgl + o, idesc_w, 1);
-                        umma_tf32(d_b, desc_ones + o, dgl + o, idesc_b, 1);
-                        if (!p.stacked) umma_tf32(d_w, dxl + o, dgh + o, idesc_w, 1);
-                    }
-                    umma_commit(&bar_opempty[ro.idx]);   // the operand buffer may be overwritten once these MMAs have read it
-                }
-                __syncwarp();
-                ro.advance(p.opbufs);
-            }
-        }
-        if (elect_one()) umma_commit(&bar_done);
-        __syncwarp();
-    } else {
-        // =============================== worker warps ===============================
-        const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
-        const int n_cs = p.n_gs + p.n_xs;
-        const uint32_t lo_x = (p.stacked ? 2u : 4u) * p.lbo, lo_g = static_cast<uint32_t>(p.n_gs) * p.lbo;
-        const uint32_t r0_step = static_cast<uint32_t>(p.G * C * N);
-        uint32_t r0_lo = static_cast<uint32_t>((g_begin * C * N) & 3);
-        Ring rs, ro;
-        for (int it = 0; it < n_tiles; ++it) {
-            const bool last = it == n_tiles - 1;
-            const int rows_t = (last ? last_ng : p.G) * N;
-            const int rows_csr = last ? last_ng * C * N : static_cast<int>(r0_step);
-            const uint32_t st = base + p.off_stage + static_cast<uint32_t>(rs.idx) * p.stage_bytes;
-            mbar_wait(&bar_full[rs.idx], rs.phase);
-            const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
-            const int e_first = static_cast<int>(lds_u32(rp_addr));
-            const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
-            const int e_lo = e_first & ~3;
-            const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
-            const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);   // entry e at col_addr + 4 e
-            const uint32_t val_addr = st + p.st_val - 4u * static_cast<uint32_t>(e_lo);
+    // one phase bit per barrier slot and role (ring sizes may differ per job)
+    uint32_t ph_a = 0, ph_b = 0, ph_done = 0;
 
-            for (int c0 = 0; c0 < rows_t; c0 += R) {
-                const int rc8 = (min(R, rows_t - c0) + 7) & ~7;   // rows the MMAs of this chunk read (zero rows past the tile)
-                const int n_rb = (rc8 + 31) >> 5;
-                mbar_wait(&bar_opempty[ro.idx], ro.phase ^ 1u);
-                tc_fence_after_sync();
-                const uint32_t op = base + p.off_op + static_cast<uint32_t>(ro.idx) * p.op_bytes;
-                for (int j = warp; j < n_cs * n_rb; j += kWorkWarps) {
-                    const int cs = j / n_rb, rb = j - cs * n_rb;
-                    const int rl = rb * 32 + lane;          // row inside the chunk
-                    const int r = c0 + rl;                  // row inside the tile
-                    const bool valid = r < rows_t;
-                    float acc[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
-                    uint32_t line_hi, line_lo;
-                    if (cs < p.n_gs) {
-                        // ---- G slab: gather over the row's entries of channel c ----
-                        const int c = cs / p.spc, s = cs - c * p.spc;
-                        const int gl = r / N, node = r - gl * N;
-                        int e = e_first, e_end = e_first;
-                        if (valid) {
-                            const uint32_t ra = rp_addr + 4u * static_cast<uint32_t>((gl * C + c) * N + node);
-                            e = static_cast<int>(lds_u32(ra));
-                            e_end = static_cast<int>(lds_u32(ra + 4u));
-                        }
-                        const uint32_t ubase = st + p.st_du + static_cast<uint32_t>(gl * N) * pitch_u + static_cast<uint32_t>(s) * 128u + (s7 << 4);
-                        if (staged) {
-                            uint32_t ce = col_addr + 4u * static_cast<uint32_t>(e), ve = val_addr + 4u * static_cast<uint32_t>(e);
-                            const uint32_t cend = col_addr + 4u * static_cast<uint32_t>(e_end);
-                            uint32_t cn = lds_u32(ce);   // one entry of look-ahead; reading one past the row is harmless (slack)
-                            float vn = lds_f32(ve);
-#pragma unroll 1
-                            while (ce < cend) {
-                                const uint32_t ua = ubase + cn * pitch_u;
-                                const float v = vn;
-                                ce += 4;
-                                ve += 4;
-                                cn = lds_u32(ce);
-                                vn = lds_f32(ve);
-                                float uv[8][4];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) lds_f<4>(uv[i], ua ^ (static_cast<uint32_t>(i) << 4));
-#pragma unroll
-                                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                                    for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = fmaf(v, uv[i][jj], acc[4 * i + jj]);
-                            }
-                        } else {   // unusually dense tile: the CSR slice did not fit the stage, entries come from global memory
-                            for (; e < e_end; ++e) {
-                                const uint32_t ua = ubase + static_cast<uint32_t>(__ldg(p.col + e)) * pitch_u;
-                                const float v = __ldg(p.val + e);
-                                float uv[8][4];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) lds_f<4>(uv[i], ua ^ (static_cast<uint32_t>(i) << 4));
-#pragma unroll
-                                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                                    for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = fmaf(v, uv[i][jj], acc[4 * i + jj]);
-                            }
-                        }
-                        line_hi = op + p.op_g + static_cast<uint32_t>(cs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
-                        line_lo = line_hi + lo_g;
-                    } else {
-                        // ---- x slab: the row's 128 bytes, same rotated chunk order ----
-                        const int xs = cs - p.n_gs;
-                        if (valid) {
-                            const uint32_t xa = st + static_cast<uint32_t>(r) * pitch_x + static_cast<uint32_t>(xs) * 128u + (s7 << 4);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float t[4];
-                                lds_f<4>(t, xa ^ (static_cast<uint32_t>(i) << 4));
-#pragma unroll
-                                for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = t[jj];
-                            }
-                        }
-                        line_hi = op + static_cast<uint32_t>(xs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
-                        line_lo = line_hi + lo_x;
+    for (int jb = 0; jb < n_jobs; ++jb) {
+        const DwParams& p = b.job[jb];
+        const int C = p.C, N = p.N, f_in = p.f_in, f_out = p.f_out, Ng = p.Ng, S = p.n_stages, R = p.R;
+        const uint32_t pitch_x = static_cast<uint32_t>(f_in) * 4u, pitch_u = static_cast<uint32_t>(f_out) * 4u;
+        const int64_t g_begin = static_cast<int64_t>(blockIdx.x) * p.graphs_per_cta;
+        const int64_t left = p.n_graphs - g_begin;
+        const int n_graphs_cta = static_cast<int>(left < p.graphs_per_cta ? (left > 0 ? left : 0) : p.graphs_per_cta);
+        const int n_tiles = (n_graphs_cta + p.G - 1) / p.G;
+        const int last_ng = n_graphs_cta - (n_tiles - 1) * p.G;
+        const uint32_t tm = tmem + p.tm_off;
+
+        if (jb > 0) bar_cta_roles();   // the previous job has finished with shared memory (its MMAs have completed)
+        if (warp != kWarpTma) {
+            // Only what no worker ever writes has to be zeroed: the ones operand (M = 64: two 32-row chunks; column 0 of every K
+            // row is 1.0: element m = 0 sits in granule 0 -> position (row & 3) << 5 of the row's line) and the M-padding chunks
+            // of the X operand (f_in < 64 stacked / f_in < 128 split).  Chunks that hold data are fully rewritten for every
+            // operand chunk, rows past a short chunk are written as zeros by the workers, the MMAs read whole K steps only.
+            constexpr int kSetup = kBlock - 32;
+            const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const uint32_t n16_ones = (2u * p.lbo) >> 4;
+            for (uint32_t i = tid; i < n16_ones; i += kSetup) sts_f<4>(base + p.off_ones + (i << 4), z4);
+            const int half = p.stacked ? 2 : 4;       // chunks per hi / lo half of the X operand
+            const uint32_t lbo16 = p.lbo >> 4;
+            for (int ob = 0; ob < p.opbufs; ++ob)
+                for (int ch = 0; ch < 2 * half; ++ch)
+                    if ((ch % half) >= p.n_xs) {
+                        const uint32_t cb = base + p.off_op + static_cast<uint32_t>(ob) * p.op_bytes + static_cast<uint32_t>(ch) * p.lbo;
+                        for (uint32_t i = tid; i < lbo16; i += kSetup) sts_f<4>(cb + (i << 4), z4);
                     }
-                    __syncwarp();
-                    if (rl < rc8) store_split(line_hi, line_lo, static_cast<uint32_t>(rl), s7, acc);
+            asm volatile("bar.sync 3, %0;" ::"n"(kSetup) : "memory");
+            if (tid < R) {
+                const float one[1] = {1.0f};
+                sts_f<1>(base + p.off_ones + static_cast<uint32_t>(tid) * 128u + ((static_cast<uint32_t>(tid) & 3u) << 5), one);
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 3, %0;" ::"n"(kSetup) : "memory");
+        }
+
+        if (warp == kWarpTma) {
+            // =============================== TMA producer ===============================
+            if (lane == 0) {
+                int s = 0;
+                for (int it = 0; it < n_tiles; ++it) {
+                    mbar_wait_relaxed(&bar_empty[s], ((ph_a >> s) & 1u) ^ 1u);
+                    ph_a ^= 1u << s;
+                    const int64_t g0 = g_begin + static_cast<int64_t>(it) * p.G;
+                    const int ng = (it == n_tiles - 1) ? last_ng : p.G;
+                    const int64_t r0 = g0 * C * N;
+                    const int rows_csr = ng * C * N;
+                    unsigned char* st = gen + p.off_stage + static_cast<size_t>(s) * p.stage_bytes;
+                    uint64_t* full = &bar_full[s];
+                    const int64_t rp_lo = r0 & ~3ll;
+                    const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
+                    const uint32_t x_bytes = static_cast<uint32_t>(ng * N) * pitch_x, u_bytes = static_cast<uint32_t>(ng * N) * pitch_u;
+                    mbar_expect_tx_only(full, x_bytes + u_bytes + 4u * rp_cnt);
+                    bulk_g2s(st + p.st_du, p.du + g0 * N * f_out, u_bytes, full);
+                    bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
+                    bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
+                    const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
+                    const int32_t e_lo = e_first & ~3;
+                    const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
+                    const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap) && e_cnt != 0;
+                    mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the one arrival of the phase
+                    if (staged) {
+                        bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
+                        bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
+                    }
+                    if (++s == S) s = 0;
                 }
-                fence_proxy_async_smem();   // operands are read by the tensor core through the async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_opfull[ro.idx]);
-                ro.advance(p.opbufs);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[rs.idx]);   // this warp is done reading the stage
-            rs.advance(S);
-            r0_lo += r0_step;
-        }
-
-        // ---- per-CTA partial: accumulator rows -> [(f_in + 1), Ng] (last row = column sums of G = dbias partial) ----
-        mbar_wait(&bar_done, 0);
-        tc_fence_after_sync();
-        float* part_out = p.partial + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(f_in) + 1) * Ng;
-        const int q = warp & 3, h = warp >> 2;            // TMEM lane quarter, column phase
-        const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
-        const int row = q * 32 + lane;                    // accumulator row = TMEM lane
-        const uint32_t scratch = base + p.off_op;         // operands are dead now: [64][Ng + 4] floats for the Xlo half
-        const uint32_t spitch = static_cast<uint32_t>(Ng + 4) * 4u;
-        if (p.stacked) {
-            if (q >= 2) {
-                for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
-                    float v[16];
-                    tmem_ld16(tmem + lane_bits + static_cast<uint32_t>(j * 16), v);
-                    tmem_ld_wait();
-                    tmem_ld_fence(v);
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float o[4] = {v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]};
-                        sts_f<4>(scratch + static_cast<uint32_t>(row - 64) * spitch + 4u * static_cast<uint32_t>(j * 16 + 4 * qd), o);
+        } else if (warp == kWarpMma) {
+            // =============================== MMA issuer ===============================
+            const uint32_t idesc_w = umma_idesc_tf32(128, Ng) | kUmmaMajorMnA | kUmmaMajorMnB;
+            const uint32_t idesc_b = umma_idesc_tf32(64, Ng) | kUmmaMajorMnA | kUmmaMajorMnB;
+            const uint32_t d_w = tm, d_b = tm + static_cast<uint32_t>(Ng);
+            const uint64_t desc_ones = umma_desc_mn32(base + p.off_ones, p.lbo, 512u);
+            const uint32_t lbo16 = p.lbo >> 4;
+            int ob = 0;
+            uint32_t acc = 0;
+            for (int it = 0; it < n_tiles; ++it) {
+                const int rows_t = ((it == n_tiles - 1) ? last_ng : p.G) * N;
+                for (int c0 = 0; c0 < rows_t; c0 += R) {
+                    const int ksteps = (min(R, rows_t - c0) + 7) >> 3;
+                    mbar_wait(&bar_opfull[ob], (ph_a >> ob) & 1u);
+                    ph_a ^= 1u << ob;
+                    tc_fence_after_sync();
+                    __syncwarp();
+                    if (elect_one()) {
+                        const uint32_t op = base + p.off_op + static_cast<uint32_t>(ob) * p.op_bytes;
+                        const uint64_t dxh = umma_desc_mn32(op, p.lbo, 512u);                         // Xhi (stacked: [Xhi ; Xlo])
+                        const uint64_t dxl = dxh + static_cast<uint64_t>(4u * lbo16);                 // Xlo (not stacked)
+                        const uint64_t dgh = umma_desc_mn32(op + p.op_g, p.lbo, 512u);                // Ghi
+                        const uint64_t dgl = dgh + static_cast<uint64_t>(static_cast<uint32_t>(p.n_gs) * lbo16);   // Glo
+                        for (int ks = 0; ks < ksteps; ++ks) {   // 8 rows (1024 B) per K step
+                            const uint64_t o = static_cast<uint64_t>(64 * ks);
+                            umma_tf32(d_w, dxh + o, dgh + o, idesc_w, acc);
+                            umma_tf32(d_b, desc_ones + o, dgh + o, idesc_b, acc);
+                            acc = 1;
+                            umma_tf32(d_w, dxh + o, dgl + o, idesc_w, 1);
+                            umma_tf32(d_b, desc_ones + o, dgl + o, idesc_b, 1);
+                            if (!p.stacked) umma_tf32(d_w, dxl + o, dgh + o, idesc_w, 1);
+                        }
+                        umma_commit(&bar_opempty[ob]);   // the operand buffer may be overwritten once these MMAs have read it
                     }
+                    __syncwarp();
+                    if (++ob == p.opbufs) ob = 0;
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kWorkWarps * 32) : "memory");
-            if (q < 2) {
+            if (elect_one()) umma_commit(&bar_done);
+            __syncwarp();
+            mbar_wait(&bar_done, ph_done & 1u);   // all MMAs of this job have completed (operands + accumulators final)
+            ph_done ^= 1u;
+        } else {
+            // =============================== worker warps ===============================
+            const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
+            const int n_cs = p.n_gs + p.n_xs;
+            const uint32_t lo_x = (p.stacked ? 2u : 4u) * p.lbo, lo_g = static_cast<uint32_t>(p.n_gs) * p.lbo;
+            const uint32_t r0_step = static_cast<uint32_t>(p.G * C * N);
+            uint32_t r0_lo = static_cast<uint32_t>((g_begin * C * N) & 3);
+            int s = 0, ob = 0;
+            for (int it = 0; it < n_tiles; ++it) {
+                const bool last = it == n_tiles - 1;
+                const int rows_t = (last ? last_ng : p.G) * N;
+                const int rows_csr = last ? last_ng * C * N : static_cast<int>(r0_step);
+                const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
+                mbar_wait(&bar_full[s], (ph_a >> s) & 1u);
+                ph_a ^= 1u << s;
+                const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
+                const int e_first = static_cast<int>(lds_u32(rp_addr));
+                const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
+                const int e_lo = e_first & ~3;
+                const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
+                const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);   // entry e at col_addr + 4 e
+                const uint32_t val_addr = st + p.st_val - 4u * static_cast<uint32_t>(e_lo);
+
+                for (int c0 = 0; c0 < rows_t; c0 += R) {
+                    const int rc8 = (min(R, rows_t - c0) + 7) & ~7;   // rows the MMAs of this chunk read (zero rows past the tile)
+                    const int n_rb = (rc8 + 31) >> 5;
+                    mbar_wait(&bar_opempty[ob], ((ph_b >> ob) & 1u) ^ 1u);
+                    ph_b ^= 1u << ob;
+                    tc_fence_after_sync();
+                    const uint32_t op = base + p.off_op + static_cast<uint32_t>(ob) * p.op_bytes;
+                    for (int j = warp; j < n_cs * n_rb; j += kWorkWarps) {
+                        const int cs = j / n_rb, rb = j - cs * n_rb;
+                        const int rl = rb * 32 + lane;          // row inside the chunk
+                        const int r = c0 + rl;                  // row inside the tile
+                        const bool valid = r < rows_t;
+                        float acc[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+                        uint32_t line_hi, line_lo;
+                        if (cs < p.n_gs) {
+                            // ---- G slab: gather over the row's entries of channel c ----
+                            const int c = cs / p.spc, sl = cs - c * p.spc;
+                            const int gl = r / N, node = r - gl * N;
+                            int e = e_first, e_end = e_first;
+                            if (valid) {
+                                const uint32_t ra = rp_addr + 4u * static_cast<uint32_t>((gl * C + c) * N + node);
+                                e = static_cast<int>(lds_u32(ra));
+                                e_end = static_cast<int>(lds_u32(ra + 4u));
+                            }
+                            const uint32_t ubase = st + p.st_du + static_cast<uint32_t>(gl * N) * pitch_u + static_cast<uint32_t>(sl) * 128u + (s7 << 4);
+                            if (staged) {
+                                uint32_t ce = col_addr + 4u * static_cast<uint32_t>(e), ve = val_addr + 4u * static_cast<uint32_t>(e);
+                                const uint32_t cend = col_addr + 4u * static_cast<uint32_t>(e_end);
+                                uint32_t cn = lds_u32(ce);   // one entry of look-ahead; reading one past the row is harmless (slack)
+                                float vn = lds_f32(ve);
+#pragma unroll 1
+                                while (ce < cend) {
+                                    const uint32_t ua = ubase + cn * pitch_u;
+                                    const float v = vn;
+                                    ce += 4;
+                                    ve += 4;
+                                    cn = lds_u32(ce);
+                                    vn = lds_f32(ve);
+                                    float uv[8][4];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) lds_f<4>(uv[i], ua ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                        for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = fmaf(v, uv[i][jj], acc[4 * i + jj]);
+                                }
+                            } else {   // unusually dense tile: the CSR slice did not fit the stage, entries come from global memory
+                                for (; e < e_end; ++e) {
+                                    const uint32_t ua = ubase + static_cast<uint32_t>(__ldg(p.col + e)) * pitch_u;
+                                    const float v = __ldg(p.val + e);
+                                    float uv[8][4];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) lds_f<4>(uv[i], ua ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                        for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = fmaf(v, uv[i][jj], acc[4 * i + jj]);
+                                }
+                            }
+                            line_hi = op + p.op_g + static_cast<uint32_t>(cs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
+                            line_lo = line_hi + lo_g;
+                        } else {
+                            // ---- x slab: the row's 128 bytes, same rotated chunk order ----
+                            const int xs = cs - p.n_gs;
+                            if (valid) {
+                                const uint32_t xa = st + static_cast<uint32_t>(r) * pitch_x + static_cast<uint32_t>(xs) * 128u + (s7 << 4);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float t[4];
+                                    lds_f<4>(t, xa ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = t[jj];
+                                }
+                            }
+                            line_hi = op + static_cast<uint32_t>(xs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
+                            line_lo = line_hi + lo_x;
+                        }
+                        __syncwarp();
+                        if (rl < rc8) store_split(line_hi, line_lo, static_cast<uint32_t>(rl), s7, acc);
+                    }
+                    fence_proxy_async_smem();   // operands are read by the tensor core through the async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_opfull[ob]);
+                    if (++ob == p.opbufs) ob = 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[s]);   // this warp is done reading the stage
+                if (++s == S) s = 0;
+                r0_lo += r0_step;
+            }
+        }
+    }
+
+    // ---- per-CTA partials: accumulator rows -> [(f_in + 1), Ng] per job (last row = column sums of G = dbias partial) ----
+    bar_cta_roles();          // the MMA warp has seen the last job's MMAs complete
+    tc_fence_after_sync();
+    if (warp < kWorkWarps) {
+        for (int jb = 0; jb < n_jobs; ++jb) {
+            const DwParams& p = b.job[jb];
+            const int f_in = p.f_in, Ng = p.Ng;
+            const uint32_t tm = tmem + p.tm_off;
+            float* part_out = p.partial + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(f_in) + 1) * Ng;
+            const int q = warp & 3, h = warp >> 2;            // TMEM lane quarter, column phase
+            const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+            const int row = q * 32 + lane;                    // accumulator row = TMEM lane
+            const uint32_t scratch = base + p.off_op;         // operands are dead now: [64][Ng + 4] floats for the Xlo half
+            const uint32_t spitch = static_cast<uint32_t>(Ng + 4) * 4u;
+            if (p.stacked) {
+                if (q >= 2) {
+                    for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                        float v[16];
+                        tmem_ld16(tm + lane_bits + static_cast<uint32_t>(j * 16), v);
+                        tmem_ld_wait();
+                        tmem_ld_fence(v);
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const float o[4] = {v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]};
+                            sts_f<4>(scratch + static_cast<uint32_t>(row - 64) * spitch + 4u * static_cast<uint32_t>(j * 16 + 4 * qd), o);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kWorkWarps * 32) : "memory");
+                if (q < 2) {
+                    for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                        float v[16];
+                        tmem_ld16(tm + lane_bits + static_cast<uint32_t>(j * 16), v);
+                        tmem_ld_wait();
+                        tmem_ld_fence(v);
+                        if (row < f_in) {
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                float l4[4];
+                                lds_f<4>(l4, scratch + static_cast<uint32_t>(row) * spitch + 4u * static_cast<uint32_t>(j * 16 + 4 * qd));
+                                *reinterpret_cast<float4*>(part_out + static_cast<size_t>(row) * Ng + j * 16 + 4 * qd) =
+                                    make_float4(v[4 * qd] + l4[0], v[4 * qd + 1] + l4[1], v[4 * qd + 2] + l4[2], v[4 * qd + 3] + l4[3]);
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kWorkWarps * 32) : "memory");   // scratch is reused by the next job
+            } else {
                 for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
                     float v[16];
-                    tmem_ld16(tmem + lane_bits + static_cast<uint32_t>(j * 16), v);
+                    tmem_ld16(tm + lane_bits + static_cast<uint32_t>(j * 16), v);
                     tmem_ld_wait();
                     tmem_ld_fence(v);
                     if (row < f_in) {
 #pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            float l4[4];
-                            lds_f<4>(l4, scratch + static_cast<uint32_t>(row) * spitch + 4u * static_cast<uint32_t>(j * 16 + 4 * qd));
+                        for (int qd = 0; qd < 4; ++qd)
                             *reinterpret_cast<float4*>(part_out + static_cast<size_t>(row) * Ng + j * 16 + 4 * qd) =
-                                make_float4(v[4 * qd] + l4[0], v[4 * qd + 1] + l4[1], v[4 * qd + 2] + l4[2], v[4 * qd + 3] + l4[3]);
-                        }
+                                make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
                     }
                 }
             }
-        } else {
-            for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
-                float v[16];
-                tmem_ld16(tmem + lane_bits + static_cast<uint32_t>(j * 16), v);
-                tmem_ld_wait();
-                tmem_ld_fence(v);
-                if (row < f_in) {
+            if (q == 0) {   // dbias accumulator: row 0 of the M = 64 block = TMEM lane 0
+                for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
+                    float v[16];
+                    tmem_ld16(tm + static_cast<uint32_t>(Ng + j * 16), v);
+                    tmem_ld_wait();
+                    tmem_ld_fence(v);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd)
-                        *reinterpret_cast<float4*>(part_out + static_cast<size_t>(row) * Ng + j * 16 + 4 * qd) =
-                            make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
-                }
-            }
-        }
-        if (q == 0) {   // dbias accumulator: row 0 of the M = 64 block = TMEM lane 0
-            for (int j = h; j * 16 < Ng; j += kWorkWarps / 4) {
-                float v[16];
-                tmem_ld16(tmem + static_cast<uint32_t>(Ng + j * 16), v);
-                tmem_ld_wait();
-                tmem_ld_fence(v);
-                if (lane == 0) {
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd)
-                        *reinterpret_cast<float4*>(part_out + static_cast<size_t>(f_in) * Ng + j * 16 + 4 * qd) =
-                            make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                        for (int qd = 0; qd < 4; ++qd)
+                            *reinterpret_cast<float4*>(part_out + static_cast<size_t>(f_in) * Ng + j * 16 + 4 * qd) =
+                                make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                    }
                 }
             }
         }
@@ -399,7 +450,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwP
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kWarpMma) tmem_dealloc(tmem, p.tmem_cols);
+    if (warp == kWarpMma) tmem_dealloc(tmem, b.tmem_cols);
 }
 
 inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -488,24 +539,56 @@ int fused_dw_splits(int64_t n_graphs, int channels, int n_nodes, int f_in, int f
     return static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
 }
 
-// partial[grid][(f_in + 1)][channels * f_out]; no reduction
-int launch_graphconv_fused_dw_partial(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
-                                      int channels, int n_nodes, const float* x, int f_in, const float* du, int f_out,
-                                      float* partial, size_t partial_bytes, int* splits_out, cudaStream_t st) {
-    DwParams p{};
-    KGCN_REQUIRE(plan_dw(p, n_graphs, channels, n_nodes, f_in, f_out), KGCN_ERR_UNSUPPORTED,
-                 "fused GraphConv weight gradient: unsupported shape");
-    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
-    const size_t need = static_cast<size_t>(grid) * (static_cast<size_t>(f_in) + 1) * p.Ng * sizeof(float);
-    KGCN_REQUIRE(partial != nullptr && partial_bytes >= need && aligned16(partial), KGCN_ERR_WORKSPACE,
-                 "fused GraphConv weight gradient: workspace %zu < %zu bytes", partial_bytes, need);
-    p.rowptr = rowptr_t; p.col = col_t; p.val = val_t; p.x = x; p.du = du;
-    p.partial = partial;
-    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_total)));
-    launch_pdl(graphconv_fused_dw_kernel, grid, kBlock, p.smem_total, st, p);
+// jobs[k]: partial_k[grid][(f_in_k + 1)][channels * f_out_k]; no reduction.  All jobs share (n_graphs, channels, n_nodes).
+int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, int* splits_out,
+                                   cudaStream_t st) {
+    KGCN_REQUIRE(n_jobs >= 1 && n_jobs <= kDwMaxJobs, KGCN_ERR_BAD_SHAPE, "fused GraphConv weight gradient: 1..%d jobs", kDwMaxJobs);
+    DwBatch b{};
+    b.n_jobs = n_jobs;
+    uint32_t cols = 0, smem = 0;
+    for (int k = 0; k < n_jobs; ++k) {
+        DwParams& p = b.job[k];
+        const DwJob& j = jobs[k];
+        KGCN_REQUIRE(plan_dw(p, n_graphs, channels, n_nodes, j.f_in, j.f_out), KGCN_ERR_UNSUPPORTED,
+                     "fused GraphConv weight gradient: unsupported shape");
+        KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv weight gradient: graph ranges differ");
+        const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
+        const size_t need = static_cast<size_t>(grid) * (static_cast<size_t>(j.f_in) + 1) * p.Ng * sizeof(float);
+        KGCN_REQUIRE(j.partial != nullptr && j.partial_bytes >= need && aligned16(j.partial), KGCN_ERR_WORKSPACE,
+                     "fused GraphConv weight gradient: workspace %zu < %zu bytes", j.partial_bytes, need);
+        p.rowptr = j.rowptr_t; p.col = j.col_t; p.val = j.val_t; p.x = j.x; p.du = j.du;
+        p.partial = j.partial;
+        p.tm_off = cols;
+        cols += 2u * static_cast<uint32_t>(p.Ng);
+        smem = std::max(smem, p.smem_total);
+    }
+    KGCN_REQUIRE(cols <= 512, KGCN_ERR_UNSUPPORTED, "fused GraphConv weight gradient: %u tensor-memory columns for %d jobs", cols, n_jobs);
+    uint32_t alloc = 32;
+    while (alloc < cols) alloc <<= 1;
+    b.tmem_cols = alloc;
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));
+    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    launch_pdl(graphconv_fused_dw_kernel, grid, kBlock, smem, st, b);
     KGCN_LAUNCH_OK("graphconv_fused_dw_kernel");
     if (splits_out != nullptr) *splits_out = static_cast<int>(grid);
     return KGCN_OK;
+}
+
+// how many consecutive jobs (same batch) fit one launch: 2 * channels * f_out tensor-memory columns each, 512 in total
+int fused_dw_jobs_per_launch(int channels, const int* f_out, int n_jobs) {
+    int cols = 0, k = 0;
+    for (; k < n_jobs && k < kDwMaxJobs; ++k) {
+        cols += 2 * channels * f_out[k];
+        if (cols > 512) break;
+    }
+    return k;
+}
+
+int launch_graphconv_fused_dw_partial(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                      int channels, int n_nodes, const float* x, int f_in, const float* du, int f_out,
+                                      float* partial, size_t partial_bytes, int* splits_out, cudaStream_t st) {
+    const DwJob job{rowptr_t, col_t, val_t, x, du, partial, partial_bytes, f_in, f_out};
+    return launch_graphconv_fused_dw_jobs(&job, 1, n_graphs, channels, n_nodes, splits_out, st);
 }
 
 int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs, int channels,

@@ -306,7 +306,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
         fence_mbar_init();
     }
     if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
-    {   // zero the B operand region: K / N padding must contribute exact zeros
+    if ((f_out & 15) != 0) {   // B rows n >= f_out (up to Np) are read by the MMAs: they must be exact zeros.  Every other byte
+        // the MMAs read (n < f_out, k < Kp) is written by the staging below, zeros for the K padding included.
         const uint32_t n16 = (p.off_ystage - p.off_whi) >> 4;
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t i = tid; i < n16; i += kBlock) sts_f<4>(base + p.off_whi + (i << 4), z4);
@@ -409,6 +410,12 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
                     const uint32_t off = sw128_offset(n, c * f_in + f4, p.w_atom);
                     sts_f<4>(base + p.off_whi + off, hi);
                     sts_f<4>(base + p.off_wlo + off, lo);
+                }
+                const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // no bias: the row-sum columns K .. K + 7 of Z meet exact zeros
+                for (int idx = tid; idx < f_out * 2; idx += kStagers) {
+                    const uint32_t off = sw128_offset(idx >> 1, K + ((idx & 1) << 2), p.w_atom);
+                    sts_f<4>(base + p.off_whi + off, z4);
+                    sts_f<4>(base + p.off_wlo + off, z4);
                 }
             }
         }
@@ -730,6 +737,465 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
     if (warp == kWarpMma) tmem_dealloc(tmem, 512);
 }
 
+
+// ================================================================================================================
+// Chained layers: ONE launch runs several fused layers back to back over the same batch.  A CTA owns the same graph
+// range in every job, and a graph's rows never leave the CTA (the aggregation is graph-local), so job j + 1 may start
+// on a CTA as soon as THAT CTA has finished job j: no grid-wide dependency, no launch / drain / fill per layer.
+//   forward chain   x -> GraphConv_0 -> .. -> GraphConv_{L-1}                      (EPI 0: activation epilogue)
+//   dx chain        dU_{L-1} -> dU_{L-2} -> ..  each job (A^T, dU_l, W_l^T) x act'(x_l)   (EPI 1)
+// Job boundary = one CTA-wide barrier: the epilogue warps have fenced their global stores towards the async proxy (the
+// next job's TMA reads them), all MMAs that read the B operand have completed, every stage has been consumed.  The
+// mbarriers are NOT re-initialised: every role tracks one phase bit per barrier slot, so ring sizes may differ per job.
+constexpr int kV4MaxJobs = 4;
+struct V4Batch {
+    int n_jobs;
+    V4Params job[kV4MaxJobs];
+};
+
+__device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ TileRange cta_range_of(const V4Params& p) {
+    TileRange t;
+    t.g_begin = static_cast<int64_t>(blockIdx.x) * p.graphs_per_cta;
+    const int64_t left = p.n_graphs - t.g_begin;
+    t.n_graphs_cta = static_cast<int>(left < p.graphs_per_cta ? (left > 0 ? left : 0) : p.graphs_per_cta);
+    t.n_tiles = (t.n_graphs_cta + p.G - 1) / p.G;
+    return t;
+}
+
+// [W ; bias] (or W^T) of one job -> (hi, lo) K-major SWIZZLE_128B B operand, by `n_thr` threads (index t)
+__device__ __forceinline__ void stage_b_operand(const V4Params& p, uint32_t base, int t, int n_thr) {
+    const int C = p.C, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp;
+    if ((f_out & 15) != 0) {   // B rows n >= f_out (up to Np) are read by the MMAs and not written below: exact zeros
+        const uint32_t n16 = (p.off_ystage - p.off_whi) >> 4;
+        const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t i = t; i < n16; i += n_thr) sts_f<4>(base + p.off_whi + (i << 4), z4);
+        asm volatile("bar.sync 3, %0;" ::"n"(512) : "memory");   // the stagers (aggregation + epilogue warps)
+    }
+    if (p.w_trans == 0) {
+        const int nq_n = f_out >> 2, kq_n = Kp >> 2;
+        for (int idx = t; idx < kq_n * nq_n; idx += n_thr) {
+            const int n0 = (idx % nq_n) << 2, k4 = (idx / nq_n) << 2;
+            float4 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kk = k4 + j;
+                r[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (kk < K) {
+                    const int c = kk / f_in, f = kk - c * f_in;
+                    r[j] = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride + static_cast<size_t>(f) * p.w_ld + n0));
+                } else if (kk - K < C && p.bias != nullptr) {
+                    r[j] = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(kk - K) * p.w_ld + n0));
+                }
+            }
+            const float tt[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x}, {r[0].y, r[1].y, r[2].y, r[3].y},
+                                    {r[0].z, r[1].z, r[2].z, r[3].z}, {r[0].w, r[1].w, r[2].w, r[3].w}};
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hi[j] = tf32_hi(tt[nn][j]);
+                    lo[j] = tt[nn][j] - hi[j];
+                }
+                const uint32_t off = sw128_offset(n0 + nn, k4, p.w_atom);
+                sts_f<4>(base + p.off_whi + off, hi);
+                sts_f<4>(base + p.off_wlo + off, lo);
+            }
+        }
+    } else {
+        const int kq = f_in >> 2;
+        for (int idx = t; idx < f_out * C * kq; idx += n_thr) {
+            const int n = idx / (C * kq), r = idx - n * (C * kq), c = r / kq, f4 = (r - c * kq) << 2;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride + static_cast<size_t>(n) * p.w_ld + f4));
+            const float tt[4] = {v.x, v.y, v.z, v.w};
+            float hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hi[j] = tf32_hi(tt[j]);
+                lo[j] = tt[j] - hi[j];
+            }
+            const uint32_t off = sw128_offset(n, c * f_in + f4, p.w_atom);
+            sts_f<4>(base + p.off_whi + off, hi);
+            sts_f<4>(base + p.off_wlo + off, lo);
+        }
+        const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // no bias: the row-sum columns K .. K + 7 of Z meet exact zeros
+        for (int idx = t; idx < f_out * 2; idx += n_thr) {
+            const uint32_t off = sw128_offset(idx >> 1, K + ((idx & 1) << 2), p.w_atom);
+            sts_f<4>(base + p.off_whi + off, z4);
+            sts_f<4>(base + p.off_wlo + off, z4);
+        }
+    }
+    fence_proxy_async_smem();   // B is read by the tensor core through the async proxy
+}
+
+template <int EPI>
+__global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
+    __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_jobs = b.n_jobs;
+
+    if (tid == 0) {
+        for (int i = 0; i < kV4MaxStages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], kAggWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_zfull[i], kAggWarps);
+            mbar_init(&bar_zempty[i], 1);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
+    pdl_wait();   // everything above overlaps the previous kernel's tail
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == kWarpTma) {
+        // =============================== TMA producer ===============================
+        reg_dec<kRegsMisc>();
+        uint32_t ph_empty = 0;   // one phase bit per barrier slot (ring sizes may change between jobs)
+        for (int j = 0; j < n_jobs; ++j) {
+            const V4Params& p = b.job[j];
+            if (j > 0) bar_all_roles();   // the previous job's outputs are complete and visible to the async proxy
+            if (lane == 0) {
+                const int C_csr = p.C_csr, N = p.N, f_in = p.f_in, S = p.n_stages;
+                const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
+                const TileRange tr = cta_range_of(p);
+                const int n_tiles = tr.n_tiles;
+                const int last_ng = tr.n_graphs_cta - (n_tiles - 1) * p.G;
+                int s = 0;
+                for (int it = 0; it < n_tiles; ++it) {
+                    mbar_wait_relaxed(&bar_empty[s], ((ph_empty >> s) & 1u) ^ 1u);
+                    ph_empty ^= 1u << s;
+                    const int64_t g0 = tr.g_begin + static_cast<int64_t>(it) * p.G;
+                    const int ng = (it == n_tiles - 1) ? last_ng : p.G;
+                    const int64_t r0 = g0 * C_csr * N;
+                    const int rows_csr = ng * C_csr * N;
+                    unsigned char* st = gen + p.off_stage + static_cast<size_t>(s) * p.stage_bytes;
+                    uint64_t* full = &bar_full[s];
+                    const int64_t rp_lo = r0 & ~3ll;
+                    const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
+                    const uint32_t x_bytes = static_cast<uint32_t>(ng) * static_cast<uint32_t>(N) * pitch;
+                    mbar_expect_tx_only(full, x_bytes + 4u * rp_cnt);
+                    bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
+                    bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
+                    const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
+                    const int32_t e_lo = e_first & ~3;
+                    const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
+                    const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap) && e_cnt != 0;
+                    mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the one arrival of the phase
+                    if (staged) {
+                        bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
+                        bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
+                    }
+                    if (++s == S) s = 0;
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp < kAggWarps) {
+        // =============================== aggregation warps ===============================
+        reg_inc<kRegsAgg>();
+        uint32_t ph_full = 0, ph_zempty = 0;
+        const int wq = warp & 3;          // TMEM lane quarter of this warp
+        const int phase = warp >> 2;      // slab phase: slabs phase, phase + 2, ...
+        const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
+        const bool p1 = (s7 & 1u) != 0, p2 = (s7 & 2u) != 0, p4 = (s7 & 4u) != 0;
+        const int w = wq * 32 + lane;     // tile row = TMEM lane
+        const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
+        for (int j = 0; j < n_jobs; ++j) {
+            const V4Params& p = b.job[j];
+            if (j > 0) bar_all_roles();
+            stage_b_operand(p, base, tid, 512);
+            const int N = p.N, f_in = p.f_in, K = p.K, Kp = p.Kp, S = p.n_stages;
+            const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
+            if (warp < 4) {   // the unused row-sum columns K + C .. K + 7 of every Z buffer stay zero for the whole job
+                const uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int zb = 0; zb < p.zbufs; ++zb) {
+                    const uint32_t zc = tmem + (static_cast<uint32_t>(warp * 32) << 16) + p.tm_z + static_cast<uint32_t>(zb * 2 * Kp);
+                    tmem_st8(zc + K, z8);
+                    tmem_st8(zc + Kp + K, z8);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(544) : "memory");   // stagers + the MMA warp
+            tc_fence_after_sync();
+            const TileRange tr = cta_range_of(p);
+            const int n_tiles = tr.n_tiles;
+            const int last_ng = tr.n_graphs_cta - (n_tiles - 1) * p.G;
+            const int gl = w / N, node = w - gl * N;
+            const int full_rows = p.G * N;
+            const uint32_t r0_step = static_cast<uint32_t>(p.G * p.C_csr * N);
+            uint32_t r0_lo = static_cast<uint32_t>((tr.g_begin * p.C_csr * N) & 3);
+            const uint32_t z_stride = static_cast<uint32_t>(2 * Kp);
+            const uint32_t row_rp_off = 4u * static_cast<uint32_t>((gl * p.C_csr + p.c_begin) * N + node);
+            const uint32_t row_x_off = static_cast<uint32_t>(gl * N) * pitch + (s7 << 4);
+            int s = 0, zi = 0;
+            for (int it = 0; it < n_tiles; ++it) {
+                const bool last = it == n_tiles - 1;
+                const int rows = last ? last_ng * N : full_rows;
+                const int rows_csr = last ? last_ng * p.C_csr * N : static_cast<int>(r0_step);
+                const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
+                mbar_wait(&bar_full[s], (ph_full >> s) & 1u);
+                ph_full ^= 1u << s;
+                const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
+                const int e_first = static_cast<int>(lds_u32(rp_addr));
+                const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
+                const int e_lo = e_first & ~3;
+                const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
+                const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);
+                const uint32_t val_addr = st + p.st_val - 4u * static_cast<uint32_t>(e_lo);
+                const bool valid = w < rows;
+
+                mbar_wait(&bar_zempty[zi], ((ph_zempty >> zi) & 1u) ^ 1u);
+                ph_zempty ^= 1u << zi;
+                tc_fence_after_sync();
+                const uint32_t zc = tmem + lane_sel + p.tm_z + static_cast<uint32_t>(zi) * z_stride;
+                const uint32_t row_rp = rp_addr + row_rp_off;
+                const uint32_t row_x = st + row_x_off;
+                int c = 0, fs = phase;
+                for (int slab = phase; slab < p.n_slabs; slab += 2) {
+                    while (fs >= p.slabs_per_ch) { fs -= p.slabs_per_ch; ++c; }
+                    int rs_ = e_first, re_ = e_first;
+                    if (valid) {
+                        const uint32_t ra = row_rp + 4u * static_cast<uint32_t>(c * N);
+                        rs_ = static_cast<int>(lds_u32(ra));
+                        re_ = static_cast<int>(lds_u32(ra + 4u));
+                    }
+                    const uint32_t xbase = row_x + static_cast<uint32_t>(fs) * 128u;
+                    float acc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+                    float deg = 0.0f;
+                    if (staged) gather_row<true>(acc, deg, rs_, re_, col_addr, val_addr, p.col, p.val, xbase, pitch);
+                    else gather_row<false>(acc, deg, rs_, re_, col_addr, val_addr, p.col, p.val, xbase, pitch);
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float a0 = acc[4 * i + jj], a1 = acc[4 * (i + 1) + jj];
+                            acc[4 * i + jj] = p1 ? a1 : a0;
+                            acc[4 * (i + 1) + jj] = p1 ? a0 : a1;
+                        }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if ((i & 2) == 0)
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const float a0 = acc[4 * i + jj], a1 = acc[4 * (i + 2) + jj];
+                                acc[4 * i + jj] = p2 ? a1 : a0;
+                                acc[4 * (i + 2) + jj] = p2 ? a0 : a1;
+                            }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float a0 = acc[4 * i + jj], a1 = acc[4 * (i + 4) + jj];
+                            acc[4 * i + jj] = p4 ? a1 : a0;
+                            acc[4 * (i + 4) + jj] = p4 ? a0 : a1;
+                        }
+                    __syncwarp();
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        hi[i] = __float_as_uint(acc[i]) & 0xFFFFE000u;
+                        lo[i] = __float_as_uint(acc[i] - __uint_as_float(hi[i]));
+                    }
+                    tmem_st32(zc + static_cast<uint32_t>(slab * 32), hi);
+                    tmem_st32(zc + static_cast<uint32_t>(Kp + slab * 32), lo);
+                    if (fs == 0) {
+                        const float h = tf32_hi(deg);
+                        tmem_st1(zc + static_cast<uint32_t>(K + c), __float_as_uint(h));
+                        tmem_st1(zc + static_cast<uint32_t>(Kp + K + c), __float_as_uint(deg - h));
+                    }
+                    fs += 2;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[s]);
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_zfull[zi]);
+                if (++s == S) s = 0;
+                if (++zi == p.zbufs) zi = 0;
+                r0_lo += r0_step;
+            }
+        }
+    } else if (warp >= kWarpMma) {
+        reg_dec<kRegsMisc>();
+        uint32_t ph_zfull = 0, ph_tempty = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            const V4Params& p = b.job[j];
+            if (j > 0) bar_all_roles();
+            if (warp != kWarpMma) continue;
+            // =============================== MMA issuer ===============================
+            asm volatile("bar.sync 1, %0;" ::"n"(544) : "memory");   // B operand staged, Z padding columns zeroed
+            tc_fence_after_sync();
+            const int Kp = p.Kp, Np = p.Np;
+            const TileRange tr = cta_range_of(p);
+            const int n_tiles = tr.n_tiles;
+            const uint32_t idesc = umma_idesc_tf32(128, Np);
+            const uint64_t dwhi = umma_desc_sw128(base + p.off_whi), dwlo = umma_desc_sw128(base + p.off_wlo);
+            const uint32_t w_atom16 = p.w_atom >> 4;
+            const int ks = Kp >> 3;
+            int zi = 0, ai = 0;
+            for (int it = 0; it < n_tiles; ++it) {
+                mbar_wait(&bar_zfull[zi], (ph_zfull >> zi) & 1u);
+                ph_zfull ^= 1u << zi;
+                mbar_wait(&bar_tempty[ai], ((ph_tempty >> ai) & 1u) ^ 1u);
+                ph_tempty ^= 1u << ai;
+                tc_fence_after_sync();
+                const uint32_t d = tmem + static_cast<uint32_t>(ai * Np);
+                const uint32_t zhi = tmem + p.tm_z + static_cast<uint32_t>(zi * 2 * Kp), zlo = zhi + static_cast<uint32_t>(Kp);
+                __syncwarp();
+                if (elect_one()) {
+                    switch (ks) {
+                        case 5: issue_tile<5>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        case 9: issue_tile<9>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        case 13: issue_tile<13>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        case 17: issue_tile<17>(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16); break;
+                        default: issue_tile_loop(d, zhi, zlo, dwhi, dwlo, idesc, w_atom16, ks);
+                    }
+                    umma_commit(&bar_zempty[zi]);
+                    umma_commit(&bar_tfull[ai]);
+                }
+                __syncwarp();
+                if (++zi == p.zbufs) zi = 0;
+                if (++ai == p.abufs) ai = 0;
+            }
+        }
+    } else {
+        // =============================== epilogue warps ===============================
+        reg_dec<kRegsEpi>();
+        uint32_t ph_tfull = 0;
+        const int e = warp - kWarpEpi0;
+        const int wq = e & 3, h = e >> 2;
+        const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
+        const uint32_t l7 = static_cast<uint32_t>(lane) & 7u;
+        const int colq = static_cast<int>(l7) * 4;
+        const int row0 = wq * 32 + (lane >> 3);
+        for (int j = 0; j < n_jobs; ++j) {
+            const V4Params& p = b.job[j];
+            if (j > 0) bar_all_roles();
+            stage_b_operand(p, base, tid - kWarpEpi0 * 32 + kAggWarps * 32, 512);
+            asm volatile("bar.sync 1, %0;" ::"n"(544) : "memory");
+            const int N = p.N, f_out = p.f_out, Np = p.Np;
+            const TileRange tr = cta_range_of(p);
+            const int n_tiles = tr.n_tiles;
+            const int last_ng = tr.n_graphs_cta - (n_tiles - 1) * p.G;
+            const uint32_t ys = base + p.off_ystage + static_cast<uint32_t>(e) * 4096u;
+            const int n_cslabs = (Np + 31) >> 5;
+            const int full_rows = p.G * N;
+            const uint32_t yrow = ys + static_cast<uint32_t>(lane) * 128u;
+            const uint32_t ysrc = ys + (static_cast<uint32_t>(lane) >> 3) * 128u;
+            const size_t y_ld = static_cast<size_t>(p.y_ld);
+            float* y_tile = p.y + (tr.g_begin * N + row0) * y_ld + colq;
+            const size_t y_step = static_cast<size_t>(full_rows) * y_ld;
+            int ai = 0;
+            for (int it = 0; it < n_tiles; ++it) {
+                const int rows = (it == n_tiles - 1) ? last_ng * N : full_rows;
+                mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
+                ph_tfull ^= 1u << ai;
+                tc_fence_after_sync();
+                const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
+                for (int cs = h; cs < n_cslabs; cs += 2) {
+                    float v0[16], v1[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
+                    tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
+                    if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
+                    tmem_ld_wait();
+                    tmem_ld_fence(v0);
+                    tmem_ld_fence(v1);
+                    if (cs + 2 >= n_cslabs) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[ai]);
+                    }
+                    act16_rt(v0, p.act);
+                    act16_rt(v1, p.act);
+                    if (cs * 32 + 32 > p.f_valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                            if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                        }
+                    }
+                    tmem_ld_fence(v0);
+                    tmem_ld_fence(v1);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
+                        const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
+                        sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
+                        sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                    }
+                    __syncwarp();
+                    const bool col_ok = cs * 32 + colq < f_out;
+                    float* ycs = y_tile + cs * 32;
+                    if (EPI == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                            float t[4];
+                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                            if (row0 + 4 * k < rows && col_ok)
+                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                        }
+                    } else {
+                        const float* mcs = p.mul_src + (ycs - p.y);   // same [rows, y_ld] layout as the output
+                        float4 mv[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            mv[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (row0 + 4 * k < rows && col_ok) mv[k] = __ldg(reinterpret_cast<const float4*>(mcs + static_cast<size_t>(4 * k) * y_ld));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                            float t[4];
+                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                            if (row0 + 4 * k < rows && col_ok)
+                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) =
+                                    make_float4(t[0] * act_grad_from_output(mv[k].x, p.mul_act), t[1] * act_grad_from_output(mv[k].y, p.mul_act),
+                                                t[2] * act_grad_from_output(mv[k].z, p.mul_act), t[3] * act_grad_from_output(mv[k].w, p.mul_act));
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (h >= n_cslabs) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[ai]);
+                }
+                if (++ai == p.abufs) ai = 0;
+                y_tile += y_step;
+            }
+            // this CTA's outputs of the job: visible to the next job's TMA loads (async proxy) after the role barrier
+            __threadfence();
+            fence_proxy_async_all();
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kWarpMma) tmem_dealloc(tmem, 512);
+}
+
 inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) shares the 227 KB
@@ -868,6 +1334,53 @@ int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const f
         if (rc) return rc;
     }
     return KGCN_OK;
+}
+
+// ---- chained launch: jobs[k] over the same (n_graphs, channels, n_nodes); job k + 1 usually reads job k's output ----
+bool fused_v4_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    V4Params p{};
+    return fused_v4_enabled() && plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out, channels) && p.n_split == 1;
+}
+
+int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st) {
+    KGCN_REQUIRE(n_jobs >= 1 && n_jobs <= kV4MaxJobs, KGCN_ERR_BAD_SHAPE, "fused GraphConv chain: 1..%d jobs", kV4MaxJobs);
+    V4Batch b{};
+    b.n_jobs = n_jobs;
+    uint32_t smem = 0;
+    bool any_mul = false;
+    for (int k = 0; k < n_jobs; ++k) {
+        const V4ChainJob& j = jobs[k];
+        V4Params& p = b.job[k];
+        KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, j.f_in, j.f_out, channels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
+                     "fused GraphConv chain: job %d (%d -> %d) has no single-CTA plan", k, j.f_in, j.f_out);
+        KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: graph ranges differ");
+        p.c_begin = 0;
+        p.rowptr = j.rowptr; p.col = j.col; p.val = j.val; p.x = j.x; p.y = j.y;
+        p.act = j.act;
+        p.acc_in = 0;
+        p.y_ld = j.f_out;
+        p.w_trans = j.w_transposed ? 1 : 0;
+        p.w_ld = j.w_transposed ? j.f_in : j.f_out;
+        p.w_cstride = j.f_in * j.f_out;
+        p.w = j.w;
+        p.bias = j.w_transposed ? nullptr : j.bias;
+        p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : p.f_out;
+        p.mul_src = j.mul_src;
+        p.mul_act = j.mul_act;
+        p.dbg = nullptr;
+        any_mul = any_mul || j.mul_src != nullptr;
+        smem = std::max(smem, p.smem_total);
+    }
+    for (int k = 0; k < n_jobs; ++k)
+        KGCN_REQUIRE((jobs[k].mul_src != nullptr) == any_mul, KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: mixed epilogues");
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));
+    auto go = [&](auto kernel) -> int {
+        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        launch_pdl(kernel, grid, kBlock, smem, st, b);
+        KGCN_LAUNCH_OK("graphconv_fused_v4_chain_kernel");
+        return KGCN_OK;
+    };
+    return any_mul ? go(graphconv_fused_v4_chain_kernel<1>) : go(graphconv_fused_v4_chain_kernel<0>);
 }
 
 }  // namespace kgcn

@@ -165,12 +165,25 @@ __global__ void __launch_bounds__(kReadoutThreads, 1) readout_kernel(
             const float4* xs = reinterpret_cast<const float4*>(x_nodes + b0 * row_elems);
             float4* us = reinterpret_cast<float4*>(du_nodes + b0 * row_elems);
             const float4* dgs = reinterpret_cast<const float4*>(dg + b0 * feat);
-            for (int64_t idx = threadIdx.x; idx < n4; idx += kReadoutThreads) {
-                const int64_t row = idx / f4;
-                const int c4 = static_cast<int>(idx - row * f4), i = static_cast<int>(row / n_nodes);
-                const float4 xv = xs[idx], gv = dgs[i * f4 + c4];
-                us[idx] = make_float4(gv.x * act_grad_from_output(xv.x, act), gv.y * act_grad_from_output(xv.y, act),
-                                      gv.z * act_grad_from_output(xv.z, act), gv.w * act_grad_from_output(xv.w, act));
+            // batches of 8 independent 16-byte loads per thread: the pass is one or two memory round trips, not n4 / 512
+            for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 8 * kReadoutThreads) {
+                float4 xv[8], gv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t idx = i0 + static_cast<int64_t>(u) * kReadoutThreads;
+                    if (idx < n4) {
+                        const int64_t row = idx / f4;
+                        xv[u] = xs[idx];
+                        gv[u] = dgs[static_cast<int>(row / n_nodes) * f4 + static_cast<int>(idx - row * f4)];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t idx = i0 + static_cast<int64_t>(u) * kReadoutThreads;
+                    if (idx < n4)
+                        us[idx] = make_float4(gv[u].x * act_grad_from_output(xv[u].x, act), gv[u].y * act_grad_from_output(xv[u].y, act),
+                                              gv[u].z * act_grad_from_output(xv[u].z, act), gv[u].w * act_grad_from_output(xv[u].w, act));
+                }
             }
         } else {
             const int64_t n1 = static_cast<int64_t>(n_here) * row_elems;

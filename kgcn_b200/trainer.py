@@ -201,6 +201,19 @@ class Trainer:
         self.fused_step = (not ref_order and not s.dense_dim and all(n > 0 for n in self.splits) and fused_ok(self.dims) and
                            os.environ.get("KGCN_FUSED_STEP", "1") != "0")
         self.partials, self._segments = [], None
+        L = len(s.conv_dims)
+        self._dims_c = (ctypes.c_int32 * (L + 1))(*self.dims)
+        self._ldims_c = (ctypes.c_int32 * (L + 1))(*self.ldims)
+        # chained launches: all forward layers in one launch, all dx layers in one launch (CTA-local layer-to-layer hand-off)
+        self.chain = (self.fused_step and L <= 4 and os.environ.get("KGCN_CHAIN", "1") != "0" and
+                      bool(lib.kgcn_graphconv_chain_supported(B, C, N, L, self._dims_c)))
+        self.du = [torch.empty(B, N, self.dims[i + 1], **f32) for i in range(L)] if self.chain else None
+        if self.chain:
+            arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() if t is not None else None for t in ts])
+            self._w_ptrs = arr([self.pviews["conv%d/kernel" % i] for i in range(L)])
+            self._b_ptrs = arr([self.pviews["conv%d/bias" % i] for i in range(L)])
+            self._y_ptrs = arr(self.acts[1:L + 1])
+            self._du_ptrs = arr(self.du)
         if self.fused_step:
             segs = (_lib.GradSegment * len(s.conv_dims))()
             for i, n in enumerate(self.splits):
@@ -209,6 +222,8 @@ class Trainer:
                 segs[i] = _lib.GradSegment(offs["conv%d/kernel" % i], offs["conv%d/bias" % i], buf.data_ptr(), n, self.dims[i],
                                            self.dims[i + 1], C)
             self._segments = segs
+            self._part_ptrs = (ctypes.c_void_p * L)(*[t.data_ptr() for t in self.partials])
+            self._part_bytes = (ctypes.c_size_t * L)(*[t.numel() * 4 for t in self.partials])
         self.p2p = None
         if self.world_size > 1 and (p2p if p2p is not None else os.environ.get("KGCN_P2P", "1") != "0"):
             self.p2p = PeerExchange(self.n_params, self.rank, self.world_size, self.pg, self.device)
@@ -321,6 +336,12 @@ class Trainer:
             raise ValueError("batch features are %d wide, the trainer stores %d (DeviceBatch.from_host(..., pad_to=trainer.dims[0]))"
                              % (x.shape[-1], self.dims[0]))
         self.acts[0] = x
+        if self.chain:
+            L = len(s.conv_dims)
+            check(lib.kgcn_graphconv_chain_fwd_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), B, C, N, L, self._dims_c, self._ldims_c,
+                                                   ptr(x), self._w_ptrs, self._b_ptrs, self._y_ptrs, self.act, st))
+            self._last_nodes = self.acts[L]
+            return self.dims[-1], 0
         for i in range(len(s.conv_dims)):
             y, f, d = self.acts[i + 1], self.dims[i], self.dims[i + 1]
             w, b = self.pviews["conv%d/kernel" % i], self.pviews["conv%d/bias" % i]
@@ -349,7 +370,8 @@ class Trainer:
                 ptr(self.prediction), ptr(self.stats), ptr(self.dlogits) if train else None, ptr(self.dgathered) if train else None,
                 ptr(self.pgviews["dense/kernel"]) if train else None, ptr(self.pgviews["dense/bias"]) if train else None)
         if train and self.fused_step:   # + dU of the last graph layer (dgathered broadcast over the nodes, times act')
-            check(lib.kgcn_gather_readout_xent_du_f32(*args, self.act, ptr(self.dact[0]), ptr(self.ws), self.ws.numel(), st))
+            du_top = self.du[-1] if self.chain else self.dact[0]
+            check(lib.kgcn_gather_readout_xent_du_f32(*args, self.act, ptr(du_top), ptr(self.ws), self.ws.numel(), st))
         else:
             check(lib.kgcn_gather_readout_xent_f32(*args, ptr(self.ws), self.ws.numel(), st))
 
@@ -358,6 +380,16 @@ class Trainer:
         gradient of the layer below, so dact[cur] always holds a ready dU; weight gradients stay as per-CTA partials."""
         s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
         csr = batch.csr
+        if self.chain:
+            L = len(s.conv_dims)
+            if L > 1:   # du[L-1] (head) -> du[L-2] -> .. -> du[0], one launch
+                x_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in self.acts[:L]])
+                check(lib.kgcn_graphconv_chain_dx_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c,
+                                                      x_ptrs, self._w_ptrs, self._du_ptrs, self.act, st))
+            x_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in self.acts[:L]])
+            check(lib.kgcn_graphconv_chain_dw_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c, x_ptrs,
+                                                  self._du_ptrs, self._part_ptrs, self._part_bytes, st))
+            return
         cur = 0
         for i in range(len(s.conv_dims) - 1, -1, -1):
             fin, fout = self.dims[i], self.dims[i + 1]

@@ -103,6 +103,34 @@ def test_graph_replay_equals_eager():
     assert abs(sa[0] - sb[0]) <= 1e-5 * abs(sa[0]) and sa[1] == sb[1]
 
 
+@pytest.mark.parametrize("B,N,C,F,conv_dims", [
+    (700, 32, 1, 64, [64, 64]),        # C2 widths, 5 graphs per CTA: two tiles per job
+    (40, 50, 1, 75, [50, 50, 50]),     # C3: three chained layers on padded widths
+    (300, 50, 3, 75, [50, 50, 50]),    # C4: first layer needs channel groups -> no chain (falls back to per-layer launches)
+    (9, 32, 1, 32, [64]),              # a single layer
+])
+def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkeypatch):
+    """All forward layers in ONE launch and all dx layers in ONE launch (CTA-local hand-off between layers) give bit-identical
+    parameters to one launch per layer: same kernels, same tiles, same accumulation order."""
+    from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
+    counts, idx, val, x, labels, mask, adjs, p = make_case(B, N, C, F, conv_dims, None, seed=B + N)
+    spec = NetSpec(F, conv_dims, N, channels=C, label_dim=2, act="sigmoid")
+    monkeypatch.setenv("KGCN_CHAIN", "1")
+    a = Trainer(spec, B, seed=3)
+    monkeypatch.setenv("KGCN_CHAIN", "0")
+    b = Trainer(spec, B, seed=3)
+    assert not b.chain and a.fused_step and b.fused_step
+    assert a.chain == (C == 1)
+    batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=a.dims[0])
+    for _ in range(3):
+        a.step_eager(batch)
+        b.step_eager(batch)
+    torch.cuda.synchronize()
+    assert torch.equal(a.logits, b.logits)
+    assert torch.equal(a.grads, b.grads)
+    assert torch.equal(a.params, b.params)
+
+
 def test_training_reduces_loss_on_ring_task():
     """C2 generator (ring-size classification) is learnable: cost_sum falls over 60 steps."""
     from kgcn_b200 import synth
