@@ -335,6 +335,27 @@ int kgcn_graphconv_chain_dx_f32(const int32_t* rowptr_t, const int32_t* col_t, c
                                 int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
                                 const float* const* x, const float* const* w, float* const* du, int32_t act, void* stream);
 
+/* The graph-local part of a whole training step in ONE launch: forward layers 0 .. L-1, the readout head fused into the last
+ * layer's epilogue (GraphGather + Dense(n_labels) + softmax cross-entropy on the CTA's own tiles, example_model/model.py:56-69;
+ * kgcn_gather_readout_xent_du_f32's mathematics), and the dx chain of kgcn_graphconv_chain_dx_f32.  The last layer's
+ * activations are never written: its epilogue stores du[L-1] = d gathered (.) act'(H_{L-1}) directly.
+ *   y[l] (l < L-1) layer outputs; du[l] dU of layer l (all L written); w / bias as in kgcn_graphconv_chain_fwd_f32;
+ *   head_w [dims[L]][n_labels] (rows beyond the logical width zero), head_b [n_labels] or NULL, labels [B][n_labels],
+ *   mask [B] or NULL; outputs logits / prediction [B][n_labels], gathered [B][dims[L]] (each may be NULL);
+ *   head_partial [kgcn_gcn_step_chain_grid(...)][dims[L] * n_labels + 8]: per-CTA {dW_dense | db_dense (padded to 4) |
+ *   cost_sum, correct_count, 0, 0}, reduced by kgcn_reduce_adam_f32 (segments with rows = 0 + stats_partial).
+ * kgcn_gcn_step_chain_grid returns the number of CTAs (= partial blocks), 0 when the network is not supported
+ * (needs kgcn_graphconv_chain_supported, dims[L] <= 64, n_labels <= 4, 2 L - 1 <= 6 jobs). */
+int32_t kgcn_gcn_step_chain_grid(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                 int32_t n_labels);
+int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
+                            const int32_t* col_t, const float* val_t, int64_t n_graphs, int32_t channels, int32_t n_nodes,
+                            int32_t n_layers, const int32_t* dims, const int32_t* dims_valid, const float* x,
+                            const float* const* w, const float* const* bias, float* const* y, float* const* du, int32_t act,
+                            const float* head_w, const float* head_b, int32_t n_labels, const float* labels, const float* mask,
+                            float inv_batch, float* logits, float* prediction, float* gathered, float* head_partial,
+                            void* stream);
+
 /* Weight-gradient partials of ALL layers (kgcn_graphconv_bwd_partial_f32 with dx == NULL, layer by layer) in as few launches
  * as tensor memory allows (2 * channels * dims[l + 1] accumulator columns per layer, 512 per launch): x[l] = input of layer l,
  * du[l] = its dU, partial[l] / partial_bytes[l] its partial blocks.  HOST arrays of n_layers entries. */
@@ -364,6 +385,8 @@ typedef struct kgcn_grad_segment {
     int64_t kernel_off, bias_off;
     const float* partial;
     int32_t splits, rows, cols, channels;
+    int64_t stride;      /* floats between the splits' blocks; 0 = (rows + 1) * channels * cols.  rows = 0: a flat
+                            gradient of `cols` floats at bias_off (kernel_off ignored) -- the fused head's Dense kernel */
 } kgcn_grad_segment;
 typedef struct kgcn_p2p_group {
     int32_t rank, world;
@@ -371,9 +394,12 @@ typedef struct kgcn_p2p_group {
     void* mailbox[8];
     int32_t* error_flag;
 } kgcn_p2p_group;
+/* stats_partial (may be NULL): per-CTA {cost_sum, correct_count} of the fused head every stats_stride floats, summed in CTA
+ * order into stats_out[0..1] by one extra block of the same launch. */
 int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* v, int64_t n, const kgcn_grad_segment* segments,
                          int32_t n_segments, float lr, float beta1, float beta2, float eps, float grad_scale,
-                         int32_t* step_state, const kgcn_p2p_group* group, void* stream);
+                         int32_t* step_state, const kgcn_p2p_group* group, const float* stats_partial,
+                         int32_t stats_splits, int64_t stats_stride, float* stats_out, void* stream);
 /* Peer-mapped device buffers for the exchange above (cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the 64-byte
  * handle travels between the ranks' processes through any host channel, e.g. torch.distributed.all_gather).  HOST calls. */
 int kgcn_p2p_alloc(size_t n_bytes, void** device_ptr, unsigned char* handle64);

@@ -95,9 +95,12 @@ SIGNATURES = {
     "kgcn_graphconv_chain_supported": (_i32, [_i64, _i32, _i32, _i32, _vp]),
     "kgcn_graphconv_chain_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "kgcn_graphconv_chain_dx_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "kgcn_gcn_step_chain_grid": (_i32, [_i64, _i32, _i32, _i32, _vp, _i32]),
+    "kgcn_gcn_step_chain_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                               _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
     "kgcn_graphconv_chain_dw_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kgcn_reduce_partials_f32": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "kgcn_reduce_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
+    "kgcn_reduce_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "kgcn_p2p_alloc": (ctypes.c_int, [_sz, _vp, _vp]),
     "kgcn_p2p_open": (ctypes.c_int, [_vp, _vp]),
     "kgcn_p2p_close": (ctypes.c_int, [_vp]),
@@ -114,7 +117,7 @@ SIGNATURES = {
 class GradSegment(ctypes.Structure):
     """kgcn_grad_segment (include/kgcn_b200.h)."""
     _fields_ = [("kernel_off", _i64), ("bias_off", _i64), ("partial", _vp), ("splits", _i32), ("rows", _i32), ("cols", _i32),
-                ("channels", _i32)]
+                ("channels", _i32), ("stride", _i64)]
 
 
 class P2PGroup(ctypes.Structure):

@@ -128,6 +128,20 @@ int launch_splitk_reduce_ch(const float* partial, int splits, int64_t M, int n_p
 int launch_act_grad(const float* y, const float* dy, float* du, int64_t n, int feat, int act,
                     const int32_t* enabled, int n_nodes, bool dy_bcast, cudaStream_t st);
 
+// Readout head fused into the epilogue of a chain job (training step): GraphGather + Dense(n_labels) + softmax
+// cross-entropy; the job then stores dU = d gathered (.) act'(H) instead of H.
+struct V4Head {
+    int n_labels;
+    const float* w;        // [f_out][n_labels]
+    const float* b;        // [n_labels] or NULL
+    const float* labels;   // [B][n_labels]
+    const float* mask;     // [B] or NULL
+    float inv_batch;
+    float* logits;         // [B][n_labels] or NULL
+    float* prediction;     // [B][n_labels] or NULL
+    float* gathered;       // [B][f_out] or NULL
+    float* partial;        // [grid][f_out * n_labels + 8]
+};
 // One job of a chained fused-layer launch (graphconv_fused_v4.cu): y = epilogue((A . x) . W) on the job's own widths.
 struct V4ChainJob {
     const int32_t* rowptr;
@@ -138,9 +152,12 @@ struct V4ChainJob {
     const float* bias;      // [C][f_out] or NULL (ignored when w_transposed)
     float* y;               // [B, N, f_out]
     int f_in, f_out, act, w_transposed;
-    const float* mul_src;   // y *= act'(mul_src) of activation mul_act (all jobs of a chain or none)
+    const float* mul_src;   // y *= act'(mul_src) of activation mul_act
     int mul_act, f_out_valid;
+    const V4Head* head = nullptr;
 };
+bool fused_v4_head_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels);
+int fused_v4_chain_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 bool fused_v4_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);
 

@@ -338,3 +338,47 @@ extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_
     }
     return KGCN_OK;
 }
+
+extern "C" int32_t kgcn_gcn_step_chain_grid(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
+                                            const int32_t* dims, int32_t n_labels) {
+    if (!kgcn_graphconv_chain_supported(n_graphs, channels, n_nodes, n_layers, dims)) return 0;
+    if (2 * n_layers - 1 > 6 || n_labels < 1 || n_labels > 4) return 0;
+    if (!fused_v4_head_chainable(n_graphs, channels, n_nodes, dims[n_layers - 1], dims[n_layers], n_labels)) return 0;
+    return fused_v4_chain_grid(n_graphs, channels, n_nodes, dims[0], dims[1]);
+}
+
+extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
+                                       const int32_t* col_t, const float* val_t, int64_t n_graphs, int32_t channels,
+                                       int32_t n_nodes, int32_t n_layers, const int32_t* dims, const int32_t* dims_valid,
+                                       const float* x, const float* const* w, const float* const* bias, float* const* y,
+                                       float* const* du, int32_t act, const float* head_w, const float* head_b,
+                                       int32_t n_labels, const float* labels, const float* mask, float inv_batch,
+                                       float* logits, float* prediction, float* gathered, float* head_partial,
+                                       void* stream) {
+    KGCN_REQUIRE(rowptr && col && val && rowptr_t && col_t && val_t && dims && x && w && y && du && head_w && labels && head_partial,
+                 KGCN_ERR_NULL, "gcn_step_chain: NULL pointer argument");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && 2 * n_layers - 1 <= 6, KGCN_ERR_BAD_SHAPE,
+                 "gcn_step_chain: bad shape (1..3 layers)");
+    KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "gcn_step_chain: unknown act %d", act);
+    const int L = n_layers;
+    V4ChainJob jobs[6];
+    V4Head head{n_labels, head_w, head_b, labels, mask, inv_batch, logits, prediction, gathered, head_partial};
+    const float* in = x;
+    int k = 0;
+    for (int l = 0; l < L; ++l, ++k) {
+        float* out = (l == L - 1) ? du[L - 1] : y[l];
+        KGCN_REQUIRE(w[l] && out, KGCN_ERR_NULL, "gcn_step_chain: NULL weight / output of layer %d", l);
+        KGCN_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w[l]) && (!bias || aligned16(bias[l])), KGCN_ERR_MISALIGNED,
+                     "gcn_step_chain: 16-byte alignment required");
+        jobs[k] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, out, dims[l], dims[l + 1], act, 0, nullptr,
+                             KGCN_ACT_NONE, dims_valid ? dims_valid[l + 1] : dims[l + 1], (l == L - 1) ? &head : nullptr};
+        in = out;
+    }
+    for (int l = L - 1; l >= 1; --l, ++k) {   // du[l - 1] = (sum_c A_c^T . du[l] . W_l,c^T) (.) act'(y[l - 1])
+        KGCN_REQUIRE(du[l] && du[l - 1] && y[l - 1], KGCN_ERR_NULL, "gcn_step_chain: NULL pointer at dx of layer %d", l);
+        KGCN_REQUIRE(aligned16(du[l]) && aligned16(du[l - 1]), KGCN_ERR_MISALIGNED, "gcn_step_chain: 16-byte alignment required");
+        jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
+                             y[l - 1], act, 0, nullptr};
+    }
+    return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+}

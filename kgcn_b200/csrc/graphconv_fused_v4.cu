@@ -62,6 +62,19 @@ struct V4Params {
     int C_csr, c_begin;   // the CSR holds C_csr channels per graph; this launch contracts channels [c_begin, c_begin + C)
     int acc_in;           // add the existing y before the activation (second launch of a layer split over channel groups)
     int f_valid;          // output columns >= f_valid (of this slice) are written as exact zeros: feature padding stays inert
+    // fused readout head (last forward job of a training step): GraphGather + Dense(n_labels) + softmax cross-entropy on the
+    // epilogue's own tiles (example_model/model.py:56-69); the job then writes dU = dg (.) act'(H) instead of H
+    int head, n_labels;
+    const float* head_w;       // [f_out][n_labels] dense/kernel (padded rows are zero)
+    const float* head_b;       // [n_labels] or NULL
+    const float* labels;       // [B][n_labels]
+    const float* mask;         // [B] or NULL
+    float inv_batch;
+    float* logits;             // [B][n_labels] (may be NULL)
+    float* prediction;         // [B][n_labels] (may be NULL)
+    float* gathered;           // [B][f_out]    (may be NULL)
+    float* head_partial;       // [grid][f_out * n_labels + 8]: dW_dense | db_dense (4) | cost_sum, correct_count, 0, 0
+    uint32_t off_head;
     const float* mul_src; // optional [rows, y_ld]: the output is multiplied by act'(mul_src) of activation mul_act (backward:
     int mul_act;          // dx . act'(x) = the dU of the layer below, so no separate activation-gradient pass is needed)
     uint32_t off_whi, off_wlo, off_ystage, off_stage, stage_bytes, st_rp, st_col, st_val, smem_total;
@@ -747,7 +760,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
 // Job boundary = one CTA-wide barrier: the epilogue warps have fenced their global stores towards the async proxy (the
 // next job's TMA reads them), all MMAs that read the B operand have completed, every stage has been consumed.  The
 // mbarriers are NOT re-initialised: every role tracks one phase bit per barrier slot, so ring sizes may differ per job.
-constexpr int kV4MaxJobs = 4;
+constexpr int kV4MaxJobs = 6;
 struct V4Batch {
     int n_jobs;
     V4Params job[kV4MaxJobs];
@@ -831,7 +844,6 @@ __device__ __forceinline__ void stage_b_operand(const V4Params& p, uint32_t base
     fence_proxy_async_smem();   // B is read by the tensor core through the async proxy
 }
 
-template <int EPI>
 __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
@@ -1080,7 +1092,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         }
     } else {
         // =============================== epilogue warps ===============================
-        reg_dec<kRegsEpi>();
+        reg_dec<kRegsEpi>();   // the registers the aggregation warps take come from here and from the MMA / TMA warpgroup
         uint32_t ph_tfull = 0;
         const int e = warp - kWarpEpi0;
         const int wq = e & 3, h = e >> 2;
@@ -1088,6 +1100,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         const uint32_t l7 = static_cast<uint32_t>(lane) & 7u;
         const int colq = static_cast<int>(l7) * 4;
         const int row0 = wq * 32 + (lane >> 3);
+        const int te = tid - kWarpEpi0 * 32;   // 0 .. 255 inside the epilogue group
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
             if (j > 0) bar_all_roles();
@@ -1105,49 +1118,257 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const size_t y_ld = static_cast<size_t>(p.y_ld);
             float* y_tile = p.y + (tr.g_begin * N + row0) * y_ld + colq;
             const size_t y_step = static_cast<size_t>(full_rows) * y_ld;
+            const bool head = p.head != 0;
+            const bool mul = p.mul_src != nullptr;
+            // ---- head state (training step, last forward job) ----
+            const int L = p.n_labels, Fs = f_out;
+            const uint32_t hs_gsum = base + p.off_head;                                            // [4][G][Fs]
+            const uint32_t hs_dg = hs_gsum + static_cast<uint32_t>(4 * p.G * Fs) * 4u;             // [G][Fs]
+            const uint32_t hs_wd = hs_dg + static_cast<uint32_t>(p.G * Fs) * 4u;                   // [Fs][L]
+            const uint32_t hs_hp = hs_wd + static_cast<uint32_t>(Fs * L) * 4u;                     // [8][Fs * L + 8]
+            float hw_acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, hb_acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float cost_acc = 0.0f, corr_acc = 0.0f;
+            if (head) {
+                for (int i = te; i < Fs * L; i += 256) {
+                    const float wv[1] = {__ldg(p.head_w + i)};
+                    sts_f<1>(hs_wd + 4u * static_cast<uint32_t>(i), wv);
+                }
+                asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+            }
             int ai = 0;
             for (int it = 0; it < n_tiles; ++it) {
-                const int rows = (it == n_tiles - 1) ? last_ng * N : full_rows;
+                const int ng = (it == n_tiles - 1) ? last_ng : p.G;
+                const int rows = ng * N;
                 mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
                 ph_tfull ^= 1u << ai;
                 tc_fence_after_sync();
                 const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
-                for (int cs = h; cs < n_cslabs; cs += 2) {
-                    float v0[16], v1[16];
+                if (!head) {
+                    for (int cs = h; cs < n_cslabs; cs += 2) {
+                        float v0[16], v1[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
-                    tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
-                    if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
-                    tmem_ld_wait();
-                    tmem_ld_fence(v0);
-                    tmem_ld_fence(v1);
-                    if (cs + 2 >= n_cslabs) {
+                        for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
+                        tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
+                        if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
+                        tmem_ld_wait();
+                        tmem_ld_fence(v0);
+                        tmem_ld_fence(v1);
+                        if (cs + 2 >= n_cslabs) {
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bar_tempty[ai]);
+                        }
+                        act16_rt(v0, p.act);
+                        act16_rt(v1, p.act);
+                        if (cs * 32 + 32 > p.f_valid) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                                if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                            }
+                        }
+                        tmem_ld_fence(v0);
+                        tmem_ld_fence(v1);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
+                            const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                        }
+                        __syncwarp();
+                        const bool col_ok = cs * 32 + colq < f_out;
+                        float* ycs = y_tile + cs * 32;
+                        if (!mul) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                                float t[4];
+                                lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                                if (row0 + 4 * k < rows && col_ok)
+                                    *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                            }
+                        } else {
+                            const float* mcs = p.mul_src + (ycs - p.y);   // same [rows, y_ld] layout as the output
+                            float4 mv[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                mv[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                if (row0 + 4 * k < rows && col_ok) mv[k] = __ldg(reinterpret_cast<const float4*>(mcs + static_cast<size_t>(4 * k) * y_ld));
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                                float t[4];
+                                lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                                if (row0 + 4 * k < rows && col_ok)
+                                    *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) =
+                                        make_float4(t[0] * act_grad_from_output(mv[k].x, p.mul_act), t[1] * act_grad_from_output(mv[k].y, p.mul_act),
+                                                    t[2] * act_grad_from_output(mv[k].z, p.mul_act), t[3] * act_grad_from_output(mv[k].w, p.mul_act));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (h >= n_cslabs) {
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                     }
-                    act16_rt(v0, p.act);
-                    act16_rt(v1, p.act);
-                    if (cs * 32 + 32 > p.f_valid) {
+                } else {
+                    // ======== fused head: this warp owns tile rows 32 wq .. 32 wq + 31 and columns 32 h .. 32 h + 31 ========
+                    const int cs = h;
+                    const bool has_cols = cs < n_cslabs;
+                    float v0[16], v1[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
-                            if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                    for (int i = 0; i < 16; ++i) { v0[i] = 0.0f; v1[i] = 0.0f; }
+                    if (has_cols) {
+                        tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
+                        if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
+                        tmem_ld_wait();
+                        tmem_ld_fence(v0);
+                        tmem_ld_fence(v1);
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[ai]);       // the accumulator is in registers: hand it back
+                    if (has_cols) {
+                        act16_rt(v0, p.act);
+                        act16_rt(v1, p.act);
+                        if (cs * 32 + 32 > p.f_valid) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                                if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                            }
+                        }
+                        tmem_ld_fence(v0);
+                        tmem_ld_fence(v1);
+                        // (a) the 32 x 32 block of H -> the warp's staging tile; per-graph column sums over this warp's rows
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
+                            const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                        }
+                        __syncwarp();
+                        const int r_lo = wq * 32, r_hi = min(rows, r_lo + 32);
+                        if (r_lo < r_hi) {
+                            const int g_first = r_lo / N, g_last = (r_hi - 1) / N;
+                            for (int g = g_first; g <= g_last; ++g) {
+                                const int ra = max(g * N, r_lo) - r_lo, rb = min(g * N + N, r_hi) - r_lo;
+                                float sum = 0.0f;
+                                for (int r = ra; r < rb; ++r)   // lane c reads column c: chunk (c >> 2) sits at (c >> 2) ^ (r & 7)
+                                    sum += lds_f32(ys + static_cast<uint32_t>(r) * 128u +
+                                                   (((static_cast<uint32_t>(lane) >> 2) ^ (static_cast<uint32_t>(r) & 7u)) << 4) +
+                                                   ((static_cast<uint32_t>(lane) & 3u) << 2));
+                                const float o[1] = {sum};
+                                sts_f<1>(hs_gsum + 4u * static_cast<uint32_t>((wq * p.G + g) * Fs + cs * 32 + lane), o);
+                            }
                         }
                     }
-                    tmem_ld_fence(v0);
-                    tmem_ld_fence(v1);
+                    asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                    // (b) one warp per graph: GraphGather sum, logits, softmax cross-entropy, d logits, d gathered
+                    const int64_t g0_tile = tr.g_begin + static_cast<int64_t>(it) * p.G;
+                    for (int g = e; g < ng; g += kEpiWarps) {
+                        const int64_t bg = g0_tile + g;
+                        const int q_lo = (g * N) >> 5, q_hi = (g * N + N - 1) >> 5;
+                        float gv[2] = {0.0f, 0.0f};
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
-                        const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
-                        sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
-                        sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                        for (int k = 0; k < 2; ++k)
+                            if (lane + 32 * k < Fs)
+                                for (int q = q_lo; q <= q_hi; ++q)
+                                    gv[k] += lds_f32(hs_gsum + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane + 32 * k));
+                        if (p.gathered != nullptr) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                if (lane + 32 * k < Fs) p.gathered[bg * Fs + lane + 32 * k] = gv[k];
+                        }
+                        float z[4] = {0.f, 0.f, 0.f, 0.f}, yl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (l < L) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)
+                                    if (lane + 32 * k < Fs) acc = fmaf(gv[k], lds_f32(hs_wd + 4u * static_cast<uint32_t>((lane + 32 * k) * L + l)), acc);
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                                z[l] = acc + (p.head_b ? __ldg(p.head_b + l) : 0.0f);
+                                yl[l] = __ldg(p.labels + bg * L + l);
+                            }
+                        float zmax = z[0];
+#pragma unroll
+                        for (int l = 1; l < 4; ++l)
+                            if (l < L) zmax = fmaxf(zmax, z[l]);
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (l < L) sum += expf(z[l] - zmax);
+                        const float lse = logf(sum) + zmax;
+                        const float m = p.mask ? __ldg(p.mask + bg) : 1.0f;
+                        float cost = 0.0f, ysum = 0.0f;
+                        int arg_p = 0, arg_y = 0;
+                        float zbest = z[0], ybest = yl[0];
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (l < L) {
+                                cost -= yl[l] * (z[l] - lse);
+                                ysum += yl[l];
+                                if (l > 0 && z[l] > zbest) { zbest = z[l]; arg_p = l; }
+                                if (l > 0 && yl[l] > ybest) { ybest = yl[l]; arg_y = l; }
+                            }
+                        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (l < L) {
+                                const float pr = expf(z[l] - lse);
+                                dz[l] = m * p.inv_batch * (pr * ysum - yl[l]);
+                                if (lane == 0) {
+                                    if (p.logits) p.logits[bg * L + l] = z[l];
+                                    if (p.prediction) p.prediction[bg * L + l] = pr;
+                                }
+                                hb_acc[l] += dz[l];
+                            }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            if (lane + 32 * k < Fs) {
+                                float dgv = 0.0f;
+#pragma unroll
+                                for (int l = 0; l < 4; ++l)
+                                    if (l < L) {
+                                        dgv = fmaf(dz[l], lds_f32(hs_wd + 4u * static_cast<uint32_t>((lane + 32 * k) * L + l)), dgv);
+                                        hw_acc[k][l] = fmaf(gv[k], dz[l], hw_acc[k][l]);
+                                    }
+                                const float o[1] = {dgv};
+                                sts_f<1>(hs_dg + 4u * static_cast<uint32_t>(g * Fs + lane + 32 * k), o);
+                            }
+                        cost_acc += m * cost;
+                        corr_acc += m * (arg_p == arg_y ? 1.0f : 0.0f);
                     }
-                    __syncwarp();
-                    const bool col_ok = cs * 32 + colq < f_out;
-                    float* ycs = y_tile + cs * 32;
-                    if (EPI == 0) {
+                    asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                    // (c) dU = dg[graph of the row] (.) act'(H), staged and stored like an activation tile
+                    if (has_cols) {
+                        const int r = wq * 32 + lane;
+                        const int g = (r < rows) ? r / N : 0;
+                        const uint32_t dga = hs_dg + 4u * static_cast<uint32_t>(g * Fs + cs * 32);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            float d0[4], d1[4];
+                            lds_f<4>(d0, dga + 16u * static_cast<uint32_t>(c4));
+                            lds_f<4>(d1, dga + 16u * static_cast<uint32_t>(c4 + 4));
+                            float t0[4], t1[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                t0[i] = d0[i] * act_grad_from_output(v0[4 * c4 + i], p.act);
+                                t1[i] = d1[i] * act_grad_from_output(v1[4 * c4 + i], p.act);
+                            }
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                        }
+                        __syncwarp();
+                        const bool col_ok = cs * 32 + colq < f_out;
+                        float* ycs = y_tile + cs * 32;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
@@ -1156,34 +1377,37 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             if (row0 + 4 * k < rows && col_ok)
                                 *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
                         }
-                    } else {
-                        const float* mcs = p.mul_src + (ycs - p.y);   // same [rows, y_ld] layout as the output
-                        float4 mv[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            mv[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                            if (row0 + 4 * k < rows && col_ok) mv[k] = __ldg(reinterpret_cast<const float4*>(mcs + static_cast<size_t>(4 * k) * y_ld));
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
-                            float t[4];
-                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
-                            if (row0 + 4 * k < rows && col_ok)
-                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) =
-                                    make_float4(t[0] * act_grad_from_output(mv[k].x, p.mul_act), t[1] * act_grad_from_output(mv[k].y, p.mul_act),
-                                                t[2] * act_grad_from_output(mv[k].z, p.mul_act), t[3] * act_grad_from_output(mv[k].w, p.mul_act));
-                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                }
-                if (h >= n_cslabs) {
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                 }
                 if (++ai == p.abufs) ai = 0;
                 y_tile += y_step;
+            }
+            if (head) {
+                // per-CTA partial of the head's parameter gradients and statistics: the 8 warps' sums, added in warp order
+                const uint32_t mine = hs_hp + static_cast<uint32_t>(e) * static_cast<uint32_t>(Fs * L + 8) * 4u;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (lane + 32 * k < Fs)
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (l < L) {
+                                const float o[1] = {hw_acc[k][l]};
+                                sts_f<1>(mine + 4u * static_cast<uint32_t>((lane + 32 * k) * L + l), o);
+                            }
+                if (lane == 0) {
+                    const float o4[4] = {hb_acc[0], hb_acc[1], hb_acc[2], hb_acc[3]};
+                    const float s4[4] = {cost_acc, corr_acc, 0.0f, 0.0f};
+                    sts_f<4>(mine + 4u * static_cast<uint32_t>(Fs * L), o4);
+                    sts_f<4>(mine + 4u * static_cast<uint32_t>(Fs * L + 4), s4);
+                }
+                asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                float* hp_out = p.head_partial + static_cast<size_t>(blockIdx.x) * (Fs * L + 8);
+                for (int i = te; i < Fs * L + 8; i += 256) {
+                    float acc = 0.0f;
+                    for (int w8 = 0; w8 < kEpiWarps; ++w8) acc += lds_f32(hs_hp + 4u * static_cast<uint32_t>(w8 * (Fs * L + 8) + i));
+                    hp_out[i] = acc;
+                }
             }
             // this CTA's outputs of the job: visible to the next job's TMA loads (async proxy) after the role barrier
             __threadfence();
@@ -1202,7 +1426,12 @@ constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) sh
 
 // One candidate plan: `n_split` output-column slices of f_out_total / n_split columns (each slice is its own CTA row of
 // the grid with its own [W ; bias] slice resident in shared memory), G graphs per tile.
-bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G, int C_csr) {
+uint32_t head_smem_bytes(int G, int f_out, int n_labels) {
+    return static_cast<uint32_t>(5 * G * f_out + f_out * n_labels + kEpiWarps * (f_out * n_labels + 8)) * 4u;
+}
+
+bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G, int C_csr,
+                 int head_labels = 0) {
     if (f_out_total % n_split != 0) return false;
     const int f_out = f_out_total / n_split;
     if (f_out % 4 != 0 || f_out > 256 || (n_split > 1 && f_out % 32 != 0)) return false;
@@ -1232,6 +1461,11 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     p.off_whi = off; off += n_watoms * p.w_atom;
     p.off_wlo = off; off += n_watoms * p.w_atom;
     p.off_ystage = off; off += kEpiWarps * 4096u;
+    p.off_head = off;
+    if (head_labels > 0) {
+        if (n_split != 1 || f_out > 64 || f_out % 32 != 0 || head_labels > 4 || p.G > 16) return false;
+        off += (head_smem_bytes(p.G, f_out, head_labels) + 127u) & ~127u;
+    }
     p.off_stage = off;
     p.C_csr = C_csr;
     p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C_csr), 4));
@@ -1250,11 +1484,11 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
 // Preference: whole output width in one CTA and full 128-row tiles; wide layers (F = 128: [W ; bias] hi / lo alone is
 // 160 KB) fall back to column slices -- each slice aggregates the tile again (the second reader hits L2) -- and to
 // fewer graphs per tile until at least two TMA stages fit.
-bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int C_csr) {
+bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int C_csr, int head_labels = 0) {
     if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || C_csr > 8 || C < 1 || C > C_csr) return false;
     for (int n_split = 1; n_split <= 4; n_split *= 2)
         for (int G = std::max(1, 128 / N); G >= 1; G = (G > 1 ? G / 2 : 0))
-            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G, C_csr)) return true;
+            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G, C_csr, head_labels)) return true;
     return false;
 }
 
@@ -1347,11 +1581,11 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
     V4Batch b{};
     b.n_jobs = n_jobs;
     uint32_t smem = 0;
-    bool any_mul = false;
     for (int k = 0; k < n_jobs; ++k) {
         const V4ChainJob& j = jobs[k];
         V4Params& p = b.job[k];
-        KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, j.f_in, j.f_out, channels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
+        const int labels = j.head != nullptr ? j.head->n_labels : 0;
+        KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, j.f_in, j.f_out, channels, labels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
                      "fused GraphConv chain: job %d (%d -> %d) has no single-CTA plan", k, j.f_in, j.f_out);
         KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: graph ranges differ");
         p.c_begin = 0;
@@ -1367,20 +1601,35 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : p.f_out;
         p.mul_src = j.mul_src;
         p.mul_act = j.mul_act;
+        p.head = 0;
+        if (j.head != nullptr) {
+            const V4Head& hd = *j.head;
+            KGCN_REQUIRE(j.mul_src == nullptr && hd.w && hd.labels && hd.partial && hd.n_labels >= 1 && hd.n_labels <= 4,
+                         KGCN_ERR_BAD_SHAPE, "fused GraphConv chain: bad head (1..4 labels)");
+            p.head = 1;
+            p.n_labels = hd.n_labels;
+            p.head_w = hd.w; p.head_b = hd.b; p.labels = hd.labels; p.mask = hd.mask; p.inv_batch = hd.inv_batch;
+            p.logits = hd.logits; p.prediction = hd.prediction; p.gathered = hd.gathered; p.head_partial = hd.partial;
+        }
         p.dbg = nullptr;
-        any_mul = any_mul || j.mul_src != nullptr;
         smem = std::max(smem, p.smem_total);
     }
-    for (int k = 0; k < n_jobs; ++k)
-        KGCN_REQUIRE((jobs[k].mul_src != nullptr) == any_mul, KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: mixed epilogues");
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));
-    auto go = [&](auto kernel) -> int {
-        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        launch_pdl(kernel, grid, kBlock, smem, st, b);
-        KGCN_LAUNCH_OK("graphconv_fused_v4_chain_kernel");
-        return KGCN_OK;
-    };
-    return any_mul ? go(graphconv_fused_v4_chain_kernel<1>) : go(graphconv_fused_v4_chain_kernel<0>);
+    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_v4_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    launch_pdl(graphconv_fused_v4_chain_kernel, grid, kBlock, smem, st, b);
+    KGCN_LAUNCH_OK("graphconv_fused_v4_chain_kernel");
+    return KGCN_OK;
+}
+
+bool fused_v4_head_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels) {
+    V4Params p{};
+    return fused_v4_enabled() && n_labels >= 1 && plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out, channels, n_labels) && p.n_split == 1;
+}
+
+int fused_v4_chain_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    V4Params p{};
+    if (!plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out, channels)) return 0;
+    return static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
 }
 
 }  // namespace kgcn

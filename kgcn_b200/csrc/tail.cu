@@ -33,6 +33,7 @@ struct TailSegment {
     long long kernel_off, bias_off;   // offsets into the flat buffers; kernel [C][rows][cols], bias [C][cols] (-1: none)
     const float* partial;             // [splits][(rows + 1)][C * cols]
     int splits, rows, cols, channels;
+    long long stride;                 // floats between splits
 };
 
 struct TailParams {
@@ -49,6 +50,11 @@ struct TailParams {
     unsigned long long* ll[kMaxWorld];   // peer-mapped mailboxes [2][world][n_pad] of {value, step}
     long long n_pad;
     int* error_flag;                  // set when a peer never shows up (bounded spin)
+    const float* stats_partial;       // optional: [stats_splits] x {cost_sum, correct_count, ..} every stats_stride floats
+    long long stats_stride;
+    int stats_splits;
+    float* stats_out;                 // [2]
+    int n_blocks;                     // blocks that own parameters; one more block reduces the statistics
 };
 
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -64,8 +70,32 @@ __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailPar
     pdl_prologue();
     __shared__ float4 red[32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long i = (static_cast<long long>(blockIdx.x) * 32 + lane) * 4;   // first of this lane's 4 elements
     const int t = p.step_state[0] + 1;
+    if (static_cast<int>(blockIdx.x) >= p.n_blocks) {
+        // ---- the extra block: per-CTA statistics of the fused head -> stats_out, summed in CTA order ----
+        if (threadIdx.x < 2) {
+            float acc = 0.0f;
+            for (int k = 0; k < p.stats_splits; k += 16) {
+                float val[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) val[j] = (k + j < p.stats_splits) ? __ldcg(p.stats_partial + static_cast<long long>(k + j) * p.stats_stride + threadIdx.x) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (k + j < p.stats_splits) acc += val[j];
+            }
+            p.stats_out[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(p.step_state + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+                p.step_state[0] = t;
+                p.step_state[1] = 0;
+            }
+        }
+        return;
+    }
+    const long long i = (static_cast<long long>(blockIdx.x) * 32 + lane) * 4;   // first of this lane's 4 elements
 
     // ---- which gradient are elements i .. i + 3?  (segment offsets and widths are multiples of 4) ----
     const float* src = nullptr;
@@ -75,7 +105,7 @@ __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailPar
 #pragma unroll 1
         for (int s = 0; s < p.n_segments; ++s) {
             const TailSegment& g = p.seg[s];
-            const long long total = static_cast<long long>(g.rows + 1) * g.channels * g.cols;
+            const long long total = g.stride;
             const long long k = i - g.kernel_off, kb = i - g.bias_off;
             if (k >= 0 && k < static_cast<long long>(g.channels) * g.rows * g.cols) {
                 const int c = static_cast<int>(k / (static_cast<long long>(g.rows) * g.cols));
@@ -195,7 +225,8 @@ using namespace kgcn;
 
 extern "C" int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* v, int64_t n, const kgcn_grad_segment* segments,
                                     int32_t n_segments, float lr, float beta1, float beta2, float eps, float grad_scale,
-                                    int32_t* step_state, const kgcn_p2p_group* group, void* stream) {
+                                    int32_t* step_state, const kgcn_p2p_group* group, const float* stats_partial,
+                                    int32_t stats_splits, int64_t stats_stride, float* stats_out, void* stream) {
     KGCN_REQUIRE(param && grad && m && v && step_state, KGCN_ERR_NULL, "reduce_adam: NULL pointer argument");
     KGCN_REQUIRE(n >= 0 && n % 4 == 0 && n_segments >= 0 && n_segments <= kMaxSegments && (n_segments == 0 || segments != nullptr),
                  KGCN_ERR_BAD_SHAPE, "reduce_adam: bad n (a multiple of 4) / n_segments (at most %d segments)", kMaxSegments);
@@ -209,15 +240,23 @@ extern "C" int kgcn_reduce_adam_f32(float* param, float* grad, float* m, float* 
     p.n_segments = n_segments;
     for (int s = 0; s < n_segments; ++s) {
         const kgcn_grad_segment& g = segments[s];
-        KGCN_REQUIRE(g.partial != nullptr && g.splits > 0 && g.rows > 0 && g.cols > 0 && g.channels > 0 && g.kernel_off >= 0 &&
+        KGCN_REQUIRE(g.partial != nullptr && g.splits > 0 && g.rows >= 0 && g.cols > 0 && g.channels > 0 && g.kernel_off >= 0 &&
                          g.kernel_off + static_cast<int64_t>(g.channels) * g.rows * g.cols <= n &&
                          (g.bias_off < 0 || g.bias_off + static_cast<int64_t>(g.channels) * g.cols <= n),
                      KGCN_ERR_BAD_SHAPE, "reduce_adam: segment %d is out of range", s);
         KGCN_REQUIRE(g.cols % 4 == 0 && g.kernel_off % 4 == 0 && (g.bias_off < 0 || g.bias_off % 4 == 0) && aligned16(g.partial),
                      KGCN_ERR_MISALIGNED, "reduce_adam: segment %d: offsets and width must be multiples of 4 floats", s);
-        p.seg[s] = TailSegment{g.kernel_off, g.bias_off, g.partial, g.splits, g.rows, g.cols, g.channels};
+        const long long dflt = static_cast<long long>(g.rows + 1) * g.channels * g.cols;
+        KGCN_REQUIRE(g.stride == 0 || (g.stride >= dflt && g.stride % 4 == 0), KGCN_ERR_BAD_SHAPE, "reduce_adam: segment %d: bad stride", s);
+        p.seg[s] = TailSegment{g.kernel_off, g.bias_off, g.partial, g.splits, g.rows, g.cols, g.channels, g.stride ? g.stride : dflt};
     }
-    const unsigned blocks = static_cast<unsigned>(ceil_div<int64_t>(n, kTailElems));
+    unsigned blocks = static_cast<unsigned>(ceil_div<int64_t>(n, kTailElems));
+    p.n_blocks = static_cast<int>(blocks);
+    if (stats_partial != nullptr) {
+        KGCN_REQUIRE(stats_out != nullptr && stats_splits > 0 && stats_stride >= 2, KGCN_ERR_BAD_SHAPE, "reduce_adam: bad statistics partials");
+        p.stats_partial = stats_partial; p.stats_splits = stats_splits; p.stats_stride = stats_stride; p.stats_out = stats_out;
+        ++blocks;
+    }
     p.rank = 0;
     p.world = 1;
     if (group != nullptr && group->world > 1) {

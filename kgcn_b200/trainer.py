@@ -214,13 +214,29 @@ class Trainer:
             self._b_ptrs = arr([self.pviews["conv%d/bias" % i] for i in range(L)])
             self._y_ptrs = arr(self.acts[1:L + 1])
             self._du_ptrs = arr(self.du)
+        # the graph-local part of the step (forward layers + fused readout head + dx chain) as ONE launch
+        self.step_grid = 0
+        want_p2p = p2p if p2p is not None else os.environ.get("KGCN_P2P", "1") != "0"
+        if self.chain and os.environ.get("KGCN_STEP_CHAIN", "1") != "0" and (self.world_size == 1 or want_p2p):
+            self.step_grid = int(lib.kgcn_gcn_step_chain_grid(B, C, N, L, self._dims_c, s.label_dim))
+        self.step_chain = self.step_grid > 0
         if self.fused_step:
-            segs = (_lib.GradSegment * len(s.conv_dims))()
+            n_seg = len(s.conv_dims) + (2 if self.step_chain else 0)
+            segs = (_lib.GradSegment * n_seg)()
             for i, n in enumerate(self.splits):
                 buf = torch.empty(n * (self.dims[i] + 1) * C * self.dims[i + 1], **f32)
                 self.partials.append(buf)
                 segs[i] = _lib.GradSegment(offs["conv%d/kernel" % i], offs["conv%d/bias" % i], buf.data_ptr(), n, self.dims[i],
-                                           self.dims[i + 1], C)
+                                           self.dims[i + 1], C, 0)
+            if self.step_chain:
+                # per-CTA head partials {dW_dense [F * L] | db_dense (4) | cost_sum, correct_count, 0, 0}
+                FL = self.f_head * s.label_dim
+                self.head_partial = torch.zeros(self.step_grid * (FL + 8), **f32)
+                hp = self.head_partial.data_ptr()
+                segs[L] = _lib.GradSegment(0, offs["dense/kernel"], hp, self.step_grid, 0, FL, 1, FL + 8)
+                segs[L + 1] = _lib.GradSegment(0, offs["dense/bias"], hp + 4 * FL, self.step_grid, 0, 4, 1, FL + 8)
+                self._stats_partial = hp + 4 * (FL + 4)
+                self._stats_stride = FL + 8
             self._segments = segs
             self._part_ptrs = (ctypes.c_void_p * L)(*[t.data_ptr() for t in self.partials])
             self._part_bytes = (ctypes.c_size_t * L)(*[t.numel() * 4 for t in self.partials])
@@ -440,10 +456,14 @@ class Trainer:
         """The step's tail.  Fused step / peer exchange: ONE launch reduces the weight-gradient partials, all-reduces over
         NVLink peer memory and applies Adam; otherwise plain Adam on the (already NCCL-reduced) flat gradient buffer."""
         if self.fused_step or self.p2p is not None:
-            segs, n_seg = (self._segments, len(self._segments)) if self.fused_step else (None, 0)
+            n_conv = len(self.spec.conv_dims)
+            use_head = self.step_chain and self._head_in_chain
+            segs, n_seg = (self._segments, n_conv + (2 if use_head else 0)) if self.fused_step else (None, 0)
             group = ctypes.byref(self.p2p.group) if self.p2p is not None else None
             check(lib.kgcn_reduce_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
-                                           segs, n_seg, self.lr, 0.9, 0.999, 1e-8, 1.0, ptr(self.step_state), group, st))
+                                           segs, n_seg, self.lr, 0.9, 0.999, 1e-8, 1.0, ptr(self.step_state), group,
+                                           self._stats_partial if use_head else None, self.step_grid if use_head else 0,
+                                           self._stats_stride if use_head else 0, ptr(self.stats) if use_head else None, st))
         else:
             check(lib.kgcn_adam_f32(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.n_params,
                                     self.lr, 0.9, 0.999, 1e-8, 1, 1.0, ptr(self.step_state), st))
@@ -472,8 +492,31 @@ class Trainer:
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=False)
 
-    def _fwd_bwd(self, batch):
+    def _step_chain(self, batch, st):
+        """Forward layers + fused readout head + dx chain: ONE launch; then the weight-gradient jobs."""
+        s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
+        csr, L = batch.csr, len(self.spec.conv_dims)
+        x = batch.features
+        if x.shape[-1] != self.dims[0]:
+            raise ValueError("batch features are %d wide, the trainer stores %d" % (x.shape[-1], self.dims[0]))
+        self.acts[0] = x
+        check(lib.kgcn_gcn_step_chain_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t),
+                                          B, C, N, L, self._dims_c, self._ldims_c, ptr(x), self._w_ptrs, self._b_ptrs, self._y_ptrs,
+                                          self._du_ptrs, self.act, ptr(self.pviews["dense/kernel"]), ptr(self.pviews["dense/bias"]),
+                                          s.label_dim, ptr(batch.labels), ptr(batch.mask), 1.0 / (B * self.world_size), ptr(self.logits),
+                                          ptr(self.prediction), ptr(self.gathered), ptr(self.head_partial), st))
+        x_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in self.acts[:L]])
+        check(lib.kgcn_graphconv_chain_dw_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c, x_ptrs,
+                                              self._du_ptrs, self._part_ptrs, self._part_bytes, st))
+
+    _head_in_chain = False
+
+    def _fwd_bwd(self, batch, allow_step_chain=True):
         st = torch.cuda.current_stream().cuda_stream
+        self._head_in_chain = bool(self.step_chain and allow_step_chain)
+        if self._head_in_chain:
+            self._step_chain(batch, st)
+            return
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=True)
         if self.fused_step:
@@ -484,7 +527,7 @@ class Trainer:
             self._backward(batch, f, st)
 
     def step_eager(self, batch, apply_update=True):
-        self._fwd_bwd(batch)
+        self._fwd_bwd(batch, allow_step_chain=apply_update)   # without the tail launch the head's gradients need the head kernel
         st = torch.cuda.current_stream().cuda_stream
         if not apply_update:
             if self.fused_step and self.single_graph:

@@ -116,19 +116,31 @@ def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkey
     counts, idx, val, x, labels, mask, adjs, p = make_case(B, N, C, F, conv_dims, None, seed=B + N)
     spec = NetSpec(F, conv_dims, N, channels=C, label_dim=2, act="sigmoid")
     monkeypatch.setenv("KGCN_CHAIN", "1")
+    monkeypatch.setenv("KGCN_STEP_CHAIN", "0")
     a = Trainer(spec, B, seed=3)
     monkeypatch.setenv("KGCN_CHAIN", "0")
     b = Trainer(spec, B, seed=3)
-    assert not b.chain and a.fused_step and b.fused_step
-    assert a.chain == (C == 1)
+    monkeypatch.setenv("KGCN_CHAIN", "1")
+    monkeypatch.setenv("KGCN_STEP_CHAIN", "1")
+    c = Trainer(spec, B, seed=3)          # + the readout head fused into the last forward layer's epilogue
+    assert not b.chain and a.fused_step and b.fused_step and not a.step_chain
+    assert a.chain == (C == 1) and c.step_chain == (C == 1)
     batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=a.dims[0])
     for _ in range(3):
         a.step_eager(batch)
         b.step_eager(batch)
+        c.step_eager(batch)
     torch.cuda.synchronize()
     assert torch.equal(a.logits, b.logits)
     assert torch.equal(a.grads, b.grads)
     assert torch.equal(a.params, b.params)
+    # the fused head adds the node rows per warp quarter instead of in index order: equal up to fp32 summation order
+    close(c.logits, a.logits.cpu().numpy(), 1e-5)
+    close(c.grads, a.grads.cpu().numpy(), 1e-4)
+    close(c.params, a.params.cpu().numpy(), 1e-4)
+    sa, sc = a.read_stats(), c.read_stats()
+    assert abs(sa[0] - sc[0]) <= 1e-4 * abs(sa[0]) and sa[1] == sc[1]
+    assert int(c.step_state[0].item()) == 3
 
 
 def test_training_reduces_loss_on_ring_task():
