@@ -222,6 +222,26 @@ __device__ __forceinline__ void act16_rt(float (&v)[16], int act) {
     }
 }
 
+// t[i] *= act'(y[i]) with the activation switch outside the element loop (compact code: the epilogue paths run once or
+// twice per job at small batches, so every extra instruction is an instruction-cache miss, not an issue slot)
+template <int ACT>
+__device__ __forceinline__ void mul_act_grad4(float (&t)[4], const float (&y)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (ACT == KGCN_ACT_RELU) t[i] = y[i] > 0.0f ? t[i] : 0.0f;
+        else if (ACT == KGCN_ACT_SIGMOID) t[i] *= y[i] * (1.0f - y[i]);
+        else if (ACT == KGCN_ACT_TANH) t[i] *= 1.0f - y[i] * y[i];
+    }
+}
+__device__ __forceinline__ void mul_act_grad4_rt(float (&t)[4], const float (&y)[4], int act) {
+    switch (act) {
+        case KGCN_ACT_RELU: mul_act_grad4<KGCN_ACT_RELU>(t, y); break;
+        case KGCN_ACT_SIGMOID: mul_act_grad4<KGCN_ACT_SIGMOID>(t, y); break;
+        case KGCN_ACT_TANH: mul_act_grad4<KGCN_ACT_TANH>(t, y); break;
+        default: break;
+    }
+}
+
 // KS K-steps of one 3xTF32 pass, unrolled so every operand address is a constant add
 template <int KS>
 __device__ __forceinline__ void issue_tile(uint32_t d, uint32_t zhi, uint32_t zlo, uint64_t dwhi, uint64_t dwlo, uint32_t idesc,
@@ -763,8 +783,13 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
 constexpr int kV4MaxJobs = 6;
 struct V4Batch {
     int n_jobs;
+    long long* dbg;   // tuning aid (kgcn_debug_v4_chain_times): [CTA][64] clock64 stamps, see tools/chain_timeline.py
     V4Params job[kV4MaxJobs];
 };
+// stamp slot: job * 16 + event; events: 0 job start (agg), 1 first stage landed, 2 agg tile 0 done, 3 agg last tile done,
+// 4 MMA first issue done, 5 MMA last issue done, 6 epi first accumulator ready, 7 epi first tile stored, 8 epi last tile stored,
+// 9 TMA first issue, 10 B operand staged, 11 epi job end (after fences)
+#define V4_STAMP(ev) do { if (b.dbg != nullptr && lane == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 128 + j * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -785,7 +810,7 @@ __device__ __forceinline__ void stage_b_operand(const V4Params& p, uint32_t base
         const uint32_t n16 = (p.off_ystage - p.off_whi) >> 4;
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t i = t; i < n16; i += n_thr) sts_f<4>(base + p.off_whi + (i << 4), z4);
-        asm volatile("bar.sync 3, %0;" ::"n"(512) : "memory");   // the stagers (aggregation + epilogue warps)
+        asm volatile("bar.sync 3, %0;" ::"n"(256) : "memory");   // the stagers (the epilogue warps)
     }
     if (p.w_trans == 0) {
         const int nq_n = f_out >> 2, kq_n = Kp >> 2;
@@ -854,6 +879,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_jobs = b.n_jobs;
+    if (b.dbg != nullptr && tid == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 128 + 126] = clock64();
 
     if (tid == 0) {
         for (int i = 0; i < kV4MaxStages; ++i) {
@@ -901,6 +927,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     const int64_t rp_lo = r0 & ~3ll;
                     const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
                     const uint32_t x_bytes = static_cast<uint32_t>(ng) * static_cast<uint32_t>(N) * pitch;
+                    if (it == 0) V4_STAMP(9);
                     mbar_expect_tx_only(full, x_bytes + 4u * rp_cnt);
                     bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
                     bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
@@ -931,7 +958,9 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
             if (j > 0) bar_all_roles();
-            stage_b_operand(p, base, tid, 512);
+            if (warp == 0) V4_STAMP(0);
+            // (the B operand is staged by the epilogue warps, which have nothing else to do until the first accumulator is
+            // ready; the aggregation starts as soon as the first tile has landed)
             const int N = p.N, f_in = p.f_in, K = p.K, Kp = p.Kp, S = p.n_stages;
             const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
             if (warp < 4) {   // the unused row-sum columns K + C .. K + 7 of every Z buffer stay zero for the whole job
@@ -941,11 +970,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     tmem_st8(zc + K, z8);
                     tmem_st8(zc + Kp + K, z8);
                 }
-                tmem_st_wait();
-                tc_fence_before_sync();
+                tmem_st_wait();   // ordered before this warp's first zfull arrival, which the MMA warp waits for
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(544) : "memory");   // stagers + the MMA warp
-            tc_fence_after_sync();
             const TileRange tr = cta_range_of(p);
             const int n_tiles = tr.n_tiles;
             const int last_ng = tr.n_graphs_cta - (n_tiles - 1) * p.G;
@@ -964,6 +990,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
                 mbar_wait(&bar_full[s], (ph_full >> s) & 1u);
                 ph_full ^= 1u << s;
+                if (warp == 0 && it == 0) V4_STAMP(1);
                 const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
                 const int e_first = static_cast<int>(lds_u32(rp_addr));
                 const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
@@ -1042,6 +1069,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_zfull[zi]);
+                if (warp == 0 && it == 0) V4_STAMP(2);
+                if (warp == 0 && it == n_tiles - 1) V4_STAMP(3);
                 if (++s == S) s = 0;
                 if (++zi == p.zbufs) zi = 0;
                 r0_lo += r0_step;
@@ -1055,7 +1084,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             if (j > 0) bar_all_roles();
             if (warp != kWarpMma) continue;
             // =============================== MMA issuer ===============================
-            asm volatile("bar.sync 1, %0;" ::"n"(544) : "memory");   // B operand staged, Z padding columns zeroed
+            asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");   // B operand staged (epilogue warps)
             tc_fence_after_sync();
             const int Kp = p.Kp, Np = p.Np;
             const TileRange tr = cta_range_of(p);
@@ -1086,6 +1115,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     umma_commit(&bar_tfull[ai]);
                 }
                 __syncwarp();
+                if (it == 0) V4_STAMP(4);
+                if (it == n_tiles - 1) V4_STAMP(5);
                 if (++zi == p.zbufs) zi = 0;
                 if (++ai == p.abufs) ai = 0;
             }
@@ -1104,8 +1135,9 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
             if (j > 0) bar_all_roles();
-            stage_b_operand(p, base, tid - kWarpEpi0 * 32 + kAggWarps * 32, 512);
-            asm volatile("bar.sync 1, %0;" ::"n"(544) : "memory");
+            stage_b_operand(p, base, te, 256);
+            asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");
+            if (e == 0) V4_STAMP(10);
             const int N = p.N, f_out = p.f_out, Np = p.Np;
             const TileRange tr = cta_range_of(p);
             const int n_tiles = tr.n_tiles;
@@ -1124,15 +1156,18 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const int L = p.n_labels, Fs = f_out;
             const uint32_t hs_gsum = base + p.off_head;                                            // [4][G][Fs]
             const uint32_t hs_dg = hs_gsum + static_cast<uint32_t>(4 * p.G * Fs) * 4u;             // [G][Fs]
-            const uint32_t hs_wd = hs_dg + static_cast<uint32_t>(p.G * Fs) * 4u;                   // [Fs][L]
-            const uint32_t hs_hp = hs_wd + static_cast<uint32_t>(Fs * L) * 4u;                     // [8][Fs * L + 8]
-            float hw_acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, hb_acc[4] = {0.f, 0.f, 0.f, 0.f};
-            float cost_acc = 0.0f, corr_acc = 0.0f;
+            const uint32_t hs_wd = hs_dg + static_cast<uint32_t>(p.G * Fs) * 4u;                   // [Fs][L] + bias [4]
+            const uint32_t hs_hp = hs_wd + static_cast<uint32_t>(Fs * L + 4) * 4u;                 // [8][Fs * L + 8] per-warp sums
+            const uint32_t hs_zs = hs_hp + static_cast<uint32_t>(kEpiWarps * (Fs * L + 8)) * 4u;   // [8][4] d logits of the warp's graph
+            const uint32_t my_hp = hs_hp + static_cast<uint32_t>(e * (Fs * L + 8)) * 4u;
             if (head) {
-                for (int i = te; i < Fs * L; i += 256) {
-                    const float wv[1] = {__ldg(p.head_w + i)};
+                for (int i = te; i < Fs * L + 4; i += 256) {
+                    const int bi = i - Fs * L;
+                    const float wv[1] = {bi < 0 ? __ldg(p.head_w + i) : ((bi < L && p.head_b != nullptr) ? __ldg(p.head_b + bi) : 0.0f)};
                     sts_f<1>(hs_wd + 4u * static_cast<uint32_t>(i), wv);
                 }
+                const float z1[1] = {0.0f};
+                for (int i = te; i < kEpiWarps * (Fs * L + 8); i += 256) sts_f<1>(hs_hp + 4u * static_cast<uint32_t>(i), z1);
                 asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
             }
             int ai = 0;
@@ -1142,6 +1177,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
                 ph_tfull ^= 1u << ai;
                 tc_fence_after_sync();
+                if (e == 0 && it == 0) V4_STAMP(6);
                 const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
                 if (!head) {
                     for (int cs = h; cs < n_cslabs; cs += 2) {
@@ -1201,10 +1237,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                 const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
                                 float t[4];
                                 lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                                const float yv[4] = {mv[k].x, mv[k].y, mv[k].z, mv[k].w};
+                                mul_act_grad4_rt(t, yv, p.mul_act);
                                 if (row0 + 4 * k < rows && col_ok)
-                                    *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) =
-                                        make_float4(t[0] * act_grad_from_output(mv[k].x, p.mul_act), t[1] * act_grad_from_output(mv[k].y, p.mul_act),
-                                                    t[2] * act_grad_from_output(mv[k].z, p.mul_act), t[3] * act_grad_from_output(mv[k].w, p.mul_act));
+                                    *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
                             }
                         }
                         __syncwarp();
@@ -1218,20 +1254,25 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     // ======== fused head: this warp owns tile rows 32 wq .. 32 wq + 31 and columns 32 h .. 32 h + 31 ========
                     const int cs = h;
                     const bool has_cols = cs < n_cslabs;
-                    float v0[16], v1[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { v0[i] = 0.0f; v1[i] = 0.0f; }
+                    const int64_t g0_tile = tr.g_begin + static_cast<int64_t>(it) * p.G;
+                    // label l (lane l) and mask of the graph this warp will finish (cold HBM lines): requested now, needed after (a)
+                    float y_lane = 0.0f, m0 = 1.0f;
+                    if (e < ng) {
+                        if (lane < L) y_lane = __ldg(p.labels + (g0_tile + e) * L + lane);
+                        if (p.mask) m0 = __ldg(p.mask + g0_tile + e);
+                    }
                     if (has_cols) {
+                        float v0[16], v1[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
                         tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
                         if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
                         tmem_ld_wait();
                         tmem_ld_fence(v0);
                         tmem_ld_fence(v1);
-                    }
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_tempty[ai]);       // the accumulator is in registers: hand it back
-                    if (has_cols) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[ai]);       // the accumulator is in registers: hand it back
                         act16_rt(v0, p.act);
                         act16_rt(v1, p.act);
                         if (cs * 32 + 32 > p.f_valid) {
@@ -1243,7 +1284,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                         }
                         tmem_ld_fence(v0);
                         tmem_ld_fence(v1);
-                        // (a) the 32 x 32 block of H -> the warp's staging tile; per-graph column sums over this warp's rows
+                        // (a) the 32 x 32 block of H -> the warp's staging tile (it stays there until (c)); per-graph column
+                        // sums over this warp's rows, four independent partial sums per lane
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
                             const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
@@ -1255,116 +1297,127 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                         const int r_lo = wq * 32, r_hi = min(rows, r_lo + 32);
                         if (r_lo < r_hi) {
                             const int g_first = r_lo / N, g_last = (r_hi - 1) / N;
+                            const uint32_t cbase = ys + ((static_cast<uint32_t>(lane) & 3u) << 2);
+                            const uint32_t cch = static_cast<uint32_t>(lane) >> 2;   // lane c reads column c: chunk c >> 2 sits at (c >> 2) ^ (r & 7)
                             for (int g = g_first; g <= g_last; ++g) {
                                 const int ra = max(g * N, r_lo) - r_lo, rb = min(g * N + N, r_hi) - r_lo;
-                                float sum = 0.0f;
-                                for (int r = ra; r < rb; ++r)   // lane c reads column c: chunk (c >> 2) sits at (c >> 2) ^ (r & 7)
-                                    sum += lds_f32(ys + static_cast<uint32_t>(r) * 128u +
-                                                   (((static_cast<uint32_t>(lane) >> 2) ^ (static_cast<uint32_t>(r) & 7u)) << 4) +
-                                                   ((static_cast<uint32_t>(lane) & 3u) << 2));
-                                const float o[1] = {sum};
+                                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                                int r = ra;
+                                for (; r + 4 <= rb; r += 4) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)
+                                        s4[u] += lds_f32(cbase + static_cast<uint32_t>(r + u) * 128u + ((cch ^ (static_cast<uint32_t>(r + u) & 7u)) << 4));
+                                }
+                                for (; r < rb; ++r) s4[0] += lds_f32(cbase + static_cast<uint32_t>(r) * 128u + ((cch ^ (static_cast<uint32_t>(r) & 7u)) << 4));
+                                const float o[1] = {(s4[0] + s4[1]) + (s4[2] + s4[3])};
                                 sts_f<1>(hs_gsum + 4u * static_cast<uint32_t>((wq * p.G + g) * Fs + cs * 32 + lane), o);
                             }
                         }
+                    } else {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                     }
+                    if (e == 0 && it == 0) V4_STAMP(12);
                     asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
-                    // (b) one warp per graph: GraphGather sum, logits, softmax cross-entropy, d logits, d gathered
-                    const int64_t g0_tile = tr.g_begin + static_cast<int64_t>(it) * p.G;
+                    if (e == 0 && it == 0) V4_STAMP(13);
+                    // (b) one warp per graph: GraphGather sum, logits, softmax cross-entropy, d logits, d gathered.  Lane l holds
+                    // label l's quantities; loops over labels are rolled (this code runs once per tile: keep it small)
                     for (int g = e; g < ng; g += kEpiWarps) {
                         const int64_t bg = g0_tile + g;
                         const int q_lo = (g * N) >> 5, q_hi = (g * N + N - 1) >> 5;
-                        float gv[2] = {0.0f, 0.0f};
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            if (lane + 32 * k < Fs)
-                                for (int q = q_lo; q <= q_hi; ++q)
-                                    gv[k] += lds_f32(hs_gsum + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane + 32 * k));
-                        if (p.gathered != nullptr) {
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                if (lane + 32 * k < Fs) p.gathered[bg * Fs + lane + 32 * k] = gv[k];
+                        float yl = y_lane, m = m0;
+                        if (g != e) {   // more than 8 graphs per tile (small graphs): the later ones load their own
+                            yl = lane < L ? __ldg(p.labels + bg * L + lane) : 0.0f;
+                            m = p.mask ? __ldg(p.mask + bg) : 1.0f;
                         }
-                        float z[4] = {0.f, 0.f, 0.f, 0.f}, yl[4] = {0.f, 0.f, 0.f, 0.f};
+                        float gv0 = 0.0f, gv1 = 0.0f;
+                        for (int q = q_lo; q <= q_hi; ++q) {
+                            gv0 += lds_f32(hs_gsum + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane));
+                            if (Fs > 32) gv1 += lds_f32(hs_gsum + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane + 32));
+                        }
+                        if (p.gathered != nullptr) {
+                            p.gathered[bg * Fs + lane] = gv0;
+                            if (Fs > 32) p.gathered[bg * Fs + lane + 32] = gv1;
+                        }
+                        float zl = -3.0e38f;
+#pragma unroll 1
+                        for (int l = 0; l < L; ++l) {
+                            float acc = gv0 * lds_f32(hs_wd + 4u * static_cast<uint32_t>(lane * L + l));
+                            if (Fs > 32) acc = fmaf(gv1, lds_f32(hs_wd + 4u * static_cast<uint32_t>((lane + 32) * L + l)), acc);
 #pragma unroll
-                        for (int l = 0; l < 4; ++l)
-                            if (l < L) {
-                                float acc = 0.0f;
+                            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                            if (lane == l) zl = acc + lds_f32(hs_wd + 4u * static_cast<uint32_t>(Fs * L + l));
+                        }
+                        float zmax = zl, ymax = lane < L ? yl : -3.0e38f;
 #pragma unroll
-                                for (int k = 0; k < 2; ++k)
-                                    if (lane + 32 * k < Fs) acc = fmaf(gv[k], lds_f32(hs_wd + 4u * static_cast<uint32_t>((lane + 32 * k) * L + l)), acc);
+                        for (int o = 16; o > 0; o >>= 1) {
+                            zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                            ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+                        }
+                        float ex = lane < L ? expf(zl - zmax) : 0.0f, ysum = lane < L ? yl : 0.0f;
 #pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                                z[l] = acc + (p.head_b ? __ldg(p.head_b + l) : 0.0f);
-                                yl[l] = __ldg(p.labels + bg * L + l);
+                        for (int o = 16; o > 0; o >>= 1) {
+                            ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                            ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
+                        }
+                        const float lse = logf(ex) + zmax;
+                        float cost = lane < L ? -yl * (zl - lse) : 0.0f;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+                        const int arg_p = __ffs(__ballot_sync(0xffffffffu, lane < L && zl == zmax)) - 1;   // first maximum wins
+                        const int arg_y = __ffs(__ballot_sync(0xffffffffu, lane < L && yl == ymax)) - 1;
+                        const float pr = lane < L ? expf(zl - lse) : 0.0f;
+                        const float dzl = m * p.inv_batch * (pr * ysum - yl);
+                        if (lane < L) {
+                            if (p.logits) p.logits[bg * L + lane] = zl;
+                            if (p.prediction) p.prediction[bg * L + lane] = pr;
+                            const float o[1] = {dzl};
+                            sts_f<1>(hs_zs + 4u * static_cast<uint32_t>(e * 4 + lane), o);
+                            const float bacc[1] = {lds_f32(my_hp + 4u * static_cast<uint32_t>(Fs * L + lane)) + dzl};
+                            sts_f<1>(my_hp + 4u * static_cast<uint32_t>(Fs * L + lane), bacc);
+                        }
+                        if (lane == 0) {
+                            const float c2[2] = {lds_f32(my_hp + 4u * static_cast<uint32_t>(Fs * L + 4)) + m * cost,
+                                                 lds_f32(my_hp + 4u * static_cast<uint32_t>(Fs * L + 5)) + m * (arg_p == arg_y ? 1.0f : 0.0f)};
+                            sts_f<2>(my_hp + 4u * static_cast<uint32_t>(Fs * L + 4), c2);
+                        }
+                        __syncwarp();
+                        float dg0 = 0.0f, dg1 = 0.0f;
+#pragma unroll 1
+                        for (int l = 0; l < L; ++l) {   // d gathered and this warp's share of dW_dense (lane owns features lane, lane + 32)
+                            const float dz = lds_f32(hs_zs + 4u * static_cast<uint32_t>(e * 4 + l));
+                            const uint32_t i0 = 4u * static_cast<uint32_t>(lane * L + l), i1 = 4u * static_cast<uint32_t>((lane + 32) * L + l);
+                            dg0 = fmaf(dz, lds_f32(hs_wd + i0), dg0);
+                            const float a0[1] = {fmaf(gv0, dz, lds_f32(my_hp + i0))};
+                            sts_f<1>(my_hp + i0, a0);
+                            if (Fs > 32) {
+                                dg1 = fmaf(dz, lds_f32(hs_wd + i1), dg1);
+                                const float a1[1] = {fmaf(gv1, dz, lds_f32(my_hp + i1))};
+                                sts_f<1>(my_hp + i1, a1);
                             }
-                        float zmax = z[0];
-#pragma unroll
-                        for (int l = 1; l < 4; ++l)
-                            if (l < L) zmax = fmaxf(zmax, z[l]);
-                        float sum = 0.0f;
-#pragma unroll
-                        for (int l = 0; l < 4; ++l)
-                            if (l < L) sum += expf(z[l] - zmax);
-                        const float lse = logf(sum) + zmax;
-                        const float m = p.mask ? __ldg(p.mask + bg) : 1.0f;
-                        float cost = 0.0f, ysum = 0.0f;
-                        int arg_p = 0, arg_y = 0;
-                        float zbest = z[0], ybest = yl[0];
-#pragma unroll
-                        for (int l = 0; l < 4; ++l)
-                            if (l < L) {
-                                cost -= yl[l] * (z[l] - lse);
-                                ysum += yl[l];
-                                if (l > 0 && z[l] > zbest) { zbest = z[l]; arg_p = l; }
-                                if (l > 0 && yl[l] > ybest) { ybest = yl[l]; arg_y = l; }
-                            }
-                        float dz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int l = 0; l < 4; ++l)
-                            if (l < L) {
-                                const float pr = expf(z[l] - lse);
-                                dz[l] = m * p.inv_batch * (pr * ysum - yl[l]);
-                                if (lane == 0) {
-                                    if (p.logits) p.logits[bg * L + l] = z[l];
-                                    if (p.prediction) p.prediction[bg * L + l] = pr;
-                                }
-                                hb_acc[l] += dz[l];
-                            }
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            if (lane + 32 * k < Fs) {
-                                float dgv = 0.0f;
-#pragma unroll
-                                for (int l = 0; l < 4; ++l)
-                                    if (l < L) {
-                                        dgv = fmaf(dz[l], lds_f32(hs_wd + 4u * static_cast<uint32_t>((lane + 32 * k) * L + l)), dgv);
-                                        hw_acc[k][l] = fmaf(gv[k], dz[l], hw_acc[k][l]);
-                                    }
-                                const float o[1] = {dgv};
-                                sts_f<1>(hs_dg + 4u * static_cast<uint32_t>(g * Fs + lane + 32 * k), o);
-                            }
-                        cost_acc += m * cost;
-                        corr_acc += m * (arg_p == arg_y ? 1.0f : 0.0f);
+                        }
+                        const float o0[1] = {dg0}, o1[1] = {dg1};
+                        sts_f<1>(hs_dg + 4u * static_cast<uint32_t>(g * Fs + lane), o0);
+                        if (Fs > 32) sts_f<1>(hs_dg + 4u * static_cast<uint32_t>(g * Fs + lane + 32), o1);
+                        __syncwarp();
                     }
+                    if (e == 0 && it == 0) V4_STAMP(14);
                     asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
-                    // (c) dU = dg[graph of the row] (.) act'(H), staged and stored like an activation tile
+                    if (e == 0 && it == 0) V4_STAMP(15);
+                    // (c) dU = dg[graph of the row] (.) act'(H): H is re-read from the warp's staging tile and replaced in place,
+                    // then the tile leaves like an activation tile
                     if (has_cols) {
                         const int r = wq * 32 + lane;
                         const int g = (r < rows) ? r / N : 0;
                         const uint32_t dga = hs_dg + 4u * static_cast<uint32_t>(g * Fs + cs * 32);
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            float d0[4], d1[4];
-                            lds_f<4>(d0, dga + 16u * static_cast<uint32_t>(c4));
-                            lds_f<4>(d1, dga + 16u * static_cast<uint32_t>(c4 + 4));
-                            float t0[4], t1[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                t0[i] = d0[i] * act_grad_from_output(v0[4 * c4 + i], p.act);
-                                t1[i] = d1[i] * act_grad_from_output(v1[4 * c4 + i], p.act);
-                            }
-                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
-                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+#pragma unroll 2
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            float d[4], hv[4];
+                            lds_f<4>(d, dga + 16u * static_cast<uint32_t>(c4));
+                            lds_f<4>(hv, yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4));
+                            mul_act_grad4_rt(d, hv, p.act);
+                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), d);
                         }
                         __syncwarp();
                         const bool col_ok = cs * 32 + colq < f_out;
@@ -1380,27 +1433,13 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                         __syncwarp();
                     }
                 }
+                if (e == 0 && it == 0) V4_STAMP(7);
+                if (e == 0 && it == n_tiles - 1) V4_STAMP(8);
                 if (++ai == p.abufs) ai = 0;
                 y_tile += y_step;
             }
             if (head) {
                 // per-CTA partial of the head's parameter gradients and statistics: the 8 warps' sums, added in warp order
-                const uint32_t mine = hs_hp + static_cast<uint32_t>(e) * static_cast<uint32_t>(Fs * L + 8) * 4u;
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    if (lane + 32 * k < Fs)
-#pragma unroll
-                        for (int l = 0; l < 4; ++l)
-                            if (l < L) {
-                                const float o[1] = {hw_acc[k][l]};
-                                sts_f<1>(mine + 4u * static_cast<uint32_t>((lane + 32 * k) * L + l), o);
-                            }
-                if (lane == 0) {
-                    const float o4[4] = {hb_acc[0], hb_acc[1], hb_acc[2], hb_acc[3]};
-                    const float s4[4] = {cost_acc, corr_acc, 0.0f, 0.0f};
-                    sts_f<4>(mine + 4u * static_cast<uint32_t>(Fs * L), o4);
-                    sts_f<4>(mine + 4u * static_cast<uint32_t>(Fs * L + 4), s4);
-                }
                 asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
                 float* hp_out = p.head_partial + static_cast<size_t>(blockIdx.x) * (Fs * L + 8);
                 for (int i = te; i < Fs * L + 8; i += 256) {
@@ -1412,11 +1451,13 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             // this CTA's outputs of the job: visible to the next job's TMA loads (async proxy) after the role barrier
             __threadfence();
             fence_proxy_async_all();
+            if (e == 0) V4_STAMP(11);
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (b.dbg != nullptr && tid == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 128 + 127] = clock64();
     if (warp == kWarpMma) tmem_dealloc(tmem, 512);
 }
 
@@ -1427,7 +1468,7 @@ constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) sh
 // One candidate plan: `n_split` output-column slices of f_out_total / n_split columns (each slice is its own CTA row of
 // the grid with its own [W ; bias] slice resident in shared memory), G graphs per tile.
 uint32_t head_smem_bytes(int G, int f_out, int n_labels) {
-    return static_cast<uint32_t>(5 * G * f_out + f_out * n_labels + kEpiWarps * (f_out * n_labels + 8)) * 4u;
+    return static_cast<uint32_t>(5 * G * f_out + f_out * n_labels + 4 + kEpiWarps * (f_out * n_labels + 8) + kEpiWarps * 4) * 4u;
 }
 
 bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G, int C_csr,
@@ -1525,6 +1566,7 @@ bool fused_v4_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, i
 }
 
 static long long* g_dbg_v4 = nullptr;
+static long long* g_dbg_chain = nullptr;
 
 int launch_graphconv_fused_v4(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs, int channels,
                               int n_nodes, const float* x, int f_in, const float* w, const float* bias, int f_out, int act,
@@ -1580,6 +1622,7 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
     KGCN_REQUIRE(n_jobs >= 1 && n_jobs <= kV4MaxJobs, KGCN_ERR_BAD_SHAPE, "fused GraphConv chain: 1..%d jobs", kV4MaxJobs);
     V4Batch b{};
     b.n_jobs = n_jobs;
+    b.dbg = g_dbg_chain;
     uint32_t smem = 0;
     for (int k = 0; k < n_jobs; ++k) {
         const V4ChainJob& j = jobs[k];
@@ -1637,3 +1680,5 @@ int fused_v4_chain_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, i
 // Tuning hook (not part of the documented ABI): device buffer of [148][16] + [148][2] int64 phase cycle sums of the v4
 // kernel (aggregation warp 0, MMA warp, epilogue warp 0, producer; see tools/phase_times_v4.py for the slot names).
 extern "C" void kgcn_debug_v4_times(long long* device_buffer) { kgcn::g_dbg_v4 = device_buffer; }
+// same for the chained kernel: [grid][128] clock64 stamps (slot = job * 16 + event, 126 = kernel entry, 127 = kernel exit)
+extern "C" void kgcn_debug_v4_chain_times(long long* device_buffer) { kgcn::g_dbg_chain = device_buffer; }
