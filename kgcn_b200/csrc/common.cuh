@@ -156,6 +156,9 @@ struct V4ChainJob {
     int mul_act, f_out_valid;
     const V4Head* head = nullptr;
 };
+// graphconv_fused_v5.cu: the transposed-product kernel for wide layers (weights resident in tensor memory), same job struct
+bool fused_v5_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
+int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);
 bool fused_v4_head_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels);
 int fused_v4_chain_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 bool fused_v4_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);

@@ -52,6 +52,15 @@ int launch_graphconv_fused_bwd(const int32_t* rowptr_t, const int32_t* col_t, co
 
 namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Wide layers (F = 128) have no single-CTA plan in the v4 kernel ([W ; bias] hi / lo does not fit shared memory next to the
+// stages): they run on the transposed-product kernel with the weights in tensor memory.
+inline bool prefer_v5(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
+    return !fused_v4_chainable(n_graphs, channels, n_nodes, f_in, f_out) && fused_v5_plannable(n_graphs, channels, n_nodes, f_in, f_out);
+}
+inline bool ptrs_aligned16(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f, const void* g) {
+    return aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d) && aligned16(e) && aligned16(f) && aligned16(g);
+}
 }  // namespace
 
 }  // namespace kgcn
@@ -80,6 +89,11 @@ extern "C" int kgcn_graphconv_fwd_f32(const int32_t* rowptr, const int32_t* col,
     if (n_graphs == 0) return KGCN_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+    if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && prefer_v5(n_graphs, channels, n_nodes, f_in, f_out) &&
+        ptrs_aligned16(x, y, rowptr, col, val, w, bias)) {
+        const V4ChainJob job{rowptr, col, val, x, w, bias, y, f_in, f_out, act, 0, nullptr, KGCN_ACT_NONE, f_out};
+        return launch_graphconv_fused_v5_chain(&job, 1, n_graphs, channels, n_nodes, st);
+    }
     if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && fused_v4_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y, rowptr, col, val, w, bias))
         return launch_graphconv_fused_v4(rowptr, col, val, n_graphs, channels, n_nodes, x, f_in, w, bias, f_out, act, y, st);
     if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && fused_fwd_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y))
@@ -141,7 +155,11 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
                                          nullptr, n_nodes, dy_bcast, st);
                 if (rc) return rc;
             }
-            if (dx != nullptr && fused_v4_eligible(n_graphs, channels, n_nodes, f_out, f_in, du_in, dx, rowptr_t, col_t, val_t, w, nullptr)) {
+            if (dx != nullptr && prefer_v5(n_graphs, channels, n_nodes, f_out, f_in) && ptrs_aligned16(du_in, dx, rowptr_t, col_t, val_t, w, nullptr)) {
+                const V4ChainJob job{rowptr_t, col_t, val_t, du_in, w, nullptr, dx, f_out, f_in, KGCN_ACT_NONE, 1, nullptr, KGCN_ACT_NONE, f_in};
+                int rc = launch_graphconv_fused_v5_chain(&job, 1, n_graphs, channels, n_nodes, st);
+                if (rc) return rc;
+            } else if (dx != nullptr && fused_v4_eligible(n_graphs, channels, n_nodes, f_out, f_in, du_in, dx, rowptr_t, col_t, val_t, w, nullptr)) {
                 int rc = launch_graphconv_fused_v4(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, du_in, f_out, w, nullptr, f_in,
                                                    KGCN_ACT_NONE, dx, st, /*w_transposed=*/true);
                 if (rc) return rc;
@@ -201,7 +219,7 @@ extern "C" int kgcn_graphconv_bwd_f32(const int32_t* rowptr_t, const int32_t* co
 extern "C" int32_t kgcn_graphconv_bwd_splits(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in, int32_t f_out,
                                              int32_t need_dx) {
     if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || f_in <= 0 || f_out <= 0) return 0;
-    if (need_dx && !fused_v4_plannable(n_graphs, channels, n_nodes, f_out, f_in)) return 0;
+    if (need_dx && !fused_v4_plannable(n_graphs, channels, n_nodes, f_out, f_in) && !fused_v5_plannable(n_graphs, channels, n_nodes, f_out, f_in)) return 0;
     return fused_dw_splits(n_graphs, channels, n_nodes, f_in, f_out);
 }
 
@@ -215,7 +233,12 @@ extern "C" int kgcn_graphconv_bwd_partial_f32(const int32_t* rowptr_t, const int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KGCN_REQUIRE(fused_dw_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, du, rowptr_t, col_t, val_t), KGCN_ERR_UNSUPPORTED,
                  "graphconv_bwd_partial: shape / alignment not supported by the fused weight-gradient kernel (see kgcn_graphconv_bwd_splits)");
-    if (dx != nullptr) {
+    if (dx != nullptr && prefer_v5(n_graphs, channels, n_nodes, f_out, f_in) && ptrs_aligned16(du, dx, rowptr_t, col_t, val_t, w, x)) {
+        const V4ChainJob job{rowptr_t, col_t, val_t, du, w, nullptr, dx, f_out, f_in, KGCN_ACT_NONE, 1,
+                             act_below != KGCN_ACT_NONE ? x : nullptr, act_below, f_in};
+        int rc = launch_graphconv_fused_v5_chain(&job, 1, n_graphs, channels, n_nodes, st);
+        if (rc) return rc;
+    } else if (dx != nullptr) {
         KGCN_REQUIRE(fused_v4_eligible(n_graphs, channels, n_nodes, f_out, f_in, du, dx, rowptr_t, col_t, val_t, w, nullptr),
                      KGCN_ERR_UNSUPPORTED, "graphconv_bwd_partial: shape / alignment not supported by the fused layer kernel");
         int rc = launch_graphconv_fused_v4(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, du, f_out, w, nullptr, f_in,
@@ -245,7 +268,7 @@ extern "C" int kgcn_graphconv_fwd_padded_f32(const int32_t* rowptr, const int32_
 
 extern "C" int32_t kgcn_graphconv_fwd_fused(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t f_in, int32_t f_out) {
     if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || f_in <= 0 || f_out <= 0) return 0;
-    return fused_v4_plannable(n_graphs, channels, n_nodes, f_in, f_out) ? 1 : 0;
+    return (fused_v4_plannable(n_graphs, channels, n_nodes, f_in, f_out) || fused_v5_plannable(n_graphs, channels, n_nodes, f_in, f_out)) ? 1 : 0;
 }
 
 extern "C" int kgcn_reduce_partials_f32(const float* partial, int32_t splits, int32_t f_in, int32_t f_out, int32_t channels,
@@ -256,14 +279,24 @@ extern "C" int kgcn_reduce_partials_f32(const float* partial, int32_t splits, in
 }
 
 // ---- chained launches for the step loop: all forward layers / all dx layers of a network in ONE launch each ----
+// 1: every layer (and every dx) has a single-CTA plan in the v4 kernel; 2: in the v5 kernel (wide layers); 0: neither
+static int chain_kind(int64_t n_graphs, int channels, int n_nodes, int n_layers, const int32_t* dims) {
+    bool v4 = true, v5 = true;
+    for (int l = 0; l < n_layers; ++l) {
+        v4 = v4 && fused_v4_chainable(n_graphs, channels, n_nodes, dims[l], dims[l + 1]);
+        v5 = v5 && fused_v5_plannable(n_graphs, channels, n_nodes, dims[l], dims[l + 1]);
+        if (l > 0) {
+            v4 = v4 && fused_v4_chainable(n_graphs, channels, n_nodes, dims[l + 1], dims[l]);
+            v5 = v5 && fused_v5_plannable(n_graphs, channels, n_nodes, dims[l + 1], dims[l]);
+        }
+    }
+    return v4 ? 1 : (v5 ? 2 : 0);
+}
+
 extern "C" int32_t kgcn_graphconv_chain_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
                                                   const int32_t* dims) {
     if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || n_layers < 1 || n_layers > 4 || dims == nullptr) return 0;
-    for (int l = 0; l < n_layers; ++l) {
-        if (!fused_v4_chainable(n_graphs, channels, n_nodes, dims[l], dims[l + 1])) return 0;            // forward layer l
-        if (l > 0 && !fused_v4_chainable(n_graphs, channels, n_nodes, dims[l + 1], dims[l])) return 0;    // dx of layer l
-    }
-    return 1;
+    return chain_kind(n_graphs, channels, n_nodes, n_layers, dims);
 }
 
 extern "C" int kgcn_graphconv_chain_fwd_f32(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
@@ -283,6 +316,10 @@ extern "C" int kgcn_graphconv_chain_fwd_f32(const int32_t* rowptr, const int32_t
         jobs[l] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, y[l], dims[l], dims[l + 1], act, 0, nullptr,
                              KGCN_ACT_NONE, dims_valid ? dims_valid[l + 1] : dims[l + 1]};
         in = y[l];
+    }
+    if (chain_kind(n_graphs, channels, n_nodes, n_layers, dims) == 2) {
+        KGCN_REQUIRE(dims_valid == nullptr || dims_valid[n_layers] > 0, KGCN_ERR_BAD_SHAPE, "graphconv_chain_fwd: bad dims_valid");
+        return launch_graphconv_fused_v5_chain(jobs, n_layers, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
     }
     return launch_graphconv_fused_v4_chain(jobs, n_layers, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
 }
@@ -306,6 +343,8 @@ extern "C" int kgcn_graphconv_chain_dx_f32(const int32_t* rowptr_t, const int32_
         jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
                              x[l], act == KGCN_ACT_NONE ? KGCN_ACT_NONE : act, 0};
     }
+    if (chain_kind(n_graphs, channels, n_nodes, n_layers, dims) == 2)
+        return launch_graphconv_fused_v5_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
     return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
 }
 
@@ -341,7 +380,7 @@ extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_
 
 extern "C" int32_t kgcn_gcn_step_chain_grid(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
                                             const int32_t* dims, int32_t n_labels) {
-    if (!kgcn_graphconv_chain_supported(n_graphs, channels, n_nodes, n_layers, dims)) return 0;
+    if (kgcn_graphconv_chain_supported(n_graphs, channels, n_nodes, n_layers, dims) != 1) return 0;
     if (2 * n_layers - 1 > 6 || n_labels < 1 || n_labels > 4) return 0;
     if (!fused_v4_head_chainable(n_graphs, channels, n_nodes, dims[n_layers - 1], dims[n_layers], n_labels)) return 0;
     return fused_v4_chain_grid(n_graphs, channels, n_nodes, dims[0], dims[1]);

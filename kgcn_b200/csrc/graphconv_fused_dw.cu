@@ -500,12 +500,13 @@ bool plan_dw_try(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
 bool plan_dw(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
     if (n_graphs <= 0 || C < 1 || C > 8 || N < 1 || N > 128) return false;
     if (f_in % 32 != 0 || f_out % 32 != 0 || f_in > 128 || f_in < 32 || C * f_out > 256) return false;
-    // preference: double-buffered operands and >= 2 stages; tiles of whole graphs up to 64 rows, chunks of up to 64 rows
+    // preference: >= 2 stages always; double-buffered operands as long as a chunk still fills the warps (>= 32 rows), then
+    // single-buffered 64 / 32-row chunks (wide layers: F = 128), 16-row chunks last
     const int g_max = std::max(1, 64 / N);
-    for (int opbufs = 2; opbufs >= 1; --opbufs)
-        for (int R = 64; R >= 16; R /= 2)
-            for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
-                if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, R, opbufs, 2)) return true;
+    const int order[6][2] = {{2, 64}, {2, 32}, {1, 64}, {1, 32}, {2, 16}, {1, 16}};
+    for (const auto& o : order)
+        for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
+            if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, o[1], o[0], 2)) return true;
     return plan_dw_try(p, n_graphs, C, N, f_in, f_out, 1, 32, 1, 1);
 }
 

@@ -367,8 +367,9 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
 using namespace kgcn;
 
 static int readout_blocks(int64_t n_graphs) {
-    int64_t nb = ceil_div<int64_t>(n_graphs, kReadoutThreads / 32);   // one graph per warp in phase 1
-    nb = std::min<int64_t>(nb, kNumSMs);
+    // every SM takes a slice: the node-row passes (GraphGather sums, the dU rows of the training step) move the whole
+    // activation tensor and want all of them; phase 1 (a warp per graph) is tiny either way
+    int64_t nb = std::min<int64_t>(n_graphs, kNumSMs);
     nb = std::max<int64_t>(nb, ceil_div<int64_t>(n_graphs, kReadoutMaxSlice));
     return static_cast<int>(nb);
 }

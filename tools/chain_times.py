@@ -18,6 +18,7 @@ host = bench.make_host_batches(w, ROT, seed=1)
 batches = [DeviceBatch.from_host(d["counts"], d["indices"], d["values"], d["features"], d["labels"], N, pad_to=tr.dims[0]) for d in host]
 L = len(w["conv_dims"])
 st = lambda: torch.cuda.current_stream().cuda_stream
+print("padded", tr.padded, "fused_step", tr.fused_step, "chain", tr.chain, "step_chain", tr.step_chain)
 for b in batches[:2]:
     tr.step_eager(b)
 torch.cuda.synchronize()
@@ -40,14 +41,18 @@ def dw_one(i): check(lib.kgcn_graphconv_chain_dw_f32(ptr(batches[i].csr.rowptr_t
     tr._dims_c, xp(batches[i]), tr._du_ptrs, tr._part_ptrs, tr._part_bytes, st()))
 def head(i):
     tr._last_nodes = tr.acts[L]; tr._head(batches[i], tr.f_head, st(), train=False)
+def head_du(i):
+    tr._last_nodes = tr.acts[L]; tr._head_in_chain = False; tr._head(batches[i], tr.f_head, st(), train=True)
 def tail(i):
-    tr._head_in_chain = True; tr._optimizer(st())
+    tr._head_in_chain = tr.step_chain; tr._optimizer(st())
 def whole(i): tr.step_eager(batches[i])
 
 for name, fn in (("step chain (fwd x%d + head + dx x%d)" % (L, L - 1), step_chain), ("fwd chain x%d" % L, fwd_chain), ("fwd single job", fwd_one),
-                 ("dx chain x%d" % (L - 1), dx_chain), ("dW chain x%d" % L, dw_chain), ("dW single job", dw_one), ("head kernel (infer)", head),
+                 ("dx chain x%d" % (L - 1), dx_chain), ("dW chain x%d" % L, dw_chain), ("dW single job", dw_one), ("head kernel (infer)", head), ("head kernel (train: + dU)", head_du),
                  ("tail", tail), ("whole step", whole)):
     if L == 1 and "dx" in name: continue
+    if "step chain" in name and not tr.step_chain: continue
+    if ("chain" in name or "single job" in name) and not tr.chain: continue
     for i in range(ROT): fn(i)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
