@@ -155,7 +155,12 @@ struct V4ChainJob {
     const float* mul_src;   // y *= act'(mul_src) of activation mul_act
     int mul_act, f_out_valid;
     const V4Head* head = nullptr;
+    int c_begin = 0, c_count = 0;   // channel group [c_begin, c_begin + c_count) of the CSR's channels (0 = all)
+    int acc_in = 0;                 // add the existing y before the activation (later group of a layer split over channel groups)
 };
+// channels per job a forward layer needs in a chain: `channels` (one job), fewer (K = C * f_in beyond tensor memory: channel
+// groups, the later ones accumulate), 0 = no single-CTA plan
+int fused_v4_chain_group(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int head_labels);
 // graphconv_fused_v5.cu: the transposed-product kernel for wide layers (weights resident in tensor memory), same job struct
 bool fused_v5_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);

@@ -279,17 +279,44 @@ extern "C" int kgcn_reduce_partials_f32(const float* partial, int32_t splits, in
 }
 
 // ---- chained launches for the step loop: all forward layers / all dx layers of a network in ONE launch each ----
-// 1: every layer (and every dx) has a single-CTA plan in the v4 kernel; 2: in the v5 kernel (wide layers); 0: neither
+// forward jobs of one layer appended to jobs[k..]: one job, or several over channel groups (the later ones accumulate into y
+// and the last activates).  Returns the new job count, -1 when the layer has no single-CTA plan or the table is full.
+static int add_fwd_jobs(V4ChainJob* jobs, int k, int k_max, const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
+                        const float* w, const float* bias, float* y, int f_in, int f_out, int f_valid, int act, const V4Head* head,
+                        int64_t n_graphs, int channels, int n_nodes) {
+    const int cg = fused_v4_chain_group(n_graphs, channels, n_nodes, f_in, f_out, head ? head->n_labels : 0);
+    if (cg == 0) return -1;
+    for (int c0 = 0; c0 < channels; c0 += cg) {
+        if (k >= k_max) return -1;
+        const int cn = std::min(cg, channels - c0);
+        const bool first = c0 == 0, last = c0 + cn == channels;
+        V4ChainJob j{rowptr, col, val, x, w, bias, y, f_in, f_out, last ? act : KGCN_ACT_NONE, 0, nullptr, KGCN_ACT_NONE,
+                     last ? f_valid : f_out, last ? head : nullptr};
+        j.c_begin = c0;
+        j.c_count = cn;
+        j.acc_in = first ? 0 : 1;
+        jobs[k++] = j;
+    }
+    return k;
+}
+
+// 1: every layer (possibly over channel groups) and every dx has a single-CTA plan in the v4 kernel, at most 6 forward jobs;
+// 2: every layer and dx runs on the v5 kernel (wide layers); 0: neither
 static int chain_kind(int64_t n_graphs, int channels, int n_nodes, int n_layers, const int32_t* dims) {
     bool v4 = true, v5 = true;
+    int fwd_jobs = 0;
     for (int l = 0; l < n_layers; ++l) {
-        v4 = v4 && fused_v4_chainable(n_graphs, channels, n_nodes, dims[l], dims[l + 1]);
+        const int cg = fused_v4_chain_group(n_graphs, channels, n_nodes, dims[l], dims[l + 1], 0);
+        v4 = v4 && cg > 0;
+        if (cg > 0) fwd_jobs += (channels + cg - 1) / cg;
         v5 = v5 && fused_v5_plannable(n_graphs, channels, n_nodes, dims[l], dims[l + 1]);
         if (l > 0) {
             v4 = v4 && fused_v4_chainable(n_graphs, channels, n_nodes, dims[l + 1], dims[l]);
             v5 = v5 && fused_v5_plannable(n_graphs, channels, n_nodes, dims[l + 1], dims[l]);
         }
     }
+    v4 = v4 && fwd_jobs <= 6;
+    v5 = v5 && n_layers <= 4;
     return v4 ? 1 : (v5 ? 2 : 0);
 }
 
@@ -307,21 +334,28 @@ extern "C" int kgcn_graphconv_chain_fwd_f32(const int32_t* rowptr, const int32_t
     KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 4, KGCN_ERR_BAD_SHAPE,
                  "graphconv_chain_fwd: bad shape (1..4 layers)");
     KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "graphconv_chain_fwd: unknown act %d", act);
-    V4ChainJob jobs[4];
+    V4ChainJob jobs[6];
     const float* in = x;
+    const int kind = chain_kind(n_graphs, channels, n_nodes, n_layers, dims);
+    KGCN_REQUIRE(kind != 0, KGCN_ERR_UNSUPPORTED, "graphconv_chain_fwd: network not supported (kgcn_graphconv_chain_supported)");
+    int k = 0;
     for (int l = 0; l < n_layers; ++l) {
         KGCN_REQUIRE(w[l] && y[l], KGCN_ERR_NULL, "graphconv_chain_fwd: NULL weight / output of layer %d", l);
         KGCN_REQUIRE(aligned16(in) && aligned16(y[l]) && aligned16(w[l]) && (!bias || aligned16(bias[l])) && aligned16(rowptr) &&
                          aligned16(col) && aligned16(val), KGCN_ERR_MISALIGNED, "graphconv_chain_fwd: 16-byte alignment required");
-        jobs[l] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, y[l], dims[l], dims[l + 1], act, 0, nullptr,
-                             KGCN_ACT_NONE, dims_valid ? dims_valid[l + 1] : dims[l + 1]};
+        const int fv = dims_valid ? dims_valid[l + 1] : dims[l + 1];
+        if (kind == 2) {
+            jobs[k++] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, y[l], dims[l], dims[l + 1], act, 0, nullptr,
+                                   KGCN_ACT_NONE, fv};
+        } else {
+            k = add_fwd_jobs(jobs, k, 6, rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, y[l], dims[l], dims[l + 1], fv, act, nullptr,
+                             n_graphs, channels, n_nodes);
+            KGCN_REQUIRE(k > 0, KGCN_ERR_UNSUPPORTED, "graphconv_chain_fwd: layer %d has no plan", l);
+        }
         in = y[l];
     }
-    if (chain_kind(n_graphs, channels, n_nodes, n_layers, dims) == 2) {
-        KGCN_REQUIRE(dims_valid == nullptr || dims_valid[n_layers] > 0, KGCN_ERR_BAD_SHAPE, "graphconv_chain_fwd: bad dims_valid");
-        return launch_graphconv_fused_v5_chain(jobs, n_layers, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
-    }
-    return launch_graphconv_fused_v4_chain(jobs, n_layers, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+    if (kind == 2) return launch_graphconv_fused_v5_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+    return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int kgcn_graphconv_chain_dx_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
@@ -380,10 +414,16 @@ extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_
 
 extern "C" int32_t kgcn_gcn_step_chain_grid(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
                                             const int32_t* dims, int32_t n_labels) {
-    if (kgcn_graphconv_chain_supported(n_graphs, channels, n_nodes, n_layers, dims) != 1) return 0;
-    if (2 * n_layers - 1 > 6 || n_labels < 1 || n_labels > 4) return 0;
-    if (!fused_v4_head_chainable(n_graphs, channels, n_nodes, dims[n_layers - 1], dims[n_layers], n_labels)) return 0;
-    return fused_v4_chain_grid(n_graphs, channels, n_nodes, dims[0], dims[1]);
+    if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || n_layers < 1 || n_layers > 4 || dims == nullptr) return 0;
+    if (chain_kind(n_graphs, channels, n_nodes, n_layers, dims) != 1 || n_labels < 1 || n_labels > 4) return 0;
+    int jobs = n_layers - 1;   // dx jobs
+    for (int l = 0; l < n_layers; ++l) {
+        const int cg = fused_v4_chain_group(n_graphs, channels, n_nodes, dims[l], dims[l + 1], l == n_layers - 1 ? n_labels : 0);
+        if (cg == 0) return 0;
+        jobs += (channels + cg - 1) / cg;
+    }
+    if (jobs > 6) return 0;
+    return fused_v4_chain_grid(n_graphs, channels, n_nodes, dims[n_layers - 1], dims[n_layers]);
 }
 
 extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
@@ -396,21 +436,22 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
                                        void* stream) {
     KGCN_REQUIRE(rowptr && col && val && rowptr_t && col_t && val_t && dims && x && w && y && du && head_w && labels && head_partial,
                  KGCN_ERR_NULL, "gcn_step_chain: NULL pointer argument");
-    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && 2 * n_layers - 1 <= 6, KGCN_ERR_BAD_SHAPE,
-                 "gcn_step_chain: bad shape (1..3 layers)");
+    KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 4, KGCN_ERR_BAD_SHAPE,
+                 "gcn_step_chain: bad shape (1..4 layers)");
     KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "gcn_step_chain: unknown act %d", act);
     const int L = n_layers;
     V4ChainJob jobs[6];
     V4Head head{n_labels, head_w, head_b, labels, mask, inv_batch, logits, prediction, gathered, head_partial};
     const float* in = x;
     int k = 0;
-    for (int l = 0; l < L; ++l, ++k) {
+    for (int l = 0; l < L; ++l) {
         float* out = (l == L - 1) ? du[L - 1] : y[l];
         KGCN_REQUIRE(w[l] && out, KGCN_ERR_NULL, "gcn_step_chain: NULL weight / output of layer %d", l);
         KGCN_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w[l]) && (!bias || aligned16(bias[l])), KGCN_ERR_MISALIGNED,
                      "gcn_step_chain: 16-byte alignment required");
-        jobs[k] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, out, dims[l], dims[l + 1], act, 0, nullptr,
-                             KGCN_ACT_NONE, dims_valid ? dims_valid[l + 1] : dims[l + 1], (l == L - 1) ? &head : nullptr};
+        k = add_fwd_jobs(jobs, k, 6, rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, out, dims[l], dims[l + 1],
+                         dims_valid ? dims_valid[l + 1] : dims[l + 1], act, (l == L - 1) ? &head : nullptr, n_graphs, channels, n_nodes);
+        KGCN_REQUIRE(k > 0 && k + (L - 1 - l) <= 6, KGCN_ERR_UNSUPPORTED, "gcn_step_chain: network not supported (kgcn_gcn_step_chain_grid)");
         in = out;
     }
     for (int l = L - 1; l >= 1; --l, ++k) {   // du[l - 1] = (sum_c A_c^T . du[l] . W_l,c^T) (.) act'(y[l - 1])

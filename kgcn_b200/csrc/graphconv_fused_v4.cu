@@ -1152,6 +1152,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const size_t y_step = static_cast<size_t>(full_rows) * y_ld;
             const bool head = p.head != 0;
             const bool mul = p.mul_src != nullptr;
+            const bool accin = p.acc_in != 0;
             // ---- head state (training step, last forward job) ----
             const int L = p.n_labels, Fs = f_out;
             const uint32_t hs_gsum = base + p.off_head;                                            // [4][G][Fs]
@@ -1194,13 +1195,15 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                         }
-                        act16_rt(v0, p.act);
-                        act16_rt(v1, p.act);
-                        if (cs * 32 + 32 > p.f_valid) {
+                        if (!accin) {
+                            act16_rt(v0, p.act);
+                            act16_rt(v1, p.act);
+                            if (cs * 32 + 32 > p.f_valid) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
-                                if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                                for (int i = 0; i < 16; ++i) {
+                                    if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                                    if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                                }
                             }
                         }
                         tmem_ld_fence(v0);
@@ -1215,7 +1218,31 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                         __syncwarp();
                         const bool col_ok = cs * 32 + colq < f_out;
                         float* ycs = y_tile + cs * 32;
-                        if (!mul) {
+                        if (accin) {   // later channel group of a layer: add the partial pre-activation already in y, then activate
+                            const int cbase = cs * 32 + colq;
+#pragma unroll 2
+                            for (int k = 0; k < 8; ++k) {
+                                const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                                float t[4];
+                                lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                                if (row0 + 4 * k < rows && col_ok) {
+                                    float4* dst = reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld);
+                                    const float4 o = *dst;
+                                    t[0] += o.x; t[1] += o.y; t[2] += o.z; t[3] += o.w;
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) {
+                                        switch (p.act) {
+                                            case KGCN_ACT_RELU: t[jj] = fast_act<KGCN_ACT_RELU>(t[jj]); break;
+                                            case KGCN_ACT_SIGMOID: t[jj] = fast_act<KGCN_ACT_SIGMOID>(t[jj]); break;
+                                            case KGCN_ACT_TANH: t[jj] = fast_act<KGCN_ACT_TANH>(t[jj]); break;
+                                            default: break;
+                                        }
+                                        if (cbase + jj >= p.f_valid) t[jj] = 0.0f;
+                                    }
+                                    *dst = make_float4(t[0], t[1], t[2], t[3]);
+                                }
+                            }
+                        } else if (!mul) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
@@ -1628,19 +1655,22 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         const V4ChainJob& j = jobs[k];
         V4Params& p = b.job[k];
         const int labels = j.head != nullptr ? j.head->n_labels : 0;
-        KGCN_REQUIRE(plan_v4(p, n_graphs, channels, n_nodes, j.f_in, j.f_out, channels, labels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
+        const int cn = j.c_count > 0 ? j.c_count : channels;
+        KGCN_REQUIRE(j.c_begin >= 0 && j.c_begin + cn <= channels, KGCN_ERR_BAD_SHAPE, "fused GraphConv chain: bad channel group");
+        KGCN_REQUIRE(plan_v4(p, n_graphs, cn, n_nodes, j.f_in, j.f_out, channels, labels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
                      "fused GraphConv chain: job %d (%d -> %d) has no single-CTA plan", k, j.f_in, j.f_out);
         KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: graph ranges differ");
-        p.c_begin = 0;
+        KGCN_REQUIRE(!(j.acc_in && (j.mul_src != nullptr || j.head != nullptr)), KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: accumulate + other epilogue");
+        p.c_begin = j.c_begin;
         p.rowptr = j.rowptr; p.col = j.col; p.val = j.val; p.x = j.x; p.y = j.y;
         p.act = j.act;
-        p.acc_in = 0;
+        p.acc_in = j.acc_in;
         p.y_ld = j.f_out;
         p.w_trans = j.w_transposed ? 1 : 0;
         p.w_ld = j.w_transposed ? j.f_in : j.f_out;
         p.w_cstride = j.f_in * j.f_out;
-        p.w = j.w;
-        p.bias = j.w_transposed ? nullptr : j.bias;
+        p.w = j.w + static_cast<size_t>(j.c_begin) * p.w_cstride;
+        p.bias = (j.w_transposed || j.bias == nullptr) ? nullptr : j.bias + static_cast<size_t>(j.c_begin) * j.f_out;
         p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : p.f_out;
         p.mul_src = j.mul_src;
         p.mul_act = j.mul_act;
@@ -1662,6 +1692,17 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
     launch_pdl(graphconv_fused_v4_chain_kernel, grid, kBlock, smem, st, b);
     KGCN_LAUNCH_OK("graphconv_fused_v4_chain_kernel");
     return KGCN_OK;
+}
+
+int fused_v4_chain_group(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int head_labels) {
+    if (!fused_v4_enabled()) return 0;
+    V4Params p{};
+    for (int cg = channels; cg >= 1; --cg) {
+        // the head rides on the LAST group's job; earlier groups are plain jobs (they need no head shared memory)
+        if (plan_v4(p, n_graphs, cg, n_nodes, f_in, f_out, channels, head_labels) && p.n_split == 1) return cg;
+        if (head_labels > 0) break;   // the fused head needs the whole layer in one job's epilogue state only on the last group: keep it simple
+    }
+    return 0;
 }
 
 bool fused_v4_head_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels) {

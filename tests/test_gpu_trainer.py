@@ -106,7 +106,7 @@ def test_graph_replay_equals_eager():
 @pytest.mark.parametrize("B,N,C,F,conv_dims", [
     (700, 32, 1, 64, [64, 64]),        # C2 widths, 5 graphs per CTA: two tiles per job
     (40, 50, 1, 75, [50, 50, 50]),     # C3: three chained layers on padded widths
-    (300, 50, 3, 75, [50, 50, 50]),    # C4: first layer needs channel groups -> no chain (falls back to per-layer launches)
+    (300, 50, 3, 75, [50, 50, 50]),    # C4: the first layer runs as two chained jobs over channel groups {0,1} + {2}
     (9, 32, 1, 32, [64]),              # a single layer
 ])
 def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkeypatch):
@@ -124,7 +124,7 @@ def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkey
     monkeypatch.setenv("KGCN_STEP_CHAIN", "1")
     c = Trainer(spec, B, seed=3)          # + the readout head fused into the last forward layer's epilogue
     assert not b.chain and a.fused_step and b.fused_step and not a.step_chain
-    assert a.chain == (C == 1) and c.step_chain == (C == 1)
+    assert a.chain and c.step_chain
     batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=a.dims[0])
     for _ in range(3):
         a.step_eager(batch)
