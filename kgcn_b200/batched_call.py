@@ -30,6 +30,6 @@ class BatchedSpMDT:
         out = _plugin.run(csr, flat, rhs.contiguous(), "per_matrix")
         return list(out[:, 0].unbind(0))
 
-    def call_packed(self, csr, rhs):
+    def call_packed(self, csr, rhs, flat_values=None):
         """rhs [B, C, K, F] -> [B, R, F] (channel sum = the tf.reduce_sum of layers.py:103)."""
-        return _plugin.run(csr, None, rhs.contiguous(), "sum")
+        return _plugin.run(csr, flat_values, rhs.contiguous(), "sum")

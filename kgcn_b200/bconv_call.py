@@ -30,6 +30,6 @@ class BatchedConv:
         out = _plugin.run(csr, flat, rhs, "sum")                                  # [B, R, F]
         return list(out.unbind(0))
 
-    def call_packed(self, csr, rhs):
+    def call_packed(self, csr, rhs, flat_values=None):
         """rhs [B, C, K, F] -> [B, R, F]."""
-        return _plugin.run(csr, None, rhs.contiguous(), "sum")
+        return _plugin.run(csr, flat_values, rhs.contiguous(), "sum")

@@ -28,6 +28,6 @@ class BatchedSpMM:
         out = _plugin.run(csr, flat, rhs, "per_matrix")                           # [N, 1, R, F]
         return list(out[:, 0].unbind(0))
 
-    def call_packed(self, csr, rhs):
+    def call_packed(self, csr, rhs, flat_values=None):
         """rhs [B, C, K, F] -> [B, C, R, F]: the B*C independent products in one launch."""
-        return _plugin.run(csr, None, rhs.contiguous(), "per_matrix")
+        return _plugin.run(csr, flat_values, rhs.contiguous(), "per_matrix")

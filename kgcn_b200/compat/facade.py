@@ -350,3 +350,29 @@ class ModelRunner:
                 raise KeyError("%s: no value for variable(s) %s" % (self._restore_strict, ", ".join(fresh)))
         model, prediction, cost_opt, cost_sum, metrics = out[:5]
         return {"model": model, "prediction": prediction, "cost_opt": cost_opt, "cost_sum": cost_sum, "metrics": metrics}
+
+    def train_step(self, feed, learning_rate=None):
+        """``sess.run([train_step, cost_sum, metrics], feed_dict)`` of the fit loop (kgcn/core.py:267-269) with the
+        optimizer ``build_optimizer`` creates (core.py:121-127): ``tf.train.AdamOptimizer(learning_rate).minimize(cost_opt)``
+        with TensorFlow's defaults (beta1 0.9, beta2 0.999, epsilon 1e-8) and TensorFlow's update formula -- the library's
+        ``kgcn_adam_f32`` over each trainable variable with its own ``<var>/Adam`` / ``<var>/Adam_1`` slots.  Returns
+        the dict of :meth:`run` (values of the step BEFORE the update, like the fetches of one ``sess.run``)."""
+        from .._lib import check, lib, ptr
+        out = self.run(feed)
+        lr = float(self.config.get("learning_rate", 0.01) if learning_rate is None else learning_rate)
+        names = [k for k, p in self.store.params.items() if p.requires_grad]
+        params = [self.store.params[k] for k in names]
+        grads = torch.autograd.grad(out["cost_opt"], params, allow_unused=True)
+        self.adam_step = getattr(self, "adam_step", 0) + 1
+        slots = self.__dict__.setdefault("adam_slots", {})
+        stream = torch.cuda.current_stream().cuda_stream
+        with torch.no_grad():
+            for k, p, g in zip(names, params, grads):
+                if g is None:                       # TF: variables without a gradient are skipped by minimize()
+                    continue
+                if k not in slots:
+                    slots[k] = (torch.zeros_like(p), torch.zeros_like(p))
+                m, v = slots[k]
+                check(lib.kgcn_adam_f32(ptr(p), ptr(g.contiguous()), ptr(m), ptr(v), p.numel(), lr, 0.9, 0.999, 1e-8,
+                                        self.adam_step, 1.0, None, stream))
+        return out

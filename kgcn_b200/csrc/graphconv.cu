@@ -15,7 +15,7 @@ namespace kgcn {
 
 // implemented in graphconv_fused.cu
 bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x,
-                        const float* y);
+                        const float* y, const int32_t* rowptr, const int32_t* col, const float* val);
 int launch_graphconv_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_graphs,
                                int channels, int n_nodes, const float* x, int f_in, const float* w, const float* bias,
                                int f_out, int act, float* y, cudaStream_t st);
@@ -96,7 +96,7 @@ extern "C" int kgcn_graphconv_fwd_f32(const int32_t* rowptr, const int32_t* col,
     }
     if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && fused_v4_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y, rowptr, col, val, w, bias))
         return launch_graphconv_fused_v4(rowptr, col, val, n_graphs, channels, n_nodes, x, f_in, w, bias, f_out, act, y, st);
-    if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && fused_fwd_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y))
+    if (!(flags & KGCN_FLAG_REFERENCE_ORDER) && fused_fwd_eligible(n_graphs, channels, n_nodes, f_in, f_out, x, y, rowptr, col, val))
         return launch_graphconv_fused_fwd(rowptr, col, val, n_graphs, channels, n_nodes, x, f_in, w, bias, f_out, act,
                                           y, st);
 

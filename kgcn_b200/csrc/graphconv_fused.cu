@@ -652,10 +652,10 @@ bool plan(FusedParams& p, int64_t n_graphs, int channels, int n_nodes, int f_in,
 }  // namespace
 
 bool fused_fwd_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, const float* x,
-                        const float* y) {
+                        const float* y, const int32_t* rowptr, const int32_t* col, const float* val) {
     FusedParams p{};
     if (n_graphs <= 0 || !plan(p, n_graphs, channels, n_nodes, f_in, f_out)) return false;
-    return aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 3u) == 0 && n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
+    return aligned16(x) && aligned16(rowptr) && aligned16(col) && aligned16(val) && (reinterpret_cast<uintptr_t>(y) & 3u) == 0 && n_graphs * static_cast<int64_t>(n_nodes) < (1ll << 31);
 }
 
 static long long* g_dbg = nullptr;   // set through kgcn_debug_fused_times (tuning only)

@@ -62,6 +62,56 @@ def _init_tensor(initializer, shape, fan_in, fan_out, device):
     raise ValueError("unsupported initializer %r" % (initializer,))
 
 
+class PendingActivation(torch.Tensor):
+    """Output of ``GraphConv`` / ``GraphDense`` under the ``tensorflow``-named façade while the activation is still open.
+
+    The shipped models write ``layer = GraphConv(...)(x, adj=adjs); layer = tf.sigmoid(layer)`` (example_model/model.py:
+    41-46).  Run eagerly that would be one library launch plus a separate elementwise pass.  Under the façade the layer
+    returns this placeholder tensor instead (shape / dtype / device are real, no storage); ``torch.sigmoid`` /
+    ``relu`` / ``tanh`` applied to it launch the layer ONCE with that activation fused in the kernel's epilogue, and any
+    other use launches it with no activation and proceeds on the result.  Outside the façade layers return plain tensors."""
+
+    @staticmethod
+    def __new__(cls, shape, like, thunk):
+        t = torch.Tensor._make_wrapper_subclass(cls, tuple(int(v) for v in shape), dtype=like.dtype, device=like.device)
+        t._thunk, t._values = thunk, {}
+        return t
+
+    def materialize(self, act=None):
+        """The layer output with ``act`` applied: one fused launch per distinct activation asked for (normally exactly one)."""
+        if act not in self._values:
+            self._values[act] = _apply_act_torch(self._values[None], act) if None in self._values else self._thunk(act)
+        return self._values[act]
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in _PENDING_METADATA:
+            return super().__torch_function__(func, types, args, kwargs)
+        act = _PENDING_FUSABLE.get(func)
+        if act is not None and len(args) == 1 and not any(kwargs.values()) and isinstance(args[0], cls):
+            return args[0].materialize(act)
+        args, kwargs = torch.utils._pytree.tree_map(_materialized, (args, kwargs))
+        return func(*args, **kwargs)
+
+
+PendingActivation.__torch_dispatch__ = classmethod(   # below the Python API (not reached from the façade): same rule
+    lambda cls, func, types, args=(), kwargs=None: func(*torch.utils._pytree.tree_map(_materialized, args),
+                                                        **torch.utils._pytree.tree_map(_materialized, kwargs or {})))
+
+
+def _materialized(t):
+    return t.materialize() if isinstance(t, PendingActivation) else t
+
+
+_PENDING_FUSABLE = {torch.sigmoid: "sigmoid", torch.Tensor.sigmoid: "sigmoid", torch.nn.functional.sigmoid: "sigmoid",
+                    torch.relu: "relu", torch.Tensor.relu: "relu", torch.nn.functional.relu: "relu",
+                    torch.tanh: "tanh", torch.Tensor.tanh: "tanh", torch.nn.functional.tanh: "tanh"}
+_PENDING_METADATA = {torch.Tensor.shape.__get__, torch.Tensor.device.__get__, torch.Tensor.dtype.__get__,
+                     torch.Tensor.ndim.__get__, torch.Tensor.is_cuda.__get__, torch.Tensor.dim, torch.Tensor.size,
+                     torch.Tensor.numel}
+
+
 def _shape_of(t):
     """Static shape of one element of a list input: a tensor, a packed batch, or a SparseTensorValue-like triple
     (the block-diagonal adjacency of BatchGraphConv, kgcn/layers.py:388-390)."""
@@ -107,6 +157,7 @@ class Layer(torch.nn.Module):
         self.built = True
 
     def forward(self, inputs, *args, **kwargs):
+        inputs = [_materialized(t) for t in inputs] if isinstance(inputs, (list, tuple)) else _materialized(inputs)
         if not self.built:
             first = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
             self._build_device = first.device
@@ -155,7 +206,14 @@ class GraphConv(Layer):
     def call(self, inputs, adj=None):
         if adj is None:
             raise ValueError("GraphConv needs adj=")
-        csr = as_batched_csr(adj, inputs.device)
+        flat = None
+        if (enabled_bconv or enabled_bspmm or enabled_batched) and _values_require_grad(adj):
+            # adjacency attributions (visualization.py): the registered d-values gradient of the plugin ops needs the
+            # value tensors on the tape (kgcn/bspmm_call.py:49-54), so this batch is packed with its permutation
+            from . import _plugin
+            csr, flat, _ = _plugin.pack_sparse_list(adj, inputs.device, nested=True)
+        else:
+            csr = as_batched_csr(adj, inputs.device)
         act = ops.act_id(self.activation)
         B, N, _ = inputs.shape
         if enabled_bconv or enabled_bspmm or enabled_batched:
@@ -164,19 +222,34 @@ class GraphConv(Layer):
             fw = torch.stack([ops.GraphDenseFunction.apply(inputs, self.w[c], self.bias[c].reshape(-1), 0, None)
                               for c in range(self.adj_channel_num)], dim=1)          # [B, C, N, F_out]
             if enabled_bconv:
-                out = self.bconv_obj.call_packed(csr, fw)
+                out = self.bconv_obj.call_packed(csr, fw, flat)
             elif enabled_bspmm:
-                out = self.bspmm_obj.call_packed(csr, fw).sum(dim=1) if self.adj_channel_num > 1 else \
-                    self.bspmm_obj.call_packed(csr, fw)[:, 0]
+                out = self.bspmm_obj.call_packed(csr, fw, flat).sum(dim=1) if self.adj_channel_num > 1 else \
+                    self.bspmm_obj.call_packed(csr, fw, flat)[:, 0]
             else:
-                out = self.bspmdt_obj.call_packed(csr, fw)
+                out = self.bspmdt_obj.call_packed(csr, fw, flat)
             return _apply_act_torch(out, self.activation)
         w, bias = self._stacked()
         flags = _lib.FLAG_REFERENCE_ORDER if self.reference_order else _lib.FLAG_DEFAULT
+        if self.activation is None and _active_store() is not None:   # façade: the model applies tf.sigmoid next
+            return PendingActivation((B, N, self.output_dim), inputs,
+                                     lambda a: ops.GraphConvFunction.apply(inputs, w, bias, csr, ops.act_id(a), flags))
         return ops.GraphConvFunction.apply(inputs, w, bias, csr, act, flags)
 
     def compute_output_shape(self, input_shape):
         return input_shape[0], input_shape[1], self.output_dim
+
+
+def _values_require_grad(adj):
+    """True when ``adj`` is the reference's list[B][C] of triples and any ``values`` entry is a tensor on the autograd tape."""
+    if isinstance(adj, BatchedCSR):
+        return False
+    for row in adj:
+        for sp in (row if isinstance(row, (list, tuple)) and not hasattr(row, "indices") else [row]):
+            v = sp.values if hasattr(sp, "values") and hasattr(sp, "dense_shape") else sp[1]
+            if torch.is_tensor(v) and v.requires_grad:
+                return True
+    return False
 
 
 def _apply_act_torch(x, activation):
@@ -225,6 +298,11 @@ class GraphDense(Layer):
             x = x.unsqueeze(0)
         if enabled_node_nums is not None and not torch.is_tensor(enabled_node_nums):
             enabled_node_nums = torch.as_tensor(enabled_node_nums, dtype=torch.int32, device=x.device)
+        if self.activation is None and enabled_node_nums is None and shape is None and inputs.dim() == 3 \
+                and _active_store() is not None:                          # façade: GraphDense(50)(h); tf.sigmoid(...)
+            kernel, bias = self.kernel, self.bias
+            return PendingActivation(tuple(x.shape[:2]) + (self.units,), x,
+                                     lambda a: ops.GraphDenseFunction.apply(x, kernel, bias, ops.act_id(a), None))
         out = ops.GraphDenseFunction.apply(x, self.kernel, self.bias, ops.act_id(fused), enabled_node_nums)
         if callable(self.activation):
             out = self.activation(out)

@@ -37,6 +37,9 @@ def integrated_gradients(score_fn, features, adj_values=None, divide_number=10, 
             fed[name] = v.requires_grad_(True)
         score = score_fn(fed["features"], fed.get("adjs"))
         grads = torch.autograd.grad(score, list(fed.values()), allow_unused=True)
+        if "adjs" in fed and grads[list(fed).index("adjs")] is None:
+            raise ValueError("score_fn did not use adj_values on the autograd tape: hand them to BatchedSpMM / BatchedConv or a "
+                             "plugin-mode GraphConv (load_bspmm) as the `values` of the sparse triples")
         for (name, t), g in zip(inputs.items(), grads):
             if g is None:
                 continue

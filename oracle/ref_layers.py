@@ -254,6 +254,32 @@ def bconv(sp_matrices, dense_matrices, adjoint_a=False, adjoint_b=False):
     return out
 
 
+def bconv_grad(sp_matrices, dense_matrices, grads, adjoint_a=False, adjoint_b=False):
+    """bconv_call.py:28-70 (_bconv_grad).  ``sp_matrices`` / ``dense_matrices`` are list[B][C], ``grads`` list[B] (one
+    per output).  The incoming gradient of output b is replicated for its C channels (:46, batch-major / channel-minor
+    like the inputs), the dense gradients are ONE Bspmm over all B*C matrices with ``adjoint_a = not adj_a`` (:57), and
+    the value gradients gather rows of dY and of the dense operand per stored entry (:62-67).
+    Returns (a_values_grads list[B*C], b_grads list[B*C]) in the flat order of the op's inputs."""
+    C = len(sp_matrices[0])
+    flat_sp = [a for row in sp_matrices for a in row]
+    flat_d = [d for row in dense_matrices for d in row]
+    addn_grad = [g for g in grads for _ in range(C)]                           # :46
+    b_grads = bspmm(flat_sp, addn_grad, adjoint_a=not adjoint_a, adjoint_b=adjoint_b)   # :57
+    if adjoint_b:
+        b_grads = [g.T for g in b_grads]                                       # :59-60
+    a_values_grads = []
+    for t, (a, b) in enumerate(zip(flat_sp, flat_d)):
+        idx = np.asarray(a[0]).reshape(-1, 2)
+        rows, cols = idx[:, 0], idx[:, 1]
+        g = np.asarray(addn_grad[t], F32)
+        bb = np.asarray(b, F32)
+        bb = bb.T if adjoint_b else bb
+        pa = g[rows if not adjoint_a else cols]                                # :65
+        pb = bb[cols if not adjoint_a else rows]                               # :66
+        a_values_grads.append((pa * pb).sum(axis=1, dtype=F32))                # :67
+    return a_values_grads, b_grads
+
+
 def bspmdt(sp_matrices, dense, adjoint_a=False, adjoint_b=False):
     """batched_call.py:21-26: N COO matrices times one stacked dense [N*rows, cols]."""
     n = len(sp_matrices)

@@ -17,6 +17,10 @@ image).  Each primitive cites the TF op it stands for:
   keras Layer (add_weight / build / __call__), Dense, BatchNormalization (learning phase 0: moving statistics,
   exactly what the reference trainer runs; ``tf.layers.batch_normalization(training=True)``:
   batch statistics)
+
+``install_model_level`` adds the symbols the reference's MODEL files touch on top of the layers (example_model/model.py:
+placeholders, tf.sigmoid, softmax, softmax cross-entropy, reduce_mean, cast / equal / argmax, contrib.keras Dense and
+Dropout at learning phase 0), so ``oracle/make_c1_golden.py`` can execute a model file unchanged.
 """
 import collections
 import sys
@@ -252,4 +256,69 @@ def install():
             "tensorflow.keras.layers": klayers, "tensorflow.python": python, "tensorflow.python.keras": pykeras,
             "tensorflow.python.keras.layers": klayers}
     sys.modules.update(mods)
+    return tf
+
+
+class _Placeholder:
+    """tf.placeholder / tf.sparse_placeholder: an identity the reference's construct_feed keys its feed_dict with."""
+
+    def __init__(self, dtype, shape=None, name=None, sparse=False):
+        self.dtype, self.shape, self.name, self.sparse = dtype, shape, name, sparse
+
+    def __repr__(self):
+        return "<placeholder %s>" % self.name
+
+
+class Dropout(Layer):
+    """keras Dropout called without ``training=`` under the reference trainer: learning phase 0 -> identity
+    (SURVEY.md App. A.10)."""
+
+    def __init__(self, rate=0.0, **kwargs):
+        super().__init__(**kwargs)
+        self.rate = rate
+
+    def call(self, inputs, **kwargs):
+        return inputs
+
+
+def _softmax(x, axis=-1, name=None):
+    x = np.asarray(x, F32)
+    e = np.exp(x - x.max(axis=axis, keepdims=True), dtype=F32)
+    return T(e / e.sum(axis=axis, keepdims=True, dtype=F32))
+
+
+def _softmax_xent(labels=None, logits=None, **kwargs):
+    """tf.nn.softmax_cross_entropy_with_logits_v2: -sum(labels * log_softmax(logits)) over the last axis."""
+    z = np.asarray(logits, F32)
+    z = z - z.max(axis=-1, keepdims=True)
+    logp = z - np.log(np.exp(z, dtype=F32).sum(axis=-1, keepdims=True, dtype=F32), dtype=F32)
+    return T(-(np.asarray(labels, F32) * logp).sum(axis=-1, dtype=F32))
+
+
+def install_model_level():
+    """install() plus the model-file symbols.  Returns the stand-in module."""
+    tf = install()
+    tf.bool = np.bool_
+    tf.placeholder = lambda dtype, shape=None, name=None: _Placeholder(dtype, shape, name)
+    tf.sparse_placeholder = lambda dtype, shape=None, name=None: _Placeholder(dtype, shape, name, sparse=True)
+    tf.disable_v2_behavior = lambda: None
+    tf.sigmoid = lambda x, name=None: T(_ACT["sigmoid"](np.asarray(x, F32)))
+    tf.tanh = lambda x, name=None: T(_ACT["tanh"](np.asarray(x, F32)))
+    tf.reduce_mean = lambda x, axis=None, keepdims=False: T(np.mean(np.asarray(x, F32), axis=axis, keepdims=keepdims, dtype=F32))
+    tf.cast = lambda x, dtype: np.asarray(x).astype(dtype)
+    tf.equal = lambda a, b: np.asarray(a) == np.asarray(b)
+    tf.argmax = lambda x, axis=None, **k: np.argmax(np.asarray(x), axis=axis)
+    tf.nn.softmax = _softmax
+    tf.nn.sigmoid = tf.sigmoid
+    tf.nn.tanh = tf.tanh
+    tf.nn.softmax_cross_entropy_with_logits_v2 = _softmax_xent
+    tf.nn.softmax_cross_entropy_with_logits = _softmax_xent
+    klayers = sys.modules["tensorflow.python.keras.layers"]
+    klayers.Dropout = Dropout
+    contrib = types.ModuleType("tensorflow.contrib")
+    ckeras = types.ModuleType("tensorflow.contrib.keras")
+    ckeras.layers = klayers
+    contrib.keras = ckeras
+    tf.contrib = contrib
+    sys.modules.update({"tensorflow.contrib": contrib, "tensorflow.contrib.keras": ckeras})
     return tf

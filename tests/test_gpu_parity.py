@@ -417,6 +417,63 @@ def test_plugin_ops_forward_and_gradients(K):
     close(st.grad, np.concatenate(R.bspmm(first, dy[:B], adjoint_a=True), 0), 1e-4)
 
 
+@pytest.mark.parametrize("adjoint_a", [False, True])
+@pytest.mark.parametrize("B,C,N,F", [(4, 2, 8, 16), (3, 3, 50, 50), (5, 1, 32, 64)])
+def test_bconv_registered_gradient(K, B, C, N, F, adjoint_a):
+    """``_bconv_grad`` (kgcn/bconv_call.py:28-70): dY replicated over the channels, dense gradients through
+    ``adjoint_a = not adj_a``, value gradients per stored entry -- through BatchedConv().call and autograd, i.e. the
+    "sum"-layout backward of ops.BspmmFunction."""
+    rng = np.random.default_rng(100 * B + C)
+    adjs, _ = random_batch(rng, B, N, C, F)
+    dense = [[rng.standard_normal((N, F)).astype(np.float32) for _ in range(C)] for _ in range(B)]
+    STV = K["feed"].SparseTensorValue
+    vals = [[dev(a[1]).requires_grad_(True) for a in row] for row in adjs]
+    dts = [[dev(d).requires_grad_(True) for d in row] for row in dense]
+    sp = [[STV(a[0], v, a[2]) for a, v in zip(row, vrow)] for row, vrow in zip(adjs, vals)]
+    outs = K["bconv"].BatchedConv().call(sp, dts, adjoint_a=adjoint_a)
+    for o, w in zip(outs, R.bconv(adjs, dense, adjoint_a=adjoint_a)):
+        close(o, w)
+    dy = [rng.standard_normal((N, F)).astype(np.float32) for _ in range(B)]
+    torch.autograd.backward(outs, [dev(g) for g in dy])
+    want_dv, want_db = R.bconv_grad(adjs, dense, dy, adjoint_a=adjoint_a)
+    t = 0
+    for b in range(B):
+        for c in range(C):
+            close(dts[b][c].grad, want_db[t], 1e-4)
+            if adjs[b][c][1].shape[0]:
+                close(vals[b][c].grad, want_dv[t], 1e-4)
+            t += 1
+
+
+@pytest.mark.parametrize("B,N,fi,fo", [(6, 10, 3, 16), (4, 50, 75, 64), (1, 200, 32, 32)])
+def test_batch_graph_conv_backward(K, B, N, fi, fo):
+    """BatchGraphConv (kgcn/layers.py:363-398), ``relu(A (x W + b))`` on one block-diagonal matrix: gradients of x, W and
+    bias against float64 torch-CPU autograd of the oracle's formula (oracle/ref_layers.batch_graph_conv)."""
+    rng = np.random.default_rng(fi + fo)
+    adjs, x = random_batch(rng, B, N, 1, fi)
+    idx = np.concatenate([adjs[b][0][0] + b * N for b in range(B)])
+    val = np.concatenate([adjs[b][0][1] for b in range(B)])
+    big = (idx, val, [B * N, B * N])
+    w, bias = R.glorot_uniform(rng, fi, fo), rng.uniform(-0.5, 0.5, fo).astype(np.float32)
+    layer = K["layers"].BatchGraphConv(fo)
+    xt = dev(x.reshape(B * N, fi)).requires_grad_(True)
+    layer([xt, big])
+    with torch.no_grad():
+        layer.w.copy_(dev(w)); layer.bias.copy_(dev(bias).reshape(layer.bias.shape))
+    y = layer([xt, big])
+    close(y, R.batch_graph_conv(x.reshape(B * N, fi), big, w, bias))
+    dy = rng.standard_normal((B * N, fo)).astype(np.float32)
+    y.backward(dev(dy))
+    A = torch.zeros(B * N, B * N, dtype=torch.float64)
+    A.index_put_((torch.as_tensor(idx[:, 0]).long(), torch.as_tensor(idx[:, 1]).long()), torch.as_tensor(val, dtype=torch.float64), accumulate=True)
+    x64 = torch.tensor(x.reshape(B * N, fi), dtype=torch.float64, requires_grad=True)
+    w64, b64 = torch.tensor(w, dtype=torch.float64, requires_grad=True), torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+    torch.relu(A @ (x64 @ w64 + b64)).backward(torch.tensor(dy, dtype=torch.float64))
+    close(xt.grad, x64.grad.numpy(), 1e-4)
+    close(layer.w.grad, w64.grad.numpy(), 1e-4)
+    close(layer.bias.grad.reshape(-1), b64.grad.numpy(), 1e-4)
+
+
 @pytest.mark.parametrize("mode", ["bspmm", "bconv", "batched"])
 def test_layer_plugin_branches_equal_default(K, mode):
     """--bspmm / --bconv / --batched (layers.py:68-104) compute the same function as the default branch."""

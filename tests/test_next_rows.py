@@ -295,6 +295,51 @@ def test_integrated_gradients_completeness():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["bspmm", "bconv", "batched"])
+def test_plugin_mode_graphconv_returns_adjacency_value_gradients(mode):
+    """A plugin-mode GraphConv (kgcn/layers.py:68-104) fed triples whose ``values`` are tensors on the tape: the registered
+    d-values gradient of the plugin op (kgcn/bspmm_call.py:49-54, bconv_call.py:62-67) reaches them -- what the adjacency
+    attribution of kgcn/visualization.py needs.  Checked against float64 torch-CPU autograd on dense adjacencies."""
+    import types
+    from kgcn_b200 import layers as L
+    rng = np.random.default_rng(5)
+    B, N, C, F, H = 4, 7, 2, 5, 6
+    adjs = rand_unique_adjs(rng, B, N, C, density=0.4, full_rows=False)
+    x = rng.standard_normal((B, N, F)).astype(np.float32)
+    L.load_bspmm(types.SimpleNamespace(bspmm=mode == "bspmm", bconv=mode == "bconv", batched=mode == "batched"))
+    try:
+        conv = L.GraphConv(H, C)
+        vals = [[dev(a[1]).requires_grad_(True) for a in row] for row in adjs]
+        sp = [[(a[0], v, a[2]) for a, v in zip(row, vrow)] for row, vrow in zip(adjs, vals)]
+        xt = dev(x).requires_grad_(True)
+        y = conv(xt, adj=sp)
+        dy = rng.standard_normal((B, N, H)).astype(np.float32)
+        y.backward(dev(dy))
+    finally:
+        L.load_bspmm(types.SimpleNamespace(bspmm=False, bconv=False, batched=False))
+    w64 = [torch.tensor(conv.w[c].detach().cpu().numpy(), dtype=torch.float64) for c in range(C)]
+    b64 = [torch.tensor(conv.bias[c].detach().cpu().numpy(), dtype=torch.float64) for c in range(C)]
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    v64 = [[torch.tensor(a[1], dtype=torch.float64, requires_grad=True) for a in row] for row in adjs]
+    out = []
+    for b in range(B):
+        acc = 0
+        for c in range(C):
+            idx = np.asarray(adjs[b][c][0]).reshape(-1, 2)
+            A = torch.zeros(N, N, dtype=torch.float64).index_put((torch.as_tensor(idx[:, 0]).long(), torch.as_tensor(idx[:, 1]).long()),
+                                                                 v64[b][c], accumulate=True)
+            acc = acc + A @ (x64[b] @ w64[c] + b64[c])
+        out.append(acc)
+    torch.stack(out).backward(torch.tensor(dy, dtype=torch.float64))
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), x64.grad.numpy(), rtol=1e-4, atol=1e-5)
+    for b in range(B):
+        for c in range(C):
+            if len(adjs[b][c][1]):
+                assert vals[b][c].grad is not None, (mode, b, c)
+                np.testing.assert_allclose(vals[b][c].grad.cpu().numpy(), v64[b][c].grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("B,N,C,F", [(5, 3, 1, 4), (7, 10, 2, 3), (33, 32, 1, 64), (9, 50, 3, 50), (6, 64, 2, 128), (2, 300, 1, 48),
                                      (40, 32, 2, 64)])
 def test_gin_aggregate_fused_epsilon_forward_backward(B, N, C, F):
