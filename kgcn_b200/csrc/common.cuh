@@ -161,6 +161,7 @@ struct V4ChainJob {
 // channels per job a forward layer needs in a chain: `channels` (one job), fewer (K = C * f_in beyond tensor memory: channel
 // groups, the later ones accumulate), 0 = no single-CTA plan
 int fused_v4_chain_group(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int head_labels);
+bool soft_jobs_enabled();   // graphconv_fused_dw.cu: KGCN_SOFT_JOBS (A-B knob, default on)
 // graphconv_fused_v5.cu: the transposed-product kernel for wide layers (weights resident in tensor memory), same job struct
 bool fused_v5_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);

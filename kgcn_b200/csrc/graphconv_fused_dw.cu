@@ -51,6 +51,7 @@ struct DwParams {
     uint32_t off_ones, off_op, op_bytes, op_g, lbo, off_stage, stage_bytes, st_du, st_rp, st_col, st_val, smem_total;
     uint32_t tmem_cols;
     uint32_t tm_off;         // first tensor-memory column of this job's accumulators (dW at tm_off, dbias at tm_off + Ng)
+    int fresh;               // 0: same plan as the previous job of the launch -- no job boundary at all (soft boundary)
 };
 
 struct Ring {
@@ -98,6 +99,10 @@ __device__ __forceinline__ void store_split(uint32_t line_hi, uint32_t line_lo, 
 // Several layers' weight gradients in ONE launch ("jobs"): after the dx chain every layer's dU exists, so the CTA walks
 // its graph range once per layer, each job with its own accumulators in tensor memory (columns tm_off .. tm_off + 2 Ng).
 // Job boundary: the MMA warp waits for its last MMAs, then one CTA barrier -- shared-memory layouts may differ per job.
+// Consecutive jobs with the SAME plan (the equal-width hidden layers of a network) have no boundary: the jobs are
+// independent (each reads its own x / dU and owns its accumulators), the padding and the ones operand stay valid, and
+// every ring continues with its per-slot phase bits -- the producer runs ahead into the next job while the last MMAs
+// of the previous one are still in flight, so the chain pays fill and drain once.
 constexpr int kDwMaxJobs = 4;
 struct DwBatch {
     int n_jobs;
@@ -150,8 +155,8 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
         const int last_ng = n_graphs_cta - (n_tiles - 1) * p.G;
         const uint32_t tm = tmem + p.tm_off;
 
-        if (jb > 0) bar_cta_roles();   // the previous job has finished with shared memory (its MMAs have completed)
-        if (warp != kWarpTma) {
+        if (jb > 0 && p.fresh) bar_cta_roles();   // the previous job has finished with shared memory (its MMAs have completed)
+        if (warp != kWarpTma && p.fresh) {
             // Only what no worker ever writes has to be zeroed: the ones operand (M = 64: two 32-row chunks; column 0 of every K
             // row is 1.0: element m = 0 sits in granule 0 -> position (row & 3) << 5 of the row's line) and the M-padding chunks
             // of the X operand (f_in < 64 stacked / f_in < 128 split).  Chunks that hold data are fully rewritten for every
@@ -248,10 +253,12 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                     if (++ob == p.opbufs) ob = 0;
                 }
             }
-            if (elect_one()) umma_commit(&bar_done);
-            __syncwarp();
-            mbar_wait(&bar_done, ph_done & 1u);   // all MMAs of this job have completed (operands + accumulators final)
-            ph_done ^= 1u;
+            if (jb + 1 == n_jobs || b.job[jb + 1].fresh) {
+                if (elect_one()) umma_commit(&bar_done);
+                __syncwarp();
+                mbar_wait(&bar_done, ph_done & 1u);   // all MMAs so far have completed (operands + accumulators final)
+                ph_done ^= 1u;
+            }
         } else {
             // =============================== worker warps ===============================
             const uint32_t s7 = static_cast<uint32_t>(lane) & 7u;
@@ -520,6 +527,14 @@ bool fused_dw_enabled() {
     return on;
 }
 
+bool soft_jobs_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KGCN_SOFT_JOBS");   // A-B knob: 0 restores the hard (barrier) boundary between all jobs of a chain
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
+
 size_t fused_dw_partial_bytes(int f_in, int n_total) {
     return static_cast<size_t>(kNumSMs) * (static_cast<size_t>(f_in) + 1) * n_total * sizeof(float);
 }
@@ -560,6 +575,7 @@ int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_grap
         p.rowptr = j.rowptr_t; p.col = j.col_t; p.val = j.val_t; p.x = j.x; p.du = j.du;
         p.partial = j.partial;
         p.tm_off = cols;
+        p.fresh = (k == 0 || !soft_jobs_enabled() || j.f_in != jobs[k - 1].f_in || j.f_out != jobs[k - 1].f_out) ? 1 : 0;
         cols += 2u * static_cast<uint32_t>(p.Ng);
         smem = std::max(smem, p.smem_total);
     }

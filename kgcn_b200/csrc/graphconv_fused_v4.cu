@@ -80,6 +80,11 @@ struct V4Params {
     uint32_t off_whi, off_wlo, off_ystage, off_stage, stage_bytes, st_rp, st_col, st_val, smem_total;
     uint32_t w_atom;      // bytes between K atoms of the B operand
     uint32_t tm_z;        // first TMEM column of Z buffer 0 (accumulators at columns 0 and Np)
+    int soft;             // chained job with the same plan as its predecessor: no CTA barrier, tile-wise hand-over
+    int soft_next;        // the next job of the chain is soft: publish every finished tile (fence + counter)
+    int wbufs, wsel;      // B operand buffers (chain: 2 = the next soft job's [W ; bias] is staged during this job), buffer of this job
+    int prestaged;        // this job's B operand was staged by the epilogue warps during the previous job
+    uint32_t w_pair;      // bytes of one (hi, lo) B operand buffer
     long long* dbg;
 };
 
@@ -777,12 +782,19 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
 // on a CTA as soon as THAT CTA has finished job j: no grid-wide dependency, no launch / drain / fill per layer.
 //   forward chain   x -> GraphConv_0 -> .. -> GraphConv_{L-1}                      (EPI 0: activation epilogue)
 //   dx chain        dU_{L-1} -> dU_{L-2} -> ..  each job (A^T, dU_l, W_l^T) x act'(x_l)   (EPI 1)
-// Job boundary = one CTA-wide barrier: the epilogue warps have fenced their global stores towards the async proxy (the
+// HARD job boundary = one CTA-wide barrier: the epilogue warps have fenced their global stores towards the async proxy (the
 // next job's TMA reads them), all MMAs that read the B operand have completed, every stage has been consumed.  The
 // mbarriers are NOT re-initialised: every role tracks one phase bit per barrier slot, so ring sizes may differ per job.
+// SOFT job boundary (consecutive jobs with the same plan, i.e. identical shared / tensor memory layout and tiling): no
+// barrier at all.  Tile t of job j + 1 depends only on tile t of job j (same graphs), so the epilogue warps publish every
+// finished tile -- stores, fence.proxy.async, release-increment of a shared counter -- and the TMA producer of job j + 1
+// acquires the counter before it loads tile t.  All rings simply continue; the aggregation of (j + 1, 0) overlaps the
+// epilogue of (j, last).  With two B operand buffers the epilogue warps stage [W ; bias] of job j + 1 into the free one at
+// the start of job j (while its first accumulator is still being produced), so the MMAs of job j + 1 wait for nothing but Z.
 constexpr int kV4MaxJobs = 6;
 struct V4Batch {
     int n_jobs;
+    int tile_fence_gpu;   // A-B knob (KGCN_CHAIN_TILE_FENCE=1): membar.gl before the proxy fence of a published tile
     long long* dbg;   // tuning aid (kgcn_debug_v4_chain_times): [CTA][64] clock64 stamps, see tools/chain_timeline.py
     V4Params job[kV4MaxJobs];
 };
@@ -791,6 +803,14 @@ struct V4Batch {
 // 9 TMA first issue, 10 B operand staged, 11 epi job end (after fences)
 #define V4_STAMP(ev) do { if (b.dbg != nullptr && lane == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 128 + j * 16 + (ev)] = clock64(); } while (0)
 
+__device__ __forceinline__ uint32_t ld_acquire_cta_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_cta_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -807,7 +827,7 @@ __device__ __forceinline__ TileRange cta_range_of(const V4Params& p) {
 __device__ __forceinline__ void stage_b_operand(const V4Params& p, uint32_t base, int t, int n_thr) {
     const int C = p.C, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp;
     if ((f_out & 15) != 0) {   // B rows n >= f_out (up to Np) are read by the MMAs and not written below: exact zeros
-        const uint32_t n16 = (p.off_ystage - p.off_whi) >> 4;
+        const uint32_t n16 = p.w_pair >> 4;
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t i = t; i < n16; i += n_thr) sts_f<4>(base + p.off_whi + (i << 4), z4);
         asm volatile("bar.sync 3, %0;" ::"n"(256) : "memory");   // the stagers (the epilogue warps)
@@ -874,6 +894,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
     __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bar_wfull;   // B operand of a prestaged (soft) job written by all epilogue warps
+    __shared__ uint32_t tiles_done;   // epilogue-warp arrivals: 8 per finished tile, over all jobs (soft job boundaries)
 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
@@ -882,6 +904,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     if (b.dbg != nullptr && tid == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 128 + 126] = clock64();
 
     if (tid == 0) {
+        tiles_done = 0;
+        mbar_init(&bar_wfull, kEpiWarps);
         for (int i = 0; i < kV4MaxStages; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], kAggWarps);
@@ -905,9 +929,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         // =============================== TMA producer ===============================
         reg_dec<kRegsMisc>();
         uint32_t ph_empty = 0;   // one phase bit per barrier slot (ring sizes may change between jobs)
+        uint32_t tiles_before = 0;   // tiles of all earlier jobs
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0) bar_all_roles();   // the previous job's outputs are complete and visible to the async proxy
+            if (j > 0 && !p.soft) bar_all_roles();   // the previous job's outputs are complete and visible to the async proxy
             if (lane == 0) {
                 const int C_csr = p.C_csr, N = p.N, f_in = p.f_in, S = p.n_stages;
                 const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
@@ -918,6 +943,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 for (int it = 0; it < n_tiles; ++it) {
                     mbar_wait_relaxed(&bar_empty[s], ((ph_empty >> s) & 1u) ^ 1u);
                     ph_empty ^= 1u << s;
+                    if (p.soft) {   // tile `it` of the previous job (same graphs) has been stored and fenced by all epilogue warps
+                        const uint32_t need = static_cast<uint32_t>(kEpiWarps) * (tiles_before - static_cast<uint32_t>(n_tiles) + static_cast<uint32_t>(it) + 1u);
+                        while (ld_acquire_cta_u32(&tiles_done) < need) __nanosleep(20);
+                    }
                     const int64_t g0 = tr.g_begin + static_cast<int64_t>(it) * p.G;
                     const int ng = (it == n_tiles - 1) ? last_ng : p.G;
                     const int64_t r0 = g0 * C_csr * N;
@@ -942,6 +971,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     }
                     if (++s == S) s = 0;
                 }
+                tiles_before += static_cast<uint32_t>(n_tiles);
             }
             __syncwarp();
         }
@@ -957,13 +987,13 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0) bar_all_roles();
+            if (j > 0 && !p.soft) bar_all_roles();
             if (warp == 0) V4_STAMP(0);
             // (the B operand is staged by the epilogue warps, which have nothing else to do until the first accumulator is
             // ready; the aggregation starts as soon as the first tile has landed)
             const int N = p.N, f_in = p.f_in, K = p.K, Kp = p.Kp, S = p.n_stages;
             const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
-            if (warp < 4) {   // the unused row-sum columns K + C .. K + 7 of every Z buffer stay zero for the whole job
+            if (warp < 4 && !p.soft) {   // the unused row-sum columns K + C .. K + 7 of every Z buffer stay zero for the whole job (and its soft successors)
                 const uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (int zb = 0; zb < p.zbufs; ++zb) {
                     const uint32_t zc = tmem + (static_cast<uint32_t>(warp * 32) << 16) + p.tm_z + static_cast<uint32_t>(zb * 2 * Kp);
@@ -1078,19 +1108,25 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         }
     } else if (warp >= kWarpMma) {
         reg_dec<kRegsMisc>();
-        uint32_t ph_zfull = 0, ph_tempty = 0;
+        uint32_t ph_zfull = 0, ph_tempty = 0, ph_wfull = 0;
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0) bar_all_roles();
+            if (j > 0 && !p.soft) bar_all_roles();
             if (warp != kWarpMma) continue;
             // =============================== MMA issuer ===============================
-            asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");   // B operand staged (epilogue warps)
+            if (!p.prestaged) {
+                asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");   // B operand staged (epilogue warps)
+            } else {   // staged into the other buffer while the previous job ran
+                mbar_wait(&bar_wfull, ph_wfull & 1u);
+                ph_wfull ^= 1u;
+            }
             tc_fence_after_sync();
             const int Kp = p.Kp, Np = p.Np;
             const TileRange tr = cta_range_of(p);
             const int n_tiles = tr.n_tiles;
             const uint32_t idesc = umma_idesc_tf32(128, Np);
-            const uint64_t dwhi = umma_desc_sw128(base + p.off_whi), dwlo = umma_desc_sw128(base + p.off_wlo);
+            const uint32_t wb = base + static_cast<uint32_t>(p.wsel) * p.w_pair;
+            const uint64_t dwhi = umma_desc_sw128(wb + p.off_whi), dwlo = umma_desc_sw128(wb + p.off_wlo);
             const uint32_t w_atom16 = p.w_atom >> 4;
             const int ks = Kp >> 3;
             int zi = 0, ai = 0;
@@ -1134,10 +1170,20 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         const int te = tid - kWarpEpi0 * 32;   // 0 .. 255 inside the epilogue group
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0) bar_all_roles();
-            stage_b_operand(p, base, te, 256);
-            asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");
+            if (j > 0 && !p.soft) bar_all_roles();
+            if (!p.prestaged) {
+                stage_b_operand(p, base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256);
+                asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");
+            }
             if (e == 0) V4_STAMP(10);
+            // the next soft job's B operand goes into the other buffer now, while the first accumulator of this job is
+            // still being produced (every MMA that read that buffer had completed when the epilogue warps left the job
+            // before this one)
+            if (j + 1 < n_jobs && b.job[j + 1].prestaged) {
+                stage_b_operand(b.job[j + 1], base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, te, 256);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_wfull);
+            }
             const int N = p.N, f_out = p.f_out, Np = p.Np;
             const TileRange tr = cta_range_of(p);
             const int n_tiles = tr.n_tiles;
@@ -1460,6 +1506,12 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                         __syncwarp();
                     }
                 }
+                if (p.soft_next) {   // publish the tile to the next job's TMA loads (async proxy), then count it
+                    if (b.tile_fence_gpu) __threadfence();
+                    fence_proxy_async_all();
+                    __syncwarp();
+                }
+                if (lane == 0) red_release_cta_add_u32(&tiles_done, 1u);
                 if (e == 0 && it == 0) V4_STAMP(7);
                 if (e == 0 && it == n_tiles - 1) V4_STAMP(8);
                 if (++ai == p.abufs) ai = 0;
@@ -1476,8 +1528,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 }
             }
             // this CTA's outputs of the job: visible to the next job's TMA loads (async proxy) after the role barrier
-            __threadfence();
-            fence_proxy_async_all();
+            if (j + 1 < n_jobs && !p.soft_next) {
+                __threadfence();
+                fence_proxy_async_all();
+            }
             if (e == 0) V4_STAMP(11);
         }
     }
@@ -1499,7 +1553,7 @@ uint32_t head_smem_bytes(int G, int f_out, int n_labels) {
 }
 
 bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G, int C_csr,
-                 int head_labels = 0) {
+                 int head_labels = 0, int wbufs = 1) {
     if (f_out_total % n_split != 0) return false;
     const int f_out = f_out_total / n_split;
     if (f_out % 4 != 0 || f_out > 256 || (n_split > 1 && f_out % 32 != 0)) return false;
@@ -1528,6 +1582,9 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     uint32_t off = 0;
     p.off_whi = off; off += n_watoms * p.w_atom;
     p.off_wlo = off; off += n_watoms * p.w_atom;
+    p.w_pair = off;
+    p.wbufs = wbufs; p.wsel = 0; p.prestaged = 0; p.soft = 0; p.soft_next = 0;
+    off += static_cast<uint32_t>(wbufs - 1) * p.w_pair;
     p.off_ystage = off; off += kEpiWarps * 4096u;
     p.off_head = off;
     if (head_labels > 0) {
@@ -1552,11 +1609,11 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
 // Preference: whole output width in one CTA and full 128-row tiles; wide layers (F = 128: [W ; bias] hi / lo alone is
 // 160 KB) fall back to column slices -- each slice aggregates the tile again (the second reader hits L2) -- and to
 // fewer graphs per tile until at least two TMA stages fit.
-bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int C_csr, int head_labels = 0) {
+bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int C_csr, int head_labels = 0, int wbufs = 1) {
     if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || C_csr > 8 || C < 1 || C > C_csr) return false;
     for (int n_split = 1; n_split <= 4; n_split *= 2)
         for (int G = std::max(1, 128 / N); G >= 1; G = (G > 1 ? G / 2 : 0))
-            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G, C_csr, head_labels)) return true;
+            if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G, C_csr, head_labels, wbufs)) return true;
     return false;
 }
 
@@ -1590,6 +1647,14 @@ bool fused_v4_eligible(int64_t n_graphs, int channels, int n_nodes, int f_in, in
 bool fused_v4_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out) {
     V4Params p{};
     return fused_v4_enabled() && plan_v4_group(p, n_graphs, channels, n_nodes, f_in, f_out) > 0;
+}
+
+static bool wbufs2_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KGCN_CHAIN_WBUFS");   // A-B knob: 1 keeps a single B operand buffer in chained launches
+        return e == nullptr || atoi(e) != 1;
+    }();
+    return on;
 }
 
 static long long* g_dbg_v4 = nullptr;
@@ -1651,14 +1716,42 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
     b.n_jobs = n_jobs;
     b.dbg = g_dbg_chain;
     uint32_t smem = 0;
+    {
+        const char* e = getenv("KGCN_CHAIN_TILE_FENCE");
+        b.tile_fence_gpu = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    }
+    int head_k = -1;
+    for (int k = 0; k < n_jobs; ++k)
+        if (jobs[k].head != nullptr) head_k = k;
+    auto cn_of = [&](const V4ChainJob& j) { return j.c_count > 0 ? j.c_count : channels; };
+    int labels_prev = 0;
     for (int k = 0; k < n_jobs; ++k) {
         const V4ChainJob& j = jobs[k];
         V4Params& p = b.job[k];
-        const int labels = j.head != nullptr ? j.head->n_labels : 0;
-        const int cn = j.c_count > 0 ? j.c_count : channels;
+        const int own_labels = j.head != nullptr ? j.head->n_labels : 0;
+        const int cn = cn_of(j);
         KGCN_REQUIRE(j.c_begin >= 0 && j.c_begin + cn <= channels, KGCN_ERR_BAD_SHAPE, "fused GraphConv chain: bad channel group");
-        KGCN_REQUIRE(plan_v4(p, n_graphs, cn, n_nodes, j.f_in, j.f_out, channels, labels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
+        KGCN_REQUIRE(plan_v4(p, n_graphs, cn, n_nodes, j.f_in, j.f_out, channels, own_labels) && p.n_split == 1, KGCN_ERR_UNSUPPORTED,
                      "fused GraphConv chain: job %d (%d -> %d) has no single-CTA plan", k, j.f_in, j.f_out);
+        // Richer layouts, taken only when they cost neither tile height nor more than the stages a short job needs: (1) the
+        // head's shared memory also in the other jobs of the head job's shape, so that their plans are identical and the
+        // boundaries between them can be soft; (2) a second B operand buffer, so that a soft job's [W ; bias] is staged
+        // during its predecessor (latency-bound regime only: few tiles per CTA and job).
+        int labels = own_labels;
+        if (soft_jobs_enabled()) {
+            const bool head_shape = head_k >= 0 && cn == cn_of(jobs[head_k]) && j.f_in == jobs[head_k].f_in && j.f_out == jobs[head_k].f_out;
+            const int want_labels = head_shape ? jobs[head_k].head->n_labels : own_labels;
+            const int tiles_per_cta = (p.graphs_per_cta + p.G - 1) / p.G;
+            V4Params q{};
+            for (int wb = (tiles_per_cta <= 4 && wbufs2_enabled() ? 2 : 1); wb >= 1; --wb) {
+                if ((wb > 1 || want_labels != own_labels) && plan_v4(q, n_graphs, cn, n_nodes, j.f_in, j.f_out, channels, want_labels, wb) &&
+                    q.n_split == 1 && q.G == p.G && q.abufs == p.abufs && q.zbufs == p.zbufs && q.n_stages >= std::min(p.n_stages, 2)) {
+                    p = q;
+                    labels = want_labels;
+                    break;
+                }
+            }
+        }
         KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: graph ranges differ");
         KGCN_REQUIRE(!(j.acc_in && (j.mul_src != nullptr || j.head != nullptr)), KGCN_ERR_UNSUPPORTED, "fused GraphConv chain: accumulate + other epilogue");
         p.c_begin = j.c_begin;
@@ -1685,6 +1778,15 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
             p.logits = hd.logits; p.prediction = hd.prediction; p.gathered = hd.gathered; p.head_partial = hd.partial;
         }
         p.dbg = nullptr;
+        p.soft = (k > 0 && soft_jobs_enabled() && cn == cn_of(jobs[k - 1]) && j.f_in == jobs[k - 1].f_in && j.f_out == jobs[k - 1].f_out &&
+                  labels == labels_prev && p.G == b.job[k - 1].G && p.n_stages == b.job[k - 1].n_stages && p.off_stage == b.job[k - 1].off_stage &&
+                  p.wbufs == b.job[k - 1].wbufs)
+                     ? 1 : 0;
+        p.soft_next = 0;
+        if (p.soft) b.job[k - 1].soft_next = 1;
+        p.wsel = (p.soft && p.wbufs == 2) ? (b.job[k - 1].wsel ^ 1) : 0;
+        p.prestaged = (p.soft && p.wbufs == 2) ? 1 : 0;
+        labels_prev = labels;
         smem = std::max(smem, p.smem_total);
     }
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));

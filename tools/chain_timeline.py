@@ -19,7 +19,7 @@ dbg = torch.zeros(148 * 128, dtype=torch.int64, device="cuda")
 hook = _lib.lib.kgcn_debug_v4_chain_times; hook.argtypes = [ctypes.c_void_p]; hook.restype = None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); flush.zero_()
 hook(dbg.data_ptr())
-tr._step_chain(batches[0], torch.cuda.current_stream().cuda_stream)
+tr.step_chain and tr._step_chain(batches[0], torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize(); hook(None)
 t = dbg.cpu().numpy().reshape(148, 128)
 t = t[t[:, 126] > 0]
