@@ -301,16 +301,28 @@ class Bench:
             tr.capture(("train", i), batches[i])
         for i in range(n_rot):
             tr.capture(("infer", i), batches[i], train=False)
+        # the training loop over the resident batches as ONE graph of n_rot consecutive steps (Trainer.capture_many): steps
+        # are linked by programmatic dependent launch; a remainder of < n_rot steps runs as single-step graphs
+        epoch = tr.single_graph and not args.single_step_graphs
+        if epoch:
+            tr.capture_many(("train", "epoch"), batches)
         self.note("%s: graphs captured, %d launches/step" % (key, launches_per_step))
 
+        def run_steps(kind, k):
+            i = 0
+            if kind == "train" and epoch:
+                for _ in range(k // n_rot):
+                    tr.replay(("train", "epoch"))
+                i = k - k % n_rot
+            for j in range(i, k):
+                tr.replay((kind, j % n_rot))
+
         def timed(kind, k, wu):
-            for i in range(wu):
-                tr.replay((kind, i % n_rot))
+            run_steps(kind, max(wu, n_rot) if (kind == "train" and epoch) else wu)   # at least one replay of the multi-step graph
             self.barrier()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            for i in range(k):
-                tr.replay((kind, i % n_rot))
+            run_steps(kind, k)
             e.record()
             self.barrier()
             return self.max_over_ranks(s.elapsed_time(e))
@@ -484,7 +496,8 @@ class Bench:
                          "batch_per_gpu": B, "global_batch": mols, "n_nodes": N, "feature_dim": F, "conv_dims": w["conv_dims"], "channels": C,
                          "nnz_per_graph": nnz_mean / B, "parallelism": "dp%d" % world,
                          "l2": "rotating %d resident batches (%.0f MB of inputs > 126 MB L2)" % (n_rot, n_rot * (B * N * tr.dims[0] * 4 + 12 * nnz_mean) / 1e6),
-                         "launch": "one CUDA graph replay per step", "data_seed": "1234 + rank",
+                         "launch": ("one CUDA graph per %d consecutive steps (Trainer.capture_many), remainder as single-step graphs" % n_rot)
+                                   if epoch else "one CUDA graph replay per step", "data_seed": "1234 + rank",
                          "data": "generated on the device (torch device RNG + kgcn_pack_coo_device)" if w["gen"] == "device" else "host numpy generator"}
         return res, tr
 
@@ -583,6 +596,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--only-primary", action="store_true", help="skip the c3 / c4 / c5 sub-measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step instead of one per pass over the resident batches")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

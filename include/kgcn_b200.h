@@ -67,6 +67,11 @@ typedef enum kgcn_act { KGCN_ACT_NONE = 0, KGCN_ACT_RELU = 1, KGCN_ACT_SIGMOID =
 #define KGCN_FLAG_DEFAULT 0          /* library picks the fastest kernel that meets fp32 parity        */
 #define KGCN_FLAG_REFERENCE_ORDER 1  /* force the decomposed W-first path: (X.W + b) with exact-fp32    */
                                      /* FFMA, then A.( ), i.e. the operation order of layers.py:112-113 */
+#define KGCN_FLAG_INPUTS_STABLE 4    /* kgcn_gcn_step_chain_f32 only: x and the CSR arrays were complete before the   */
+                                    /* PREVIOUS kernel on this stream was launched (a resident batch, not one a packer */
+                                    /* or a copy just produced), so the launch may read them while that kernel -- e.g.  */
+                                    /* the previous step's reduce + all-reduce + Adam -- is still running (programmatic */
+                                    /* dependent launch); parameters are read only after it has completed            */
 #define KGCN_FLAG_DY_BROADCAST 2     /* backward only: dy is [n_graphs, f_out] and stands for the same   */
                                      /* row repeated over all n_nodes (gradient of GraphGather,         */
                                      /* layers.py:164): fuses the broadcast into the backward           */
@@ -345,7 +350,8 @@ int kgcn_graphconv_chain_dx_f32(const int32_t* rowptr_t, const int32_t* col_t, c
  *   head_partial [kgcn_gcn_step_chain_grid(...)][dims[L] * n_labels + 8]: per-CTA {dW_dense | db_dense (padded to 4) |
  *   cost_sum, correct_count, 0, 0}, reduced by kgcn_reduce_adam_f32 (segments with rows = 0 + stats_partial).
  * kgcn_gcn_step_chain_grid returns the number of CTAs (= partial blocks), 0 when the network is not supported
- * (needs kgcn_graphconv_chain_supported, dims[L] <= 64, n_labels <= 4, 2 L - 1 <= 6 jobs). */
+ * (needs kgcn_graphconv_chain_supported, dims[L] <= 64, n_labels <= 4, 2 L - 1 <= 6 jobs).
+ * flags: KGCN_FLAG_DEFAULT or KGCN_FLAG_INPUTS_STABLE. */
 int32_t kgcn_gcn_step_chain_grid(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
                                  int32_t n_labels);
 int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
@@ -354,7 +360,7 @@ int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const flo
                             const float* const* w, const float* const* bias, float* const* y, float* const* du, int32_t act,
                             const float* head_w, const float* head_b, int32_t n_labels, const float* labels, const float* mask,
                             float inv_batch, float* logits, float* prediction, float* gathered, float* head_partial,
-                            void* stream);
+                            uint32_t flags, void* stream);
 
 /* Weight-gradient partials of ALL layers (kgcn_graphconv_bwd_partial_f32 with dx == NULL, layer by layer) in as few launches
  * as tensor memory allows (2 * channels * dims[l + 1] accumulator columns per layer, 512 per launch): x[l] = input of layer l,

@@ -19,6 +19,7 @@ ACT_IDS = {None: 0, "none": 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 FLAG_DEFAULT = 0
 FLAG_REFERENCE_ORDER = 1
 FLAG_DY_BROADCAST = 2
+FLAG_INPUTS_STABLE = 4
 
 
 class KgcnError(RuntimeError):
@@ -97,7 +98,7 @@ SIGNATURES = {
     "kgcn_graphconv_chain_dx_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "kgcn_gcn_step_chain_grid": (_i32, [_i64, _i32, _i32, _i32, _vp, _i32]),
     "kgcn_gcn_step_chain_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
-                                               _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
+                                               _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, ctypes.c_uint32, _vp]),
     "kgcn_graphconv_chain_dw_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kgcn_reduce_partials_f32": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "kgcn_reduce_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),

@@ -168,7 +168,9 @@ int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
 bool fused_v4_head_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels);
 int fused_v4_chain_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
 bool fused_v4_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
-int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);
+// early_inputs: job 0's x / CSR may be read before the previous kernel of the stream has completed (KGCN_FLAG_INPUTS_STABLE)
+int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st,
+                                    bool early_inputs = false);
 
 // One job of a multi-layer weight-gradient launch (graphconv_fused_dw.cu)
 struct DwJob {

@@ -433,7 +433,7 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
                                        float* const* du, int32_t act, const float* head_w, const float* head_b,
                                        int32_t n_labels, const float* labels, const float* mask, float inv_batch,
                                        float* logits, float* prediction, float* gathered, float* head_partial,
-                                       void* stream) {
+                                       uint32_t flags, void* stream) {
     KGCN_REQUIRE(rowptr && col && val && rowptr_t && col_t && val_t && dims && x && w && y && du && head_w && labels && head_partial,
                  KGCN_ERR_NULL, "gcn_step_chain: NULL pointer argument");
     KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 4, KGCN_ERR_BAD_SHAPE,
@@ -460,5 +460,6 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
         jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
                              y[l - 1], act, 0, nullptr};
     }
-    return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+    return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream),
+                                           (flags & KGCN_FLAG_INPUTS_STABLE) != 0);
 }

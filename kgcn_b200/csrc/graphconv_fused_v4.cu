@@ -794,6 +794,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
 constexpr int kV4MaxJobs = 6;
 struct V4Batch {
     int n_jobs;
+    int early;            // job 0's inputs are stable: only the epilogue warps (parameters, all global writes) wait for the
+                          // previous grid; the TMA producer and the aggregation start while it is still running
     int tile_fence_gpu;   // A-B knob (KGCN_CHAIN_TILE_FENCE=1): membar.gl before the proxy fence of a published tile
     long long* dbg;   // tuning aid (kgcn_debug_v4_chain_times): [CTA][64] clock64 stamps, see tools/chain_timeline.py
     V4Params job[kV4MaxJobs];
@@ -919,7 +921,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         fence_mbar_init();
     }
     if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
-    pdl_wait();   // everything above overlaps the previous kernel's tail
+    if (!b.early) pdl_wait();   // everything above overlaps the previous kernel's tail
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -1168,6 +1170,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         const int colq = static_cast<int>(l7) * 4;
         const int row0 = wq * 32 + (lane >> 3);
         const int te = tid - kWarpEpi0 * 32;   // 0 .. 255 inside the epilogue group
+        if (b.early) pdl_wait();   // parameters (and every buffer this kernel writes) belong to the previous grid until it completes
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
             if (j > 0 && !p.soft) bar_all_roles();
@@ -1710,11 +1713,13 @@ bool fused_v4_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, i
     return fused_v4_enabled() && plan_v4(p, n_graphs, channels, n_nodes, f_in, f_out, channels) && p.n_split == 1;
 }
 
-int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st) {
+int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st,
+                                    bool early_inputs) {
     KGCN_REQUIRE(n_jobs >= 1 && n_jobs <= kV4MaxJobs, KGCN_ERR_BAD_SHAPE, "fused GraphConv chain: 1..%d jobs", kV4MaxJobs);
     V4Batch b{};
     b.n_jobs = n_jobs;
     b.dbg = g_dbg_chain;
+    b.early = early_inputs ? 1 : 0;
     uint32_t smem = 0;
     {
         const char* e = getenv("KGCN_CHAIN_TILE_FENCE");

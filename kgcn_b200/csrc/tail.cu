@@ -67,6 +67,11 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 }
 
 __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailParams p) {
+    // All CTAs of this small grid are resident at once, so the dependent launch can be released right away: the next step's
+    // first kernel (kgcn_gcn_step_chain_f32 with KGCN_FLAG_INPUTS_STABLE) then loads and aggregates its first tiles while
+    // this kernel reduces, exchanges and updates; whatever it reads of this kernel's results comes after its own
+    // griddepcontrol.wait.  Kernels that wait at their entry simply park there.
+    pdl_launch_dependents();
     pdl_prologue();
     __shared__ float4 red[32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -492,8 +492,9 @@ class Trainer:
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=False)
 
-    def _step_chain(self, batch, st):
-        """Forward layers + fused readout head + dx chain: ONE launch; then the weight-gradient jobs."""
+    def _step_chain(self, batch, st, stable=False):
+        """Forward layers + fused readout head + dx chain: ONE launch; then the weight-gradient jobs.  ``stable``: the
+        batch was complete before the previous kernel on this stream was launched (KGCN_FLAG_INPUTS_STABLE)."""
         s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
         csr, L = batch.csr, len(self.spec.conv_dims)
         x = batch.features
@@ -504,18 +505,19 @@ class Trainer:
                                           B, C, N, L, self._dims_c, self._ldims_c, ptr(x), self._w_ptrs, self._b_ptrs, self._y_ptrs,
                                           self._du_ptrs, self.act, ptr(self.pviews["dense/kernel"]), ptr(self.pviews["dense/bias"]),
                                           s.label_dim, ptr(batch.labels), ptr(batch.mask), 1.0 / (B * self.world_size), ptr(self.logits),
-                                          ptr(self.prediction), ptr(self.gathered), ptr(self.head_partial), st))
+                                          ptr(self.prediction), ptr(self.gathered), ptr(self.head_partial),
+                                          _lib.FLAG_INPUTS_STABLE if stable else _lib.FLAG_DEFAULT, st))
         x_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in self.acts[:L]])
         check(lib.kgcn_graphconv_chain_dw_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c, x_ptrs,
                                               self._du_ptrs, self._part_ptrs, self._part_bytes, st))
 
     _head_in_chain = False
 
-    def _fwd_bwd(self, batch, allow_step_chain=True):
+    def _fwd_bwd(self, batch, allow_step_chain=True, stable=False):
         st = torch.cuda.current_stream().cuda_stream
         self._head_in_chain = bool(self.step_chain and allow_step_chain)
         if self._head_in_chain:
-            self._step_chain(batch, st)
+            self._step_chain(batch, st, stable)
             return
         f, _ = self._forward(batch, st)
         self._head(batch, f, st, train=True)
@@ -526,8 +528,8 @@ class Trainer:
         else:
             self._backward(batch, f, st)
 
-    def step_eager(self, batch, apply_update=True):
-        self._fwd_bwd(batch, allow_step_chain=apply_update)   # without the tail launch the head's gradients need the head kernel
+    def step_eager(self, batch, apply_update=True, stable=False):
+        self._fwd_bwd(batch, allow_step_chain=apply_update, stable=stable)   # without the tail launch the head's gradients need the head kernel
         st = torch.cuda.current_stream().cuda_stream
         if not apply_update:
             if self.fused_step and self.single_graph:
@@ -577,6 +579,23 @@ class Trainer:
             if getattr(self, "_opt_graph", None) is None:
                 self._opt_graph = self._capture_fn(lambda: self._plain_adam(), warm_fn=None)
             self.graphs[key] = (self._capture_fn(lambda: self._fwd_bwd(batch)), "allreduce", self._opt_graph)
+        return self.graphs[key]
+
+    def capture_many(self, key, batches):
+        """Several consecutive training steps (one per batch, in order) as ONE graph -- the loop over batches that are
+        resident in HBM (a whole epoch fits).  Inside the graph the steps are linked by programmatic
+        dependent launch, so step k + 1's first kernel is resident, has loaded and aggregated its first tiles while step
+        k's reduce + all-reduce + Adam launch is still running (every step after the first is launched with
+        KGCN_FLAG_INPUTS_STABLE), and the per-graph launch gap is paid once per replay instead of once per step."""
+        if not self.single_graph:
+            raise ValueError("capture_many needs the single-graph step (p2p gradient exchange or one GPU)")
+        batches = list(batches)
+
+        def run():
+            for k, batch in enumerate(batches):
+                self.step_eager(batch, stable=k > 0)
+
+        self.graphs[key] = (self._capture_fn(run, warm_fn=lambda: self._fwd_bwd(batches[0])),)
         return self.graphs[key]
 
     def _plain_adam(self):

@@ -103,6 +103,32 @@ def test_graph_replay_equals_eager():
     assert abs(sa[0] - sb[0]) <= 1e-5 * abs(sa[0]) and sa[1] == sb[1]
 
 
+@pytest.mark.parametrize("B,N,F,conv_dims", [(700, 32, 64, [64, 64]), (300, 50, 75, [50, 50, 50])])
+def test_multi_step_graph_equals_eager_steps(B, N, F, conv_dims):
+    """Trainer.capture_many: several steps over different resident batches in ONE graph -- every step after the first is
+    launched with KGCN_FLAG_INPUTS_STABLE, i.e. loads and aggregates its first tiles while the previous step's reduce + Adam
+    launch still runs -- leaves exactly the parameters of the same steps run one by one, replay after replay."""
+    from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
+    spec = NetSpec(F, conv_dims, N)
+    a, b = Trainer(spec, B, seed=11), Trainer(spec, B, seed=11)
+    assert a.step_chain and torch.equal(a.params, b.params)
+    batches = []
+    for k in range(4):
+        counts, idx, val, x, labels, mask, _, _ = make_case(B, N, 1, F, conv_dims, None, seed=20 + k)
+        batches.append(DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=a.dims[0]))
+    b.capture_many("epoch", batches)
+    assert int(b.step_state[0].item()) == 0
+    for rep in range(3):
+        for batch in batches:
+            a.step_eager(batch)
+        b.replay("epoch")
+        torch.cuda.synchronize()
+        assert torch.equal(a.params, b.params), rep
+    assert int(b.step_state[0].item()) == 12
+    sa, sb = a.read_stats(), b.read_stats()
+    assert abs(sa[0] - sb[0]) <= 1e-5 * abs(sa[0]) and sa[1] == sb[1]
+
+
 @pytest.mark.parametrize("B,N,C,F,conv_dims", [
     (700, 32, 1, 64, [64, 64]),        # C2 widths, 5 graphs per CTA: two tiles per job
     (40, 50, 1, 75, [50, 50, 50]),     # C3: three chained layers on padded widths

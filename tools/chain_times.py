@@ -28,7 +28,7 @@ def step_chain(i): tr._step_chain(batches[i], st()) if False else check(lib.kgcn
     ptr(batches[i].csr.rowptr), ptr(batches[i].csr.col), ptr(batches[i].csr.val), ptr(batches[i].csr.rowptr_t), ptr(batches[i].csr.col_t),
     ptr(batches[i].csr.val_t), B, C, N, L, tr._dims_c, tr._ldims_c, ptr(batches[i].features), tr._w_ptrs, tr._b_ptrs, tr._y_ptrs, tr._du_ptrs,
     tr.act, ptr(tr.pviews["dense/kernel"]), ptr(tr.pviews["dense/bias"]), 2, ptr(batches[i].labels), ptr(batches[i].mask), 1.0 / B,
-    ptr(tr.logits), ptr(tr.prediction), ptr(tr.gathered), ptr(tr.head_partial), st()))
+    ptr(tr.logits), ptr(tr.prediction), ptr(tr.gathered), ptr(tr.head_partial), 0, st()))
 def fwd_chain(i): check(lib.kgcn_graphconv_chain_fwd_f32(ptr(batches[i].csr.rowptr), ptr(batches[i].csr.col), ptr(batches[i].csr.val), B, C, N, L,
     tr._dims_c, tr._ldims_c, ptr(batches[i].features), tr._w_ptrs, tr._b_ptrs, tr._y_ptrs, tr.act, st()))
 def fwd_one(i): check(lib.kgcn_graphconv_chain_fwd_f32(ptr(batches[i].csr.rowptr), ptr(batches[i].csr.col), ptr(batches[i].csr.val), B, C, N, 1,
@@ -46,10 +46,11 @@ def head_du(i):
 def tail(i):
     tr._head_in_chain = tr.step_chain; tr._optimizer(st())
 def whole(i): tr.step_eager(batches[i])
+def whole_stable(i): tr.step_eager(batches[i], stable=i > 0)
 
 for name, fn in (("step chain (fwd x%d + head + dx x%d)" % (L, L - 1), step_chain), ("fwd chain x%d" % L, fwd_chain), ("fwd single job", fwd_one),
                  ("dx chain x%d" % (L - 1), dx_chain), ("dW chain x%d" % L, dw_chain), ("dW single job", dw_one), ("head kernel (infer)", head), ("head kernel (train: + dU)", head_du),
-                 ("tail", tail), ("whole step", whole)):
+                 ("tail", tail), ("whole step", whole), ("whole step, inputs stable", whole_stable)):
     if L == 1 and "dx" in name: continue
     if "step chain" in name and not tr.step_chain: continue
     if ("chain" in name or "single job" in name) and not tr.chain: continue
