@@ -247,6 +247,32 @@ __device__ __forceinline__ void mul_act_grad4_rt(float (&t)[4], const float (&y)
     }
 }
 
+// Chained kernel: the activation of a network is a template parameter (ACT = the one non-trivial activation of all jobs,
+// -1 = mixed: runtime switch), so only ONE activation's code is in the instruction stream -- at the chain's sizes most
+// paths run once or twice per launch and instruction fetch, not issue, bounds them.
+template <int ACT>
+__device__ __forceinline__ void act16_sel(float (&v)[16], int act) {
+    if (ACT == -1) act16_rt(v, act);
+    else if (ACT != KGCN_ACT_NONE && act != KGCN_ACT_NONE) act16<ACT>(v);
+}
+template <int ACT>
+__device__ __forceinline__ void mul_act_grad4_sel(float (&t)[4], const float (&y)[4], int act) {
+    if (ACT == -1) mul_act_grad4_rt(t, y, act);
+    else if (ACT != KGCN_ACT_NONE && act != KGCN_ACT_NONE) mul_act_grad4<ACT>(t, y);
+}
+template <int ACT>
+__device__ __forceinline__ float act1_sel(float x, int act) {
+    if (ACT == -1) {
+        switch (act) {
+            case KGCN_ACT_RELU: return fast_act<KGCN_ACT_RELU>(x);
+            case KGCN_ACT_SIGMOID: return fast_act<KGCN_ACT_SIGMOID>(x);
+            case KGCN_ACT_TANH: return fast_act<KGCN_ACT_TANH>(x);
+            default: return x;
+        }
+    }
+    return (ACT != KGCN_ACT_NONE && act != KGCN_ACT_NONE) ? fast_act<(ACT < 0 ? 0 : ACT)>(x) : x;
+}
+
 // KS K-steps of one 3xTF32 pass, unrolled so every operand address is a constant add
 template <int KS>
 __device__ __forceinline__ void issue_tile(uint32_t d, uint32_t zhi, uint32_t zlo, uint64_t dwhi, uint64_t dwlo, uint32_t idesc,
@@ -813,6 +839,22 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_u32(const uint32_t* p) {
 __device__ __forceinline__ void red_release_cta_add_u32(uint32_t* p, uint32_t v) {
     asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+// end of one tile's epilogue (any variant): publish the tile to a soft successor's TMA loads (stores -> async proxy), count it,
+// advance the accumulator ring and the output pointer
+#define PUBLISH_TILE()                                                     \
+    do {                                                                   \
+        if (p.soft_next) {                                                 \
+            if (b.tile_fence_gpu) __threadfence();                         \
+            fence_proxy_async_all();                                       \
+            __syncwarp();                                                  \
+        }                                                                  \
+        if (lane == 0) red_release_cta_add_u32(&tiles_done, 1u);           \
+        if (e == 0 && it == 0) V4_STAMP(7);                                \
+        if (e == 0 && it == n_tiles - 1) V4_STAMP(8);                      \
+        if (++ai == p.abufs) ai = 0;                                       \
+        y_tile += y_step;                                                  \
+    } while (0)
+
 __device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -825,8 +867,19 @@ __device__ __forceinline__ TileRange cta_range_of(const V4Params& p) {
     return t;
 }
 
-// [W ; bias] (or W^T) of one job -> (hi, lo) K-major SWIZZLE_128B B operand, by `n_thr` threads (index t)
-__device__ __forceinline__ void stage_b_operand(const V4Params& p, uint32_t base, int t, int n_thr) {
+// [W ; bias] (or W^T) of one job -> (hi, lo) K-major SWIZZLE_128B B operand at `base` (+ off_whi / off_wlo), by `n_thr`
+// threads (index t).  ONE copy of this code in the kernel (it runs once or twice per job: a real call, scalar arguments --
+// a reference to the kernel parameters would force a local copy of the whole parameter block).
+struct StageB {
+    const float* w;
+    const float* bias;
+    int C, f_in, f_out, K, Kp, w_trans, w_ld, w_cstride;
+    uint32_t w_atom, off_whi, off_wlo, w_pair;
+};
+__device__ __forceinline__ StageB stage_args(const V4Params& p) {
+    return StageB{p.w, p.bias, p.C, p.f_in, p.f_out, p.K, p.Kp, p.w_trans, p.w_ld, p.w_cstride, p.w_atom, p.off_whi, p.off_wlo, p.w_pair};
+}
+__device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int t, int n_thr) {
     const int C = p.C, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp;
     if ((f_out & 15) != 0) {   // B rows n >= f_out (up to Np) are read by the MMAs and not written below: exact zeros
         const uint32_t n16 = p.w_pair >> 4;
@@ -891,6 +944,7 @@ __device__ __forceinline__ void stage_b_operand(const V4Params& p, uint32_t base
     fence_proxy_async_smem();   // B is read by the tensor core through the async proxy
 }
 
+template <int ACT>
 __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
@@ -1175,7 +1229,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const V4Params& p = b.job[j];
             if (j > 0 && !p.soft) bar_all_roles();
             if (!p.prestaged) {
-                stage_b_operand(p, base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256);
+                stage_b_operand(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256);
                 asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");
             }
             if (e == 0) V4_STAMP(10);
@@ -1183,7 +1237,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             // still being produced (every MMA that read that buffer had completed when the epilogue warps left the job
             // before this one)
             if (j + 1 < n_jobs && b.job[j + 1].prestaged) {
-                stage_b_operand(b.job[j + 1], base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, te, 256);
+                stage_b_operand(stage_args(b.job[j + 1]), base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, te, 256);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_wfull);
             }
@@ -1204,9 +1258,9 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const bool accin = p.acc_in != 0;
             // ---- head state (training step, last forward job) ----
             const int L = p.n_labels, Fs = f_out;
-            const uint32_t hs_gsum = base + p.off_head;                                            // [4][G][Fs]
-            const uint32_t hs_dg = hs_gsum + static_cast<uint32_t>(4 * p.G * Fs) * 4u;             // [G][Fs]
-            const uint32_t hs_wd = hs_dg + static_cast<uint32_t>(p.G * Fs) * 4u;                   // [Fs][L] + bias [4]
+            const uint32_t hs_gsum = base + p.off_head;                                            // [2 tiles][4][G][Fs]
+            const uint32_t hs_dg = hs_gsum + static_cast<uint32_t>(2 * 4 * p.G * Fs) * 4u;         // [2][G][Fs]
+            const uint32_t hs_wd = hs_dg + static_cast<uint32_t>(2 * p.G * Fs) * 4u;               // [Fs][L] + bias [4]
             const uint32_t hs_hp = hs_wd + static_cast<uint32_t>(Fs * L + 4) * 4u;                 // [8][Fs * L + 8] per-warp sums
             const uint32_t hs_zs = hs_hp + static_cast<uint32_t>(kEpiWarps * (Fs * L + 8)) * 4u;   // [8][4] d logits of the warp's graph
             const uint32_t my_hp = hs_hp + static_cast<uint32_t>(e * (Fs * L + 8)) * 4u;
@@ -1221,15 +1275,15 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
             }
             int ai = 0;
-            for (int it = 0; it < n_tiles; ++it) {
-                const int ng = (it == n_tiles - 1) ? last_ng : p.G;
-                const int rows = ng * N;
-                mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
-                ph_tfull ^= 1u << ai;
-                tc_fence_after_sync();
-                if (e == 0 && it == 0) V4_STAMP(6);
-                const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
-                if (!head) {
+            if (!head) {
+                for (int it = 0; it < n_tiles; ++it) {
+                    const int ng = (it == n_tiles - 1) ? last_ng : p.G;
+                    const int rows = ng * N;
+                    mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
+                    ph_tfull ^= 1u << ai;
+                    tc_fence_after_sync();
+                    if (e == 0 && it == 0) V4_STAMP(6);
+                    const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
                     for (int cs = h; cs < n_cslabs; cs += 2) {
                         float v0[16], v1[16];
 #pragma unroll
@@ -1245,8 +1299,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                         }
                         if (!accin) {
-                            act16_rt(v0, p.act);
-                            act16_rt(v1, p.act);
+                            act16_sel<ACT>(v0, p.act);
+                            act16_sel<ACT>(v1, p.act);
                             if (cs * 32 + 32 > p.f_valid) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
@@ -1280,12 +1334,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                     t[0] += o.x; t[1] += o.y; t[2] += o.z; t[3] += o.w;
 #pragma unroll
                                     for (int jj = 0; jj < 4; ++jj) {
-                                        switch (p.act) {
-                                            case KGCN_ACT_RELU: t[jj] = fast_act<KGCN_ACT_RELU>(t[jj]); break;
-                                            case KGCN_ACT_SIGMOID: t[jj] = fast_act<KGCN_ACT_SIGMOID>(t[jj]); break;
-                                            case KGCN_ACT_TANH: t[jj] = fast_act<KGCN_ACT_TANH>(t[jj]); break;
-                                            default: break;
-                                        }
+                                        t[jj] = act1_sel<ACT>(t[jj], p.act);
                                         if (cbase + jj >= p.f_valid) t[jj] = 0.0f;
                                     }
                                     *dst = make_float4(t[0], t[1], t[2], t[3]);
@@ -1314,7 +1363,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                 float t[4];
                                 lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
                                 const float yv[4] = {mv[k].x, mv[k].y, mv[k].z, mv[k].w};
-                                mul_act_grad4_rt(t, yv, p.mul_act);
+                                mul_act_grad4_sel<ACT>(t, yv, p.mul_act);
                                 if (row0 + 4 * k < rows && col_ok)
                                     *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
                             }
@@ -1326,91 +1375,107 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                     }
-                } else {
-                    // ======== fused head: this warp owns tile rows 32 wq .. 32 wq + 31 and columns 32 h .. 32 h + 31 ========
-                    const int cs = h;
-                    const bool has_cols = cs < n_cslabs;
-                    const int64_t g0_tile = tr.g_begin + static_cast<int64_t>(it) * p.G;
+
+                    PUBLISH_TILE();
+                }
+            } else {
+                // ======== fused head.  This warp owns tile rows 32 wq .. 32 wq + 31 and columns 32 h .. 32 h + 31.  Tiles are taken
+                // in groups: the whole job when its tiles fit the accumulators (the latency-bound case: (b) and both barriers are
+                // paid once per job), else one tile at a time.  H stays in tensor memory between (a) and (c). ========
+                const int cs = h;
+                const bool has_cols = cs < n_cslabs;
+                const int gmax = n_tiles <= p.abufs ? n_tiles : 1;
+                const uint32_t gs_stride = static_cast<uint32_t>(4 * p.G * Fs) * 4u, dg_stride = static_cast<uint32_t>(p.G * Fs) * 4u;
+                for (int it0 = 0; it0 < n_tiles; it0 += gmax) {
+                    const int gsz = min(gmax, n_tiles - it0);
+                    const int64_t g0_grp = tr.g_begin + static_cast<int64_t>(it0) * p.G;
+                    const int ng_grp = min(gsz * p.G, tr.n_graphs_cta - it0 * p.G);   // graphs of the group
                     // label l (lane l) and mask of the graph this warp will finish (cold HBM lines): requested now, needed after (a)
                     float y_lane = 0.0f, m0 = 1.0f;
-                    if (e < ng) {
-                        if (lane < L) y_lane = __ldg(p.labels + (g0_tile + e) * L + lane);
-                        if (p.mask) m0 = __ldg(p.mask + g0_tile + e);
+                    if (e < ng_grp) {
+                        if (lane < L) y_lane = __ldg(p.labels + (g0_grp + e) * L + lane);
+                        if (p.mask) m0 = __ldg(p.mask + g0_grp + e);
                     }
-                    if (has_cols) {
-                        float v0[16], v1[16];
+                    // (a) per tile: activation, per-graph column sums over this warp's rows (four independent partial sums per lane)
+                    int aa = ai;
+                    for (int u = 0; u < gsz; ++u) {
+                        const int it = it0 + u;
+                        const int rows = ((it == n_tiles - 1) ? last_ng : p.G) * N;
+                        mbar_wait_relaxed(&bar_tfull[aa], (ph_tfull >> aa) & 1u);
+                        ph_tfull ^= 1u << aa;
+                        tc_fence_after_sync();
+                        if (e == 0 && it == 0) V4_STAMP(6);
+                        if (has_cols) {
+                            const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(aa * Np);
+                            float v0[16], v1[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
-                        tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
-                        if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
-                        tmem_ld_wait();
-                        tmem_ld_fence(v0);
-                        tmem_ld_fence(v1);
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_tempty[ai]);       // the accumulator is in registers: hand it back
-                        act16_rt(v0, p.act);
-                        act16_rt(v1, p.act);
-                        if (cs * 32 + 32 > p.f_valid) {
+                            for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
+                            tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
+                            if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
+                            tmem_ld_wait();
+                            tmem_ld_fence(v0);
+                            tmem_ld_fence(v1);
+                            act16_sel<ACT>(v0, p.act);
+                            act16_sel<ACT>(v1, p.act);
+                            if (cs * 32 + 32 > p.f_valid) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
-                                if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
-                            }
-                        }
-                        tmem_ld_fence(v0);
-                        tmem_ld_fence(v1);
-                        // (a) the 32 x 32 block of H -> the warp's staging tile (it stays there until (c)); per-graph column
-                        // sums over this warp's rows, four independent partial sums per lane
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
-                            const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
-                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
-                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
-                        }
-                        __syncwarp();
-                        const int r_lo = wq * 32, r_hi = min(rows, r_lo + 32);
-                        if (r_lo < r_hi) {
-                            const int g_first = r_lo / N, g_last = (r_hi - 1) / N;
-                            const uint32_t cbase = ys + ((static_cast<uint32_t>(lane) & 3u) << 2);
-                            const uint32_t cch = static_cast<uint32_t>(lane) >> 2;   // lane c reads column c: chunk c >> 2 sits at (c >> 2) ^ (r & 7)
-                            for (int g = g_first; g <= g_last; ++g) {
-                                const int ra = max(g * N, r_lo) - r_lo, rb = min(g * N + N, r_hi) - r_lo;
-                                float s4[4] = {0.f, 0.f, 0.f, 0.f};
-                                int r = ra;
-                                for (; r + 4 <= rb; r += 4) {
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u)
-                                        s4[u] += lds_f32(cbase + static_cast<uint32_t>(r + u) * 128u + ((cch ^ (static_cast<uint32_t>(r + u) & 7u)) << 4));
+                                for (int i = 0; i < 16; ++i) {
+                                    if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                                    if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
                                 }
-                                for (; r < rb; ++r) s4[0] += lds_f32(cbase + static_cast<uint32_t>(r) * 128u + ((cch ^ (static_cast<uint32_t>(r) & 7u)) << 4));
-                                const float o[1] = {(s4[0] + s4[1]) + (s4[2] + s4[3])};
-                                sts_f<1>(hs_gsum + 4u * static_cast<uint32_t>((wq * p.G + g) * Fs + cs * 32 + lane), o);
                             }
+                            tmem_ld_fence(v0);
+                            tmem_ld_fence(v1);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4) {
+                                const float t0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
+                                const float t1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
+                                sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), t0);
+                                sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), t1);
+                            }
+                            __syncwarp();
+                            const int r_lo = wq * 32, r_hi = min(rows, r_lo + 32);
+                            if (r_lo < r_hi) {
+                                const int g_first = r_lo / N, g_last = (r_hi - 1) / N;
+                                const uint32_t cbase = ys + ((static_cast<uint32_t>(lane) & 3u) << 2);
+                                const uint32_t cch = static_cast<uint32_t>(lane) >> 2;   // lane c reads column c: chunk c >> 2 sits at (c >> 2) ^ (r & 7)
+                                for (int g = g_first; g <= g_last; ++g) {
+                                    const int ra = max(g * N, r_lo) - r_lo, rb = min(g * N + N, r_hi) - r_lo;
+                                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                                    int r = ra;
+                                    for (; r + 4 <= rb; r += 4) {
+#pragma unroll
+                                        for (int q4 = 0; q4 < 4; ++q4)
+                                            s4[q4] += lds_f32(cbase + static_cast<uint32_t>(r + q4) * 128u + ((cch ^ (static_cast<uint32_t>(r + q4) & 7u)) << 4));
+                                    }
+                                    for (; r < rb; ++r) s4[0] += lds_f32(cbase + static_cast<uint32_t>(r) * 128u + ((cch ^ (static_cast<uint32_t>(r) & 7u)) << 4));
+                                    const float o[1] = {(s4[0] + s4[1]) + (s4[2] + s4[3])};
+                                    sts_f<1>(hs_gsum + static_cast<uint32_t>(u) * gs_stride + 4u * static_cast<uint32_t>((wq * p.G + g) * Fs + cs * 32 + lane), o);
+                                }
+                            }
+                            __syncwarp();   // the staging tile is reused by the next tile of the group
                         }
-                    } else {
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_tempty[ai]);
+                        if (++aa == p.abufs) aa = 0;
                     }
-                    if (e == 0 && it == 0) V4_STAMP(12);
+                    if (e == 0 && it0 == 0) V4_STAMP(12);
                     asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
-                    if (e == 0 && it == 0) V4_STAMP(13);
-                    // (b) one warp per graph: GraphGather sum, logits, softmax cross-entropy, d logits, d gathered.  Lane l holds
-                    // label l's quantities; loops over labels are rolled (this code runs once per tile: keep it small)
-                    for (int g = e; g < ng; g += kEpiWarps) {
-                        const int64_t bg = g0_tile + g;
+                    if (e == 0 && it0 == 0) V4_STAMP(13);
+                    // (b) one warp per graph of the group: GraphGather sum, logits, softmax cross-entropy, d logits, d gathered.  Lane l
+                    // holds label l's quantities; loops over labels are rolled (this code runs once per group: keep it small)
+                    for (int gi = e; gi < ng_grp; gi += kEpiWarps) {
+                        const int u = gi / p.G, g = gi - u * p.G;
+                        const int64_t bg = g0_grp + gi;
+                        const uint32_t gsum_u = hs_gsum + static_cast<uint32_t>(u) * gs_stride;
                         const int q_lo = (g * N) >> 5, q_hi = (g * N + N - 1) >> 5;
                         float yl = y_lane, m = m0;
-                        if (g != e) {   // more than 8 graphs per tile (small graphs): the later ones load their own
+                        if (gi != e) {   // more than 8 graphs per group (small graphs): the later ones load their own
                             yl = lane < L ? __ldg(p.labels + bg * L + lane) : 0.0f;
                             m = p.mask ? __ldg(p.mask + bg) : 1.0f;
                         }
                         float gv0 = 0.0f, gv1 = 0.0f;
                         for (int q = q_lo; q <= q_hi; ++q) {
-                            gv0 += lds_f32(hs_gsum + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane));
-                            if (Fs > 32) gv1 += lds_f32(hs_gsum + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane + 32));
+                            gv0 += lds_f32(gsum_u + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane));
+                            if (Fs > 32) gv1 += lds_f32(gsum_u + 4u * static_cast<uint32_t>((q * p.G + g) * Fs + lane + 32));
                         }
                         if (p.gathered != nullptr) {
                             p.gathered[bg * Fs + lane] = gv0;
@@ -1474,51 +1539,77 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             }
                         }
                         const float o0[1] = {dg0}, o1[1] = {dg1};
-                        sts_f<1>(hs_dg + 4u * static_cast<uint32_t>(g * Fs + lane), o0);
-                        if (Fs > 32) sts_f<1>(hs_dg + 4u * static_cast<uint32_t>(g * Fs + lane + 32), o1);
+                        sts_f<1>(hs_dg + static_cast<uint32_t>(u) * dg_stride + 4u * static_cast<uint32_t>(g * Fs + lane), o0);
+                        if (Fs > 32) sts_f<1>(hs_dg + static_cast<uint32_t>(u) * dg_stride + 4u * static_cast<uint32_t>(g * Fs + lane + 32), o1);
                         __syncwarp();
                     }
-                    if (e == 0 && it == 0) V4_STAMP(14);
+                    if (e == 0 && it0 == 0) V4_STAMP(14);
                     asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
-                    if (e == 0 && it == 0) V4_STAMP(15);
-                    // (c) dU = dg[graph of the row] (.) act'(H): H is re-read from the warp's staging tile and replaced in place,
-                    // then the tile leaves like an activation tile
-                    if (has_cols) {
-                        const int r = wq * 32 + lane;
-                        const int g = (r < rows) ? r / N : 0;
-                        const uint32_t dga = hs_dg + 4u * static_cast<uint32_t>(g * Fs + cs * 32);
-#pragma unroll 2
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            float d[4], hv[4];
-                            lds_f<4>(d, dga + 16u * static_cast<uint32_t>(c4));
-                            lds_f<4>(hv, yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4));
-                            mul_act_grad4_rt(d, hv, p.act);
-                            sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), d);
-                        }
-                        __syncwarp();
-                        const bool col_ok = cs * 32 + colq < f_out;
-                        float* ycs = y_tile + cs * 32;
+                    if (e == 0 && it0 == 0) V4_STAMP(15);
+                    // (c) per tile: dU = dg[graph of the row] (.) act'(H) with H re-read from tensor memory (the accumulator is handed
+                    // back here), transposed through the warp's staging tile; the tile leaves like an activation tile
+                    for (int u = 0; u < gsz; ++u) {
+                        const int it = it0 + u;
+                        const int rows = ((it == n_tiles - 1) ? last_ng : p.G) * N;
+                        if (has_cols) {
+                            const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
+                            float v0[16], v1[16];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
-                            float t[4];
-                            lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
-                            if (row0 + 4 * k < rows && col_ok)
-                                *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                            for (int i = 0; i < 16; ++i) v1[i] = 0.0f;
+                            tmem_ld16(ta + static_cast<uint32_t>(cs * 32), v0);
+                            if (cs * 32 + 16 < Np) tmem_ld16(ta + static_cast<uint32_t>(cs * 32 + 16), v1);
+                            tmem_ld_wait();
+                            tmem_ld_fence(v0);
+                            tmem_ld_fence(v1);
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bar_tempty[ai]);       // the accumulator is in registers: hand it back
+                            act16_sel<ACT>(v0, p.act);
+                            act16_sel<ACT>(v1, p.act);
+                            if (cs * 32 + 32 > p.f_valid) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    if (cs * 32 + i >= p.f_valid) v0[i] = 0.0f;
+                                    if (cs * 32 + 16 + i >= p.f_valid) v1[i] = 0.0f;
+                                }
+                            }
+                            tmem_ld_fence(v0);
+                            tmem_ld_fence(v1);
+                            const int r = wq * 32 + lane;
+                            const int g = (r < rows) ? r / N : 0;
+                            const uint32_t dga = hs_dg + static_cast<uint32_t>(u) * dg_stride + 4u * static_cast<uint32_t>(g * Fs + cs * 32);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4) {
+                                float d0[4], d1[4];
+                                lds_f<4>(d0, dga + 16u * static_cast<uint32_t>(c4));
+                                lds_f<4>(d1, dga + 16u * static_cast<uint32_t>(c4 + 4));
+                                const float h0[4] = {v0[4 * c4], v0[4 * c4 + 1], v0[4 * c4 + 2], v0[4 * c4 + 3]};
+                                const float h1[4] = {v1[4 * c4], v1[4 * c4 + 1], v1[4 * c4 + 2], v1[4 * c4 + 3]};
+                                mul_act_grad4_sel<ACT>(d0, h0, p.act);
+                                mul_act_grad4_sel<ACT>(d1, h1, p.act);
+                                sts_f<4>(yrow + ((static_cast<uint32_t>(c4) ^ l7) << 4), d0);
+                                sts_f<4>(yrow + ((static_cast<uint32_t>(c4 + 4) ^ l7) << 4), d1);
+                            }
+                            __syncwarp();
+                            const bool col_ok = cs * 32 + colq < f_out;
+                            float* ycs = y_tile + cs * 32;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
+                                float t[4];
+                                lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
+                                if (row0 + 4 * k < rows && col_ok)
+                                    *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                            }
+                            __syncwarp();
+                        } else {
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bar_tempty[ai]);
                         }
-                        __syncwarp();
+                        PUBLISH_TILE();
                     }
                 }
-                if (p.soft_next) {   // publish the tile to the next job's TMA loads (async proxy), then count it
-                    if (b.tile_fence_gpu) __threadfence();
-                    fence_proxy_async_all();
-                    __syncwarp();
-                }
-                if (lane == 0) red_release_cta_add_u32(&tiles_done, 1u);
-                if (e == 0 && it == 0) V4_STAMP(7);
-                if (e == 0 && it == n_tiles - 1) V4_STAMP(8);
-                if (++ai == p.abufs) ai = 0;
-                y_tile += y_step;
             }
             if (head) {
                 // per-CTA partial of the head's parameter gradients and statistics: the 8 warps' sums, added in warp order
@@ -1552,7 +1643,7 @@ constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) sh
 // One candidate plan: `n_split` output-column slices of f_out_total / n_split columns (each slice is its own CTA row of
 // the grid with its own [W ; bias] slice resident in shared memory), G graphs per tile.
 uint32_t head_smem_bytes(int G, int f_out, int n_labels) {
-    return static_cast<uint32_t>(5 * G * f_out + f_out * n_labels + 4 + kEpiWarps * (f_out * n_labels + 8) + kEpiWarps * 4) * 4u;
+    return static_cast<uint32_t>(2 * 5 * G * f_out + f_out * n_labels + 4 + kEpiWarps * (f_out * n_labels + 8) + kEpiWarps * 4) * 4u;   // gsum / dg of up to 2 tiles (a group)
 }
 
 bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out_total, int n_split, int G, int C_csr,
@@ -1795,10 +1886,29 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         smem = std::max(smem, p.smem_total);
     }
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));
-    KGCN_CUDA_OK(cudaFuncSetAttribute(graphconv_fused_v4_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    launch_pdl(graphconv_fused_v4_chain_kernel, grid, kBlock, smem, st, b);
-    KGCN_LAUNCH_OK("graphconv_fused_v4_chain_kernel");
-    return KGCN_OK;
+    // the one non-trivial activation of the chain (forward act, act' of the dx jobs, the head's act'), else the generic kernel
+    int chain_act = KGCN_ACT_NONE;
+    for (int k = 0; k < n_jobs; ++k) {
+        const V4Params& p = b.job[k];
+        for (const int a : {p.act, p.mul_src != nullptr ? p.mul_act : KGCN_ACT_NONE}) {
+            if (a == KGCN_ACT_NONE) continue;
+            chain_act = (chain_act == KGCN_ACT_NONE || chain_act == a) ? a : -1;
+        }
+        if (chain_act == -1) break;
+    }
+    auto go = [&](auto kernel) -> int {
+        KGCN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        launch_pdl(kernel, grid, kBlock, smem, st, b);
+        KGCN_LAUNCH_OK("graphconv_fused_v4_chain_kernel");
+        return KGCN_OK;
+    };
+    switch (chain_act) {
+        case KGCN_ACT_NONE: return go(graphconv_fused_v4_chain_kernel<KGCN_ACT_NONE>);
+        case KGCN_ACT_RELU: return go(graphconv_fused_v4_chain_kernel<KGCN_ACT_RELU>);
+        case KGCN_ACT_SIGMOID: return go(graphconv_fused_v4_chain_kernel<KGCN_ACT_SIGMOID>);
+        case KGCN_ACT_TANH: return go(graphconv_fused_v4_chain_kernel<KGCN_ACT_TANH>);
+        default: return go(graphconv_fused_v4_chain_kernel<-1>);
+    }
 }
 
 int fused_v4_chain_group(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int head_labels) {
