@@ -307,10 +307,11 @@ __device__ __noinline__ void issue_tile_loop(uint32_t d, uint32_t zhi, uint32_t 
 constexpr int kAggWarps = 8;      // warps 0-7   (warpgroups 0-1): 4 TMEM lane quarters x 2 slab phases
 constexpr int kEpiWarps = 8;      // warps 8-15  (warpgroups 2-3): 4 TMEM lane quarters x 2 column phases
 constexpr int kWarpEpi0 = 8;
-constexpr int kWarpMma = 16;      // warpgroup 4: MMA issuer, two idle warps, TMA producer
+constexpr int kWarpMma = 16;      // warpgroup 4: MMA issuer, two B-operand stager warps (chained kernel; idle in the single-layer one), TMA producer
+constexpr int kStagers = 64;      // threads of warps 17, 18
 constexpr int kWarpTma = 19;
 constexpr int kBlock = 20 * 32;
-constexpr int kRegsAgg = 128, kRegsEpi = 80, kRegsMisc = 56;
+constexpr int kRegsAgg = 128, kRegsEpi = 80, kRegsMisc = 64;   // 256 x 128 + 256 x 80 + 128 x 64 = the 640 x 96 of the launch
 
 template <int R>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -815,8 +816,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
 // barrier at all.  Tile t of job j + 1 depends only on tile t of job j (same graphs), so the epilogue warps publish every
 // finished tile -- stores, fence.proxy.async, release-increment of a shared counter -- and the TMA producer of job j + 1
 // acquires the counter before it loads tile t.  All rings simply continue; the aggregation of (j + 1, 0) overlaps the
-// epilogue of (j, last).  With two B operand buffers the epilogue warps stage [W ; bias] of job j + 1 into the free one at
-// the start of job j (while its first accumulator is still being produced), so the MMAs of job j + 1 wait for nothing but Z.
+// epilogue of (j, last).  With two B operand buffers the two stager warps write [W ; bias] of job j + 1 into the free one
+// during job j (as soon as the MMAs of job j - 1 have completed), so the MMAs of job j + 1 wait for nothing but Z.
 constexpr int kV4MaxJobs = 6;
 struct V4Batch {
     int n_jobs;
@@ -879,13 +880,15 @@ struct StageB {
 __device__ __forceinline__ StageB stage_args(const V4Params& p) {
     return StageB{p.w, p.bias, p.C, p.f_in, p.f_out, p.K, p.Kp, p.w_trans, p.w_ld, p.w_cstride, p.w_atom, p.off_whi, p.off_wlo, p.w_pair};
 }
+// (CALLER: one instance per calling role -- ptxas wants all callers of a function under the same setmaxnreg budget)
+template <int CALLER>
 __device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int t, int n_thr) {
     const int C = p.C, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp;
     if ((f_out & 15) != 0) {   // B rows n >= f_out (up to Np) are read by the MMAs and not written below: exact zeros
         const uint32_t n16 = p.w_pair >> 4;
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t i = t; i < n16; i += n_thr) sts_f<4>(base + p.off_whi + (i << 4), z4);
-        asm volatile("bar.sync 3, %0;" ::"n"(256) : "memory");   // the stagers (the epilogue warps)
+        asm volatile("bar.sync 3, %0;" ::"r"(n_thr) : "memory");   // all threads staging this operand
     }
     if (p.w_trans == 0) {
         const int nq_n = f_out >> 2, kq_n = Kp >> 2;
@@ -950,7 +953,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     __shared__ __align__(8) uint64_t bar_full[kV4MaxStages], bar_empty[kV4MaxStages];
     __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t bar_wfull;   // B operand of a prestaged (soft) job written by all epilogue warps
+    __shared__ __align__(8) uint64_t bar_wfull;    // B operand of a prestaged (soft) job written by the two stager warps
+    __shared__ __align__(8) uint64_t bar_wempty;   // all MMAs of a job have completed (its B operand buffer is free)
     __shared__ uint32_t tiles_done;   // epilogue-warp arrivals: 8 per finished tile, over all jobs (soft job boundaries)
 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -961,7 +965,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
 
     if (tid == 0) {
         tiles_done = 0;
-        mbar_init(&bar_wfull, kEpiWarps);
+        mbar_init(&bar_wfull, kStagers / 32);
+        mbar_init(&bar_wempty, 1);
         for (int i = 0; i < kV4MaxStages; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], kAggWarps);
@@ -1164,14 +1169,39 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         }
     } else if (warp >= kWarpMma) {
         reg_dec<kRegsMisc>();
-        uint32_t ph_zfull = 0, ph_tempty = 0, ph_wfull = 0;
+        uint32_t ph_zfull = 0, ph_tempty = 0, ph_wfull = 0, ph_wempty = 0;
+        if (warp == kWarpMma + 1 || warp == kWarpMma + 2) {
+            // =============================== B operand stagers ===============================
+            // [W ; bias] of a soft job is written into the free B operand buffer one job ahead, off the epilogue warps'
+            // time line; jobs that are staged at their own start (the first one, hard boundaries, one buffer) get these
+            // 64 threads on top of the 256 epilogue threads.
+            const int ts = tid - (kWarpMma + 1) * 32;
+            if (b.early) pdl_wait();   // parameters belong to the previous grid until it completes
+            for (int j = 0; j < n_jobs; ++j) {
+                const V4Params& p = b.job[j];
+                if (j > 0 && !p.soft) bar_all_roles();
+                if (j > 0) {   // every MMA of job j - 1 has completed: the buffer it read may be overwritten
+                    mbar_wait_relaxed(&bar_wempty, ph_wempty & 1u);
+                    ph_wempty ^= 1u;
+                }
+                if (!p.prestaged) {
+                    stage_b_operand<1>(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, 256 + ts, 256 + kStagers);
+                    asm volatile("bar.sync 1, %0;" ::"n"(288 + kStagers) : "memory");
+                }
+                if (j + 1 < n_jobs && b.job[j + 1].prestaged) {
+                    stage_b_operand<1>(stage_args(b.job[j + 1]), base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, ts, kStagers);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_wfull);
+                }
+            }
+        }
         for (int j = 0; j < n_jobs; ++j) {
+            if (warp != kWarpMma) break;
             const V4Params& p = b.job[j];
             if (j > 0 && !p.soft) bar_all_roles();
-            if (warp != kWarpMma) continue;
             // =============================== MMA issuer ===============================
             if (!p.prestaged) {
-                asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");   // B operand staged (epilogue warps)
+                asm volatile("bar.sync 1, %0;" ::"n"(288 + kStagers) : "memory");   // B operand staged (epilogue + stager warps)
             } else {   // staged into the other buffer while the previous job ran
                 mbar_wait(&bar_wfull, ph_wfull & 1u);
                 ph_wfull ^= 1u;
@@ -1212,6 +1242,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 if (++zi == p.zbufs) zi = 0;
                 if (++ai == p.abufs) ai = 0;
             }
+            if (elect_one()) umma_commit(&bar_wempty);   // arrives when every MMA of this job has completed
+            __syncwarp();
         }
     } else {
         // =============================== epilogue warps ===============================
@@ -1228,19 +1260,11 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
             if (j > 0 && !p.soft) bar_all_roles();
-            if (!p.prestaged) {
-                stage_b_operand(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256);
-                asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");
+            if (!p.prestaged) {   // (a prestaged job's operand was written by the stager warps during the previous job)
+                stage_b_operand<0>(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256 + kStagers);
+                asm volatile("bar.sync 1, %0;" ::"n"(288 + kStagers) : "memory");
             }
             if (e == 0) V4_STAMP(10);
-            // the next soft job's B operand goes into the other buffer now, while the first accumulator of this job is
-            // still being produced (every MMA that read that buffer had completed when the epilogue warps left the job
-            // before this one)
-            if (j + 1 < n_jobs && b.job[j + 1].prestaged) {
-                stage_b_operand(stage_args(b.job[j + 1]), base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, te, 256);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_wfull);
-            }
             const int N = p.N, f_out = p.f_out, Np = p.Np;
             const TileRange tr = cta_range_of(p);
             const int n_tiles = tr.n_tiles;
