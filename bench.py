@@ -17,6 +17,7 @@ c4 the multi-adjacency shape (3 bond types per layer), c5 config 5's per-GPU sha
 the primary line.  Prints ONE JSON line (rank 0).  DESIGN.md section 6 says how each field is measured.
 """
 import argparse
+import ctypes
 import importlib.util
 import json
 import os
@@ -413,29 +414,70 @@ class Bench:
         def head(i):
             b = batches[i % n_rot]
             tr._last_nodes = tr.acts[L]
+            tr._head_in_chain = False
             tr._head(b, tr.f_head, st(), train=True)
 
         add("readout_kernel (GraphGather + Dense + softmax-xent + dU of the last layer)", 1, head,
             4 * B * N * tr.ldims[-1] * (2 if tr.fused_step else 1))
 
         def tail(i):
+            tr._head_in_chain = bool(tr.step_chain)
             tr._optimizer(st())
 
+        nb_tail = (sum(4 * tr.splits[l] * (tr.dims[l] + 1) * C * tr.dims[l + 1] for l in range(L)) if tr.fused_step else 0) + 16 * tr.n_params
         if world == 1:
-            nb_tail = sum(4 * tr.splits[l] * (tr.dims[l] + 1) * C * tr.dims[l + 1] for l in range(L)) if tr.fused_step else 0
-            add("reduce_adam_kernel (partials -> gradient -> Adam)", 1, tail, nb_tail + 16 * tr.n_params)
+            add("reduce_adam_kernel (partials -> gradient -> Adam)", 1, tail, nb_tail)
             torch.cuda.synchronize()
-        self.note("%s: kernels timed" % key)
-        total_us = sum(k["us_per_launch"] * k["launches_per_step"] for k in kernels)
-        for k in kernels:
-            k["share_of_step"] = k["us_per_launch"] * k["launches_per_step"] / total_us
+        standalone = kernels
+        self.note("%s: standalone kernels timed" % key)
+
+        # ---- the launches the step really makes, each timed alone the same way: their sum is what `ms_per_step` pays (minus the
+        # overlap programmatic dependent launch gives inside the graph) ----
+        kernels = []
+        ld = tr.ldims
+        fwd_b = sum(4 * B * N * (ld[l] + ld[l + 1]) + csr_bytes + 4 * C * ld[l] * ld[l + 1] for l in range(L))
+        dx_b = sum(4 * B * N * (ld[l + 1] + 2 * ld[l]) + csr_bytes + 4 * C * ld[l] * ld[l + 1] for l in range(1, L))
+        dw_b = sum(4 * B * N * (ld[l] + ld[l + 1]) + csr_bytes + 4 * tr.splits[l] * (ld[l] + 1) * C * ld[l + 1] for l in range(L)) if tr.fused_step else 0
+        if tr.step_chain:
+            # forward layers (the last one writes dU instead of its activations) + head (no HBM traffic of its own) + dx jobs
+            add("graphconv_fused_v4_chain_kernel (forward x%d + readout head + dx x%d)" % (L, L - 1), 1,
+                lambda i: tr._launch_step_chain(batches[i % n_rot], st()), fwd_b + dx_b)
+            add("graphconv_fused_dw_kernel (%d weight-gradient jobs)" % L, 1, lambda i: tr._launch_dw_chain(batches[i % n_rot], st()), dw_b)
+        elif tr.chain and tr.fused_step:
+            def fwd_chain(i):
+                b = batches[i % n_rot]
+                check(lib.kgcn_graphconv_chain_fwd_f32(ptr(b.csr.rowptr), ptr(b.csr.col), ptr(b.csr.val), B, C, N, L, tr._dims_c, tr._ldims_c,
+                                                       ptr(b.features), tr._w_ptrs, tr._b_ptrs, tr._y_ptrs, tr.act, st()))
+
+            def dx_chain(i):
+                b = batches[i % n_rot]
+                xp = (ctypes.c_void_p * L)(*([b.features.data_ptr()] + [a.data_ptr() for a in tr.acts[1:L]]))
+                check(lib.kgcn_graphconv_chain_dx_f32(ptr(b.csr.rowptr_t), ptr(b.csr.col_t), ptr(b.csr.val_t), B, C, N, L, tr._dims_c, xp,
+                                                      tr._w_ptrs, tr._du_ptrs, tr.act, st()))
+
+            add("chained forward launch (%d layers)" % L, 1, fwd_chain, fwd_b)
+            add("readout_kernel (GraphGather + Dense + softmax-xent + dU of the last layer)", 1, head, 8 * B * N * ld[-1])
+            if L > 1:
+                add("chained dx launch (%d layers)" % (L - 1), 1, dx_chain, dx_b)
+            add("graphconv_fused_dw_kernel (%d weight-gradient jobs)" % L, 1, lambda i: tr._launch_dw_chain(batches[i % n_rot], st()), dw_b)
+        if kernels and world == 1:
+            add("reduce_adam_kernel (partials -> gradient -> Adam)", 1, tail, nb_tail)
+        if not kernels:
+            kernels = standalone
+        torch.cuda.synchronize()
+        self.note("%s: step kernels timed" % key)
+        for ks in (kernels, standalone):
+            total_us = sum(k["us_per_launch"] * k["launches_per_step"] for k in ks)
+            for k in ks:
+                k["share_of_step"] = k["us_per_launch"] * k["launches_per_step"] / total_us
         dom = max(kernels, key=lambda k: k["share_of_step"])
         res["kernels"] = kernels
+        res["kernels_standalone"] = standalone if standalone is not kernels else None
         res["roofline"] = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": hbm, "unit": "GB/s",
                            "frac": dom["frac"], "peak_source": self.peak_kind + " copy bandwidth (burst)",
                            "frac_of_8TBs_spec": dom["achieved"] / 8000.0, "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                            "us_per_launch": dom["us_per_launch"], "share_of_step": dom["share_of_step"],
-                           "traffic": None, "traffic_source": "see the ncu --set full summaries under profiles/ (r02*) for dram__bytes_read/write of this kernel",
+                           "traffic": None, "traffic_source": "dram__bytes_read/write of this kernel: ncu --set full summaries under profiles/ (r02_step_kernels_*.txt)",
                            "timing": "CUDA events around %d back-to-back launches (graph replay) over %d rotating batches" % (reps * n_rot, n_rot)}
         whole = 0.0
         for l in range(L):
@@ -573,7 +615,7 @@ def run_own(args):
             "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res.get("e2e"),
             "gpu_launches": int(res["launches_per_step"] * steps), "launches_per_step": res["launches_per_step"],
             "roofline": res["roofline"], "roofline_step": res["roofline_step"], "roofline_spmm": res.get("roofline_spmm"),
-            "kernels": res["kernels"], "cpu_baseline": cpu_baseline, "infer": res["infer"], "last_step": res["last_step"],
+            "kernels": res["kernels"], "kernels_standalone": res.get("kernels_standalone"), "cpu_baseline": cpu_baseline, "infer": res["infer"], "last_step": res["last_step"],
             "padded_dims": res["padded_dims"], "fused_step": res["fused_step"],
         }
         if "dp_check" in res:

@@ -501,12 +501,23 @@ class Trainer:
         if x.shape[-1] != self.dims[0]:
             raise ValueError("batch features are %d wide, the trainer stores %d" % (x.shape[-1], self.dims[0]))
         self.acts[0] = x
+        self._launch_step_chain(batch, st, stable)
+        self._launch_dw_chain(batch, st)
+
+    def _launch_step_chain(self, batch, st, stable=False):
+        s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
+        csr, L, x = batch.csr, len(self.spec.conv_dims), batch.features
         check(lib.kgcn_gcn_step_chain_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t),
                                           B, C, N, L, self._dims_c, self._ldims_c, ptr(x), self._w_ptrs, self._b_ptrs, self._y_ptrs,
                                           self._du_ptrs, self.act, ptr(self.pviews["dense/kernel"]), ptr(self.pviews["dense/bias"]),
                                           s.label_dim, ptr(batch.labels), ptr(batch.mask), 1.0 / (B * self.world_size), ptr(self.logits),
                                           ptr(self.prediction), ptr(self.gathered), ptr(self.head_partial),
                                           _lib.FLAG_INPUTS_STABLE if stable else _lib.FLAG_DEFAULT, st))
+
+    def _launch_dw_chain(self, batch, st):
+        B, N, C = self.B, self.spec.n_nodes, self.spec.channels
+        csr, L = batch.csr, len(self.spec.conv_dims)
+        self.acts[0] = batch.features
         x_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in self.acts[:L]])
         check(lib.kgcn_graphconv_chain_dw_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c, x_ptrs,
                                               self._du_ptrs, self._part_ptrs, self._part_bytes, st))
@@ -730,8 +741,11 @@ class HostFedPipeline:
         sec("mask", np.float32)[:] = np.ones(B, np.float32) if mask is None else np.asarray(mask, np.float32)
         used = self.layout["idx"][0] + 8 * nnz   # the idx section is copied only up to the entries in use
         feats = np.ascontiguousarray(pad_features(features, self.trainer.dims[0]), np.float32)   # padded on the host: one plain copy
-        return {"packed": torch.from_numpy(packed).pin_memory(), "nnz": nnz, "idx_used_end": used,
-                "features": torch.from_numpy(feats).pin_memory()}
+        # pinned staging on the GPU's own NUMA node (hostmem: the copies of all ranks of a node otherwise share one socket)
+        from . import hostmem
+        with hostmem.numa_preferred(hostmem.gpu_numa_node(self.trainer.device.index or 0)):
+            return {"packed": torch.from_numpy(packed).pin_memory(), "nnz": nnz, "idx_used_end": used,
+                    "features": torch.from_numpy(feats).pin_memory()}
 
     def h2d_bytes(self, host):
         return int(host["packed"].numel() + host["features"].numel() * 4)
