@@ -514,7 +514,7 @@ class Bench:
         # ---- end to end from pinned host buffers through the public step call ----
         if host is not None:
             max_nnz = int(max(d["values"].shape[0] for d in host) * 1.1) + 64
-            pipe = HostFedPipeline(tr, max_nnz, train=True, depth=2)
+            pipe = HostFedPipeline(tr, max_nnz, train=True, depth=int(os.environ.get("KGCN_E2E_DEPTH", "2")))
             pinned = [pipe.pin_host_batch(d["counts"], d["indices"], d["values"], d["features"], d["labels"]) for d in host]
             pipe.capture()
             e2e_steps = max(10, min(steps, 300))
