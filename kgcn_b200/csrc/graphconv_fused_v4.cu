@@ -83,7 +83,9 @@ struct V4Params {
     int soft;             // chained job with the same plan as its predecessor: no CTA barrier, tile-wise hand-over
     int soft_next;        // the next job of the chain is soft: publish every finished tile (fence + counter)
     int wbufs, wsel;      // B operand buffers (chain: 2 = the next soft job's [W ; bias] is staged during this job), buffer of this job
-    int prestaged;        // this job's B operand was staged by the epilogue warps during the previous job
+    int prestaged;        // this job's B operand was staged by the stager warps during the previous job
+    int x_prev;           // soft job whose x IS the previous job's y (same tiles): when a CTA's tiles fit the stage ring, the previous
+                          // job's epilogue writes each output tile straight into this job's stage slot (on-chip hand-over)
     uint32_t w_pair;      // bytes of one (hi, lo) B operand buffer
     long long* dbg;
 };
@@ -818,9 +820,14 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_kernel(const V4Params p) {
 // acquires the counter before it loads tile t.  All rings simply continue; the aggregation of (j + 1, 0) overlaps the
 // epilogue of (j, last).  With two B operand buffers the two stager warps write [W ; bias] of job j + 1 into the free one
 // during job j (as soon as the MMAs of job j - 1 have completed), so the MMAs of job j + 1 wait for nothing but Z.
+// ON-CHIP HAND-OVER (a soft job that reads its predecessor's output, CTA's tiles <= stages): the epilogue writes the output
+// tile it stores to HBM also into the successor's stage slot (slot = tile index; the slot's last reader was this job's
+// own aggregation of the same tile) and arrives on the slot's full barrier -- 8 epilogue-warp arrivals + the producer's one,
+// which only fetches the CSR slices.  No proxy fence, no reload: the successor's aggregation starts when the tile is stored.
 constexpr int kV4MaxJobs = 6;
 struct V4Batch {
     int n_jobs;
+    int head_job, head_setup_job;   // the job with the fused head (-1: none) and the job at whose start its shared memory is set up
     int early;            // job 0's inputs are stable: only the epilogue warps (parameters, all global writes) wait for the
                           // previous grid; the TMA producer and the aggregation start while it is still running
     int tile_fence_gpu;   // A-B knob (KGCN_CHAIN_TILE_FENCE=1): membar.gl before the proxy fence of a published tile
@@ -844,7 +851,10 @@ __device__ __forceinline__ void red_release_cta_add_u32(uint32_t* p, uint32_t v)
 // advance the accumulator ring and the output pointer
 #define PUBLISH_TILE()                                                     \
     do {                                                                   \
-        if (p.soft_next) {                                                 \
+        if (handover) {                                                    \
+            __syncwarp();                                                  \
+            if (lane == 0) mbar_arrive(&bar_full[it]);                     \
+        } else if (p.soft_next) {                                          \
             if (b.tile_fence_gpu) __threadfence();                         \
             fence_proxy_async_all();                                       \
             __syncwarp();                                                  \
@@ -856,6 +866,9 @@ __device__ __forceinline__ void red_release_cta_add_u32(uint32_t* p, uint32_t v)
         y_tile += y_step;                                                  \
     } while (0)
 
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
+}
 __device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -968,7 +981,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         mbar_init(&bar_wfull, kStagers / 32);
         mbar_init(&bar_wempty, 1);
         for (int i = 0; i < kV4MaxStages; ++i) {
-            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_full[i], 1 + kEpiWarps);   // producer + (hand-over) the epilogue warps; the producer arrives for them otherwise
             mbar_init(&bar_empty[i], kAggWarps);
         }
         for (int i = 0; i < 2; ++i) {
@@ -1004,7 +1017,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 for (int it = 0; it < n_tiles; ++it) {
                     mbar_wait_relaxed(&bar_empty[s], ((ph_empty >> s) & 1u) ^ 1u);
                     ph_empty ^= 1u << s;
-                    if (p.soft) {   // tile `it` of the previous job (same graphs) has been stored and fenced by all epilogue warps
+                    const bool handover = p.x_prev && n_tiles <= S;   // the previous job's epilogue fills x of this slot
+                    if (p.soft && !handover) {   // tile `it` of the previous job (same graphs) has been stored and fenced by all epilogue warps
                         const uint32_t need = static_cast<uint32_t>(kEpiWarps) * (tiles_before - static_cast<uint32_t>(n_tiles) + static_cast<uint32_t>(it) + 1u);
                         while (ld_acquire_cta_u32(&tiles_done) < need) __nanosleep(20);
                     }
@@ -1018,14 +1032,15 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
                     const uint32_t x_bytes = static_cast<uint32_t>(ng) * static_cast<uint32_t>(N) * pitch;
                     if (it == 0) V4_STAMP(9);
-                    mbar_expect_tx_only(full, x_bytes + 4u * rp_cnt);
-                    bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
+                    mbar_expect_tx_only(full, (handover ? 0u : x_bytes) + 4u * rp_cnt);
+                    if (!handover) bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
                     bulk_g2s(st + p.st_rp, p.rowptr + rp_lo, 4u * rp_cnt, full);
                     const int32_t e_first = __ldg(p.rowptr + r0), e_last = __ldg(p.rowptr + r0 + rows_csr);
                     const int32_t e_lo = e_first & ~3;
                     const uint32_t e_cnt = static_cast<uint32_t>((e_last - e_lo + 3) & ~3);
                     const bool staged = e_cnt <= static_cast<uint32_t>(p.cv_cap) && e_cnt != 0;
-                    mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the one arrival of the phase
+                    mbar_expect_tx(full, staged ? 8u * e_cnt : 0u);   // the producer's arrival of the phase
+                    if (!handover) mbar_arrive_cnt(full, kEpiWarps);   // nobody else fills this slot
                     if (staged) {
                         bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
                         bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
@@ -1280,6 +1295,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const bool head = p.head != 0;
             const bool mul = p.mul_src != nullptr;
             const bool accin = p.acc_in != 0;
+            // on-chip hand-over to the next job: its stage slot `it` takes this job's output tile `it` (pitch = f_out floats)
+            const bool handover = j + 1 < n_jobs && b.job[j + 1].x_prev && n_tiles <= b.job[j + 1].n_stages;
+            const uint32_t ho_pitch = static_cast<uint32_t>(f_out) * 4u;
+            const uint32_t ho_lane = static_cast<uint32_t>(row0) * ho_pitch + static_cast<uint32_t>(colq) * 4u;   // + slot + slab + 4 k rows
             // ---- head state (training step, last forward job) ----
             const int L = p.n_labels, Fs = f_out;
             const uint32_t hs_gsum = base + p.off_head;                                            // [2 tiles][4][G][Fs]
@@ -1288,14 +1307,21 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const uint32_t hs_hp = hs_wd + static_cast<uint32_t>(Fs * L + 4) * 4u;                 // [8][Fs * L + 8] per-warp sums
             const uint32_t hs_zs = hs_hp + static_cast<uint32_t>(kEpiWarps * (Fs * L + 8)) * 4u;   // [8][4] d logits of the warp's graph
             const uint32_t my_hp = hs_hp + static_cast<uint32_t>(e * (Fs * L + 8)) * 4u;
-            if (head) {
-                for (int i = te; i < Fs * L + 4; i += 256) {
-                    const int bi = i - Fs * L;
-                    const float wv[1] = {bi < 0 ? __ldg(p.head_w + i) : ((bi < L && p.head_b != nullptr) ? __ldg(p.head_b + bi) : 0.0f)};
-                    sts_f<1>(hs_wd + 4u * static_cast<uint32_t>(i), wv);
+            if (j == b.head_setup_job) {
+                // the head's Dense weights and zeroed accumulators, placed at the start of the soft run that ends in the head job
+                // (same plan, so the head's shared memory is reserved and untouched): two cold global round trips that the head
+                // job itself would otherwise wait for
+                const V4Params& hp = b.job[b.head_job];
+                const int hL = hp.n_labels, hF = hp.f_out;
+                const uint32_t h_wd = base + hp.off_head + static_cast<uint32_t>(2 * 5 * hp.G * hF) * 4u;
+                const uint32_t h_hp = h_wd + static_cast<uint32_t>(hF * hL + 4) * 4u;
+                for (int i = te; i < hF * hL + 4; i += 256) {
+                    const int bi = i - hF * hL;
+                    const float wv[1] = {bi < 0 ? __ldg(hp.head_w + i) : ((bi < hL && hp.head_b != nullptr) ? __ldg(hp.head_b + bi) : 0.0f)};
+                    sts_f<1>(h_wd + 4u * static_cast<uint32_t>(i), wv);
                 }
                 const float z1[1] = {0.0f};
-                for (int i = te; i < kEpiWarps * (Fs * L + 8); i += 256) sts_f<1>(hs_hp + 4u * static_cast<uint32_t>(i), z1);
+                for (int i = te; i < kEpiWarps * (hF * hL + 8); i += 256) sts_f<1>(h_hp + 4u * static_cast<uint32_t>(i), z1);
                 asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
             }
             int ai = 0;
@@ -1308,6 +1334,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     tc_fence_after_sync();
                     if (e == 0 && it == 0) V4_STAMP(6);
                     const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
+                    const uint32_t ho_slot = handover ? base + b.job[j + 1].off_stage + static_cast<uint32_t>(it) * b.job[j + 1].stage_bytes : 0u;
                     for (int cs = h; cs < n_cslabs; cs += 2) {
                         float v0[16], v1[16];
 #pragma unroll
@@ -1362,6 +1389,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                         if (cbase + jj >= p.f_valid) t[jj] = 0.0f;
                                     }
                                     *dst = make_float4(t[0], t[1], t[2], t[3]);
+                                    if (handover) sts_f<4>(ho_slot + ho_lane + static_cast<uint32_t>(cs) * 128u + static_cast<uint32_t>(4 * k) * ho_pitch, t);
                                 }
                             }
                         } else if (!mul) {
@@ -1370,8 +1398,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                 const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
                                 float t[4];
                                 lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
-                                if (row0 + 4 * k < rows && col_ok)
+                                if (row0 + 4 * k < rows && col_ok) {
                                     *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                                    if (handover) sts_f<4>(ho_slot + ho_lane + static_cast<uint32_t>(cs) * 128u + static_cast<uint32_t>(4 * k) * ho_pitch, t);
+                                }
                             }
                         } else {
                             const float* mcs = p.mul_src + (ycs - p.y);   // same [rows, y_ld] layout as the output
@@ -1388,8 +1418,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                 lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
                                 const float yv[4] = {mv[k].x, mv[k].y, mv[k].z, mv[k].w};
                                 mul_act_grad4_sel<ACT>(t, yv, p.mul_act);
-                                if (row0 + 4 * k < rows && col_ok)
+                                if (row0 + 4 * k < rows && col_ok) {
                                     *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                                    if (handover) sts_f<4>(ho_slot + ho_lane + static_cast<uint32_t>(cs) * 128u + static_cast<uint32_t>(4 * k) * ho_pitch, t);
+                                }
                             }
                         }
                         __syncwarp();
@@ -1575,6 +1607,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     for (int u = 0; u < gsz; ++u) {
                         const int it = it0 + u;
                         const int rows = ((it == n_tiles - 1) ? last_ng : p.G) * N;
+                        const uint32_t ho_slot = handover ? base + b.job[j + 1].off_stage + static_cast<uint32_t>(it) * b.job[j + 1].stage_bytes : 0u;
                         if (has_cols) {
                             const uint32_t ta = tmem + lane_sel + static_cast<uint32_t>(ai * Np);
                             float v0[16], v1[16];
@@ -1622,8 +1655,10 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                 const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
                                 float t[4];
                                 lds_f<4>(t, ysrc + static_cast<uint32_t>(k) * 512u + ((l7 ^ r7) << 4));
-                                if (row0 + 4 * k < rows && col_ok)
+                                if (row0 + 4 * k < rows && col_ok) {
                                     *reinterpret_cast<float4*>(ycs + static_cast<size_t>(4 * k) * y_ld) = make_float4(t[0], t[1], t[2], t[3]);
+                                    if (handover) sts_f<4>(ho_slot + ho_lane + static_cast<uint32_t>(cs) * 128u + static_cast<uint32_t>(4 * k) * ho_pitch, t);
+                                }
                             }
                             __syncwarp();
                         } else {
@@ -1701,7 +1736,7 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     p.off_whi = off; off += n_watoms * p.w_atom;
     p.off_wlo = off; off += n_watoms * p.w_atom;
     p.w_pair = off;
-    p.wbufs = wbufs; p.wsel = 0; p.prestaged = 0; p.soft = 0; p.soft_next = 0;
+    p.wbufs = wbufs; p.wsel = 0; p.prestaged = 0; p.soft = 0; p.soft_next = 0; p.x_prev = 0;
     off += static_cast<uint32_t>(wbufs - 1) * p.w_pair;
     p.off_ystage = off; off += kEpiWarps * 4096u;
     p.off_head = off;
@@ -1767,6 +1802,13 @@ bool fused_v4_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, i
     return fused_v4_enabled() && plan_v4_group(p, n_graphs, channels, n_nodes, f_in, f_out) > 0;
 }
 
+static bool handover_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KGCN_CHAIN_HANDOVER");   // A-B knob: 0 = soft jobs always reload their input through HBM / L2
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
 static bool wbufs2_enabled() {
     static const bool on = [] {
         const char* e = getenv("KGCN_CHAIN_WBUFS");   // A-B knob: 1 keeps a single B operand buffer in chained launches
@@ -1906,9 +1948,13 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         if (p.soft) b.job[k - 1].soft_next = 1;
         p.wsel = (p.soft && p.wbufs == 2) ? (b.job[k - 1].wsel ^ 1) : 0;
         p.prestaged = (p.soft && p.wbufs == 2) ? 1 : 0;
+        p.x_prev = (p.soft && handover_enabled() && j.x == jobs[k - 1].y && j.f_in == jobs[k - 1].f_out) ? 1 : 0;
         labels_prev = labels;
         smem = std::max(smem, p.smem_total);
     }
+    b.head_job = head_k;
+    b.head_setup_job = head_k;
+    while (b.head_setup_job > 0 && b.job[b.head_setup_job].soft) --b.head_setup_job;   // first job of the soft run (same plan)
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));
     // the one non-trivial activation of the chain (forward act, act' of the dx jobs, the head's act'), else the generic kernel
     int chain_act = KGCN_ACT_NONE;
