@@ -26,7 +26,9 @@ namespace {
 
 constexpr int kMaxSegments = 16;
 constexpr int kMaxWorld = 8;
-constexpr int kTailThreads = 1024;
+constexpr int kTailWarps = 32;   // (2 warps at <= 64 registers would fit beside a chained-layer CTA on every SM, so the next step
+                                 // could start everywhere under this kernel: measured slower, 8.9 vs 6.1 us alone and +6 us per step)
+constexpr int kTailThreads = kTailWarps * 32;
 constexpr int kTailElems = 128;   // elements per block: 32 lanes x 4
 
 struct TailSegment {
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailPar
     // griddepcontrol.wait.  Kernels that wait at their entry simply park there.
     pdl_launch_dependents();
     pdl_prologue();
-    __shared__ float4 red[32][33];
+    __shared__ float4 red[kTailWarps][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = p.step_state[0] + 1;
     if (static_cast<int>(blockIdx.x) >= p.n_blocks) {
@@ -136,15 +138,15 @@ __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailPar
     }
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (src != nullptr) {
-        for (int z = warp; z < splits; z += 256) {   // predicated batches of 8: up to 256 partials in ONE round trip
+        for (int z = warp; z < splits; z += 8 * kTailWarps) {   // predicated batches of 8 independent loads per lane
             float4 val[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                val[j] = (z + 32 * j < splits) ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(z + 32 * j) * stride))
+                val[j] = (z + kTailWarps * j < splits) ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(z + kTailWarps * j) * stride))
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (z + 32 * j < splits) { s.x += val[j].x; s.y += val[j].y; s.z += val[j].z; s.w += val[j].w; }
+                if (z + kTailWarps * j < splits) { s.x += val[j].x; s.y += val[j].y; s.z += val[j].z; s.w += val[j].w; }
         }
     }
     red[warp][lane] = s;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(kTailThreads) reduce_adam_kernel(const TailPar
         if (src != nullptr) {
             g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int w = 0; w < 32; ++w) { const float4 r = red[w][lane]; g4.x += r.x; g4.y += r.y; g4.z += r.z; g4.w += r.w; }
+            for (int w = 0; w < kTailWarps; ++w) { const float4 r = red[w][lane]; g4.x += r.x; g4.y += r.y; g4.z += r.z; g4.w += r.w; }
         }
         float g[4] = {g4.x, g4.y, g4.z, g4.w};
         if (p.world > 1 && i < p.n) {

@@ -8,7 +8,7 @@
 set -u
 mkdir -p gpurun_out
 ALL="tests/test_gpu_parity.py tests/test_gpu_trainer.py tests/test_next_rows.py"
-FUSED="v4_pipeline or backward_fused or full_size or step_matches_oracle"
+FUSED="v4_pipeline or backward_fused or full_size or step_matches_oracle or chained_launches or multi_step_graph or graph_replay"
 : > gpurun_out/sanitize_summary.txt
 run() {   # tool, timeout, pytest args...
     local tool=$1 tmo=$2; shift 2
