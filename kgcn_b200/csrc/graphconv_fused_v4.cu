@@ -869,7 +869,7 @@ __device__ __forceinline__ void red_release_cta_add_u32(uint32_t* p, uint32_t v)
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
 }
-__device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
+__device__ __forceinline__ void bar_all_roles() { named_barrier_sync(2, kBlock); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ TileRange cta_range_of(const V4Params& p) {
@@ -901,7 +901,7 @@ __device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int 
         const uint32_t n16 = p.w_pair >> 4;
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t i = t; i < n16; i += n_thr) sts_f<4>(base + p.off_whi + (i << 4), z4);
-        asm volatile("bar.sync 3, %0;" ::"r"(n_thr) : "memory");   // all threads staging this operand
+        named_barrier_sync(3, n_thr);   // all threads staging this operand
     }
     if (p.w_trans == 0) {
         const int nq_n = f_out >> 2, kq_n = Kp >> 2;
@@ -1201,7 +1201,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                 }
                 if (!p.prestaged) {
                     stage_b_operand<1>(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, 256 + ts, 256 + kStagers);
-                    asm volatile("bar.sync 1, %0;" ::"n"(288 + kStagers) : "memory");
+                    named_barrier_sync(1, 288 + kStagers);
                 }
                 if (j + 1 < n_jobs && b.job[j + 1].prestaged) {
                     stage_b_operand<1>(stage_args(b.job[j + 1]), base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, ts, kStagers);
@@ -1216,7 +1216,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             if (j > 0 && !p.soft) bar_all_roles();
             // =============================== MMA issuer ===============================
             if (!p.prestaged) {
-                asm volatile("bar.sync 1, %0;" ::"n"(288 + kStagers) : "memory");   // B operand staged (epilogue + stager warps)
+                named_barrier_sync(1, 288 + kStagers);   // B operand staged (epilogue + stager warps)
             } else {   // staged into the other buffer while the previous job ran
                 mbar_wait(&bar_wfull, ph_wfull & 1u);
                 ph_wfull ^= 1u;
@@ -1277,7 +1277,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             if (j > 0 && !p.soft) bar_all_roles();
             if (!p.prestaged) {   // (a prestaged job's operand was written by the stager warps during the previous job)
                 stage_b_operand<0>(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256 + kStagers);
-                asm volatile("bar.sync 1, %0;" ::"n"(288 + kStagers) : "memory");
+                named_barrier_sync(1, 288 + kStagers);
             }
             if (e == 0) V4_STAMP(10);
             const int N = p.N, f_out = p.f_out, Np = p.Np;

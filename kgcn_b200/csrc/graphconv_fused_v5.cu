@@ -72,7 +72,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
     return r;
 }
-__device__ __forceinline__ void bar_all_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
+__device__ __forceinline__ void bar_all_roles() { named_barrier_sync(2, kBlock); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -331,7 +331,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
             if (j > 0) bar_all_roles();
             if (warp != kWarpMma) continue;
             // =============================== MMA issuer ===============================
-            asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");   // W^T is in tensor memory (epilogue warps)
+            named_barrier_sync(1, 288);   // W^T is in tensor memory (epilogue warps)
             tc_fence_after_sync();
             const int K = p.K, R = p.R;
             const Range tr = cta_range(p);
@@ -414,7 +414,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
                 tmem_st_wait();
                 tc_fence_before_sync();
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(288) : "memory");
+            named_barrier_sync(1, 288);
             float bias_c[kMaxC];
 #pragma unroll
             for (int c = 0; c < kMaxC; ++c)
