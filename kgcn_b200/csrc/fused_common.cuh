@@ -11,13 +11,6 @@
 namespace kgcn {
 namespace {
 
-// Named barriers shared by several warp roles go through ONE instruction (a real call): the same barrier resource reached
-// from different program counters is legal PTX, but compute-sanitizer's synccheck reports it as divergence and stops there.
-__device__ __noinline__ void named_barrier_sync(uint32_t id, uint32_t count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t r;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));

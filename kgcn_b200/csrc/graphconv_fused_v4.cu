@@ -869,7 +869,15 @@ __device__ __forceinline__ void red_release_cta_add_u32(uint32_t* p, uint32_t v)
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
 }
-__device__ __forceinline__ void bar_all_roles() { named_barrier_sync(2, kBlock); }
+// CTA-wide barrier of all warp roles on an mbarrier (count = warps of the CTA): every thread keeps its own phase bit.  (A named
+// bar.sync reached from the roles' different program counters is legal, but compute-sanitizer's synccheck reports it.)
+#define CTA_ROLE_BARRIER()                                  \
+    do {                                                    \
+        __syncwarp();                                       \
+        if (lane == 0) mbar_arrive(&bar_roles);             \
+        mbar_wait(&bar_roles, ph_roles & 1u);               \
+        ph_roles ^= 1u;                                     \
+    } while (0)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ TileRange cta_range_of(const V4Params& p) {
@@ -897,14 +905,10 @@ __device__ __forceinline__ StageB stage_args(const V4Params& p) {
 template <int CALLER>
 __device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int t, int n_thr) {
     const int C = p.C, f_in = p.f_in, f_out = p.f_out, K = p.K, Kp = p.Kp;
-    if ((f_out & 15) != 0) {   // B rows n >= f_out (up to Np) are read by the MMAs and not written below: exact zeros
-        const uint32_t n16 = p.w_pair >> 4;
-        const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (uint32_t i = t; i < n16; i += n_thr) sts_f<4>(base + p.off_whi + (i << 4), z4);
-        named_barrier_sync(3, n_thr);   // all threads staging this operand
-    }
+    // B rows n in [f_out, Np) are read by the MMAs: the loops below run over Np rows and write them as exact zeros
+    const int Np = (f_out + 15) & ~15;
     if (p.w_trans == 0) {
-        const int nq_n = f_out >> 2, kq_n = Kp >> 2;
+        const int nq_n = Np >> 2, kq_n = Kp >> 2;
         for (int idx = t; idx < kq_n * nq_n; idx += n_thr) {
             const int n0 = (idx % nq_n) << 2, k4 = (idx / nq_n) << 2;
             float4 r[4];
@@ -912,6 +916,7 @@ __device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int 
             for (int j = 0; j < 4; ++j) {
                 const int kk = k4 + j;
                 r[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (n0 >= f_out) continue;   // f_out % 4 == 0: a quad of output columns is inside or outside as a whole
                 if (kk < K) {
                     const int c = kk / f_in, f = kk - c * f_in;
                     r[j] = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride + static_cast<size_t>(f) * p.w_ld + n0));
@@ -936,9 +941,10 @@ __device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int 
         }
     } else {
         const int kq = f_in >> 2;
-        for (int idx = t; idx < f_out * C * kq; idx += n_thr) {
+        for (int idx = t; idx < Np * C * kq; idx += n_thr) {
             const int n = idx / (C * kq), r = idx - n * (C * kq), c = r / kq, f4 = (r - c * kq) << 2;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride + static_cast<size_t>(n) * p.w_ld + f4));
+            const float4 v = n < f_out ? __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(c) * p.w_cstride + static_cast<size_t>(n) * p.w_ld + f4))
+                                       : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             const float tt[4] = {v.x, v.y, v.z, v.w};
             float hi[4], lo[4];
 #pragma unroll
@@ -951,7 +957,7 @@ __device__ __noinline__ void stage_b_operand(const StageB p, uint32_t base, int 
             sts_f<4>(base + p.off_wlo + off, lo);
         }
         const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // no bias: the row-sum columns K .. K + 7 of Z meet exact zeros
-        for (int idx = t; idx < f_out * 2; idx += n_thr) {
+        for (int idx = t; idx < Np * 2; idx += n_thr) {
             const uint32_t off = sw128_offset(idx >> 1, K + ((idx & 1) << 2), p.w_atom);
             sts_f<4>(base + p.off_whi + off, z4);
             sts_f<4>(base + p.off_wlo + off, z4);
@@ -968,6 +974,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bar_wfull;    // B operand of a prestaged (soft) job written by the two stager warps
     __shared__ __align__(8) uint64_t bar_wempty;   // all MMAs of a job have completed (its B operand buffer is free)
+    __shared__ __align__(8) uint64_t bar_w0full;   // B operand staged at the job's own start by the epilogue + stager warps
+    __shared__ __align__(8) uint64_t bar_roles;    // CTA-wide role barrier (hard job boundaries)
     __shared__ uint32_t tiles_done;   // epilogue-warp arrivals: 8 per finished tile, over all jobs (soft job boundaries)
 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -980,6 +988,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         tiles_done = 0;
         mbar_init(&bar_wfull, kStagers / 32);
         mbar_init(&bar_wempty, 1);
+        mbar_init(&bar_w0full, kEpiWarps + kStagers / 32);
+        mbar_init(&bar_roles, kBlock / 32);
         for (int i = 0; i < kV4MaxStages; ++i) {
             mbar_init(&bar_full[i], 1 + kEpiWarps);   // producer + (hand-over) the epilogue warps; the producer arrives for them otherwise
             mbar_init(&bar_empty[i], kAggWarps);
@@ -998,6 +1008,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    uint32_t ph_roles = 0;
 
     if (warp == kWarpTma) {
         // =============================== TMA producer ===============================
@@ -1006,7 +1017,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         uint32_t tiles_before = 0;   // tiles of all earlier jobs
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0 && !p.soft) bar_all_roles();   // the previous job's outputs are complete and visible to the async proxy
+            if (j > 0 && !p.soft) CTA_ROLE_BARRIER();   // the previous job's outputs are complete and visible to the async proxy
             if (lane == 0) {
                 const int C_csr = p.C_csr, N = p.N, f_in = p.f_in, S = p.n_stages;
                 const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
@@ -1063,7 +1074,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0 && !p.soft) bar_all_roles();
+            if (j > 0 && !p.soft) CTA_ROLE_BARRIER();
             if (warp == 0) V4_STAMP(0);
             // (the B operand is staged by the epilogue warps, which have nothing else to do until the first accumulator is
             // ready; the aggregation starts as soon as the first tile has landed)
@@ -1184,7 +1195,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         }
     } else if (warp >= kWarpMma) {
         reg_dec<kRegsMisc>();
-        uint32_t ph_zfull = 0, ph_tempty = 0, ph_wfull = 0, ph_wempty = 0;
+        uint32_t ph_zfull = 0, ph_tempty = 0, ph_wfull = 0, ph_wempty = 0, ph_w0full = 0;
         if (warp == kWarpMma + 1 || warp == kWarpMma + 2) {
             // =============================== B operand stagers ===============================
             // [W ; bias] of a soft job is written into the free B operand buffer one job ahead, off the epilogue warps'
@@ -1194,14 +1205,15 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             if (b.early) pdl_wait();   // parameters belong to the previous grid until it completes
             for (int j = 0; j < n_jobs; ++j) {
                 const V4Params& p = b.job[j];
-                if (j > 0 && !p.soft) bar_all_roles();
+                if (j > 0 && !p.soft) CTA_ROLE_BARRIER();
                 if (j > 0) {   // every MMA of job j - 1 has completed: the buffer it read may be overwritten
                     mbar_wait_relaxed(&bar_wempty, ph_wempty & 1u);
                     ph_wempty ^= 1u;
                 }
                 if (!p.prestaged) {
                     stage_b_operand<1>(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, 256 + ts, 256 + kStagers);
-                    named_barrier_sync(1, 288 + kStagers);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_w0full);
                 }
                 if (j + 1 < n_jobs && b.job[j + 1].prestaged) {
                     stage_b_operand<1>(stage_args(b.job[j + 1]), base + static_cast<uint32_t>(b.job[j + 1].wsel) * p.w_pair, ts, kStagers);
@@ -1213,10 +1225,11 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         for (int j = 0; j < n_jobs; ++j) {
             if (warp != kWarpMma) break;
             const V4Params& p = b.job[j];
-            if (j > 0 && !p.soft) bar_all_roles();
+            if (j > 0 && !p.soft) CTA_ROLE_BARRIER();
             // =============================== MMA issuer ===============================
-            if (!p.prestaged) {
-                named_barrier_sync(1, 288 + kStagers);   // B operand staged (epilogue + stager warps)
+            if (!p.prestaged) {   // B operand staged at this job's start (epilogue + stager warps)
+                mbar_wait(&bar_w0full, ph_w0full & 1u);
+                ph_w0full ^= 1u;
             } else {   // staged into the other buffer while the previous job ran
                 mbar_wait(&bar_wfull, ph_wfull & 1u);
                 ph_wfull ^= 1u;
@@ -1274,10 +1287,11 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
         if (b.early) pdl_wait();   // parameters (and every buffer this kernel writes) belong to the previous grid until it completes
         for (int j = 0; j < n_jobs; ++j) {
             const V4Params& p = b.job[j];
-            if (j > 0 && !p.soft) bar_all_roles();
+            if (j > 0 && !p.soft) CTA_ROLE_BARRIER();
             if (!p.prestaged) {   // (a prestaged job's operand was written by the stager warps during the previous job)
                 stage_b_operand<0>(stage_args(p), base + static_cast<uint32_t>(p.wsel) * p.w_pair, te, 256 + kStagers);
-                named_barrier_sync(1, 288 + kStagers);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_w0full);
             }
             if (e == 0) V4_STAMP(10);
             const int N = p.N, f_out = p.f_out, Np = p.Np;

@@ -72,7 +72,15 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
     return r;
 }
-__device__ __forceinline__ void bar_all_roles() { named_barrier_sync(2, kBlock); }
+// CTA-wide barrier of all warp roles on an mbarrier (count = warps of the CTA): every thread keeps its own phase bit.  (A named
+// bar.sync reached from the roles' different program counters is legal, but compute-sanitizer's synccheck reports it.)
+#define CTA_ROLE_BARRIER()                                  \
+    do {                                                    \
+        __syncwarp();                                       \
+        if (lane == 0) mbar_arrive(&bar_roles);             \
+        mbar_wait(&bar_roles, ph_roles & 1u);               \
+        ph_roles ^= 1u;                                     \
+    } while (0)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -130,14 +138,19 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_wready;   // W^T of the job is in tensor memory (written by the epilogue warps)
+    __shared__ __align__(8) uint64_t bar_roles;    // CTA-wide role barrier (job boundaries)
     __shared__ uint32_t tmem_slot;
 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_jobs = b.n_jobs;
+    uint32_t ph_roles = 0;
 
     if (tid == 0) {
+        mbar_init(&bar_wready, kEpiWarps);
+        mbar_init(&bar_roles, kBlock / 32);
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], kAggWarps);
@@ -163,7 +176,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
         uint32_t ph_empty = 0;
         for (int j = 0; j < n_jobs; ++j) {
             const V5Params& p = b.job[j];
-            if (j > 0) bar_all_roles();   // the previous job's outputs are complete and visible to the async proxy
+            if (j > 0) CTA_ROLE_BARRIER();   // the previous job's outputs are complete and visible to the async proxy
             if (lane == 0) {
                 const int C = p.C, N = p.N, f_in = p.f_in, S = p.n_stages;
                 const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
@@ -209,7 +222,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
         const uint32_t u7 = t7 ^ s7;
         for (int j = 0; j < n_jobs; ++j) {
             const V5Params& p = b.job[j];
-            if (j > 0) bar_all_roles();
+            if (j > 0) CTA_ROLE_BARRIER();
             const int N = p.N, C = p.C, f_in = p.f_in, S = p.n_stages, R = p.R;
             const uint32_t pitch = static_cast<uint32_t>(f_in) * 4u;
             const Range tr = cta_range(p);
@@ -325,13 +338,14 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
         }
     } else if (warp >= kWarpMma) {
         reg_dec<kRegsMisc>();
-        uint32_t ph_zfull = 0, ph_tempty = 0;
+        uint32_t ph_zfull = 0, ph_tempty = 0, ph_wready = 0;
         for (int j = 0; j < n_jobs; ++j) {
             const V5Params& p = b.job[j];
-            if (j > 0) bar_all_roles();
+            if (j > 0) CTA_ROLE_BARRIER();
             if (warp != kWarpMma) continue;
             // =============================== MMA issuer ===============================
-            named_barrier_sync(1, 288);   // W^T is in tensor memory (epilogue warps)
+            mbar_wait(&bar_wready, ph_wready & 1u);   // W^T is in tensor memory (epilogue warps)
+            ph_wready ^= 1u;
             tc_fence_after_sync();
             const int K = p.K, R = p.R;
             const Range tr = cta_range(p);
@@ -379,7 +393,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
         const int n = wq * 32 + lane;                     // this thread's output feature
         for (int j = 0; j < n_jobs; ++j) {
             const V5Params& p = b.job[j];
-            if (j > 0) bar_all_roles();
+            if (j > 0) CTA_ROLE_BARRIER();
             const int N = p.N, C = p.C, f_in = p.f_in, f_out = p.f_out, K = p.K, R = p.R;
             // ---- W^T -> tensor memory (hi at column k, lo at K + k): lane = output feature, warp (q, h) takes every second 32-k chunk
             {
@@ -414,7 +428,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
                 tmem_st_wait();
                 tc_fence_before_sync();
             }
-            named_barrier_sync(1, 288);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_wready);
             float bias_c[kMaxC];
 #pragma unroll
             for (int c = 0; c < kMaxC; ++c)
