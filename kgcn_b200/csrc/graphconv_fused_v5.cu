@@ -77,8 +77,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 #define CTA_ROLE_BARRIER()                                  \
     do {                                                    \
         __syncwarp();                                       \
-        if (lane == 0) mbar_arrive(&bar_roles);             \
-        mbar_wait(&bar_roles, ph_roles & 1u);               \
+        if (lane == 0) {   /* one polling lane per warp, with back-off: waiting roles must not take issue slots */ \
+            mbar_arrive(&bar_roles);                        \
+            while (!mbar_try_wait(&bar_roles, ph_roles & 1u)) __nanosleep(100); \
+        }                                                   \
+        __syncwarp();                                       \
         ph_roles ^= 1u;                                     \
     } while (0)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
