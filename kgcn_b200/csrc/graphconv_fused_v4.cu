@@ -84,6 +84,7 @@ struct V4Params {
     int soft_next;        // the next job of the chain is soft: publish every finished tile (fence + counter)
     int wbufs, wsel;      // B operand buffers (chain: 2 = the next soft job's [W ; bias] is staged during this job), buffer of this job
     int prestaged;        // this job's B operand was staged by the stager warps during the previous job
+    int hard_ord;         // jobs with a hard boundary: 1, 2, .. in launch order (phase of the role barrier)
     int x_prev;           // soft job whose x IS the previous job's y (same tiles): when a CTA's tiles fit the stage ring, the previous
                           // job's epilogue writes each output tile straight into this job's stage slot (on-chip hand-over)
     uint32_t w_pair;      // bytes of one (hi, lo) B operand buffer
@@ -876,10 +877,10 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
         __syncwarp();                                       \
         if (lane == 0) {   /* one polling lane per warp, with back-off: waiting roles must not take issue slots */ \
             mbar_arrive(&bar_roles);                        \
-            while (!mbar_try_wait(&bar_roles, ph_roles & 1u)) __nanosleep(100); \
+            while (!mbar_try_wait(&bar_roles, static_cast<uint32_t>(p.hard_ord - 1) & 1u)) {   /* phase = ordinal of the hard boundary */ \
+            }                                               \
         }                                                   \
         __syncwarp();                                       \
-        ph_roles ^= 1u;                                     \
     } while (0)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -1011,7 +1012,6 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    uint32_t ph_roles = 0;
 
     if (warp == kWarpTma) {
         // =============================== TMA producer ===============================
@@ -1231,10 +1231,12 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             if (j > 0 && !p.soft) CTA_ROLE_BARRIER();
             // =============================== MMA issuer ===============================
             if (!p.prestaged) {   // B operand staged at this job's start (epilogue + stager warps)
-                mbar_wait(&bar_w0full, ph_w0full & 1u);
+                if (lane == 0) mbar_wait_relaxed(&bar_w0full, ph_w0full & 1u);   // one polling lane, with back-off: the stagers share its scheduler
+                __syncwarp();
                 ph_w0full ^= 1u;
             } else {   // staged into the other buffer while the previous job ran
-                mbar_wait(&bar_wfull, ph_wfull & 1u);
+                if (lane == 0) mbar_wait_relaxed(&bar_wfull, ph_wfull & 1u);
+                __syncwarp();
                 ph_wfull ^= 1u;
             }
             tc_fence_after_sync();
@@ -1903,7 +1905,7 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
     for (int k = 0; k < n_jobs; ++k)
         if (jobs[k].head != nullptr) head_k = k;
     auto cn_of = [&](const V4ChainJob& j) { return j.c_count > 0 ? j.c_count : channels; };
-    int labels_prev = 0;
+    int labels_prev = 0, n_hard = 0;
     for (int k = 0; k < n_jobs; ++k) {
         const V4ChainJob& j = jobs[k];
         V4Params& p = b.job[k];
@@ -1965,6 +1967,7 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         if (p.soft) b.job[k - 1].soft_next = 1;
         p.wsel = (p.soft && p.wbufs == 2) ? (b.job[k - 1].wsel ^ 1) : 0;
         p.prestaged = (p.soft && p.wbufs == 2) ? 1 : 0;
+        p.hard_ord = (k > 0 && !p.soft) ? ++n_hard : 0;
         p.x_prev = (p.soft && handover_enabled() && j.x == jobs[k - 1].y && j.f_in == jobs[k - 1].f_out) ? 1 : 0;
         labels_prev = labels;
         smem = std::max(smem, p.smem_total);

@@ -72,18 +72,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
     return r;
 }
-// CTA-wide barrier of all warp roles on an mbarrier (count = warps of the CTA): every thread keeps its own phase bit.  (A named
-// bar.sync reached from the roles' different program counters is legal, but compute-sanitizer's synccheck reports it.)
-#define CTA_ROLE_BARRIER()                                  \
-    do {                                                    \
-        __syncwarp();                                       \
-        if (lane == 0) {   /* one polling lane per warp, with back-off: waiting roles must not take issue slots */ \
-            mbar_arrive(&bar_roles);                        \
-            while (!mbar_try_wait(&bar_roles, ph_roles & 1u)) __nanosleep(100); \
-        }                                                   \
-        __syncwarp();                                       \
-        ph_roles ^= 1u;                                     \
-    } while (0)
+// CTA-wide barrier of all warp roles at a job boundary.  A named bar.sync: legal PTX from the roles' different program
+// counters (compute-sanitizer's synccheck reports exactly that pattern as divergence, see tools/ubench/synccheck_probe.cu and
+// profiles/r02b_sanitizer.txt; the mbarrier form the chained v4 kernel uses costs this kernel 70 bytes of spills in the
+// aggregation loop: 47 vs 35 us for the two forward layers of config 5).
+#define CTA_ROLE_BARRIER() asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory")
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -142,18 +135,15 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
     __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_zfull[2], bar_zempty[2], bar_tfull[2], bar_tempty[2];
     __shared__ __align__(8) uint64_t bar_wready;   // W^T of the job is in tensor memory (written by the epilogue warps)
-    __shared__ __align__(8) uint64_t bar_roles;    // CTA-wide role barrier (job boundaries)
     __shared__ uint32_t tmem_slot;
 
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_jobs = b.n_jobs;
-    uint32_t ph_roles = 0;
 
     if (tid == 0) {
         mbar_init(&bar_wready, kEpiWarps);
-        mbar_init(&bar_roles, kBlock / 32);
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], kAggWarps);
@@ -347,7 +337,8 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
             if (j > 0) CTA_ROLE_BARRIER();
             if (warp != kWarpMma) continue;
             // =============================== MMA issuer ===============================
-            mbar_wait(&bar_wready, ph_wready & 1u);   // W^T is in tensor memory (epilogue warps)
+            if (lane == 0) mbar_wait_relaxed(&bar_wready, ph_wready & 1u);   // W^T is in tensor memory (epilogue warps); one polling lane, back-off
+            __syncwarp();
             ph_wready ^= 1u;
             tc_fence_after_sync();
             const int K = p.K, R = p.R;
