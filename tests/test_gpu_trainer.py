@@ -103,6 +103,45 @@ def test_graph_replay_equals_eager():
     assert abs(sa[0] - sb[0]) <= 1e-5 * abs(sa[0]) and sa[1] == sb[1]
 
 
+@pytest.mark.parametrize("name,B,N,C,F,conv_dims", [
+    ("c2", 1024, 32, 1, 64, [64, 64]),          # BASELINE configs at their FULL per-GPU batch
+    ("c3", 512, 50, 1, 75, [50, 50, 50]),
+    ("c4", 512, 50, 3, 75, [50, 50, 50]),
+    ("c5", 512, 64, 1, 128, [128, 128]),
+])
+def test_full_batch_training_steps_match_the_oracle(name, B, N, C, F, conv_dims):
+    """Two training steps at the BASELINE batch sizes -- the chained launches, channel groups, padded widths, the v5 kernel,
+    the fused head, the weight-gradient launch and the reduce + Adam tail exactly as bench.py runs them -- against the C
+    restatement of the reference's per-molecule path (oracle/graphconv_ref.c, pinned to the numpy oracle and through it to
+    the reference's own layers in tests/test_oracle_c.py): logits, cost, every gradient and the parameters after Adam."""
+    from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
+    from oracle import cref
+    spec = NetSpec(F, conv_dims, N, channels=C)
+    tr = Trainer(spec, B, seed=7)
+    assert tr.fused_step and tr.chain and (tr.step_chain or name == "c5")
+    ref = cref.RefNet(F, conv_dims, C, 2, act=2)
+    for k in ref.offsets:
+        ref.view(ref.params, k)[...] = tr.views[k].detach().cpu().numpy().reshape(ref.offsets[k][1])
+    for step in range(2):
+        counts, idx, val, x, labels, mask, _, _ = make_case(B, N, C, F, conv_dims, None, seed=100 + step)
+        batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=tr.dims[0])
+        stats, logits = ref.train_step(counts, idx, val, x, labels, mask, N, lr=tr.lr)
+        tr.step_eager(batch)
+        torch.cuda.synchronize()
+        close(tr.logits, logits, 1e-4)
+        cost_sum, correct = tr.read_stats()
+        assert abs(cost_sum - float(stats[0])) <= 1e-4 * abs(float(stats[0]))
+        assert abs(correct - float(stats[1])) <= 1.0          # an argmax tie may flip one molecule
+        for k in ref.offsets:
+            want = ref.view(ref.grads, k)
+            close(tr.gviews[k].reshape(want.shape), want, 2e-3)       # sums over B * N rows in fp32 (tf32 x3 products)
+        for k in ref.offsets:
+            want = ref.view(ref.params, k)
+            got = tr.views[k].detach().cpu().numpy().reshape(want.shape)
+            # Adam's first steps move every parameter by ~lr whatever the gradient's size: compare on that scale
+            np.testing.assert_allclose(got, want, rtol=0, atol=0.05 * tr.lr + 1e-6, err_msg="%s after step %d" % (k, step + 1))
+
+
 @pytest.mark.parametrize("B,N,F,conv_dims", [(700, 32, 64, [64, 64]), (300, 50, 75, [50, 50, 50])])
 def test_multi_step_graph_equals_eager_steps(B, N, F, conv_dims):
     """Trainer.capture_many: several steps over different resident batches in ONE graph -- every step after the first is
