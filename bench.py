@@ -305,21 +305,22 @@ class Bench:
         # the training loop over the resident batches as ONE graph of n_rot consecutive steps (Trainer.capture_many): steps
         # are linked by programmatic dependent launch; a remainder of < n_rot steps runs as single-step graphs
         epoch = tr.single_graph and not args.single_step_graphs
+        g_steps = min(n_rot, steps)          # steps per multi-step graph (a short run is ONE graph of exactly K steps)
         if epoch:
-            tr.capture_many(("train", "epoch"), batches)
+            tr.capture_many(("train", "epoch"), batches[:g_steps])
         self.note("%s: graphs captured, %d launches/step" % (key, launches_per_step))
 
         def run_steps(kind, k):
             i = 0
             if kind == "train" and epoch:
-                for _ in range(k // n_rot):
+                for _ in range(k // g_steps):
                     tr.replay(("train", "epoch"))
-                i = k - k % n_rot
+                i = k - k % g_steps
             for j in range(i, k):
                 tr.replay((kind, j % n_rot))
 
         def timed(kind, k, wu):
-            run_steps(kind, max(wu, n_rot) if (kind == "train" and epoch) else wu)   # at least one replay of the multi-step graph
+            run_steps(kind, max(wu, g_steps) if (kind == "train" and epoch) else wu)   # at least one replay of the multi-step graph
             self.barrier()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -538,7 +539,7 @@ class Bench:
                          "batch_per_gpu": B, "global_batch": mols, "n_nodes": N, "feature_dim": F, "conv_dims": w["conv_dims"], "channels": C,
                          "nnz_per_graph": nnz_mean / B, "parallelism": "dp%d" % world,
                          "l2": "rotating %d resident batches (%.0f MB of inputs > 126 MB L2)" % (n_rot, n_rot * (B * N * tr.dims[0] * 4 + 12 * nnz_mean) / 1e6),
-                         "launch": ("one CUDA graph per %d consecutive steps (Trainer.capture_many), remainder as single-step graphs" % n_rot)
+                         "launch": ("one CUDA graph per %d consecutive steps (Trainer.capture_many), remainder as single-step graphs" % g_steps)
                                    if epoch else "one CUDA graph replay per step", "data_seed": "1234 + rank",
                          "data": "generated on the device (torch device RNG + kgcn_pack_coo_device)" if w["gen"] == "device" else "host numpy generator"}
         return res, tr

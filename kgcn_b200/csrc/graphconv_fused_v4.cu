@@ -1412,7 +1412,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                                 }
                             }
                         } else if (!mul) {
-#pragma unroll
+#pragma unroll 2   // (rolled: this code runs once or twice per launch, its instruction fetch costs more than the loop overhead)
                             for (int k = 0; k < 8; ++k) {
                                 const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
                                 float t[4];
@@ -1571,19 +1571,19 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
                             ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
                         }
-                        float ex = lane < L ? expf(zl - zmax) : 0.0f, ysum = lane < L ? yl : 0.0f;
+                        float ex = lane < L ? __expf(zl - zmax) : 0.0f, ysum = lane < L ? yl : 0.0f;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) {
                             ex += __shfl_xor_sync(0xffffffffu, ex, o);
                             ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
                         }
-                        const float lse = logf(ex) + zmax;
+                        const float lse = __logf(ex) + zmax;
                         float cost = lane < L ? -yl * (zl - lse) : 0.0f;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
                         const int arg_p = __ffs(__ballot_sync(0xffffffffu, lane < L && zl == zmax)) - 1;   // first maximum wins
                         const int arg_y = __ffs(__ballot_sync(0xffffffffu, lane < L && yl == ymax)) - 1;
-                        const float pr = lane < L ? expf(zl - lse) : 0.0f;
+                        const float pr = lane < L ? __expf(zl - lse) : 0.0f;
                         const float dzl = m * p.inv_batch * (pr * ysum - yl);
                         if (lane < L) {
                             if (p.logits) p.logits[bg * L + lane] = zl;
@@ -1669,7 +1669,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             __syncwarp();
                             const bool col_ok = cs * 32 + colq < f_out;
                             float* ycs = y_tile + cs * 32;
-#pragma unroll
+#pragma unroll 2
                             for (int k = 0; k < 8; ++k) {
                                 const uint32_t r7 = (static_cast<uint32_t>(4 * k) + (static_cast<uint32_t>(lane) >> 3)) & 7u;
                                 float t[4];
