@@ -441,7 +441,7 @@ class Bench:
         dw_b = sum(4 * B * N * (ld[l] + ld[l + 1]) + csr_bytes + 4 * tr.splits[l] * (ld[l] + 1) * C * ld[l + 1] for l in range(L)) if tr.fused_step else 0
         if tr.step_chain:
             # forward layers (the last one writes dU instead of its activations) + head (no HBM traffic of its own) + dx jobs
-            add("graphconv_fused_v4_chain_kernel (forward x%d + readout head + dx x%d)" % (L, L - 1), 1,
+            add("chained layer launch: graphconv_fused_%s (forward x%d + readout head + dx x%d)" % ("v5_kernel" if max(tr.dims) > 96 else "v4_chain_kernel", L, L - 1), 1,
                 lambda i: tr._launch_step_chain(batches[i % n_rot], st()), fwd_b + dx_b)
             add("graphconv_fused_dw_kernel (%d weight-gradient jobs)" % L, 1, lambda i: tr._launch_dw_chain(batches[i % n_rot], st()), dw_b)
         elif tr.chain and tr.fused_step:

@@ -164,6 +164,7 @@ int fused_v4_chain_group(int64_t n_graphs, int channels, int n_nodes, int f_in, 
 bool soft_jobs_enabled();   // graphconv_fused_dw.cu: KGCN_SOFT_JOBS (A-B knob, default on)
 // graphconv_fused_v5.cu: the transposed-product kernel for wide layers (weights resident in tensor memory), same job struct
 bool fused_v5_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);
+int fused_v5_head_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels);   // 0: no fused head for this shape
 int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st);
 bool fused_v4_head_chainable(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels);
 int fused_v4_chain_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out);

@@ -415,7 +415,11 @@ extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_
 extern "C" int32_t kgcn_gcn_step_chain_grid(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
                                             const int32_t* dims, int32_t n_labels) {
     if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || n_layers < 1 || n_layers > 4 || dims == nullptr) return 0;
-    if (chain_kind(n_graphs, channels, n_nodes, n_layers, dims) != 1 || n_labels < 1 || n_labels > 4) return 0;
+    if (n_labels < 1 || n_labels > 4) return 0;
+    const int kind = chain_kind(n_graphs, channels, n_nodes, n_layers, dims);
+    if (kind == 2)   // wide layers (v5 kernel): forward jobs + head + dx jobs, at most 4 jobs
+        return 2 * n_layers - 1 <= 4 ? fused_v5_head_grid(n_graphs, channels, n_nodes, dims[n_layers - 1], dims[n_layers], n_labels) : 0;
+    if (kind != 1) return 0;
     int jobs = n_layers - 1;   // dx jobs
     for (int l = 0; l < n_layers; ++l) {
         const int cg = fused_v4_chain_group(n_graphs, channels, n_nodes, dims[l], dims[l + 1], l == n_layers - 1 ? n_labels : 0);
@@ -444,6 +448,26 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
     V4Head head{n_labels, head_w, head_b, labels, mask, inv_batch, logits, prediction, gathered, head_partial};
     const float* in = x;
     int k = 0;
+    const int kind = chain_kind(n_graphs, channels, n_nodes, n_layers, dims);
+    KGCN_REQUIRE(kind != 0, KGCN_ERR_UNSUPPORTED, "gcn_step_chain: network not supported (kgcn_gcn_step_chain_grid)");
+    if (kind == 2) {   // wide layers: the v5 kernel, one job per layer
+        KGCN_REQUIRE(2 * L - 1 <= 4, KGCN_ERR_UNSUPPORTED, "gcn_step_chain: network not supported (kgcn_gcn_step_chain_grid)");
+        for (int l = 0; l < L; ++l, ++k) {
+            float* out = (l == L - 1) ? du[L - 1] : y[l];
+            KGCN_REQUIRE(w[l] && out, KGCN_ERR_NULL, "gcn_step_chain: NULL weight / output of layer %d", l);
+            KGCN_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w[l]) && (!bias || aligned16(bias[l])), KGCN_ERR_MISALIGNED,
+                         "gcn_step_chain: 16-byte alignment required");
+            jobs[k] = V4ChainJob{rowptr, col, val, in, w[l], bias ? bias[l] : nullptr, out, dims[l], dims[l + 1], act, 0, nullptr, KGCN_ACT_NONE,
+                                 dims_valid ? dims_valid[l + 1] : dims[l + 1], (l == L - 1) ? &head : nullptr};
+            in = out;
+        }
+        for (int l = L - 1; l >= 1; --l, ++k) {
+            KGCN_REQUIRE(du[l] && du[l - 1] && y[l - 1], KGCN_ERR_NULL, "gcn_step_chain: NULL pointer at dx of layer %d", l);
+            jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
+                                 y[l - 1], act, 0, nullptr};
+        }
+        return launch_graphconv_fused_v5_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
+    }
     for (int l = 0; l < L; ++l) {
         float* out = (l == L - 1) ? du[L - 1] : y[l];
         KGCN_REQUIRE(w[l] && out, KGCN_ERR_NULL, "gcn_step_chain: NULL weight / output of layer %d", l);

@@ -33,6 +33,7 @@ constexpr int kBlock = 20 * 32;
 constexpr int kRegsAgg = 128, kRegsEpi = 80, kRegsMisc = 56;
 constexpr int kMaxJobs = 4;
 constexpr int kMaxC = 4;
+constexpr int kHeadTiles = 4;   // fused head: tiles per CTA whose column sums / d gathered are kept in shared memory at once
 
 struct V5Params {
     const int32_t* rowptr;
@@ -51,6 +52,19 @@ struct V5Params {
     uint32_t z_atom, z_half, z_buf;   // bytes: one 32-k atom (R x 128), hi -> lo, buffer -> buffer
     uint32_t off_z, off_deg, off_stage, stage_bytes, st_rp, st_col, st_val, smem_total;
     uint32_t tm_acc;        // first TMEM column of accumulator 0 (W^T hi at 0, lo at K)
+    // fused readout head (last forward job of a training step, see graphconv_fused_v4.cu): GraphGather + Dense(n_labels) +
+    // softmax cross-entropy on the epilogue's own tiles; the job then writes dU = dg (.) act'(H) instead of H
+    int head, n_labels;
+    const float* head_w;       // [f_out][n_labels]
+    const float* head_b;       // [n_labels] or NULL
+    const float* labels;       // [B][n_labels]
+    const float* mask;         // [B] or NULL
+    float inv_batch;
+    float* logits;             // [B][n_labels] (may be NULL)
+    float* prediction;         // [B][n_labels] (may be NULL)
+    float* gathered;           // [B][f_out]    (may be NULL)
+    float* head_partial;       // [grid][f_out * n_labels + 8]: dW_dense | db_dense (4) | cost_sum, correct_count, 0, 0
+    uint32_t off_head;
 };
 struct V5Batch {
     int n_jobs;
@@ -431,53 +445,302 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
             const Range tr = cta_range(p);
             const bool col_ok = n < f_out;
             const bool keep = n < p.f_valid;
-            int ai = 0;
-            for (int it = 0; it < tr.n_tiles; ++it) {
-                const int rows = ((it == tr.n_tiles - 1) ? tr.last_ng : p.G) * N;
-                const int64_t row_base = (tr.g_begin + static_cast<int64_t>(it) * p.G) * N;
-                mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
-                ph_tfull ^= 1u << ai;
-                tc_fence_after_sync();
-                const uint32_t ta = tmem + lane_sel + p.tm_acc + static_cast<uint32_t>(ai * R);
-                // row sums of tile `it`: four buffers -- the writer of tile it + 4 runs only after this tile's accumulator has
-                // been handed back (below, after the last read of degb)
-                const uint32_t degb = base + p.off_deg + static_cast<uint32_t>((it & 3) * kMaxC * R) * 4u;
-                const int half = (R / 2 + 15) & ~15;           // columns (tile rows) of this warp: [h * half, min(R, (h + 1) * half))
-                const int c_lo = h * half, c_hi = min(R, c_lo + half);
-#pragma unroll 1
-                for (int r0 = c_lo; r0 < c_hi; r0 += 16) {
-                    float v[16], mv[16];
-                    tmem_ld16(ta + static_cast<uint32_t>(r0), v);
-                    float* yrow = p.y + (row_base + r0) * f_out + n;
-                    if (p.mul_src != nullptr) {   // all 16 loads in flight before the first use
-                        const float* mrow = p.mul_src + (row_base + r0) * f_out + n;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) mv[i] = (r0 + i < rows && col_ok) ? __ldg(mrow + static_cast<size_t>(i) * f_out) : 0.0f;
-                    }
-                    tmem_ld_wait();
-                    tmem_ld_fence(v);
-#pragma unroll
-                    for (int c = 0; c < kMaxC; ++c)
-                        if (c < C && bias_c[c] != 0.0f) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaf(lds_f32(degb + 4u * static_cast<uint32_t>(c * R + r0 + i)), bias_c[c], v[i]);
-                        }
-                    if (p.act != KGCN_ACT_NONE) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fast_act_rt(v[i], p.act);
-                    }
-                    if (p.mul_src != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] *= act_grad_from_output(mv[i], p.mul_act);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (r0 + i < rows && col_ok) yrow[static_cast<size_t>(i) * f_out] = keep ? v[i] : 0.0f;
+            if (p.head) {
+                // ======== fused head.  Lane = output feature n (32 wq + lane), this warp's tile rows = columns [c_lo, c_hi) of the
+                // accumulator.  Tiles are taken in groups (see gmax): (a) activation + per-graph column sums
+                // for every tile of the group, (b) one warp per graph: gather, Dense, softmax cross-entropy, d logits, d gathered,
+                // (c) dU = dg (.) act'(H) with H re-read from tensor memory.  G <= 4 graphs per tile (N >= 32). ========
+                const int L = p.n_labels, Fs = f_out, G = p.G;
+                const int te = tid - kWarpEpi0 * 32;
+                const uint32_t hs_gsum = base + p.off_head;                                           // [kHeadTiles][2 halves][G][Fs]
+                const uint32_t hs_dg = hs_gsum + static_cast<uint32_t>(2 * kHeadTiles * G * Fs) * 4u; // [kHeadTiles][G][Fs]
+                const uint32_t hs_wd = hs_dg + static_cast<uint32_t>(kHeadTiles * G * Fs) * 4u;       // [Fs][L] + bias [4]
+                const uint32_t hs_hp = hs_wd + static_cast<uint32_t>(Fs * L + 4) * 4u;                // [8 warps][Fs * L + 8]
+                for (int i = te; i < Fs * L + 4; i += 256) {
+                    const int bi = i - Fs * L;
+                    const float wv[1] = {bi < 0 ? __ldg(p.head_w + i) : ((bi < L && p.head_b != nullptr) ? __ldg(p.head_b + bi) : 0.0f)};
+                    sts_f<1>(hs_wd + 4u * static_cast<uint32_t>(i), wv);
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_tempty[ai]);   // accumulator and row sums of this tile are consumed
-                ai ^= 1;
+                const float z1[1] = {0.0f};
+                for (int i = te; i < kEpiWarps * (Fs * L + 8); i += 256) sts_f<1>(hs_hp + 4u * static_cast<uint32_t>(i), z1);
+                asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                const uint32_t my_hp = hs_hp + static_cast<uint32_t>(e * (Fs * L + 8)) * 4u;
+                const int half = (R / 2 + 15) & ~15;
+                const int c_lo = h * half, c_hi = min(R, c_lo + half);
+                const int nq = Fs >> 5;                                   // 32-feature groups a lane of phase (b) owns (<= 4)
+                // DEFERRED mode (a CTA's tiles <= kHeadTiles: the latency-bound case): (a) is the plain epilogue -- H goes to y, the
+                // accumulator is handed back at once, so aggregation and MMAs of the next tiles overlap it -- plus the column sums of
+                // ALL tiles; then ONE (b) for all graphs of the CTA and (c) as an element-wise sweep over the CTA's rows of y (read H
+                // back from L2, write dU in place).  Otherwise groups of two tiles with H kept in tensor memory between (a) and (c).
+                const bool deferred = tr.n_tiles <= kHeadTiles;
+                const int gmax = deferred ? tr.n_tiles : 2;
+                int ai = 0;
+                for (int it0 = 0; it0 < tr.n_tiles; it0 += gmax) {
+                    const int gsz = min(gmax, tr.n_tiles - it0);
+                    const int64_t g0_grp = tr.g_begin + static_cast<int64_t>(it0) * G;
+                    const int64_t left_cta = p.n_graphs - tr.g_begin;
+                    const int n_cta = left_cta < p.graphs_per_cta ? static_cast<int>(left_cta) : p.graphs_per_cta;
+                    const int ng_grp = min(gsz * G, n_cta - it0 * G);
+                    float y_lane = 0.0f, m0 = 1.0f;     // label l (lane l) and mask of the graph this warp finishes in (b): requested early
+                    if (e < ng_grp) {
+                        if (lane < L) y_lane = __ldg(p.labels + (g0_grp + e) * L + lane);
+                        if (p.mask) m0 = __ldg(p.mask + g0_grp + e);
+                    }
+                    // (a)
+                    int aa = ai;
+                    for (int u = 0; u < gsz; ++u) {
+                        const int it = it0 + u;
+                        const int rows = ((it == tr.n_tiles - 1) ? tr.last_ng : G) * N;
+                        mbar_wait_relaxed(&bar_tfull[aa], (ph_tfull >> aa) & 1u);
+                        ph_tfull ^= 1u << aa;
+                        tc_fence_after_sync();
+                        const uint32_t ta = tmem + lane_sel + p.tm_acc + static_cast<uint32_t>(aa * R);
+                        const uint32_t degb = base + p.off_deg + static_cast<uint32_t>((it & 3) * kMaxC * R) * 4u;
+                        const uint32_t gs_u = hs_gsum + static_cast<uint32_t>((u * 2 + h) * G * Fs) * 4u + 4u * static_cast<uint32_t>(n);
+                        if (col_ok)
+                            for (int g = 0; g < G; ++g) sts_f<1>(gs_u + 4u * static_cast<uint32_t>(g * Fs), z1);
+#pragma unroll 1
+                        for (int r0 = c_lo; r0 < c_hi; r0 += 16) {
+                            float v[16];
+                            tmem_ld16(ta + static_cast<uint32_t>(r0), v);
+                            tmem_ld_wait();
+                            tmem_ld_fence(v);
+#pragma unroll
+                            for (int c = 0; c < kMaxC; ++c)
+                                if (c < C && bias_c[c] != 0.0f) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] = fmaf(lds_f32(degb + 4u * static_cast<uint32_t>(c * R + r0 + i)), bias_c[c], v[i]);
+                                }
+                            const int ga = r0 / N;                         // a 16-row chunk touches at most two graphs (N >= 32)
+                            const int split = (ga + 1) * N - r0;           // first row of the chunk that belongs to graph ga + 1
+                            float s0 = 0.0f, s1 = 0.0f;
+                            float* hrow = p.y + ((tr.g_begin + static_cast<int64_t>(it) * G) * N + r0) * f_out + n;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float hv = (r0 + i < rows && keep) ? fast_act_rt(v[i], p.act) : 0.0f;
+                                if (i < split) s0 += hv; else s1 += hv;
+                                if (deferred && r0 + i < rows && col_ok) hrow[static_cast<size_t>(i) * f_out] = hv;   // H, replaced by dU in (c)
+                            }
+                            if (col_ok) {
+                                const float a0[1] = {lds_f32(gs_u + 4u * static_cast<uint32_t>(ga * Fs)) + s0};
+                                sts_f<1>(gs_u + 4u * static_cast<uint32_t>(ga * Fs), a0);
+                                if (split < 16 && ga + 1 < G) {
+                                    const float a1[1] = {lds_f32(gs_u + 4u * static_cast<uint32_t>((ga + 1) * Fs)) + s1};
+                                    sts_f<1>(gs_u + 4u * static_cast<uint32_t>((ga + 1) * Fs), a1);
+                                }
+                            }
+                        }
+                        if (deferred) {   // the accumulator and the row sums of this tile are consumed
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bar_tempty[aa]);
+                        }
+                        aa ^= 1;
+                    }
+                    if (deferred) __threadfence_block();   // (c) reads H written by other threads of the CTA
+                    asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                    // (b) one warp per graph of the group; a lane owns features lane + 32 q
+                    for (int gi = e; gi < ng_grp; gi += kEpiWarps) {
+                        const int u = gi / G, g = gi - u * G;
+                        const int64_t bg = g0_grp + gi;
+                        float yl = y_lane, m = m0;
+                        if (gi != e) {
+                            yl = lane < L ? __ldg(p.labels + bg * L + lane) : 0.0f;
+                            m = p.mask ? __ldg(p.mask + bg) : 1.0f;
+                        }
+                        float gv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < nq) {
+                                const uint32_t a = hs_gsum + 4u * static_cast<uint32_t>((u * 2 * G + g) * Fs + q * 32 + lane);
+                                gv[q] = lds_f32(a) + lds_f32(a + 4u * static_cast<uint32_t>(G * Fs));
+                                if (p.gathered != nullptr) p.gathered[bg * Fs + q * 32 + lane] = gv[q];
+                            }
+                        float zl = -3.0e38f;
+#pragma unroll 1
+                        for (int l = 0; l < L; ++l) {
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (q < nq) acc = fmaf(gv[q], lds_f32(hs_wd + 4u * static_cast<uint32_t>((q * 32 + lane) * L + l)), acc);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                            if (lane == l) zl = acc + lds_f32(hs_wd + 4u * static_cast<uint32_t>(Fs * L + l));
+                        }
+                        float zmax = zl, ymax = lane < L ? yl : -3.0e38f;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                            ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+                        }
+                        float ex = lane < L ? __expf(zl - zmax) : 0.0f, ysum = lane < L ? yl : 0.0f;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                            ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
+                        }
+                        const float lse = __logf(ex) + zmax;
+                        float cost = lane < L ? -yl * (zl - lse) : 0.0f;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+                        const int arg_p = __ffs(__ballot_sync(0xffffffffu, lane < L && zl == zmax)) - 1;
+                        const int arg_y = __ffs(__ballot_sync(0xffffffffu, lane < L && yl == ymax)) - 1;
+                        const float pr = lane < L ? __expf(zl - lse) : 0.0f;
+                        const float dzl = m * p.inv_batch * (pr * ysum - yl);
+                        if (lane < L) {
+                            if (p.logits) p.logits[bg * L + lane] = zl;
+                            if (p.prediction) p.prediction[bg * L + lane] = pr;
+                            const float bacc[1] = {lds_f32(my_hp + 4u * static_cast<uint32_t>(Fs * L + lane)) + dzl};
+                            sts_f<1>(my_hp + 4u * static_cast<uint32_t>(Fs * L + lane), bacc);
+                        }
+                        if (lane == 0) {
+                            const float c2[2] = {lds_f32(my_hp + 4u * static_cast<uint32_t>(Fs * L + 4)) + m * cost,
+                                                 lds_f32(my_hp + 4u * static_cast<uint32_t>(Fs * L + 5)) + m * (arg_p == arg_y ? 1.0f : 0.0f)};
+                            sts_f<2>(my_hp + 4u * static_cast<uint32_t>(Fs * L + 4), c2);
+                        }
+                        float dg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                        for (int l = 0; l < L; ++l) {   // d gathered and this warp's share of dW_dense
+                            const float dz = __shfl_sync(0xffffffffu, dzl, l);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (q < nq) {
+                                    const uint32_t wi = 4u * static_cast<uint32_t>((q * 32 + lane) * L + l);
+                                    dg[q] = fmaf(dz, lds_f32(hs_wd + wi), dg[q]);
+                                    const float a0[1] = {fmaf(gv[q], dz, lds_f32(my_hp + wi))};
+                                    sts_f<1>(my_hp + wi, a0);
+                                }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < nq) {
+                                const float o0[1] = {dg[q]};
+                                sts_f<1>(hs_dg + 4u * static_cast<uint32_t>((u * G + g) * Fs + q * 32 + lane), o0);
+                            }
+                        __syncwarp();
+                    }
+                    asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                    // (c)
+                    if (deferred) {   // element-wise sweep over the CTA's rows of y: 16-byte accesses, 8 independent loads per thread in flight
+                        ai = aa;
+                        const int n_cta_rows = n_cta * N;
+                        const int f4 = Fs >> 2;
+                        float* y0 = p.y + tr.g_begin * N * static_cast<int64_t>(f_out);
+                        for (int i0 = te; i0 < n_cta_rows * f4; i0 += 8 * 256) {
+                            float4 hv[8];
+#pragma unroll
+                            for (int k8 = 0; k8 < 8; ++k8) {
+                                const int idx = i0 + k8 * 256;
+                                hv[k8] = idx < n_cta_rows * f4 ? *reinterpret_cast<const float4*>(y0 + static_cast<size_t>(idx) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int k8 = 0; k8 < 8; ++k8) {
+                                const int idx = i0 + k8 * 256;
+                                if (idx < n_cta_rows * f4) {
+                                    const int row = idx / f4, c4 = (idx - row * f4) << 2;
+                                    float d[4];
+                                    lds_f<4>(d, hs_dg + 4u * static_cast<uint32_t>((row / N) * Fs + c4));   // tile-major = graph-major: [tile][g][Fs]
+                                    const float o[4] = {d[0] * act_grad_from_output(hv[k8].x, p.act), d[1] * act_grad_from_output(hv[k8].y, p.act),
+                                                        d[2] * act_grad_from_output(hv[k8].z, p.act), d[3] * act_grad_from_output(hv[k8].w, p.act)};
+                                    *reinterpret_cast<float4*>(y0 + static_cast<size_t>(idx) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                                }
+                            }
+                        }
+                    }
+                    for (int u = 0; u < (deferred ? 0 : gsz); ++u) {
+                        const int it = it0 + u;
+                        const int rows = ((it == tr.n_tiles - 1) ? tr.last_ng : G) * N;
+                        const int64_t row_base = (tr.g_begin + static_cast<int64_t>(it) * G) * N;
+                        const uint32_t ta = tmem + lane_sel + p.tm_acc + static_cast<uint32_t>(ai * R);
+                        const uint32_t degb = base + p.off_deg + static_cast<uint32_t>((it & 3) * kMaxC * R) * 4u;
+                        const uint32_t dg_u = hs_dg + 4u * static_cast<uint32_t>(u * G * Fs + n);
+#pragma unroll 1
+                        for (int r0 = c_lo; r0 < c_hi; r0 += 16) {
+                            float v[16];
+                            tmem_ld16(ta + static_cast<uint32_t>(r0), v);
+                            float* yrow = p.y + (row_base + r0) * f_out + n;
+                            const int ga = r0 / N;
+                            const int split = (ga + 1) * N - r0;
+                            const float d0 = col_ok ? lds_f32(dg_u + 4u * static_cast<uint32_t>(ga * Fs)) : 0.0f;
+                            const float d1 = (col_ok && split < 16 && ga + 1 < G) ? lds_f32(dg_u + 4u * static_cast<uint32_t>((ga + 1) * Fs)) : 0.0f;
+                            tmem_ld_wait();
+                            tmem_ld_fence(v);
+#pragma unroll
+                            for (int c = 0; c < kMaxC; ++c)
+                                if (c < C && bias_c[c] != 0.0f) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] = fmaf(lds_f32(degb + 4u * static_cast<uint32_t>(c * R + r0 + i)), bias_c[c], v[i]);
+                                }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float hv = keep ? fast_act_rt(v[i], p.act) : 0.0f;
+                                const float du = (i < split ? d0 : d1) * act_grad_from_output(hv, p.act);
+                                if (r0 + i < rows && col_ok) yrow[static_cast<size_t>(i) * f_out] = keep ? du : 0.0f;
+                            }
+                        }
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[ai]);   // accumulator and row sums of this tile are consumed
+                        ai ^= 1;
+                    }
+                }
+                // per-CTA partial of the head's parameter gradients and statistics: the 8 warps' sums, added in warp order
+                asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                float* hp_out = p.head_partial + static_cast<size_t>(blockIdx.x) * (Fs * L + 8);
+                for (int i = te; i < Fs * L + 8; i += 256) {
+                    float acc = 0.0f;
+                    for (int w8 = 0; w8 < kEpiWarps; ++w8) acc += lds_f32(hs_hp + 4u * static_cast<uint32_t>(w8 * (Fs * L + 8) + i));
+                    hp_out[i] = acc;
+                }
+            } else {
+                int ai = 0;
+                for (int it = 0; it < tr.n_tiles; ++it) {
+                    const int rows = ((it == tr.n_tiles - 1) ? tr.last_ng : p.G) * N;
+                    const int64_t row_base = (tr.g_begin + static_cast<int64_t>(it) * p.G) * N;
+                    mbar_wait_relaxed(&bar_tfull[ai], (ph_tfull >> ai) & 1u);
+                    ph_tfull ^= 1u << ai;
+                    tc_fence_after_sync();
+                    const uint32_t ta = tmem + lane_sel + p.tm_acc + static_cast<uint32_t>(ai * R);
+                    // row sums of tile `it`: four buffers -- the writer of tile it + 4 runs only after this tile's accumulator has
+                    // been handed back (below, after the last read of degb)
+                    const uint32_t degb = base + p.off_deg + static_cast<uint32_t>((it & 3) * kMaxC * R) * 4u;
+                    const int half = (R / 2 + 15) & ~15;           // columns (tile rows) of this warp: [h * half, min(R, (h + 1) * half))
+                    const int c_lo = h * half, c_hi = min(R, c_lo + half);
+    #pragma unroll 1
+                    for (int r0 = c_lo; r0 < c_hi; r0 += 16) {
+                        float v[16], mv[16];
+                        tmem_ld16(ta + static_cast<uint32_t>(r0), v);
+                        float* yrow = p.y + (row_base + r0) * f_out + n;
+                        if (p.mul_src != nullptr) {   // all 16 loads in flight before the first use
+                            const float* mrow = p.mul_src + (row_base + r0) * f_out + n;
+    #pragma unroll
+                            for (int i = 0; i < 16; ++i) mv[i] = (r0 + i < rows && col_ok) ? __ldg(mrow + static_cast<size_t>(i) * f_out) : 0.0f;
+                        }
+                        tmem_ld_wait();
+                        tmem_ld_fence(v);
+    #pragma unroll
+                        for (int c = 0; c < kMaxC; ++c)
+                            if (c < C && bias_c[c] != 0.0f) {
+    #pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = fmaf(lds_f32(degb + 4u * static_cast<uint32_t>(c * R + r0 + i)), bias_c[c], v[i]);
+                            }
+                        if (p.act != KGCN_ACT_NONE) {
+    #pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = fast_act_rt(v[i], p.act);
+                        }
+                        if (p.mul_src != nullptr) {
+    #pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= act_grad_from_output(mv[i], p.mul_act);
+                        }
+    #pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (r0 + i < rows && col_ok) yrow[static_cast<size_t>(i) * f_out] = keep ? v[i] : 0.0f;
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[ai]);   // accumulator and row sums of this tile are consumed
+                    ai ^= 1;
+                }
             }
             // this CTA's outputs of the job: visible to the next job's TMA loads (async proxy) after the role barrier
             __threadfence();
@@ -493,7 +756,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
 inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 constexpr int kSmemMax = 227 * 1024 - 1024;
 
-bool plan_v5_try(V5Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int G) {
+bool plan_v5_try(V5Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int G, int head_labels = 0) {
     p.C = C; p.N = N; p.f_in = f_in; p.f_out = f_out; p.n_graphs = n_graphs;
     p.K = C * f_in;
     p.n_slabs = p.K / 32;
@@ -514,6 +777,12 @@ bool plan_v5_try(V5Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     uint32_t off = 0;
     p.off_z = off; off += 2u * p.z_buf;
     p.off_deg = off; off += up(4u * kMaxC * p.R * 4u, 128);
+    p.off_head = off;
+    p.head = 0;
+    if (head_labels > 0) {   // gsum [kHeadTiles][2][G][F] + dg [kHeadTiles][G][F] + Dense weights + 8 per-warp accumulator blocks
+        if (p.G > 4 || N < 32 || f_out % 32 != 0 || head_labels > 4) return false;
+        off += up(static_cast<uint32_t>(3 * kHeadTiles * p.G * f_out + f_out * head_labels + 4 + kEpiWarps * (f_out * head_labels + 8)) * 4u, 128);
+    }
     p.off_stage = off;
     p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C), 4));
     p.st_rp = up(rows_max * f_in * 4u, 128);
@@ -528,10 +797,10 @@ bool plan_v5_try(V5Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     return true;
 }
 
-bool plan_v5(V5Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
+bool plan_v5(V5Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int head_labels = 0) {
     if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out < 1 || f_out > 128 || C < 1 || C > kMaxC) return false;
     for (int G = std::max(1, 128 / N); G >= 1; G = (G > 1 ? G / 2 : 0))
-        if (plan_v5_try(p, n_graphs, C, N, f_in, f_out, G)) return true;
+        if (plan_v5_try(p, n_graphs, C, N, f_in, f_out, G, head_labels)) return true;
     return false;
 }
 
@@ -550,6 +819,13 @@ bool fused_v5_plannable(int64_t n_graphs, int channels, int n_nodes, int f_in, i
     return v5_enabled() && plan_v5(p, n_graphs, channels, n_nodes, f_in, f_out);
 }
 
+// grid of a chained launch whose last forward layer (f_in -> f_out) carries the fused head; 0 = not supported
+int fused_v5_head_grid(int64_t n_graphs, int channels, int n_nodes, int f_in, int f_out, int n_labels) {
+    V5Params p{};
+    if (!v5_enabled() || n_labels < 1 || !plan_v5(p, n_graphs, channels, n_nodes, f_in, f_out, n_labels)) return 0;
+    return static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
+}
+
 int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, cudaStream_t st) {
     KGCN_REQUIRE(n_jobs >= 1 && n_jobs <= kMaxJobs, KGCN_ERR_BAD_SHAPE, "fused GraphConv v5 chain: 1..%d jobs", kMaxJobs);
     V5Batch b{};
@@ -558,8 +834,7 @@ int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
     for (int k = 0; k < n_jobs; ++k) {
         const V4ChainJob& j = jobs[k];
         V5Params& p = b.job[k];
-        KGCN_REQUIRE(j.head == nullptr, KGCN_ERR_UNSUPPORTED, "fused GraphConv v5: no fused head");
-        KGCN_REQUIRE(plan_v5(p, n_graphs, channels, n_nodes, j.f_in, j.f_out), KGCN_ERR_UNSUPPORTED,
+        KGCN_REQUIRE(plan_v5(p, n_graphs, channels, n_nodes, j.f_in, j.f_out, j.head != nullptr ? j.head->n_labels : 0), KGCN_ERR_UNSUPPORTED,
                      "fused GraphConv v5: job %d (%d -> %d) unsupported", k, j.f_in, j.f_out);
         KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv v5 chain: graph ranges differ");
         p.rowptr = j.rowptr; p.col = j.col; p.val = j.val; p.x = j.x; p.y = j.y;
@@ -570,6 +845,15 @@ int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         p.mul_src = j.mul_src;
         p.mul_act = j.mul_act;
         p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : j.f_out;
+        if (j.head != nullptr) {
+            const V4Head& hd = *j.head;
+            KGCN_REQUIRE(j.mul_src == nullptr && !j.w_transposed && hd.w && hd.labels && hd.partial && hd.n_labels >= 1 && hd.n_labels <= 4,
+                         KGCN_ERR_BAD_SHAPE, "fused GraphConv v5: bad head (1..4 labels)");
+            p.head = 1;
+            p.n_labels = hd.n_labels;
+            p.head_w = hd.w; p.head_b = hd.b; p.labels = hd.labels; p.mask = hd.mask; p.inv_batch = hd.inv_batch;
+            p.logits = hd.logits; p.prediction = hd.prediction; p.gathered = hd.gathered; p.head_partial = hd.partial;
+        }
         smem = std::max(smem, p.smem_total);
     }
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, b.job[0].graphs_per_cta));
