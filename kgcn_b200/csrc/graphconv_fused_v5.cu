@@ -708,14 +708,9 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
                     const int c_lo = h * half, c_hi = min(R, c_lo + half);
     #pragma unroll 1
                     for (int r0 = c_lo; r0 < c_hi; r0 += 16) {
-                        float v[16], mv[16];
+                        float v[16];
                         tmem_ld16(ta + static_cast<uint32_t>(r0), v);
                         float* yrow = p.y + (row_base + r0) * f_out + n;
-                        if (p.mul_src != nullptr) {   // all 16 loads in flight before the first use
-                            const float* mrow = p.mul_src + (row_base + r0) * f_out + n;
-    #pragma unroll
-                            for (int i = 0; i < 16; ++i) mv[i] = (r0 + i < rows && col_ok) ? __ldg(mrow + static_cast<size_t>(i) * f_out) : 0.0f;
-                        }
                         tmem_ld_wait();
                         tmem_ld_fence(v);
     #pragma unroll
@@ -728,10 +723,6 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
     #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = fast_act_rt(v[i], p.act);
                         }
-                        if (p.mul_src != nullptr) {
-    #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= act_grad_from_output(mv[i], p.mul_act);
-                        }
     #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (r0 + i < rows && col_ok) yrow[static_cast<size_t>(i) * f_out] = keep ? v[i] : 0.0f;
@@ -740,6 +731,37 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_tempty[ai]);   // accumulator and row sums of this tile are consumed
                     ai ^= 1;
+                }
+                if (p.mul_src != nullptr) {
+                    // backward dx: y *= act'(mul_src) as an element-wise sweep over the CTA's rows once all tiles are stored (16-byte
+                    // accesses, 2 x 4 independent loads per thread in flight) -- inside the tile loop the 16 strided loads per chunk
+                    // were a round trip per chunk on the epilogue's critical path
+                    __threadfence_block();
+                    asm volatile("bar.sync 4, %0;" ::"n"(256) : "memory");
+                    const int te = tid - kWarpEpi0 * 32;
+                    const int64_t left_cta = p.n_graphs - tr.g_begin;
+                    const int n_cta = left_cta < p.graphs_per_cta ? static_cast<int>(left_cta) : p.graphs_per_cta;
+                    const int total4 = n_cta * N * (f_out >> 2);
+                    float* y0 = p.y + tr.g_begin * N * static_cast<int64_t>(f_out);
+                    const float* m0p = p.mul_src + tr.g_begin * N * static_cast<int64_t>(f_out);
+                    for (int i0 = te; i0 < total4; i0 += 4 * 256) {
+                        float4 yv[4], mv4[4];
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const int idx = i0 + k4 * 256;
+                            const bool ok = idx < total4;
+                            yv[k4] = ok ? *reinterpret_cast<const float4*>(y0 + static_cast<size_t>(idx) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            mv4[k4] = ok ? __ldg(reinterpret_cast<const float4*>(m0p) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const int idx = i0 + k4 * 256;
+                            if (idx < total4)
+                                *reinterpret_cast<float4*>(y0 + static_cast<size_t>(idx) * 4) =
+                                    make_float4(yv[k4].x * act_grad_from_output(mv4[k4].x, p.mul_act), yv[k4].y * act_grad_from_output(mv4[k4].y, p.mul_act),
+                                                yv[k4].z * act_grad_from_output(mv4[k4].z, p.mul_act), yv[k4].w * act_grad_from_output(mv4[k4].w, p.mul_act));
+                        }
+                    }
                 }
             }
             // this CTA's outputs of the job: visible to the next job's TMA loads (async proxy) after the role barrier
@@ -842,6 +864,7 @@ int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         p.bias = j.w_transposed ? nullptr : j.bias;
         p.w_trans = j.w_transposed ? 1 : 0;
         p.act = j.act;
+        KGCN_REQUIRE(j.mul_src == nullptr || j.f_out % 4 == 0, KGCN_ERR_UNSUPPORTED, "fused GraphConv v5: act' epilogue needs f_out %% 4 == 0");
         p.mul_src = j.mul_src;
         p.mul_act = j.mul_act;
         p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : j.f_out;
