@@ -33,4 +33,6 @@ run2 "" "KGCN_FUSED_V5=1" memcheck "${SANITIZE_TIMEOUT:-300}" $ALL
 run2 "" "KGCN_FUSED_V5=0" racecheck "${SANITIZE_TIMEOUT:-300}" tests/test_gpu_parity.py tests/test_gpu_trainer.py -k "$FUSED"
 run2 "" "KGCN_FUSED_V5=0" synccheck "${SANITIZE_TIMEOUT:-240}" tests/test_gpu_parity.py tests/test_gpu_trainer.py -k "$FUSED"
 run2 "_v5" "KGCN_FUSED_V5=1" synccheck "${SANITIZE_TIMEOUT:-240}" tests/test_gpu_parity.py -k "$V5"
-run2 "_v5" "KGCN_FUSED_V5=1 NV_COMPUTE_SANITIZER_MAX_RACECHECK_HAZARDS=100000" racecheck "${SANITIZE_TIMEOUT:-300}" tests/test_gpu_parity.py -k "$V5"
+# (the v5 step chain -- fused head, hard job boundaries on a named barrier -- goes through memcheck and racecheck; synccheck would
+# stop at the named role barrier, see profiles/r02b_sanitizer.txt)
+run2 "_v5" "KGCN_FUSED_V5=1 NV_COMPUTE_SANITIZER_MAX_RACECHECK_HAZARDS=100000" racecheck "${SANITIZE_TIMEOUT:-300}" tests/test_gpu_parity.py tests/test_gpu_trainer.py -k "$V5 or (step_matches_oracle and 64-1-128)"
