@@ -47,3 +47,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_hostmem_numa_helpers_degrade_gracefully():
+    """kgcn_b200.hostmem (NUMA placement of the pinned staging buffers): unknown nodes and disallowed nodes are no-ops,
+    an allowed node sets and restores the thread's memory policy, and the page query answers for a touched buffer."""
+    import numpy as np
+    import torch
+    from kgcn_b200 import hostmem
+    with hostmem.numa_preferred(-1) as ok:
+        assert ok is False
+    with hostmem.numa_preferred(None) as ok:
+        assert ok is False
+    with hostmem.numa_preferred(4095) as ok:          # no such node / not in Mems_allowed: preference silently skipped
+        assert ok is False
+    allowed = hostmem.mems_allowed()
+    if allowed is not None:
+        first = int(allowed.split(",")[0].split("-")[0])
+        with hostmem.numa_preferred(first) as ok:
+            t = torch.from_numpy(np.ones(1 << 16, np.uint8))
+            assert ok in (True, False)
+        assert hostmem.node_of_buffer(t) in (-1, first) or not ok
+    assert hostmem.gpu_numa_node(0) >= -1
