@@ -66,8 +66,10 @@ def bind(placeholders, fd):
     return out
 
 
-def main():
-    fix = os.path.join(ROOT, "tests", "fixtures", "c1")
+def main(out_root=None):
+    """``out_root``: write under this directory instead of the repository (tests regenerate into a scratch directory)."""
+    root = out_root or ROOT
+    fix = os.path.join(root, "tests", "fixtures", "c1")
     for rel in FILES:
         dst = os.path.join(fix, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
@@ -105,7 +107,8 @@ def main():
                     "b%d_correct_count" % k: np.float32(metrics["correct_count"])})
     for name, value in _VARIABLES.items():
         rec["var/" + name] = np.asarray(value, np.float32)
-    out = os.path.join(ROOT, "tests", "golden", "c1_sample_json.npz")
+    out = os.path.join(root, "tests", "golden", "c1_sample_json.npz")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     np.savez_compressed(out, **rec)
     print("wrote", out, "variables:", sorted(_VARIABLES))
     for k in range(len(BATCHES)):
@@ -155,4 +158,4 @@ def _build_model_fresh_scope(self, *a, **k):
 ref_model.GCN.build_model = _build_model_fresh_scope
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

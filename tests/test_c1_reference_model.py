@@ -59,6 +59,19 @@ def test_fixture_files_are_the_reference_files():
         assert filecmp.cmp(os.path.join(FIX, rel), os.path.join(REFERENCE, rel), shallow=False), rel
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "example_model")), reason="reference tree not present")
+def test_golden_regenerates_identically_from_the_reference(tmp_path):
+    """oracle/make_c1_golden.py run again on /root/reference (in a fresh interpreter: it installs the numpy TensorFlow stand-in on
+    sys.modules) reproduces every array of the committed golden bit for bit."""
+    import subprocess
+    subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "make_c1_golden.py"), str(tmp_path)], check=True, stdout=subprocess.DEVNULL)
+    new = np.load(os.path.join(str(tmp_path), "tests", "golden", "c1_sample_json.npz"))
+    old = load_golden("c1_sample_json")
+    assert sorted(new.files) == sorted(old)
+    for k in old:
+        assert new[k].dtype == old[k].dtype and np.array_equal(new[k], old[k]), k
+
+
 def test_own_ingest_feeds_what_the_reference_fed_and_oracle_reproduces_the_model():
     """kgcn_b200's load_data + DefaultModel placeholders + construct_feed give the arrays the reference fed (bit for
     bit); the oracle's layer functions on that feed reproduce the reference model's logits."""
