@@ -1781,10 +1781,17 @@ bool plan_v4_try(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
 // Preference: whole output width in one CTA and full 128-row tiles; wide layers (F = 128: [W ; bias] hi / lo alone is
 // 160 KB) fall back to column slices -- each slice aggregates the tile again (the second reader hits L2) -- and to
 // fewer graphs per tile until at least two TMA stages fit.
+int g_cap() {
+    static const int cap = [] {
+        const char* e = getenv("KGCN_V4_G");   // tuning knob: at most this many graphs per tile
+        return (e != nullptr && atoi(e) > 0) ? atoi(e) : 1 << 20;
+    }();
+    return cap;
+}
 bool plan_v4(V4Params& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int C_csr, int head_labels = 0, int wbufs = 1) {
     if (n_graphs <= 0 || N > 128 || N < 1 || f_in % 32 != 0 || f_out % 4 != 0 || C_csr > 8 || C < 1 || C > C_csr) return false;
     for (int n_split = 1; n_split <= 4; n_split *= 2)
-        for (int G = std::max(1, 128 / N); G >= 1; G = (G > 1 ? G / 2 : 0))
+        for (int G = std::min(g_cap(), std::max(1, 128 / N)); G >= 1; G = (G > 1 ? G / 2 : 0))
             if (plan_v4_try(p, n_graphs, C, N, f_in, f_out, n_split, G, C_csr, head_labels, wbufs)) return true;
     return false;
 }
