@@ -267,6 +267,43 @@ class Bench:
         torch.cuda.synchronize()
         return s.elapsed_time(e) * 1e3 / (reps * n_rot)
 
+    def spmm_large(self, hbm, reps):
+        """kgcn_bspmm_f32 alone at large batches: [config 5's global batch generated on the device, 16 x config 2's batch]."""
+        torch, dev = self.torch, self.dev
+        from kgcn_b200 import ops, synth_device
+        from kgcn_b200.csr import BatchedCSR
+        out = []
+        for name, B, N, F in (("config 5 global batch (device-generated molecules)", 4096, 64, 128), ("16 x config 2 (ring graphs)", 16384, 32, 64)):
+            if N == 64:
+                raw = synth_device.device_batches(1234, 2, B, N, F, device=dev)
+                csrs, xs = [r["csr"] for r in raw], [r["features"] for r in raw]
+                del raw
+            else:
+                host = make_host_batches(WORKLOADS["c2"], 2, seed=4321, B=B)
+                csrs = [BatchedCSR.from_flat(d["counts"], d["indices"], d["values"], N, N) for d in host]
+                xs = [torch.as_tensor(d["features"]).to(dev) for d in host]
+                del host
+            ys = [torch.empty(B, N, F, device=dev) for _ in range(2)]
+
+            def spmm(i, csrs=csrs, xs=xs, ys=ys, N=N, F=F):
+                ops.bspmm_raw(csrs[i % 2], xs[i % 2], N * F, 0, ys[i % 2], N * F, 0, F)
+
+            us = self.time_alone(spmm, 2, max(reps, 20))
+            nnz = float(np.mean([c.nnz for c in csrs]))
+            nb = 8 * B * N * F + 8 * nnz + 4 * B * (N + 1)
+
+            def copy_same(i, xs=xs, ys=ys):
+                ys[i % 2].copy_(xs[i % 2])
+
+            cus = self.time_alone(copy_same, 2, max(reps, 20))
+            out.append({"kernel": "bspmm_tile_kernel (kgcn_bspmm_f32), B=%d N=%d F=%d: %s" % (B, N, F, name), "bound": "hbm",
+                        "achieved": nb / us / 1e3, "peak": hbm, "unit": "GB/s", "frac": nb / us / 1e3 / hbm, "frac_of_8TBs_spec": nb / us / 1e3 / 8000.0,
+                        "us_per_launch": us, "algorithmic_bytes_per_launch": nb, "l2": "2 rotating batches, %.0f MB of inputs per launch" % ((nb - 4 * B * N * F) / 1e6),
+                        "same_size_copy": {"bytes": 8 * B * N * F, "us_per_launch": cus, "gbs": 8 * B * N * F / cus / 1e3}})
+            del csrs, xs, ys
+            torch.cuda.empty_cache()
+        return out
+
     # ---- one workload ----
     def measure(self, key, primary):
         torch, dist, args, world, rank, dev = self.torch, self.dist, self.args, self.world, self.rank, self.dev
@@ -512,6 +549,12 @@ class Bench:
                                     "us_per_launch": us, "algorithmic_bytes_per_launch": nb,
                                     "same_size_copy": {"bytes": 8 * B * N * Fs, "us_per_launch": cus, "gbs": 8 * B * N * Fs / cus / 1e3}}
 
+        # ---- the same SpMM kernel at the batch sizes BASELINE.json quotes its roofline target on: config 5's GLOBAL batch
+        # (4096 molecules, 64 atoms, 128 features -- one GPU holds it) and 16x config 2's batch.  One launch moves 270 / 280 MB,
+        # so launch fill / drain no longer dominates as it does at B = 1024 ----
+        if primary and world == 1 and not args.no_spmm_large:
+            res["roofline_spmm_large"] = self.spmm_large(hbm, reps)
+
         # ---- end to end from pinned host buffers through the public step call ----
         if host is not None:
             max_nnz = int(max(d["values"].shape[0] for d in host) * 1.1) + 64
@@ -616,6 +659,7 @@ def run_own(args):
             "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res.get("e2e"),
             "gpu_launches": int(res["launches_per_step"] * steps), "launches_per_step": res["launches_per_step"],
             "roofline": res["roofline"], "roofline_step": res["roofline_step"], "roofline_spmm": res.get("roofline_spmm"),
+            "roofline_spmm_large": res.get("roofline_spmm_large"),
             "kernels": res["kernels"], "kernels_standalone": res.get("kernels_standalone"), "cpu_baseline": cpu_baseline, "infer": res["infer"], "last_step": res["last_step"],
             "padded_dims": res["padded_dims"], "fused_step": res["fused_step"],
         }
@@ -639,6 +683,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--only-primary", action="store_true", help="skip the c3 / c4 / c5 sub-measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spmm-large", action="store_true", help="skip the large-batch SpMM roofline (roofline_spmm_large)")
     ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step instead of one per pass over the resident batches")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

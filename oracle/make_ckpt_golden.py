@@ -9,8 +9,10 @@ TEST INFRASTRUCTURE ONLY.  Run in the authoring container (needs ``/root/referen
 What runs: the reference's own ``kgcn/legacy/layers.py`` classes (GraphConv, GraphBatchNormalization, GraphDense,
 GraphGather), called in the order and with the arguments of ``model_rxn_3layer.py:50-88``, unchanged, under the numpy
 stand-in for the TensorFlow primitives (``oracle/tf_numpy.py``).  The weights come out of the TensorFlow-written
-checkpoint through ``kgcn_b200/tf_checkpoint.py``; every tensor's bytes are checked there against the CRC-32C that
-TensorFlow stored next to them, and the manifest records name / dtype / shape / masked CRC of all 56 entries.
+checkpoint through the oracle's OWN minimal bundle reader (``oracle/tf_bundle_min.py``, which shares no code with the
+product's ``kgcn_b200/tf_checkpoint.py``); every tensor's bytes are checked there against the CRC-32C that TensorFlow
+stored next to them, and the manifest records name / dtype / shape / masked CRC of all 56 entries.  The product's reader
+is then checked AGAINST this one (same names, dtypes, shapes, offsets, checksums, values) -- the golden does not depend on it.
 The molecules are synthetic (75 atom features, the ``--use_deepchem_feature`` width the first kernel ``[75, 128]``
 implies); the file also stores the re-serialised bytes' digests: writing the parsed checkpoint back with
 ``save_checkpoint`` reproduces TensorFlow's ``.index`` and ``.data`` files byte for byte.
@@ -34,18 +36,26 @@ tf = tf_numpy.install()
 sys.path.insert(0, REF)
 import kgcn.legacy.layers as rl_legacy  # noqa: E402  (the reference's module)
 
-from kgcn_b200 import synth, tf_checkpoint  # noqa: E402
+from oracle import tf_bundle_min  # noqa: E402
+from kgcn_b200 import synth, tf_checkpoint  # noqa: E402  (synth: numpy generators; tf_checkpoint: only as the thing CHECKED below)
 
 PREFIX = os.path.join(REF, "model", "reaction", "model.best.ckpt")
 
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
+    header, entries = tf_bundle_min.read_index(PREFIX)
+    every = tf_bundle_min.read_tensors(PREFIX)                 # verifies every tensor's CRC-32C
+    manifest = {"prefix": "model/reaction/model.best.ckpt", "num_shards": header["num_shards"],
+                "entries": [{"name": n, "dtype": np.dtype(e["dtype"]).name, "shape": list(e["shape"]), "offset": e["offset"],
+                             "size": e["size"], "crc32c_masked": e["crc32c"]} for n, e in entries.items()]}
+    # the product's reader against the oracle's (not the other way round)
     reader = tf_checkpoint.load_checkpoint(PREFIX)
-    every = {n: reader.get_tensor(n) for n in reader.entries}
-    manifest = {"prefix": "model/reaction/model.best.ckpt", "num_shards": reader.num_shards,
-                "entries": [{"name": n, "dtype": np.dtype(e.dtype).name, "shape": list(e.shape), "offset": e.offset,
-                             "size": e.size, "crc32c_masked": e.crc32c} for n, e in reader.entries.items()]}
+    assert list(reader.entries) == list(entries) and reader.num_shards == header["num_shards"]
+    for n, e in entries.items():
+        p = reader.entries[n]
+        assert (np.dtype(p.dtype), list(p.shape), p.offset, p.size, p.crc32c) == (np.dtype(e["dtype"]), list(e["shape"]), e["offset"], e["size"], e["crc32c"]), n
+        assert np.array_equal(reader.get_tensor(n), every[n]) and reader.get_tensor(n).dtype == every[n].dtype, n
     with tempfile.TemporaryDirectory() as tmp:
         tf_checkpoint.save_checkpoint(os.path.join(tmp, "again"), every)
         for ext in (".index", ".data-00000-of-00001"):
@@ -54,7 +64,8 @@ def main():
             manifest["sha256" + ext] = hashlib.sha256(theirs).hexdigest()
     json.dump(manifest, open(os.path.join(out_dir, "ckpt_reaction_manifest.json"), "w"), indent=1)
 
-    W = reader.tensors(skip_slots=True)
+    W = {n: v for n, v in every.items()
+         if n.rsplit("/", 1)[-1] not in ("Adam", "Adam_1") and n not in ("beta1_power", "beta2_power")}   # trained variables only
     rng = np.random.default_rng(2024)
     B, N, C = 12, 50, 1
     counts, idx, val, n_atoms = synth.random_molecule_coo(rng, B, N, C, return_sizes=True)

@@ -57,6 +57,27 @@ def test_reference_checkpoint_parses_and_rewrites_byte_for_byte(tmp_path):
         assert hashlib.sha256(ours).hexdigest() == m["sha256" + ext]
 
 
+def test_product_writer_and_reader_against_the_oracles_independent_bundle_reader(tmp_path):
+    """oracle/tf_bundle_min.py shares no code with kgcn_b200/tf_checkpoint.py: what the product writes must parse there
+    (table blocks, footer, protos, both CRC layers), and on the reference's own file both readers must agree."""
+    from oracle import tf_bundle_min
+    g, variables = golden_variables()
+    prefix = str(tmp_path / "model.ckpt")
+    ckpt.save_checkpoint(prefix, variables)
+    header, entries = tf_bundle_min.read_index(prefix)
+    tensors = tf_bundle_min.read_tensors(prefix)                     # verifies block and tensor CRC-32C with its own table
+    stored = {e["name"]: e for e in manifest()["entries"]}
+    assert header["num_shards"] == 1 and sorted(tensors) == sorted(variables)
+    for name, value in variables.items():
+        assert tensors[name].dtype == value.dtype and np.array_equal(tensors[name], value)
+        assert entries[name]["crc32c"] == stored[name]["crc32c_masked"] and list(entries[name]["shape"]) == list(value.shape)
+    assert tf_bundle_min.crc32c(b"123456789") == 0xE3069283          # RFC 3720 check value
+    if os.path.exists(REF_PREFIX + ".index"):
+        theirs, reader = tf_bundle_min.read_tensors(REF_PREFIX), ckpt.load_checkpoint(REF_PREFIX)
+        assert list(theirs) == list(reader.entries)
+        assert all(np.array_equal(theirs[n], reader.get_tensor(n)) for n in theirs)
+
+
 def test_trained_variables_roundtrip_and_match_tensorflows_checksums(tmp_path):
     g, variables = golden_variables()
     prefix = str(tmp_path / "model.ckpt")
