@@ -573,7 +573,7 @@ class Bench:
             h2d = int(np.mean([pipe.h2d_bytes(p) for p in pinned]))
             res["e2e"] = {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                          "path": "pinned host COO+labels (1 packed copy) + features -> H2D (copy stream, 2 slots) -> device CSR pack -> "
+                          "path": "pinned host [COO+labels+mask | features] block -> ONE H2D copy per step (copy stream, 2 slots) -> device CSR pack -> "
                                   "train step (CUDA graph) -> D2H cost_sum/correct_count, every step"}
             del pipe
         if tr.p2p is not None:

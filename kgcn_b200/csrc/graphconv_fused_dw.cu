@@ -19,6 +19,7 @@
 // At the end the CTA writes one partial block [(f_in + 1), C*f_out] (last row = dbias); a fixed-order reduction over
 // CTAs follows (splitk_reduce_kernel / the fused reduce + Adam tail).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -107,8 +108,14 @@ constexpr int kDwMaxJobs = 4;
 struct DwBatch {
     int n_jobs;
     uint32_t tmem_cols;
+    long long* dbg;   // tuning aid (kgcn_debug_dw_times): [CTA][256] clock64 stamps, see tools/dw_timeline.py
     DwParams job[kDwMaxJobs];
 };
+
+// stamp slots per CTA: 0 kernel entry, 1 workers left the job loop, 2 partials written, 3 after the setup barrier;
+// 8 + 8 * T + e for the CTA's T-th tile over all jobs: e = 0 producer issued the tile's copies, 1 worker warp 0 saw the stage full,
+// 2 worker warp 0 finished the tile's last chunk, 3 MMA warp saw the tile's first chunk, 4 MMA warp issued the tile's last chunk
+#define DW_STAMP(slot) do { if (b.dbg != nullptr && lane == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 256 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void bar_cta_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 
@@ -121,6 +128,8 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
     unsigned char* gen = smem_dyn + (base - smem_u32(smem_dyn));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_jobs = b.n_jobs;
+    if (warp == 0) DW_STAMP(0);
+    int tile_no = 0;   // tiles of all earlier jobs (stamps only)
 
     if (tid == 0) {
         for (int i = 0; i < kStagesMax; ++i) {
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
             }
             fence_proxy_async_smem();
             asm volatile("bar.sync 3, %0;" ::"n"(kSetup) : "memory");
+            if (warp == 0 && jb == 0) DW_STAMP(3);
         }
 
         if (warp == kWarpTma) {
@@ -211,6 +221,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                         bulk_g2s(st + p.st_col, p.col + e_lo, 4u * e_cnt, full);
                         bulk_g2s(st + p.st_val, p.val + e_lo, 4u * e_cnt, full);
                     }
+                    if (tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it));
                     if (++s == S) s = 0;
                 }
             }
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                     ph_a ^= 1u << ob;
                     tc_fence_after_sync();
                     __syncwarp();
+                    if (c0 == 0 && tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it) + 3);
                     if (elect_one()) {
                         const uint32_t op = base + p.off_op + static_cast<uint32_t>(ob) * p.op_bytes;
                         const uint64_t dxh = umma_desc_mn32(op, p.lbo, 512u);                         // Xhi (stacked: [Xhi ; Xlo])
@@ -250,6 +262,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                         umma_commit(&bar_opempty[ob]);   // the operand buffer may be overwritten once these MMAs have read it
                     }
                     __syncwarp();
+                    if (c0 + R >= rows_t && tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it) + 4);
                     if (++ob == p.opbufs) ob = 0;
                 }
             }
@@ -274,6 +287,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                 const uint32_t st = base + p.off_stage + static_cast<uint32_t>(s) * p.stage_bytes;
                 mbar_wait(&bar_full[s], (ph_a >> s) & 1u);
                 ph_a ^= 1u << s;
+                if (warp == 0 && tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it) + 1);
                 const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
                 const int e_first = static_cast<int>(lds_u32(rp_addr));
                 const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
@@ -371,11 +385,14 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[s]);   // this warp is done reading the stage
+                if (warp == 0 && tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it) + 2);
                 if (++s == S) s = 0;
                 r0_lo += r0_step;
             }
         }
+        tile_no += n_tiles;
     }
+    if (warp == 0) DW_STAMP(1);
 
     // ---- per-CTA partials: accumulator rows -> [(f_in + 1), Ng] per job (last row = column sums of G = dbias partial) ----
     bar_cta_roles();          // the MMA warp has seen the last job's MMAs complete
@@ -455,6 +472,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
         }
     }
 
+    if (warp == 0) DW_STAMP(2);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kWarpMma) tmem_dealloc(tmem, b.tmem_cols);
@@ -510,6 +528,13 @@ bool plan_dw(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
     // preference: >= 2 stages always; double-buffered operands as long as a chunk still fills the warps (>= 32 rows), then
     // single-buffered 64 / 32-row chunks (wide layers: F = 128), 16-row chunks last
     const int g_max = std::max(1, 64 / N);
+    static const char* forced = getenv("KGCN_DW_PLAN");   // tuning / A-B knob: "opbufs:R" tried first (e.g. 2:32)
+    if (forced != nullptr) {
+        int ob = 0, r = 0;
+        if (sscanf(forced, "%d:%d", &ob, &r) == 2 && (ob == 1 || ob == 2) && (r == 16 || r == 32 || r == 64))
+            for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
+                if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, r, ob, 2)) return true;
+    }
     const int order[6][2] = {{2, 64}, {2, 32}, {1, 64}, {1, 32}, {2, 16}, {1, 16}};
     for (const auto& o : order)
         for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
@@ -555,12 +580,15 @@ int fused_dw_splits(int64_t n_graphs, int channels, int n_nodes, int f_in, int f
     return static_cast<int>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
 }
 
+static long long* g_dbg_dw = nullptr;
+
 // jobs[k]: partial_k[grid][(f_in_k + 1)][channels * f_out_k]; no reduction.  All jobs share (n_graphs, channels, n_nodes).
 int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, int* splits_out,
                                    cudaStream_t st) {
     KGCN_REQUIRE(n_jobs >= 1 && n_jobs <= kDwMaxJobs, KGCN_ERR_BAD_SHAPE, "fused GraphConv weight gradient: 1..%d jobs", kDwMaxJobs);
     DwBatch b{};
     b.n_jobs = n_jobs;
+    b.dbg = g_dbg_dw;
     uint32_t cols = 0, smem = 0;
     for (int k = 0; k < n_jobs; ++k) {
         DwParams& p = b.job[k];
@@ -619,3 +647,7 @@ int launch_graphconv_fused_dw(const int32_t* rowptr_t, const int32_t* col_t, con
 }
 
 }  // namespace kgcn
+
+// Tuning hook (not part of the documented ABI): device buffer of [148][256] int64 clock stamps of the weight-gradient kernel
+// (see DW_STAMP and tools/dw_timeline.py).
+extern "C" void kgcn_debug_dw_times(long long* device_buffer) { kgcn::g_dbg_dw = device_buffer; }

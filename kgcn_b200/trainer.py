@@ -643,7 +643,9 @@ class _Slot:
         dev = t.device
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        self.d_packed = torch.zeros(layout["bytes"], dtype=torch.uint8, device=dev)
+        # ONE device block per slot: [packed COO / labels / mask | features] -- the step's inputs arrive in a single H2D copy
+        self.d_all = torch.zeros(layout["bytes_all"], dtype=torch.uint8, device=dev)
+        self.d_packed = self.d_all[:layout["bytes"]]
         v = lambda name, dt: self.d_packed[layout[name][0]:layout[name][1]].view(dt)
         self.d_off, self.d_idx, self.d_val = v("off", torch.int64), v("idx", torch.int32), v("val", torch.float32)
         labels, mask = v("labels", torch.float32).view(B, s.label_dim), v("mask", torch.float32)
@@ -651,8 +653,8 @@ class _Slot:
         mk = lambda: (torch.zeros(B * C * N + 1, **i32), torch.zeros(max_nnz, **i32), torch.zeros(max_nnz, **f32))
         rp, col, val = mk()
         rpt, colt, valt = mk()
-        self.batch = DeviceBatch(BatchedCSR(B, C, N, N, rp, col, val, rpt, colt, valt),
-                                 torch.zeros(B, N, t.dims[0], **f32), labels, mask)
+        feats = self.d_all[layout["feat_off"]:layout["bytes_all"]].view(torch.float32).view(B, N, t.dims[0])
+        self.batch = DeviceBatch(BatchedCSR(B, C, N, N, rp, col, val, rpt, colt, valt), feats, labels, mask)
         self.h_stats = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.copied, self.done = torch.cuda.Event(), torch.cuda.Event()
         self.graph = None
@@ -662,7 +664,7 @@ class _Slot:
 class HostFedPipeline:
     """End-to-end step from HOST buffers, the call a kGCN user makes per step (feed -> sess.run,
     kgcn/core.py:267-269): pinned host COO + features + labels are copied to static device buffers
-    (two cudaMemcpyAsync per step: one packed CSR/label/mask block, one feature block), packed to CSR
+    (ONE cudaMemcpyAsync per step: the packed COO / label / mask block and the feature block are one buffer), packed to CSR
     (+ transposed CSR) ON THE DEVICE (kgcn_pack_coo_device), the training step runs, and ``cost_sum`` /
     ``correct_count`` come back to the host.  The device part (2 pack launches + the step) is one CUDA
     graph per slot.  With ``depth`` = 2 slots the copies of step i+1 run on a copy stream while step i
@@ -680,6 +682,8 @@ class HostFedPipeline:
             self.layout[name] = (pos, pos + n)
             pos = (pos + n + 15) // 16 * 16
         self.layout["bytes"] = pos
+        self.layout["feat_off"] = (pos + 255) // 256 * 256
+        self.layout["bytes_all"] = self.layout["feat_off"] + 4 * B * s.n_nodes * t.dims[0]
         self.train = train
         self.slots = [_Slot(t, self.layout, self.max_nnz) for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=t.device)
@@ -730,7 +734,8 @@ class HostFedPipeline:
         if idx_chk.size and (int(idx_chk.min()) < 0 or int(idx_chk.max()) >= self.trainer.spec.n_nodes):
             raise _lib.KgcnIndexError(3, "adjacency index out of range [0, %d): min %d, max %d"
                                       % (self.trainer.spec.n_nodes, int(idx_chk.min()), int(idx_chk.max())))
-        packed = np.zeros(self.layout["bytes"], np.uint8)
+        blob = np.zeros(self.layout["bytes_all"], np.uint8)   # [packed block | features]: one pinned buffer, one copy per step
+        packed = blob[:self.layout["bytes"]]
         sec = lambda name, dt: packed[self.layout[name][0]:self.layout[name][1]].view(dt)
         off = sec("off", np.int64)
         off[0] = 0
@@ -740,15 +745,17 @@ class HostFedPipeline:
         sec("labels", np.float32)[:] = np.asarray(labels, np.float32).reshape(-1)
         sec("mask", np.float32)[:] = np.ones(B, np.float32) if mask is None else np.asarray(mask, np.float32)
         used = self.layout["idx"][0] + 8 * nnz   # the idx section is copied only up to the entries in use
-        feats = np.ascontiguousarray(pad_features(features, self.trainer.dims[0]), np.float32)   # padded on the host: one plain copy
+        feats = blob[self.layout["feat_off"]:].view(np.float32).reshape(B, self.trainer.spec.n_nodes, self.trainer.dims[0])
+        feats[...] = pad_features(features, self.trainer.dims[0])                                # padded on the host
         # pinned staging on the GPU's own NUMA node (hostmem: the copies of all ranks of a node otherwise share one socket)
         from . import hostmem
         with hostmem.numa_preferred(hostmem.gpu_numa_node(self.trainer.device.index or 0)):
-            return {"packed": torch.from_numpy(packed).pin_memory(), "nnz": nnz, "idx_used_end": used,
-                    "features": torch.from_numpy(feats).pin_memory()}
+            pinned = torch.from_numpy(blob).pin_memory()
+        return {"blob": pinned, "packed": pinned[:self.layout["bytes"]], "nnz": nnz, "idx_used_end": used,
+                "features": pinned[self.layout["feat_off"]:].view(torch.float32).view(feats.shape)}
 
     def h2d_bytes(self, host):
-        return int(host["packed"].numel() + host["features"].numel() * 4)
+        return int(host["blob"].numel())
 
     def submit(self, host):
         """Enqueue one step: H2D on the copy stream, graph replay + D2H of the stats on the compute stream."""
@@ -757,8 +764,7 @@ class HostFedPipeline:
             raise RuntimeError("pipeline full: collect() a result before submitting more than %d steps" % len(self.slots))
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot.done)          # the slot's previous step has finished with these buffers
-            slot.d_packed.copy_(host["packed"], non_blocking=True)
-            slot.batch.features.copy_(host["features"], non_blocking=True)
+            slot.d_all.copy_(host["blob"], non_blocking=True)
             slot.copied.record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(slot.copied)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where the end-to-end (host-fed) step of bench.py spends its time: usage e2e_breakdown.py [c2 c5 ...]
 
-For each workload, on one GPU: (a) the step's two H2D copies alone, back to back on the copy stream; (b) the device part
+For each workload, on one GPU: (a) the step's H2D copy alone, back to back on the copy stream; (b) the device part
 alone (the slot's CUDA graph: 2 pack launches + the training step), back to back on the compute stream; (c) the pack
 launches alone; (d) the pipelined loop bench.py times (HostFedPipeline.run_many).  One JSON line per workload."""
 import argparse
@@ -48,8 +48,7 @@ def main():
         with torch.cuda.stream(pipe.copy_stream):
             for i in range(n):
                 slot, h = pipe.slots[i % len(pipe.slots)], pinned[i % len(pinned)]
-                slot.d_packed.copy_(h["packed"], non_blocking=True)
-                slot.batch.features.copy_(h["features"], non_blocking=True)
+                slot.d_all.copy_(h["blob"], non_blocking=True)
         pipe.copy_stream.synchronize()
         out["copies_alone_ms"] = (time.perf_counter() - t0) / n * 1e3
         out["copies_alone_gbs"] = out["h2d_bytes"] / out["copies_alone_ms"] / 1e6
