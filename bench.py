@@ -18,6 +18,7 @@ the primary line.  Prints ONE JSON line (rank 0).  DESIGN.md section 6 says how 
 """
 import argparse
 import ctypes
+import gc
 import importlib.util
 import json
 import os
@@ -632,13 +633,21 @@ def run_own(args):
     res, tr = bench.measure(primary_key, primary=True)
     others = {}
     if args.workload is None and not args.only_primary:
+        def release():
+            # device blocks AND the pinned host blocks of the finished workload go back to the driver: a workload measured after
+            # others must see the same allocator state as one measured alone
+            gc.collect()
+            bench.torch.cuda.empty_cache()
+            if hasattr(bench.torch._C, "_host_emptyCache"):
+                bench.torch._C._host_emptyCache()
+
         del tr
-        bench.torch.cuda.empty_cache()
+        release()
         for key in ("c3", "c4", "c5"):
             r, t = bench.measure(key, primary=False)
             others[key] = r
             del t
-            bench.torch.cuda.empty_cache()
+            release()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -115,7 +115,12 @@ struct DwBatch {
 // stamp slots per CTA: 0 kernel entry, 1 workers left the job loop, 2 partials written, 3 after the setup barrier;
 // 8 + 8 * T + e for the CTA's T-th tile over all jobs: e = 0 producer issued the tile's copies, 1 worker warp 0 saw the stage full,
 // 2 worker warp 0 finished the tile's last chunk, 3 MMA warp saw the tile's first chunk, 4 MMA warp issued the tile's last chunk
+// (compiled in only with -DKGCN_DW_TIMELINE: `make TIMELINE=1`; the product build carries no stamp code)
+#ifdef KGCN_DW_TIMELINE
 #define DW_STAMP(slot) do { if (b.dbg != nullptr && lane == 0) b.dbg[static_cast<size_t>(blockIdx.x) * 256 + (slot)] = clock64(); } while (0)
+#else
+#define DW_STAMP(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void bar_cta_roles() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_jobs = b.n_jobs;
     if (warp == 0) DW_STAMP(0);
-    int tile_no = 0;   // tiles of all earlier jobs (stamps only)
+    [[maybe_unused]] int tile_no = 0;   // tiles of all earlier jobs (stamps only)
 
     if (tid == 0) {
         for (int i = 0; i < kStagesMax; ++i) {

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Timeline of the weight-gradient launch (kgcn_debug_dw_times): per tile of a CTA, when the producer issued its copies, when the
 workers saw the stage full / finished the tile's operand chunks, when the MMA warp saw the first chunk / issued the last one;
-microseconds since kernel entry, median over CTAs.  usage: dw_timeline.py [c2|c3|c5]"""
+microseconds since kernel entry, median over CTAs.  The stamps are compiled in only with
+`touch kgcn_b200/csrc/graphconv_fused_dw.cu && make -C kgcn_b200/csrc TIMELINE=1` (rebuild without it afterwards).
+usage: dw_timeline.py [c2|c3|c5]"""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
