@@ -362,6 +362,21 @@ int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const flo
                             float inv_batch, float* logits, float* prediction, float* gathered, float* head_partial,
                             uint32_t flags, void* stream);
 
+/* The same launch, which ALSO stores what its dx jobs aggregate: g_save (HOST array of n_layers device pointers, entry 0 unused)
+ * receives G_l = A^T . du[l] ([B, N, dims[l + 1]], fp32, 128-byte aligned) for l = n_layers - 1 .. 1 -- the `adjoint_a=True` product of
+ * the registered gradient (kgcn/bspmm_call.py:44), which the dx job computes anyway as the aggregate of (A^T, du[l], W_l^T).
+ * kgcn_graphconv_chain_dw_g_f32 then reads G_l instead of gathering it a second time; the results are bit-identical to the
+ * launches without g (same per-row accumulation order, same tf32 split).  channels == 1 and the v4 chained kernel only:
+ * kgcn_gcn_step_chain_g_supported(...) != 0.  g_save == NULL: exactly kgcn_gcn_step_chain_f32. */
+int32_t kgcn_gcn_step_chain_g_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims);
+int kgcn_gcn_step_chain_g_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
+                              const int32_t* col_t, const float* val_t, int64_t n_graphs, int32_t channels, int32_t n_nodes,
+                              int32_t n_layers, const int32_t* dims, const int32_t* dims_valid, const float* x,
+                              const float* const* w, const float* const* bias, float* const* y, float* const* du,
+                              float* const* g_save, int32_t act, const float* head_w, const float* head_b, int32_t n_labels,
+                              const float* labels, const float* mask, float inv_batch, float* logits, float* prediction,
+                              float* gathered, float* head_partial, uint32_t flags, void* stream);
+
 /* Weight-gradient partials of ALL layers (kgcn_graphconv_bwd_partial_f32 with dx == NULL, layer by layer) in as few launches
  * as tensor memory allows (2 * channels * dims[l + 1] accumulator columns per layer, 512 per launch): x[l] = input of layer l,
  * du[l] = its dU, partial[l] / partial_bytes[l] its partial blocks.  HOST arrays of n_layers entries. */
@@ -369,6 +384,12 @@ int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_t* col_t, c
                                 int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
                                 const float* const* x, const float* const* du, float* const* partial,
                                 const size_t* partial_bytes, void* stream);
+/* g (HOST array of n_layers device pointers or NULL; channels == 1): where g[l] != NULL, layer l's G_l = A^T . du[l] is read from
+ * there (written by kgcn_gcn_step_chain_g_f32) instead of being gathered from du[l] and the transposed CSR. */
+int kgcn_graphconv_chain_dw_g_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                  int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                  const float* const* x, const float* const* du, const float* const* g, float* const* partial,
+                                  const size_t* partial_bytes, void* stream);
 
 /* The reduction alone (gradient checks, the NCCL cross-check path): dw [channels][f_in][f_out] and dbias [channels][f_out]
  * (may be NULL) from `splits` partial blocks, summed in split order (deterministic). */

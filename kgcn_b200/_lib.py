@@ -100,6 +100,10 @@ SIGNATURES = {
     "kgcn_gcn_step_chain_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
                                                _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, ctypes.c_uint32, _vp]),
     "kgcn_graphconv_chain_dw_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kgcn_graphconv_chain_dw_g_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kgcn_gcn_step_chain_g_supported": (_i32, [_i64, _i32, _i32, _i32, _vp]),
+    "kgcn_gcn_step_chain_g_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                                 _vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, ctypes.c_uint32, _vp]),
     "kgcn_reduce_partials_f32": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "kgcn_reduce_adam_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "kgcn_p2p_alloc": (ctypes.c_int, [_sz, _vp, _vp]),

@@ -157,6 +157,8 @@ struct V4ChainJob {
     const V4Head* head = nullptr;
     int c_begin = 0, c_count = 0;   // channel group [c_begin, c_begin + c_count) of the CSR's channels (0 = all)
     int acc_in = 0;                 // add the existing y before the activation (later group of a layer split over channel groups)
+    float* zsave = nullptr;         // optional [B, N, C * f_in]: the job also stores its aggregate Z = [A_0 . x | A_1 . x | ..] (for a dx job
+                                    // that is G = A^T . dU of the layer, which the weight-gradient kernel then reads instead of gathering it again)
 };
 // channels per job a forward layer needs in a chain: `channels` (one job), fewer (K = C * f_in beyond tensor memory: channel
 // groups, the later ones accumulate), 0 = no single-CTA plan
@@ -183,6 +185,8 @@ struct DwJob {
     float* partial;        // [splits][(f_in + 1)][channels * f_out]
     size_t partial_bytes;
     int f_in, f_out;
+    const float* g = nullptr;   // optional [B, N, f_out] (channels == 1): G = A^T . dU of the layer, already computed (by the dx job of
+                                // the chained launch, V4ChainJob::zsave) -- the kernel then copies G rows instead of gathering them
 };
 int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, int* splits_out,
                                    cudaStream_t st);

@@ -386,8 +386,17 @@ extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_
                                            int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
                                            const float* const* x, const float* const* du, float* const* partial,
                                            const size_t* partial_bytes, void* stream) {
+    return kgcn_graphconv_chain_dw_g_f32(rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, n_layers, dims, x, du, nullptr, partial,
+                                         partial_bytes, stream);
+}
+
+extern "C" int kgcn_graphconv_chain_dw_g_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
+                                             int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
+                                             const float* const* x, const float* const* du, const float* const* g,
+                                             float* const* partial, const size_t* partial_bytes, void* stream) {
     KGCN_REQUIRE(rowptr_t && col_t && val_t && dims && x && du && partial && partial_bytes, KGCN_ERR_NULL,
                  "graphconv_chain_dw: NULL pointer argument");
+    KGCN_REQUIRE(g == nullptr || channels == 1, KGCN_ERR_UNSUPPORTED, "graphconv_chain_dw: precomputed G needs channels == 1");
     KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 8, KGCN_ERR_BAD_SHAPE,
                  "graphconv_chain_dw: bad shape (1..8 layers)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -403,7 +412,7 @@ extern "C" int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_
             KGCN_REQUIRE(fused_dw_eligible(n_graphs, channels, n_nodes, dims[i], dims[i + 1], x[i], du[i], rowptr_t, col_t, val_t),
                          KGCN_ERR_UNSUPPORTED, "graphconv_chain_dw: layer %d (%d -> %d) is not supported by the fused weight-gradient kernel",
                          i, dims[i], dims[i + 1]);
-            jobs[k] = DwJob{rowptr_t, col_t, val_t, x[i], du[i], partial[i], partial_bytes[i], dims[i], dims[i + 1]};
+            jobs[k] = DwJob{rowptr_t, col_t, val_t, x[i], du[i], partial[i], partial_bytes[i], dims[i], dims[i + 1], g ? g[i] : nullptr};
         }
         const int rc = launch_graphconv_fused_dw_jobs(jobs, n, n_graphs, channels, n_nodes, nullptr, st);
         if (rc) return rc;
@@ -438,8 +447,29 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
                                        int32_t n_labels, const float* labels, const float* mask, float inv_batch,
                                        float* logits, float* prediction, float* gathered, float* head_partial,
                                        uint32_t flags, void* stream) {
+    return kgcn_gcn_step_chain_g_f32(rowptr, col, val, rowptr_t, col_t, val_t, n_graphs, channels, n_nodes, n_layers, dims, dims_valid, x, w,
+                                     bias, y, du, nullptr, act, head_w, head_b, n_labels, labels, mask, inv_batch, logits, prediction,
+                                     gathered, head_partial, flags, stream);
+}
+
+extern "C" int32_t kgcn_gcn_step_chain_g_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
+                                                   const int32_t* dims) {
+    if (n_graphs <= 0 || channels != 1 || n_nodes <= 0 || n_layers < 2 || n_layers > 4 || dims == nullptr) return 0;
+    return chain_kind(n_graphs, channels, n_nodes, n_layers, dims) == 1 ? 1 : 0;   // the v4 chained kernel; not the wide-layer (v5) one
+}
+
+extern "C" int kgcn_gcn_step_chain_g_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
+                                         const int32_t* col_t, const float* val_t, int64_t n_graphs, int32_t channels,
+                                         int32_t n_nodes, int32_t n_layers, const int32_t* dims, const int32_t* dims_valid,
+                                         const float* x, const float* const* w, const float* const* bias, float* const* y,
+                                         float* const* du, float* const* g_save, int32_t act, const float* head_w,
+                                         const float* head_b, int32_t n_labels, const float* labels, const float* mask,
+                                         float inv_batch, float* logits, float* prediction, float* gathered, float* head_partial,
+                                         uint32_t flags, void* stream) {
     KGCN_REQUIRE(rowptr && col && val && rowptr_t && col_t && val_t && dims && x && w && y && du && head_w && labels && head_partial,
                  KGCN_ERR_NULL, "gcn_step_chain: NULL pointer argument");
+    KGCN_REQUIRE(g_save == nullptr || kgcn_gcn_step_chain_g_supported(n_graphs, channels, n_nodes, n_layers, dims), KGCN_ERR_UNSUPPORTED,
+                 "gcn_step_chain: storing G is not supported for this network (kgcn_gcn_step_chain_g_supported)");
     KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 4, KGCN_ERR_BAD_SHAPE,
                  "gcn_step_chain: bad shape (1..4 layers)");
     KGCN_REQUIRE(act >= KGCN_ACT_NONE && act <= KGCN_ACT_TANH, KGCN_ERR_BAD_SHAPE, "gcn_step_chain: unknown act %d", act);
@@ -483,6 +513,7 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
         KGCN_REQUIRE(aligned16(du[l]) && aligned16(du[l - 1]), KGCN_ERR_MISALIGNED, "gcn_step_chain: 16-byte alignment required");
         jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
                              y[l - 1], act, 0, nullptr};
+        if (g_save != nullptr) jobs[k].zsave = g_save[l];   // G_l = A^T . du[l]: the aggregate of this very job
     }
     return launch_graphconv_fused_v4_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream),
                                            (flags & KGCN_FLAG_INPUTS_STABLE) != 0);

@@ -41,6 +41,7 @@ struct DwParams {
     const float* val;
     const float* x;          // [B, N, f_in]
     const float* du;         // [B, N, f_out]
+    const float* g;          // optional [B, N, f_out] (C == 1): G = A^T . dU already computed -- its rows are copied, not gathered
     float* partial;          // [grid][(f_in + 1) * Ng]
     int64_t n_graphs;
     int C, N, f_in, f_out, Ng;
@@ -213,6 +214,14 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                     const int64_t rp_lo = r0 & ~3ll;
                     const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
                     const uint32_t x_bytes = static_cast<uint32_t>(ng * N) * pitch_x, u_bytes = static_cast<uint32_t>(ng * N) * pitch_u;
+                    if (p.g != nullptr) {   // G rows take the place of the dU rows; no CSR slices
+                        mbar_expect_tx(full, x_bytes + u_bytes);   // the one arrival of the phase
+                        bulk_g2s(st + p.st_du, p.g + g0 * N * f_out, u_bytes, full);
+                        bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
+                        if (tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it));
+                        if (++s == S) s = 0;
+                        continue;
+                    }
                     mbar_expect_tx_only(full, x_bytes + u_bytes + 4u * rp_cnt);
                     bulk_g2s(st + p.st_du, p.du + g0 * N * f_out, u_bytes, full);
                     bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
@@ -293,9 +302,10 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                 mbar_wait(&bar_full[s], (ph_a >> s) & 1u);
                 ph_a ^= 1u << s;
                 if (warp == 0 && tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it) + 1);
+                const bool copy_g = p.g != nullptr;   // the stage holds finished G rows where the dU rows would be
                 const uint32_t rp_addr = st + p.st_rp + 4u * (r0_lo & 3u);
-                const int e_first = static_cast<int>(lds_u32(rp_addr));
-                const int e_last = static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
+                const int e_first = copy_g ? 0 : static_cast<int>(lds_u32(rp_addr));
+                const int e_last = copy_g ? 0 : static_cast<int>(lds_u32(rp_addr + 4u * static_cast<uint32_t>(rows_csr)));
                 const int e_lo = e_first & ~3;
                 const bool staged = static_cast<uint32_t>((e_last - e_lo + 3) & ~3) <= static_cast<uint32_t>(p.cv_cap);
                 const uint32_t col_addr = st + p.st_col - 4u * static_cast<uint32_t>(e_lo);   // entry e at col_addr + 4 e
@@ -317,7 +327,21 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
 #pragma unroll
                         for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
                         uint32_t line_hi, line_lo;
-                        if (cs < p.n_gs) {
+                        if (cs < p.n_gs && copy_g) {
+                            // ---- G slab, already computed: the row's 128 bytes, same rotated chunk order as the gather leaves ----
+                            if (valid) {
+                                const uint32_t ga = st + p.st_du + static_cast<uint32_t>(r) * pitch_u + static_cast<uint32_t>(cs) * 128u + (s7 << 4);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float t[4];
+                                    lds_f<4>(t, ga ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc[4 * i + jj] = t[jj];
+                                }
+                            }
+                            line_hi = op + p.op_g + static_cast<uint32_t>(cs) * p.lbo + static_cast<uint32_t>(rl) * 128u;
+                            line_lo = line_hi + lo_g;
+                        } else if (cs < p.n_gs) {
                             // ---- G slab: gather over the row's entries of channel c ----
                             const int c = cs / p.spc, sl = cs - c * p.spc;
                             const int gl = r / N, node = r - gl * N;
@@ -606,6 +630,9 @@ int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_grap
         KGCN_REQUIRE(j.partial != nullptr && j.partial_bytes >= need && aligned16(j.partial), KGCN_ERR_WORKSPACE,
                      "fused GraphConv weight gradient: workspace %zu < %zu bytes", j.partial_bytes, need);
         p.rowptr = j.rowptr_t; p.col = j.col_t; p.val = j.val_t; p.x = j.x; p.du = j.du;
+        KGCN_REQUIRE(j.g == nullptr || (channels == 1 && aligned16(j.g)), KGCN_ERR_UNSUPPORTED,
+                     "fused GraphConv weight gradient: a precomputed G needs channels == 1 and 16-byte alignment");
+        p.g = j.g;
         p.partial = j.partial;
         p.tm_off = cols;
         p.fresh = (k == 0 || !soft_jobs_enabled() || j.f_in != jobs[k - 1].f_in || j.f_out != jobs[k - 1].f_out) ? 1 : 0;

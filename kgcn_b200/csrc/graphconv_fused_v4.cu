@@ -88,6 +88,7 @@ struct V4Params {
     int x_prev;           // soft job whose x IS the previous job's y (same tiles): when a CTA's tiles fit the stage ring, the previous
                           // job's epilogue writes each output tile straight into this job's stage slot (on-chip hand-over)
     uint32_t w_pair;      // bytes of one (hi, lo) B operand buffer
+    float* zsave;         // chained kernel, optional [rows, K]: the aggregate Z = A . x (fp32, before the tf32 split) is also stored
     long long* dbg;
 };
 
@@ -1102,6 +1103,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
             const uint32_t z_stride = static_cast<uint32_t>(2 * Kp);
             const uint32_t row_rp_off = 4u * static_cast<uint32_t>((gl * p.C_csr + p.c_begin) * N + node);
             const uint32_t row_x_off = static_cast<uint32_t>(gl * N) * pitch + (s7 << 4);
+            int64_t zrow0 = tr.g_begin * N;   // global row index of the current tile's first row (zsave only)
             int s = 0, zi = 0;
             for (int it = 0; it < n_tiles; ++it) {
                 const bool last = it == n_tiles - 1;
@@ -1150,6 +1152,19 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                             acc[4 * i + jj] = p1 ? a1 : a0;
                             acc[4 * (i + 1) + jj] = p1 ? a0 : a1;
                         }
+                    if (p.zsave != nullptr && valid) {
+                        // the row's slab of Z in fp32 (for a dx job: G = A^T . dU, which the weight-gradient launch then reads instead
+                        // of gathering it again).  After the first un-rotation stage the blocks (i, i + 1), i even, hold the 16-byte
+                        // chunks (q, q + 1), q = i ^ (s7 & 6), of the slab's 128-byte line: four 32-byte stores, one full sector each
+                        // (every lane writes another row, so a store instruction is 32 requests whatever its width)
+                        const uint64_t zrow = reinterpret_cast<uint64_t>(p.zsave) + (static_cast<uint64_t>(zrow0 + w) * static_cast<uint64_t>(K) + static_cast<uint64_t>(slab * 32)) * 4u +
+                                              ((s7 & 6u) << 4);
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2)
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(zrow ^ static_cast<uint64_t>(i << 4)),
+                                         "f"(acc[4 * i]), "f"(acc[4 * i + 1]), "f"(acc[4 * i + 2]), "f"(acc[4 * i + 3]), "f"(acc[4 * i + 4]),
+                                         "f"(acc[4 * i + 5]), "f"(acc[4 * i + 6]), "f"(acc[4 * i + 7]) : "memory");
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         if ((i & 2) == 0)
@@ -1183,6 +1198,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v4_chain_kernel(const V4Batch b)
                     }
                     fs += 2;
                 }
+                zrow0 += full_rows;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[s]);
                 tmem_st_wait();
@@ -1955,6 +1971,9 @@ int launch_graphconv_fused_v4_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : p.f_out;
         p.mul_src = j.mul_src;
         p.mul_act = j.mul_act;
+        KGCN_REQUIRE(j.zsave == nullptr || (cn == channels && (reinterpret_cast<uintptr_t>(j.zsave) & 127u) == 0 && (p.K & 31) == 0), KGCN_ERR_UNSUPPORTED,
+                     "fused GraphConv chain: the aggregate can only be stored for a whole-layer job into a 128-byte aligned buffer");
+        p.zsave = j.zsave;
         p.head = 0;
         if (j.head != nullptr) {
             const V4Head& hd = *j.head;

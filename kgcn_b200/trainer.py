@@ -220,6 +220,13 @@ class Trainer:
         if self.chain and os.environ.get("KGCN_STEP_CHAIN", "1") != "0" and (self.world_size == 1 or want_p2p):
             self.step_grid = int(lib.kgcn_gcn_step_chain_grid(B, C, N, L, self._dims_c, s.label_dim))
         self.step_chain = self.step_grid > 0
+        # the dx jobs of the step launch also store what they aggregate, G_l = A^T . dU_l, and the weight-gradient launch reads it
+        # instead of gathering it a second time (bit-identical; KGCN_GSAVE=0 is the A-B knob)
+        self.g_save = None
+        if (self.step_chain and os.environ.get("KGCN_GSAVE", "1") != "0" and
+                bool(lib.kgcn_gcn_step_chain_g_supported(B, C, N, L, self._dims_c))):
+            self.g_save = [None] + [torch.empty(B, N, self.dims[i + 1], **f32) for i in range(1, L)]
+            self._g_ptrs = arr(self.g_save)
         if self.fused_step:
             n_seg = len(s.conv_dims) + (2 if self.step_chain else 0)
             segs = (_lib.GradSegment * n_seg)()
@@ -507,20 +514,23 @@ class Trainer:
     def _launch_step_chain(self, batch, st, stable=False):
         s, B, N, C = self.spec, self.B, self.spec.n_nodes, self.spec.channels
         csr, L, x = batch.csr, len(self.spec.conv_dims), batch.features
-        check(lib.kgcn_gcn_step_chain_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t),
-                                          B, C, N, L, self._dims_c, self._ldims_c, ptr(x), self._w_ptrs, self._b_ptrs, self._y_ptrs,
-                                          self._du_ptrs, self.act, ptr(self.pviews["dense/kernel"]), ptr(self.pviews["dense/bias"]),
-                                          s.label_dim, ptr(batch.labels), ptr(batch.mask), 1.0 / (B * self.world_size), ptr(self.logits),
-                                          ptr(self.prediction), ptr(self.gathered), ptr(self.head_partial),
-                                          _lib.FLAG_INPUTS_STABLE if stable else _lib.FLAG_DEFAULT, st))
+        check(lib.kgcn_gcn_step_chain_g_f32(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t),
+                                            B, C, N, L, self._dims_c, self._ldims_c, ptr(x), self._w_ptrs, self._b_ptrs, self._y_ptrs,
+                                            self._du_ptrs, self._g_ptrs if self.g_save is not None else None, self.act,
+                                            ptr(self.pviews["dense/kernel"]), ptr(self.pviews["dense/bias"]),
+                                            s.label_dim, ptr(batch.labels), ptr(batch.mask), 1.0 / (B * self.world_size), ptr(self.logits),
+                                            ptr(self.prediction), ptr(self.gathered), ptr(self.head_partial),
+                                            _lib.FLAG_INPUTS_STABLE if stable else _lib.FLAG_DEFAULT, st))
 
     def _launch_dw_chain(self, batch, st):
         B, N, C = self.B, self.spec.n_nodes, self.spec.channels
         csr, L = batch.csr, len(self.spec.conv_dims)
         self.acts[0] = batch.features
         x_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in self.acts[:L]])
-        check(lib.kgcn_graphconv_chain_dw_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c, x_ptrs,
-                                              self._du_ptrs, self._part_ptrs, self._part_bytes, st))
+        # G of the layers above the first comes from the step launch's dx jobs (like du, written by _launch_step_chain for this batch)
+        g = self._g_ptrs if self.g_save is not None else None
+        check(lib.kgcn_graphconv_chain_dw_g_f32(ptr(csr.rowptr_t), ptr(csr.col_t), ptr(csr.val_t), B, C, N, L, self._dims_c, x_ptrs,
+                                                self._du_ptrs, g, self._part_ptrs, self._part_bytes, st))
 
     _head_in_chain = False
 

@@ -208,6 +208,44 @@ def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkey
     assert int(c.step_state[0].item()) == 3
 
 
+@pytest.mark.parametrize("B,N,F,conv_dims", [
+    (700, 32, 64, [64, 64]),          # C2 widths: ragged last tile (5 graphs per CTA, 4 + 1), one stored G
+    (1024, 32, 64, [64, 64]),         # C2 at the full batch
+    (300, 50, 75, [50, 50, 50]),      # C3 on padded widths: two stored G (layers 2 and 1), tiles of 2 graphs = 100 of 128 rows
+    (37, 20, 32, [32, 64, 32]),       # unequal widths: hard job boundaries, a different plan per weight-gradient job
+])
+def test_stored_aggregate_equals_second_gather(B, N, F, conv_dims, monkeypatch):
+    """The dx jobs of the step launch store G_l = A^T . dU_l and the weight-gradient launch copies it (kgcn_gcn_step_chain_g_f32 /
+    kgcn_graphconv_chain_dw_g_f32) -- against KGCN_GSAVE=0, where the weight-gradient launch gathers G_l again: the same per-row
+    accumulation order and the same tf32 split, so gradients and parameters must be BIT-identical, and the stored G itself equals
+    the batched SpMM of the library on (A^T, dU_l)."""
+    from kgcn_b200 import ops
+    from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
+    counts, idx, val, x, labels, mask, adjs, p = make_case(B, N, 1, F, conv_dims, None, seed=B + N)
+    spec = NetSpec(F, conv_dims, N, channels=1, label_dim=2, act="sigmoid")
+    monkeypatch.setenv("KGCN_GSAVE", "1")
+    a = Trainer(spec, B, seed=3)
+    monkeypatch.setenv("KGCN_GSAVE", "0")
+    b = Trainer(spec, B, seed=3)
+    assert a.step_chain and b.step_chain and a.g_save is not None and b.g_save is None
+    batch = DeviceBatch.from_host(counts, idx, val, x, labels, N, mask=mask, pad_to=a.dims[0])
+    for _ in range(4):
+        a.step_eager(batch)
+        b.step_eager(batch)
+    torch.cuda.synchronize()
+    assert torch.equal(a.grads, b.grads)
+    assert torch.equal(a.params, b.params)
+    for part_a, part_b in zip(a.partials, b.partials):
+        assert torch.equal(part_a, part_b)
+    csr_t = batch.csr.transposed()
+    for l in range(1, len(conv_dims)):
+        f = a.dims[l + 1]
+        want = torch.empty(B, N, f, device="cuda")
+        ops.bspmm_raw(csr_t, a.du[l], N * f, 0, want, N * f, 0, f)
+        torch.cuda.synchronize()
+        close(a.g_save[l], want.cpu().numpy(), 1e-6)
+
+
 def test_training_reduces_loss_on_ring_task():
     """C2 generator (ring-size classification) is learnable: cost_sum falls over 60 steps."""
     from kgcn_b200 import synth

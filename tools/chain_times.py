@@ -18,25 +18,20 @@ host = bench.make_host_batches(w, ROT, seed=1)
 batches = [DeviceBatch.from_host(d["counts"], d["indices"], d["values"], d["features"], d["labels"], N, pad_to=tr.dims[0]) for d in host]
 L = len(w["conv_dims"])
 st = lambda: torch.cuda.current_stream().cuda_stream
-print("padded", tr.padded, "fused_step", tr.fused_step, "chain", tr.chain, "step_chain", tr.step_chain)
+print("padded", tr.padded, "fused_step", tr.fused_step, "chain", tr.chain, "step_chain", tr.step_chain, "g_save", tr.g_save is not None)
 for b in batches[:2]:
     tr.step_eager(b)
 torch.cuda.synchronize()
 xp = lambda b: (ctypes.c_void_p * L)(*([b.features.data_ptr()] + [a.data_ptr() for a in tr.acts[1:L]]))
 
-def step_chain(i): tr._step_chain(batches[i], st()) if False else check(lib.kgcn_gcn_step_chain_f32(
-    ptr(batches[i].csr.rowptr), ptr(batches[i].csr.col), ptr(batches[i].csr.val), ptr(batches[i].csr.rowptr_t), ptr(batches[i].csr.col_t),
-    ptr(batches[i].csr.val_t), B, C, N, L, tr._dims_c, tr._ldims_c, ptr(batches[i].features), tr._w_ptrs, tr._b_ptrs, tr._y_ptrs, tr._du_ptrs,
-    tr.act, ptr(tr.pviews["dense/kernel"]), ptr(tr.pviews["dense/bias"]), 2, ptr(batches[i].labels), ptr(batches[i].mask), 1.0 / B,
-    ptr(tr.logits), ptr(tr.prediction), ptr(tr.gathered), ptr(tr.head_partial), 0, st()))
+def step_chain(i): tr._launch_step_chain(batches[i], st())   # incl. the stored G when the trainer uses it (KGCN_GSAVE)
 def fwd_chain(i): check(lib.kgcn_graphconv_chain_fwd_f32(ptr(batches[i].csr.rowptr), ptr(batches[i].csr.col), ptr(batches[i].csr.val), B, C, N, L,
     tr._dims_c, tr._ldims_c, ptr(batches[i].features), tr._w_ptrs, tr._b_ptrs, tr._y_ptrs, tr.act, st()))
 def fwd_one(i): check(lib.kgcn_graphconv_chain_fwd_f32(ptr(batches[i].csr.rowptr), ptr(batches[i].csr.col), ptr(batches[i].csr.val), B, C, N, 1,
     tr._dims_c, tr._ldims_c, ptr(batches[i].features), tr._w_ptrs, tr._b_ptrs, tr._y_ptrs, tr.act, st()))
 def dx_chain(i): check(lib.kgcn_graphconv_chain_dx_f32(ptr(batches[i].csr.rowptr_t), ptr(batches[i].csr.col_t), ptr(batches[i].csr.val_t), B, C, N, L,
     tr._dims_c, xp(batches[i]), tr._w_ptrs, tr._du_ptrs, tr.act, st()))
-def dw_chain(i): check(lib.kgcn_graphconv_chain_dw_f32(ptr(batches[i].csr.rowptr_t), ptr(batches[i].csr.col_t), ptr(batches[i].csr.val_t), B, C, N, L,
-    tr._dims_c, xp(batches[i]), tr._du_ptrs, tr._part_ptrs, tr._part_bytes, st()))
+def dw_chain(i): tr._launch_dw_chain(batches[i], st())
 def dw_one(i): check(lib.kgcn_graphconv_chain_dw_f32(ptr(batches[i].csr.rowptr_t), ptr(batches[i].csr.col_t), ptr(batches[i].csr.val_t), B, C, N, 1,
     tr._dims_c, xp(batches[i]), tr._du_ptrs, tr._part_ptrs, tr._part_bytes, st()))
 def head(i):

@@ -21,6 +21,9 @@ b = Trainer(spec, B, seed=5)          # one launch per layer
 os.environ["KGCN_CHAIN"], os.environ["KGCN_STEP_CHAIN"] = "1", "1"
 c = Trainer(spec, B, seed=5)          # whole graph-local step in one launch (fused head)
 d = Trainer(spec, B, seed=5)          # the same as multi-step CUDA graphs (early start under the previous tail)
+os.environ["KGCN_GSAVE"] = "0"
+e = Trainer(spec, B, seed=5)          # step chain whose weight-gradient launch gathers A^T.dU again instead of reading the dx jobs' copy
+os.environ["KGCN_GSAVE"] = "1"
 assert a.chain and not b.chain and c.step_chain
 host = bench.make_host_batches(w, 8, seed=77)
 batches = [DeviceBatch.from_host(h["counts"], h["indices"], h["values"], h["features"], h["labels"], N, pad_to=a.dims[0]) for h in host]
@@ -28,7 +31,7 @@ d.capture_many("epoch", batches)
 bad, rel8 = 0, None
 for s in range(steps):
     bt = batches[s % len(batches)]
-    a.step_eager(bt); b.step_eager(bt); c.step_eager(bt)
+    a.step_eager(bt); b.step_eager(bt); c.step_eager(bt); e.step_eager(bt)
     if s % len(batches) == len(batches) - 1:
         d.replay("epoch")
         torch.cuda.synchronize()
@@ -37,6 +40,9 @@ for s in range(steps):
         if not torch.equal(a.params, b.params):
             bad += 1
             print("step %d: chained != per-layer, max |diff| %.3e" % (s, float((a.params - b.params).abs().max())))
+        if not torch.equal(c.params, e.params):
+            bad += 1
+            print("step %d: stored G != second gather, max |diff| %.3e" % (s, float((c.params - e.params).abs().max())))
         if not torch.equal(c.params, d.params):
             bad += 1
             print("step %d: step chain eager != multi-step graph, max |diff| %.3e" % (s, float((c.params - d.params).abs().max())))
