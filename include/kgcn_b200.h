@@ -366,7 +366,7 @@ int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const flo
  * receives G_l = A^T . du[l] ([B, N, dims[l + 1]], fp32, 128-byte aligned) for l = n_layers - 1 .. 1 -- the `adjoint_a=True` product of
  * the registered gradient (kgcn/bspmm_call.py:44), which the dx job computes anyway as the aggregate of (A^T, du[l], W_l^T).
  * kgcn_graphconv_chain_dw_g_f32 then reads G_l instead of gathering it a second time; the results are bit-identical to the
- * launches without g (same per-row accumulation order, same tf32 split).  channels == 1 and the v4 chained kernel only:
+ * launches without g (same per-row accumulation order, same tf32 split).  channels == 1 only:
  * kgcn_gcn_step_chain_g_supported(...) != 0.  g_save == NULL: exactly kgcn_gcn_step_chain_f32. */
 int32_t kgcn_gcn_step_chain_g_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims);
 int kgcn_gcn_step_chain_g_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,

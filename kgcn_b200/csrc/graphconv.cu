@@ -455,7 +455,7 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
 extern "C" int32_t kgcn_gcn_step_chain_g_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
                                                    const int32_t* dims) {
     if (n_graphs <= 0 || channels != 1 || n_nodes <= 0 || n_layers < 2 || n_layers > 4 || dims == nullptr) return 0;
-    return chain_kind(n_graphs, channels, n_nodes, n_layers, dims) == 1 ? 1 : 0;   // the v4 chained kernel; not the wide-layer (v5) one
+    return chain_kind(n_graphs, channels, n_nodes, n_layers, dims) != 0 ? 1 : 0;   // the v4 chained kernel or the wide-layer (v5) one
 }
 
 extern "C" int kgcn_gcn_step_chain_g_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
@@ -495,6 +495,7 @@ extern "C" int kgcn_gcn_step_chain_g_f32(const int32_t* rowptr, const int32_t* c
             KGCN_REQUIRE(du[l] && du[l - 1] && y[l - 1], KGCN_ERR_NULL, "gcn_step_chain: NULL pointer at dx of layer %d", l);
             jobs[k] = V4ChainJob{rowptr_t, col_t, val_t, du[l], w[l], nullptr, du[l - 1], dims[l + 1], dims[l], KGCN_ACT_NONE, 1,
                                  y[l - 1], act, 0, nullptr};
+            if (g_save != nullptr) jobs[k].zsave = g_save[l];   // G_l = A^T . du[l]: the aggregate of this very job
         }
         return launch_graphconv_fused_v5_chain(jobs, k, n_graphs, channels, n_nodes, static_cast<cudaStream_t>(stream));
     }

@@ -44,6 +44,7 @@ struct V5Params {
     const float* bias;
     float* y;
     const float* mul_src;   // y *= act'(mul_src) of mul_act (backward dx)
+    float* zsave;           // optional [rows, K]: the aggregate Z = A . x in fp32 is also stored (a dx job's G = A^T . dU, see V4ChainJob)
     int64_t n_graphs;
     int C, N, f_in, f_out, act, mul_act, w_trans, f_valid;
     int K;                  // C * f_in
@@ -236,6 +237,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
             const int n_items_rb = (R + 31) >> 5;                  // 32-row blocks per tile
             const uint32_t r0_step = static_cast<uint32_t>(p.G * C * N);
             uint32_t r0_lo = static_cast<uint32_t>((tr.g_begin * C * N) & 3);
+            int64_t zrow0 = tr.g_begin * N;   // global row index of the current tile's first row (zsave only)
             int s = 0, zi = 0;
             for (int it = 0; it < tr.n_tiles; ++it) {
                 const bool last = it == tr.n_tiles - 1;
@@ -312,6 +314,25 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
                         }
                     }
                     __syncwarp();
+                    if (p.zsave != nullptr && valid) {
+                        // the row's slab of Z in fp32: block i holds the 16-byte chunk i ^ t of the slab's 128-byte line, so the blocks
+                        // (i, i + 1), i even, are the chunk pair starting at (i ^ t) & 6 -- in swapped order when t is odd.  Four
+                        // 32-byte stores, one full sector each (every lane writes another row: 32 requests per store whatever its width)
+                        const uint64_t zrow = reinterpret_cast<uint64_t>(p.zsave) +
+                                              (static_cast<uint64_t>(zrow0 + r) * static_cast<uint64_t>(p.K) + static_cast<uint64_t>(slab * 32)) * 4u + ((t7 & 6u) << 4);
+                        const bool odd = (t7 & 1u) != 0;
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2) {
+                            float lo4[4], hi4[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                lo4[jj] = odd ? acc[4 * (i + 1) + jj] : acc[4 * i + jj];
+                                hi4[jj] = odd ? acc[4 * i + jj] : acc[4 * (i + 1) + jj];
+                            }
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(zrow ^ static_cast<uint64_t>(i << 4)),
+                                         "f"(lo4[0]), "f"(lo4[1]), "f"(lo4[2]), "f"(lo4[3]), "f"(hi4[0]), "f"(hi4[1]), "f"(hi4[2]), "f"(hi4[3]) : "memory");
+                        }
+                    }
                     if (r < R) {
                         // the row's 128-byte line of atom `slab`: block i holds chunk i ^ t -> position (i ^ t) ^ (r & 7) = i ^ u
                         const uint32_t line = zb + static_cast<uint32_t>(slab) * p.z_atom + static_cast<uint32_t>(r) * 128u + (u7 << 4);
@@ -341,6 +362,7 @@ __global__ void __maxnreg__(96) graphconv_fused_v5_kernel(const V5Batch b) {
                 if (++s == S) s = 0;
                 zi ^= 1;
                 r0_lo += r0_step;
+                zrow0 += static_cast<int64_t>(p.G) * N;
             }
         }
     } else if (warp >= kWarpMma) {
@@ -867,6 +889,9 @@ int launch_graphconv_fused_v5_chain(const V4ChainJob* jobs, int n_jobs, int64_t 
         KGCN_REQUIRE(j.mul_src == nullptr || j.f_out % 4 == 0, KGCN_ERR_UNSUPPORTED, "fused GraphConv v5: act' epilogue needs f_out %% 4 == 0");
         p.mul_src = j.mul_src;
         p.mul_act = j.mul_act;
+        KGCN_REQUIRE(j.zsave == nullptr || ((reinterpret_cast<uintptr_t>(j.zsave) & 127u) == 0 && (p.K & 31) == 0), KGCN_ERR_UNSUPPORTED,
+                     "fused GraphConv v5: the aggregate can only be stored into a 128-byte aligned buffer");
+        p.zsave = j.zsave;
         p.f_valid = (j.f_out_valid > 0 && j.f_out_valid < j.f_out) ? j.f_out_valid : j.f_out;
         if (j.head != nullptr) {
             const V4Head& hd = *j.head;

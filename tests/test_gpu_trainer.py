@@ -213,6 +213,8 @@ def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkey
     (1024, 32, 64, [64, 64]),         # C2 at the full batch
     (300, 50, 75, [50, 50, 50]),      # C3 on padded widths: two stored G (layers 2 and 1), tiles of 2 graphs = 100 of 128 rows
     (37, 20, 32, [32, 64, 32]),       # unequal widths: hard job boundaries, a different plan per weight-gradient job
+    (512, 64, 128, [128, 128]),       # C5's shard: the wide-layer (v5) step launch stores G, 32-row operand chunks copy it
+    (21, 64, 128, [128, 128]),        # the same kernels on a batch smaller than the grid
 ])
 def test_stored_aggregate_equals_second_gather(B, N, F, conv_dims, monkeypatch):
     """The dx jobs of the step launch store G_l = A^T . dU_l and the weight-gradient launch copies it (kgcn_gcn_step_chain_g_f32 /
