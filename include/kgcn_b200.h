@@ -363,10 +363,10 @@ int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col, const flo
                             uint32_t flags, void* stream);
 
 /* The same launch, which ALSO stores what its dx jobs aggregate: g_save (HOST array of n_layers device pointers, entry 0 unused)
- * receives G_l = A^T . du[l] ([B, N, dims[l + 1]], fp32, 128-byte aligned) for l = n_layers - 1 .. 1 -- the `adjoint_a=True` product of
+ * receives G_l = [A_0^T . du[l] | A_1^T . du[l] | ..] ([B, N, channels * dims[l + 1]], fp32, 128-byte aligned) for l = n_layers - 1 .. 1 -- the `adjoint_a=True` product of
  * the registered gradient (kgcn/bspmm_call.py:44), which the dx job computes anyway as the aggregate of (A^T, du[l], W_l^T).
  * kgcn_graphconv_chain_dw_g_f32 then reads G_l instead of gathering it a second time; the results are bit-identical to the
- * launches without g (same per-row accumulation order, same tf32 split).  channels == 1 only:
+ * launches without g (same per-row accumulation order, same tf32 split).  Networks whose step launch can do it:
  * kgcn_gcn_step_chain_g_supported(...) != 0.  g_save == NULL: exactly kgcn_gcn_step_chain_f32. */
 int32_t kgcn_gcn_step_chain_g_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims);
 int kgcn_gcn_step_chain_g_f32(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* rowptr_t,
@@ -384,7 +384,7 @@ int kgcn_graphconv_chain_dw_f32(const int32_t* rowptr_t, const int32_t* col_t, c
                                 int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,
                                 const float* const* x, const float* const* du, float* const* partial,
                                 const size_t* partial_bytes, void* stream);
-/* g (HOST array of n_layers device pointers or NULL; channels == 1): where g[l] != NULL, layer l's G_l = A^T . du[l] is read from
+/* g (HOST array of n_layers device pointers or NULL): where g[l] != NULL, layer l's G_l = A^T . du[l] is read from
  * there (written by kgcn_gcn_step_chain_g_f32) instead of being gathered from du[l] and the transposed CSR. */
 int kgcn_graphconv_chain_dw_g_f32(const int32_t* rowptr_t, const int32_t* col_t, const float* val_t, int64_t n_graphs,
                                   int32_t channels, int32_t n_nodes, int32_t n_layers, const int32_t* dims,

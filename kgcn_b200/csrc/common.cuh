@@ -185,8 +185,8 @@ struct DwJob {
     float* partial;        // [splits][(f_in + 1)][channels * f_out]
     size_t partial_bytes;
     int f_in, f_out;
-    const float* g = nullptr;   // optional [B, N, f_out] (channels == 1): G = A^T . dU of the layer, already computed (by the dx job of
-                                // the chained launch, V4ChainJob::zsave) -- the kernel then copies G rows instead of gathering them
+    const float* g = nullptr;   // optional [B, N, channels * f_out]: G = [A_0^T . dU | A_1^T . dU | ..] of the layer, already computed (by the dx
+                                // job of the chained launch, V4ChainJob::zsave) -- the kernel then copies G rows instead of gathering them
 };
 int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_graphs, int channels, int n_nodes, int* splits_out,
                                    cudaStream_t st);

@@ -396,7 +396,6 @@ extern "C" int kgcn_graphconv_chain_dw_g_f32(const int32_t* rowptr_t, const int3
                                              float* const* partial, const size_t* partial_bytes, void* stream) {
     KGCN_REQUIRE(rowptr_t && col_t && val_t && dims && x && du && partial && partial_bytes, KGCN_ERR_NULL,
                  "graphconv_chain_dw: NULL pointer argument");
-    KGCN_REQUIRE(g == nullptr || channels == 1, KGCN_ERR_UNSUPPORTED, "graphconv_chain_dw: precomputed G needs channels == 1");
     KGCN_REQUIRE(n_graphs > 0 && channels > 0 && n_nodes > 0 && n_layers >= 1 && n_layers <= 8, KGCN_ERR_BAD_SHAPE,
                  "graphconv_chain_dw: bad shape (1..8 layers)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -454,7 +453,7 @@ extern "C" int kgcn_gcn_step_chain_f32(const int32_t* rowptr, const int32_t* col
 
 extern "C" int32_t kgcn_gcn_step_chain_g_supported(int64_t n_graphs, int32_t channels, int32_t n_nodes, int32_t n_layers,
                                                    const int32_t* dims) {
-    if (n_graphs <= 0 || channels != 1 || n_nodes <= 0 || n_layers < 2 || n_layers > 4 || dims == nullptr) return 0;
+    if (n_graphs <= 0 || channels <= 0 || n_nodes <= 0 || n_layers < 2 || n_layers > 4 || dims == nullptr) return 0;
     return chain_kind(n_graphs, channels, n_nodes, n_layers, dims) != 0 ? 1 : 0;   // the v4 chained kernel or the wide-layer (v5) one
 }
 

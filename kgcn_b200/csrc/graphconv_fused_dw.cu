@@ -41,7 +41,7 @@ struct DwParams {
     const float* val;
     const float* x;          // [B, N, f_in]
     const float* du;         // [B, N, f_out]
-    const float* g;          // optional [B, N, f_out] (C == 1): G = A^T . dU already computed -- its rows are copied, not gathered
+    const float* g;          // optional [B, N, C * f_out]: G = [A_0^T . dU | A_1^T . dU | ..] already computed -- its rows are copied, not gathered
     float* partial;          // [grid][(f_in + 1) * Ng]
     int64_t n_graphs;
     int C, N, f_in, f_out, Ng;
@@ -215,8 +215,9 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                     const uint32_t rp_cnt = static_cast<uint32_t>((r0 + rows_csr + 1 - rp_lo + 3) & ~3ll);
                     const uint32_t x_bytes = static_cast<uint32_t>(ng * N) * pitch_x, u_bytes = static_cast<uint32_t>(ng * N) * pitch_u;
                     if (p.g != nullptr) {   // G rows take the place of the dU rows; no CSR slices
-                        mbar_expect_tx(full, x_bytes + u_bytes);   // the one arrival of the phase
-                        bulk_g2s(st + p.st_du, p.g + g0 * N * f_out, u_bytes, full);
+                        const uint32_t g_bytes = u_bytes * static_cast<uint32_t>(C);
+                        mbar_expect_tx(full, x_bytes + g_bytes);   // the one arrival of the phase
+                        bulk_g2s(st + p.st_du, p.g + g0 * N * Ng, g_bytes, full);
                         bulk_g2s(st, p.x + g0 * N * f_in, x_bytes, full);
                         if (tile_no + it < 30) DW_STAMP(8 + 8 * (tile_no + it));
                         if (++s == S) s = 0;
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kBlock, 1) graphconv_fused_dw_kernel(const DwB
                         if (cs < p.n_gs && copy_g) {
                             // ---- G slab, already computed: the row's 128 bytes, same rotated chunk order as the gather leaves ----
                             if (valid) {
-                                const uint32_t ga = st + p.st_du + static_cast<uint32_t>(r) * pitch_u + static_cast<uint32_t>(cs) * 128u + (s7 << 4);
+                                const uint32_t ga = st + p.st_du + static_cast<uint32_t>(r) * (pitch_u * static_cast<uint32_t>(C)) + static_cast<uint32_t>(cs) * 128u + (s7 << 4);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     float t[4];
@@ -511,7 +512,10 @@ inline uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kSmemMax = 227 * 1024 - 1024;   // static __shared__ (barriers) shares the 227 KB
 
-bool plan_dw_try(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int G, int R, int opbufs, int min_stages) {
+// g_wide: the stage holds finished G rows ([rows, C * f_out]) where the dU rows and the CSR slices would be (C > 1 only: for one
+// channel G and dU have the same shape and the layout stays exactly the gather layout, so such a job can follow a gathering
+// job of the same widths without a job boundary)
+bool plan_dw_try(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out, int G, int R, int opbufs, int min_stages, bool g_wide = false) {
     p.C = C; p.N = N; p.f_in = f_in; p.f_out = f_out; p.Ng = C * f_out; p.n_graphs = n_graphs;
     p.stacked = f_in <= 64 ? 1 : 0;
     p.n_xs = f_in / 32;
@@ -534,9 +538,9 @@ bool plan_dw_try(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     off += static_cast<uint32_t>(opbufs) * p.op_bytes;
     if (p.stacked && 64u * (static_cast<uint32_t>(p.Ng) + 4u) * 4u > static_cast<uint32_t>(opbufs) * p.op_bytes) return false;   // end-of-kernel scratch
     p.off_stage = off;
-    p.cv_cap = static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C), 4));
+    p.cv_cap = g_wide ? 4 : static_cast<int>(up(std::max<uint32_t>(256, 6 * rows_max * C), 4));
     p.st_du = up(rows_max * f_in * 4u, 128);
-    p.st_rp = p.st_du + up(rows_max * f_out * 4u, 128);
+    p.st_rp = p.st_du + up(rows_max * static_cast<uint32_t>(g_wide ? p.Ng : f_out) * 4u, 128);
     p.st_col = p.st_rp + up((rows_max * C + 8) * 4u, 16);
     p.st_val = p.st_col + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u;
     p.stage_bytes = up(p.st_val + (static_cast<uint32_t>(p.cv_cap) + 4) * 4u, 128);
@@ -551,7 +555,7 @@ bool plan_dw_try(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_ou
     return cols <= 512;
 }
 
-bool plan_dw(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
+bool plan_dw(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out, bool g_wide = false) {
     if (n_graphs <= 0 || C < 1 || C > 8 || N < 1 || N > 128) return false;
     if (f_in % 32 != 0 || f_out % 32 != 0 || f_in > 128 || f_in < 32 || C * f_out > 256) return false;
     // preference: >= 2 stages always; double-buffered operands as long as a chunk still fills the warps (>= 32 rows), then
@@ -562,13 +566,13 @@ bool plan_dw(DwParams& p, int64_t n_graphs, int C, int N, int f_in, int f_out) {
         int ob = 0, r = 0;
         if (sscanf(forced, "%d:%d", &ob, &r) == 2 && (ob == 1 || ob == 2) && (r == 16 || r == 32 || r == 64))
             for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
-                if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, r, ob, 2)) return true;
+                if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, r, ob, 2, g_wide)) return true;
     }
     const int order[6][2] = {{2, 64}, {2, 32}, {1, 64}, {1, 32}, {2, 16}, {1, 16}};
     for (const auto& o : order)
         for (int G = g_max; G >= 1; G = (G > 1 ? G / 2 : 0))
-            if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, o[1], o[0], 2)) return true;
-    return plan_dw_try(p, n_graphs, C, N, f_in, f_out, 1, 32, 1, 1);
+            if (plan_dw_try(p, n_graphs, C, N, f_in, f_out, G, o[1], o[0], 2, g_wide)) return true;
+    return plan_dw_try(p, n_graphs, C, N, f_in, f_out, 1, 32, 1, 1, g_wide);
 }
 
 }  // namespace
@@ -618,24 +622,27 @@ int launch_graphconv_fused_dw_jobs(const DwJob* jobs, int n_jobs, int64_t n_grap
     DwBatch b{};
     b.n_jobs = n_jobs;
     b.dbg = g_dbg_dw;
+    bool wide_job[kDwMaxJobs] = {};
     uint32_t cols = 0, smem = 0;
     for (int k = 0; k < n_jobs; ++k) {
         DwParams& p = b.job[k];
         const DwJob& j = jobs[k];
-        KGCN_REQUIRE(plan_dw(p, n_graphs, channels, n_nodes, j.f_in, j.f_out), KGCN_ERR_UNSUPPORTED,
+        // a precomputed G is used when its (for C > 1: wider) stage layout has a plan; else the job gathers from dU as without it
+        const bool wide = j.g != nullptr && channels > 1;
+        const bool use_g = j.g != nullptr && aligned16(j.g) && (!wide || plan_dw(p, n_graphs, channels, n_nodes, j.f_in, j.f_out, true));
+        KGCN_REQUIRE((use_g && wide) || plan_dw(p, n_graphs, channels, n_nodes, j.f_in, j.f_out), KGCN_ERR_UNSUPPORTED,
                      "fused GraphConv weight gradient: unsupported shape");
+        wide_job[k] = use_g && wide;
         KGCN_REQUIRE(p.graphs_per_cta == b.job[0].graphs_per_cta, KGCN_ERR_UNSUPPORTED, "fused GraphConv weight gradient: graph ranges differ");
         const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_graphs, p.graphs_per_cta));
         const size_t need = static_cast<size_t>(grid) * (static_cast<size_t>(j.f_in) + 1) * p.Ng * sizeof(float);
         KGCN_REQUIRE(j.partial != nullptr && j.partial_bytes >= need && aligned16(j.partial), KGCN_ERR_WORKSPACE,
                      "fused GraphConv weight gradient: workspace %zu < %zu bytes", j.partial_bytes, need);
         p.rowptr = j.rowptr_t; p.col = j.col_t; p.val = j.val_t; p.x = j.x; p.du = j.du;
-        KGCN_REQUIRE(j.g == nullptr || (channels == 1 && aligned16(j.g)), KGCN_ERR_UNSUPPORTED,
-                     "fused GraphConv weight gradient: a precomputed G needs channels == 1 and 16-byte alignment");
-        p.g = j.g;
+        p.g = use_g ? j.g : nullptr;
         p.partial = j.partial;
         p.tm_off = cols;
-        p.fresh = (k == 0 || !soft_jobs_enabled() || j.f_in != jobs[k - 1].f_in || j.f_out != jobs[k - 1].f_out) ? 1 : 0;
+        p.fresh = (k == 0 || !soft_jobs_enabled() || j.f_in != jobs[k - 1].f_in || j.f_out != jobs[k - 1].f_out || wide_job[k] != wide_job[k - 1]) ? 1 : 0;
         cols += 2u * static_cast<uint32_t>(p.Ng);
         smem = std::max(smem, p.smem_total);
     }

@@ -221,11 +221,14 @@ class Trainer:
             self.step_grid = int(lib.kgcn_gcn_step_chain_grid(B, C, N, L, self._dims_c, s.label_dim))
         self.step_chain = self.step_grid > 0
         # the dx jobs of the step launch also store what they aggregate, G_l = A^T . dU_l, and the weight-gradient launch reads it
-        # instead of gathering it a second time (bit-identical; KGCN_GSAVE=0 is the A-B knob)
+        # instead of gathering it a second time (bit-identical; KGCN_GSAVE=0 is the A-B knob).  One adjacency channel only by default:
+        # with C channels G is C times as wide as dU, the copying jobs need their own (larger) stage layout and the dx jobs C times
+        # the stores -- measured slower on config 4 (216 vs 204 us per step); KGCN_GSAVE=2 forces it for any C
         self.g_save = None
-        if (self.step_chain and os.environ.get("KGCN_GSAVE", "1") != "0" and
+        g_mode = os.environ.get("KGCN_GSAVE", "1")
+        if (self.step_chain and g_mode != "0" and (C == 1 or g_mode == "2") and
                 bool(lib.kgcn_gcn_step_chain_g_supported(B, C, N, L, self._dims_c))):
-            self.g_save = [None] + [torch.empty(B, N, self.dims[i + 1], **f32) for i in range(1, L)]
+            self.g_save = [None] + [torch.empty(B, N, C * self.dims[i + 1], **f32) for i in range(1, L)]
             self._g_ptrs = arr(self.g_save)
         if self.fused_step:
             n_seg = len(s.conv_dims) + (2 if self.step_chain else 0)

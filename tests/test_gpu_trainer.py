@@ -208,24 +208,26 @@ def test_chained_launches_equal_per_layer_launches(B, N, C, F, conv_dims, monkey
     assert int(c.step_state[0].item()) == 3
 
 
-@pytest.mark.parametrize("B,N,F,conv_dims", [
-    (700, 32, 64, [64, 64]),          # C2 widths: ragged last tile (5 graphs per CTA, 4 + 1), one stored G
-    (1024, 32, 64, [64, 64]),         # C2 at the full batch
-    (300, 50, 75, [50, 50, 50]),      # C3 on padded widths: two stored G (layers 2 and 1), tiles of 2 graphs = 100 of 128 rows
-    (37, 20, 32, [32, 64, 32]),       # unequal widths: hard job boundaries, a different plan per weight-gradient job
-    (512, 64, 128, [128, 128]),       # C5's shard: the wide-layer (v5) step launch stores G, 32-row operand chunks copy it
-    (21, 64, 128, [128, 128]),        # the same kernels on a batch smaller than the grid
+@pytest.mark.parametrize("B,N,C,F,conv_dims", [
+    (700, 32, 1, 64, [64, 64]),          # C2 widths: ragged last tile (5 graphs per CTA, 4 + 1), one stored G
+    (1024, 32, 1, 64, [64, 64]),         # C2 at the full batch
+    (300, 50, 1, 75, [50, 50, 50]),      # C3 on padded widths: two stored G (layers 2 and 1), tiles of 2 graphs = 100 of 128 rows
+    (37, 20, 1, 32, [32, 64, 32]),       # unequal widths: hard job boundaries, a different plan per weight-gradient job
+    (512, 64, 1, 128, [128, 128]),       # C5's shard: the wide-layer (v5) step launch stores G, 32-row operand chunks copy it
+    (21, 64, 1, 128, [128, 128]),        # the same kernels on a batch smaller than the grid
+    (512, 50, 3, 75, [50, 50, 50]),      # C4: three bond types, G = [G_0 | G_1 | G_2] is 192 wide (its own stage layout in the copying jobs)
+    (45, 32, 2, 64, [64, 64]),           # two channels, small batch
 ])
-def test_stored_aggregate_equals_second_gather(B, N, F, conv_dims, monkeypatch):
+def test_stored_aggregate_equals_second_gather(B, N, C, F, conv_dims, monkeypatch):
     """The dx jobs of the step launch store G_l = A^T . dU_l and the weight-gradient launch copies it (kgcn_gcn_step_chain_g_f32 /
     kgcn_graphconv_chain_dw_g_f32) -- against KGCN_GSAVE=0, where the weight-gradient launch gathers G_l again: the same per-row
     accumulation order and the same tf32 split, so gradients and parameters must be BIT-identical, and the stored G itself equals
     the batched SpMM of the library on (A^T, dU_l)."""
     from kgcn_b200 import ops
     from kgcn_b200.trainer import DeviceBatch, NetSpec, Trainer
-    counts, idx, val, x, labels, mask, adjs, p = make_case(B, N, 1, F, conv_dims, None, seed=B + N)
-    spec = NetSpec(F, conv_dims, N, channels=1, label_dim=2, act="sigmoid")
-    monkeypatch.setenv("KGCN_GSAVE", "1")
+    counts, idx, val, x, labels, mask, adjs, p = make_case(B, N, C, F, conv_dims, None, seed=B + N)
+    spec = NetSpec(F, conv_dims, N, channels=C, label_dim=2, act="sigmoid")
+    monkeypatch.setenv("KGCN_GSAVE", "2")          # 2: also with several channels (off by default there: measured slower)
     a = Trainer(spec, B, seed=3)
     monkeypatch.setenv("KGCN_GSAVE", "0")
     b = Trainer(spec, B, seed=3)
@@ -242,10 +244,10 @@ def test_stored_aggregate_equals_second_gather(B, N, F, conv_dims, monkeypatch):
     csr_t = batch.csr.transposed()
     for l in range(1, len(conv_dims)):
         f = a.dims[l + 1]
-        want = torch.empty(B, N, f, device="cuda")
-        ops.bspmm_raw(csr_t, a.du[l], N * f, 0, want, N * f, 0, f)
+        want = torch.empty(B, C, N, f, device="cuda")          # per channel: A_c^T . dU_l (dU shared by the channels)
+        ops.bspmm_raw(csr_t, a.du[l], N * f, 0, want, C * N * f, N * f, f)
         torch.cuda.synchronize()
-        close(a.g_save[l], want.cpu().numpy(), 1e-6)
+        close(a.g_save[l].view(B, N, C, f), want.permute(0, 2, 1, 3).cpu().numpy(), 1e-6)
 
 
 def test_training_reduces_loss_on_ring_task():
