@@ -26,7 +26,7 @@ def main():
         B, N, F, C = w["batch_per_gpu"], w["n_nodes"], w["feature_dim"], w["channels"]
         spec = NetSpec(F, w["conv_dims"], N, channels=C, label_dim=w["label_dim"], act=w["act"])
         tr = Trainer(spec, B, device=b.dev, lr=0.01, world_size=1, seed=1234, rank=0)
-        w2 = dict(w, n_rot=4)
+        w2 = dict(w, n_rot=int(os.environ.get("E2E_HOST_BATCHES", "4")))   # bench.py rotates w["n_rot"] pinned batches (24 for c2: never cache-resident on the host)
         batches, host = b.make_batches(w2)
         if batches is None:
             batches = [DeviceBatch.from_host(d["counts"], d["indices"], d["values"], d["features"], d["labels"], N, device=b.dev,
